@@ -1,0 +1,170 @@
+/*
+ * pcq.h — C-ABI of libpcq: the B200 (sm_100a) polynomial-chaos hot path.
+ *
+ * This is the drop-in boundary for PyTUQ's PC path.  PyTUQ has no FFI of its
+ * own (it is pure Python); every entry point below cites the reference Python
+ * method whose arithmetic it replaces (paths relative to the PyTUQ tree,
+ * src/pytuq/...).  The Python shim in pytuq_b200/ binds these with ctypes and
+ * keeps the reference's PCRV / lreg signatures; INTEGRATION.md shows the stub a
+ * PyTUQ maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary.
+ *   - every function returns 0 on success, a negative pcq_status otherwise, and
+ *     never throws; pcq_last_error() returns a thread-local description.
+ *   - "_dev" entry points take DEVICE pointers and a CUDA stream handle
+ *     (cudaStream_t passed as void*; NULL = legacy default stream) and are
+ *     asynchronous with respect to the host.
+ *   - the other entry points take HOST pointers, move data themselves
+ *     (chunked H2D -> kernel -> D2H) and return when the result is in host
+ *     memory.
+ *   - all matrices are row-major (C order) float64, as numpy gives them.
+ */
+#ifndef PCQ_H_
+#define PCQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCQ_VERSION 100
+
+typedef enum pcq_status {
+    PCQ_OK = 0,
+    PCQ_ERR_ARG = -1,      /* bad argument (shape, null pointer, order out of range) */
+    PCQ_ERR_CUDA = -2,     /* a CUDA runtime call failed (see pcq_last_error) */
+    PCQ_ERR_NODEV = -3,    /* no CUDA device / device index out of range */
+    PCQ_ERR_ALLOC = -4,    /* host or device allocation failed */
+    PCQ_ERR_UNSUPPORTED = -5
+} pcq_status;
+
+typedef struct pcq_plan pcq_plan;
+
+/* ---- library / device ---------------------------------------------------- */
+
+int pcq_version(void);
+const char* pcq_last_error(void);
+/* number of visible CUDA devices, or a negative pcq_status */
+int pcq_device_count(void);
+
+/* ---- plan ------------------------------------------------------------------
+ * A plan is the device-resident form of one (multi-index, 1-D families) pair,
+ * i.e. of PCRV.mindices[jdim] + PCRV.PC1ds (rv/pcrv.py:84-115, 745-782).
+ *
+ *   sdim      s, germ dimension
+ *   nterms    K, number of multi-index rows
+ *   mi        K x s int32, row-major (host)   -- PCRV.mindices[jdim]
+ *   pmax      max over dims of PCRV.maxOrd (rv/pcrv.py:176-184); every mi entry
+ *             must be <= pmax
+ *   rec_a     (pmax+1) x s, rec_a[n*s+i] = PC1d_i.a(n)  (rv/pcrv.py:755,762,769,776)
+ *   rec_b     (pmax+1) x s, rec_b[n*s+i] = PC1d_i.b(n)  (rv/pcrv.py:756,763,770,777)
+ *             both evaluated on the host by the caller with the reference's own
+ *             Python expressions, so the constants are bit-identical
+ *   p1_scale  s, phi_1(x) = x * p1_scale[i]  (1.0 for LU/HG/nHG, sqrt(3) for nLU;
+ *             rv/pcrv.py:754,761,768,775)
+ *   device    CUDA device ordinal the plan lives on
+ */
+int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms,
+                    const int32_t* mi, int pmax,
+                    const double* rec_a, const double* rec_b,
+                    const double* p1_scale);
+int pcq_plan_destroy(pcq_plan* plan);
+/* queries: 0 sdim, 1 nterms, 2 pmax, 3 width (max non-zero orders per term),
+ *          4 device, 5 downward-closed flag, 6 number of SMs */
+int64_t pcq_plan_info(const pcq_plan* plan, int what);
+
+/* ---- K1: design matrix -----------------------------------------------------
+ * A[n,k] = prod_i phi^{(i)}_{mi[k,i]}(x[n,i])          PCRV.evalBases, rv/pcrv.py:413-442
+ * with the 1-D values from the three-term recurrence    PC1d.__call__,   rv/pcrv.py:784-804
+ * evaluated with the reference's rounding sequence ((a*x)*p_n)+(b*p_{n-1})
+ * (no FMA contraction) and the product taken over the non-zero orders in
+ * ascending dimension order, so A is bit-identical to the reference.
+ *   x  N x s, leading dimension ldx (>= s)   A  N x K, leading dimension lda (>= K)
+ */
+int pcq_eval_bases_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,
+                       double* a_dev, int64_t lda, void* stream);
+int pcq_eval_bases(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
+                   double* a_host, int64_t lda);
+
+/* ---- K2: surrogate evaluation (A never materialised) -------------------------
+ * y[n,m] = sum_k cf[m,k] * prod_i phi(...)              PCRV.evalPC, rv/pcrv.py:469-498
+ * mode 0 (exact): coefficient multiplied first, factors in dimension order,
+ *   terms summed sequentially in k order — bit-identical to the reference.
+ * mode 1 (fast): one basis product per term shared by all outputs and fused
+ *   multiply-adds; differs from mode 0 by rounding only.
+ *   cf  M x K (row m = coefficients of output m), y  N x M with leading dimension ldy
+ */
+int pcq_eval_pc_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,
+                    const double* cf_dev, int m, double* y_dev, int64_t ldy,
+                    int mode, void* stream);
+int pcq_eval_pc(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
+                const double* cf_host, int m, double* y_host, int64_t ldy, int mode);
+
+/* ---- K3: fused sufficient statistics ------------------------------------------
+ * With the augmented row  z_n = [ Psi(x_n) (K) | y_n (M) | 1 ]  of length
+ * L = K + M + 1, computes the symmetric L x L matrix  S = sum_n z_n z_n^T :
+ *     S[:K,:K]      = A^T A      anl.fita  lreg/anl.py:78 ; bcs_fit lreg/bcs.py:84,95,100
+ *     S[:K,K:K+M]   = A^T Y      lreg/anl.py:83 ; lreg/bcs.py:83
+ *     S[K:K+M,K:K+M]= Y^T Y      lreg/anl.py:57 ; lreg/bcs.py:229
+ *     S[:K,L-1]     = A^T 1,  S[K:K+M,L-1] = sum_n y_n,  S[L-1,L-1] = N
+ * A is generated tile by tile on chip from x and never written to HBM; the
+ * contraction runs on the FP64 tensor pipe (DMMA).
+ *   accumulate != 0 adds to the existing contents of s_out (for streaming and
+ *   for sample-sharded partial sums), otherwise s_out is overwritten.
+ *   y may be NULL when m == 0.
+ *   s_out  L x L, row-major, leading dimension L.
+ */
+int64_t pcq_suffstats_dim(const pcq_plan* plan, int m);   /* returns L */
+int pcq_suffstats_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,
+                      const double* y_dev, int64_t ldy, int m,
+                      double* s_dev, int accumulate, void* stream);
+int pcq_suffstats(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
+                  const double* y_host, int64_t ldy, int m, double* s_host);
+
+/* ---- K4: sufficient statistics from a materialised design matrix ---------------
+ * Same S as above but z_n = [ A[n,:] | y_n | 1 ] with A given (lreg.fita(Amat, y),
+ * lreg/lreg.py:328-339, lreg/anl.py:69-105, lreg/bcs.py:37-52).  kcols = A's column count.
+ */
+int pcq_gram_dev(int device, const double* a_dev, int64_t n, int64_t lda, int kcols,
+                 const double* y_dev, int64_t ldy, int m,
+                 double* s_dev, int accumulate, void* stream);
+int pcq_gram(int device, const double* a_host, int64_t n, int64_t lda, int kcols,
+             const double* y_host, int64_t ldy, int m, double* s_host);
+
+/* ---- K5: forward propagation with on-device germ sampling -----------------------
+ * Draws n germ samples (U(-1,1) where germ_kind[i]==0, N(0,1) where ==1;
+ * PC1d.sample, rv/pcrv.py:757,764,771,778) from a counter-based Philox4x32-10
+ * stream keyed by (seed, sample index, dimension), pushes them through evalPC
+ * and reduces per-output power sums on the fly (PCRV.sample, rv/pcrv.py:511-525
+ * followed by the moment estimates the callers take).  Nothing of size n is
+ * written unless y_dev != NULL.
+ *   sums_dev: M x 4 doubles  [sum y, sum y^2, min, max] per output (overwritten)
+ *   first_index: global index of the first sample (lets shards draw disjoint
+ *   sub-streams of one logical stream)
+ */
+int pcq_propagate_dev(pcq_plan* plan, uint64_t seed, int64_t first_index, int64_t n,
+                      const int32_t* germ_kind_host, const double* cf_dev, int m,
+                      double* sums_dev, double* y_dev, int64_t ldy, int mode,
+                      void* stream);
+/* the germ alone (same stream as above), x_dev N x s */
+int pcq_sample_germ_dev(pcq_plan* plan, uint64_t seed, int64_t first_index, int64_t n,
+                        const int32_t* germ_kind_host, double* x_dev, int64_t ldx,
+                        void* stream);
+
+/* ---- roofline denominators (micro-benchmarks) ---------------------
+ * kind 0: FP64 DFMA register-resident chain   -> TFLOP/s
+ * kind 1: FP64 DMMA (mma.sync m8n8k4 f64) chain -> TFLOP/s
+ * kind 2: HBM copy (read+write bytes)          -> GB/s
+ */
+int pcq_measure_peak(int device, int kind, double* result);
+
+/* number of kernel launches issued by this library since load (all threads) */
+int64_t pcq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCQ_H_ */

@@ -1,0 +1,459 @@
+// C-ABI of libpcq (see include/pcq.h): plans, host-pointer entry points, error plumbing.
+#include "pcq_internal.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <set>
+
+std::atomic<long long> g_pcq_launches{0};
+
+namespace {
+thread_local char g_err[512] = "";
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int device_props(int device, int* num_sms, size_t* smem_optin) {
+    int v = 0;
+    PCQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    *num_sms = v;
+    PCQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    *smem_optin = (size_t)v;
+    return PCQ_OK;
+}
+
+template <typename T>
+int dev_upload(T** dst, const T* src, size_t count) {
+    PCQ_CUDA(cudaMalloc((void**)dst, std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) PCQ_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return PCQ_OK;
+}
+
+// rows of x processed per chunk by the host-pointer entry points
+int64_t chunk_rows(int64_t bytes_per_row, int64_t n) {
+    const int64_t target = (int64_t)1 << 28;   // 256 MiB of output/input per chunk
+    int64_t r = target / std::max<int64_t>(bytes_per_row, 1);
+    r = std::max<int64_t>(r, 1024);
+    r &= ~(int64_t)15;
+    return std::min(r, std::max<int64_t>(n, 1));
+}
+
+int ensure_streams(pcq_plan* p) {
+    for (int i = 0; i < 2; ++i) {
+        if (!p->streams[i]) PCQ_CUDA(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+        if (!p->events[i]) PCQ_CUDA(cudaEventCreateWithFlags(&p->events[i], cudaEventDisableTiming));
+    }
+    return PCQ_OK;
+}
+}  // namespace
+
+void pcq_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int pcq_ensure_dev(double** buf, size_t* have, size_t bytes) {
+    if (*have >= bytes && *buf) return PCQ_OK;
+    if (*buf) {
+        PCQ_CUDA(cudaFree(*buf));
+        *buf = nullptr;
+        *have = 0;
+    }
+    cudaError_t e = cudaMalloc((void**)buf, bytes);
+    if (e != cudaSuccess) {
+        pcq_set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        *buf = nullptr;
+        return PCQ_ERR_ALLOC;
+    }
+    *have = bytes;
+    return PCQ_OK;
+}
+
+extern "C" {
+
+int pcq_version(void) { return PCQ_VERSION; }
+const char* pcq_last_error(void) { return g_err; }
+int64_t pcq_launch_count(void) { return g_pcq_launches.load(); }
+
+int pcq_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        pcq_set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+        return PCQ_ERR_NODEV;
+    }
+    return n;
+}
+
+int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms, const int32_t* mi, int pmax,
+                    const double* rec_a, const double* rec_b, const double* p1_scale) {
+    if (!out) { pcq_set_error("plan_create: out is null"); return PCQ_ERR_ARG; }
+    *out = nullptr;
+    if (sdim <= 0 || nterms <= 0 || pmax < 0 || !mi || !rec_a || !rec_b || !p1_scale) {
+        pcq_set_error("plan_create: bad argument (sdim=%d nterms=%d pmax=%d)", sdim, nterms, pmax);
+        return PCQ_ERR_ARG;
+    }
+    const int64_t nslots64 = 1 + (int64_t)pmax * sdim;
+    if (nslots64 > 65535) {
+        pcq_set_error("plan_create: 1 + pmax*sdim = %lld table slots exceed 65535", (long long)nslots64);
+        return PCQ_ERR_UNSUPPORTED;
+    }
+    int ndev = pcq_device_count();
+    if (ndev <= 0 || device < 0 || device >= ndev) {
+        pcq_set_error("plan_create: device %d not available (%d visible)", device, ndev);
+        return PCQ_ERR_NODEV;
+    }
+    // host-side compression of the multi-index: per term, the slots of its non-zero orders in
+    // ascending dimension order (rv/pcrv.py:436-438 multiplies in that order; x1.0 factors drop out)
+    int width = 1;
+    for (int k = 0; k < nterms; ++k) {
+        int nnz = 0;
+        for (int i = 0; i < sdim; ++i) {
+            const int o = mi[(size_t)k * sdim + i];
+            if (o < 0 || o > pmax) {
+                pcq_set_error("plan_create: mi[%d,%d]=%d outside [0,%d]", k, i, o, pmax);
+                return PCQ_ERR_ARG;
+            }
+            nnz += (o > 0);
+        }
+        width = std::max(width, nnz);
+    }
+    std::vector<uint16_t> descw((size_t)nterms * width, 0);
+    std::vector<unsigned long long> desc4(nterms, 0ull);
+    for (int k = 0; k < nterms; ++k) {
+        int j = 0;
+        for (int i = 0; i < sdim; ++i) {
+            const int o = mi[(size_t)k * sdim + i];
+            if (o > 0) descw[(size_t)k * width + j++] = (uint16_t)(1 + (o - 1) * sdim + i);
+        }
+        if (width <= PCQ_MAXW_FAST) {
+            unsigned long long d = 0;
+            for (int q = 0; q < width; ++q) d |= (unsigned long long)descw[(size_t)k * width + q] << (16 * q);
+            desc4[k] = d;
+        }
+    }
+    // downward-closed check (informational; lets callers pick parent-product algorithms)
+    int closed = 1;
+    {
+        std::set<std::vector<int32_t>> rows;
+        for (int k = 0; k < nterms; ++k)
+            rows.insert(std::vector<int32_t>(mi + (size_t)k * sdim, mi + (size_t)(k + 1) * sdim));
+        for (int k = 0; k < nterms && closed; ++k) {
+            std::vector<int32_t> r(mi + (size_t)k * sdim, mi + (size_t)(k + 1) * sdim);
+            for (int i = 0; i < sdim && closed; ++i) {
+                if (r[i] > 0) {
+                    r[i] -= 1;
+                    if (!rows.count(r)) closed = 0;
+                    r[i] += 1;
+                }
+            }
+        }
+    }
+
+    DeviceGuard guard(device);
+    if (!guard.ok) { pcq_set_error("plan_create: cudaSetDevice(%d) failed", device); return PCQ_ERR_CUDA; }
+    pcq_plan* p = new (std::nothrow) pcq_plan();
+    if (!p) { pcq_set_error("plan_create: out of host memory"); return PCQ_ERR_ALLOC; }
+    p->device = device;
+    p->sdim = sdim; p->nterms = nterms; p->pmax = pmax; p->nslots = (int)nslots64;
+    p->width = width; p->downward_closed = closed;
+    int rc = device_props(device, &p->num_sms, &p->smem_optin);
+    const size_t nrec = (size_t)(pmax + 1) * sdim;
+    if (rc == PCQ_OK) rc = dev_upload(&p->d_rec_a, rec_a, nrec);
+    if (rc == PCQ_OK) rc = dev_upload(&p->d_rec_b, rec_b, nrec);
+    if (rc == PCQ_OK) rc = dev_upload(&p->d_p1, p1_scale, (size_t)sdim);
+    if (rc == PCQ_OK) rc = dev_upload(&p->d_descw, descw.data(), descw.size());
+    if (rc == PCQ_OK) rc = dev_upload(&p->d_desc4, desc4.data(), desc4.size());
+    if (rc == PCQ_OK) {
+        std::vector<int> zeros(sdim, 0);
+        rc = dev_upload(&p->d_kinds, zeros.data(), zeros.size());
+    }
+    if (rc != PCQ_OK) { pcq_plan_destroy(p); return rc; }
+    *out = p;
+    return PCQ_OK;
+}
+
+int pcq_plan_destroy(pcq_plan* p) {
+    if (!p) return PCQ_OK;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
+    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_ws); cudaFree(p->d_misc);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(p->d_stage[i]); cudaFree(p->d_out[i]);
+        if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+        if (p->events[i]) cudaEventDestroy(p->events[i]);
+    }
+    delete p;
+    return PCQ_OK;
+}
+
+int64_t pcq_plan_info(const pcq_plan* p, int what) {
+    if (!p) return PCQ_ERR_ARG;
+    switch (what) {
+        case 0: return p->sdim;
+        case 1: return p->nterms;
+        case 2: return p->pmax;
+        case 3: return p->width;
+        case 4: return p->device;
+        case 5: return p->downward_closed;
+        case 6: return p->num_sms;
+        default: return PCQ_ERR_ARG;
+    }
+}
+
+// ------------------------------------------------------------------ device-pointer entry points
+int pcq_eval_bases_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double* a, int64_t lda,
+                       void* stream) {
+    if (!p || n < 0 || (n > 0 && (!x || !a)) || ldx < p->sdim || lda < p->nterms) {
+        pcq_set_error("eval_bases: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    return pcq_launch_bases(p, x, n, ldx, a, lda, (cudaStream_t)stream);
+}
+
+int pcq_eval_pc_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m,
+                    double* y, int64_t ldy, int mode, void* stream) {
+    if (!p || n < 0 || m < 0 || (n > 0 && m > 0 && (!x || !cf || !y)) || ldx < p->sdim || ldy < m) {
+        pcq_set_error("eval_pc: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    return pcq_launch_evalpc(p, x, n, ldx, cf, m, y, ldy, mode, (cudaStream_t)stream);
+}
+
+int64_t pcq_suffstats_dim(const pcq_plan* p, int m) {
+    if (!p || m < 0) return PCQ_ERR_ARG;
+    return (int64_t)p->nterms + m + 1;
+}
+
+int pcq_suffstats_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y,
+                      int64_t ldy, int m, double* s, int accumulate, void* stream) {
+    if (!p || n < 0 || m < 0 || !s || (n > 0 && !x) || (n > 0 && m > 0 && !y) || ldx < p->sdim ||
+        (m > 0 && ldy < m)) {
+        pcq_set_error("suffstats: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    return pcq_launch_gram(p, p->num_sms, p->smem_optin, x, n, ldx, nullptr, 0, 0, y, ldy, m, s,
+                           accumulate, &p->d_ws, &p->ws_bytes, (cudaStream_t)stream);
+}
+
+namespace {
+// K4 has no plan: keep one workspace per device
+struct GramCtx { double* ws = nullptr; size_t ws_bytes = 0; double* stage[2] = {nullptr, nullptr};
+                 size_t stage_bytes[2] = {0, 0}; double* s = nullptr; size_t s_bytes = 0;
+                 double* ys[2] = {nullptr, nullptr}; size_t ys_bytes[2] = {0, 0}; };
+GramCtx g_gram_ctx[64];
+}
+
+int pcq_gram_dev(int device, const double* a, int64_t n, int64_t lda, int kcols, const double* y,
+                 int64_t ldy, int m, double* s, int accumulate, void* stream) {
+    if (device < 0 || device >= 64 || n < 0 || kcols <= 0 || m < 0 || !s || (n > 0 && !a) ||
+        (n > 0 && m > 0 && !y) || lda < kcols || (m > 0 && ldy < m)) {
+        pcq_set_error("gram: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) { pcq_set_error("gram: cudaSetDevice(%d) failed", device); return PCQ_ERR_NODEV; }
+    int num_sms = 0; size_t smem_optin = 0;
+    int rc = device_props(device, &num_sms, &smem_optin);
+    if (rc != PCQ_OK) return rc;
+    GramCtx& c = g_gram_ctx[device];
+    return pcq_launch_gram(nullptr, num_sms, smem_optin, nullptr, n, 0, a, lda, kcols, y, ldy, m, s,
+                           accumulate, &c.ws, &c.ws_bytes, (cudaStream_t)stream);
+}
+
+int pcq_propagate_dev(pcq_plan* p, uint64_t seed, int64_t first_index, int64_t n,
+                      const int32_t* germ_kind, const double* cf, int m, double* sums, double* y,
+                      int64_t ldy, int mode, void* stream) {
+    if (!p || n < 0 || m <= 0 || !germ_kind || !cf || !sums || (y && ldy < m)) {
+        pcq_set_error("propagate: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    return pcq_launch_propagate(p, seed, first_index, n, germ_kind, cf, m, sums, y, ldy, mode,
+                                (cudaStream_t)stream);
+}
+
+int pcq_sample_germ_dev(pcq_plan* p, uint64_t seed, int64_t first_index, int64_t n,
+                        const int32_t* germ_kind, double* x, int64_t ldx, void* stream) {
+    if (!p || n < 0 || !germ_kind || (n > 0 && !x) || ldx < p->sdim) {
+        pcq_set_error("sample_germ: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    return pcq_launch_germ(p, seed, first_index, n, germ_kind, x, ldx, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host-pointer entry points
+// Double-buffered chunk pipeline: chunk c uses stream c&1; H2D(x) -> kernel -> D2H(result).
+// Pageable numpy memory is accepted as is (the driver stages it); the two streams overlap
+// the copies of one chunk with the kernel of the other.
+int pcq_eval_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double* a, int64_t lda) {
+    if (!p || n < 0 || (n > 0 && (!x || !a)) || ldx < p->sdim || lda < p->nterms) {
+        pcq_set_error("eval_bases: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    if (n == 0) return PCQ_OK;
+    DeviceGuard guard(p->device);
+    int rc = ensure_streams(p);
+    if (rc != PCQ_OK) return rc;
+    const int K = p->nterms, s = p->sdim;
+    const int64_t rows = chunk_rows((int64_t)K * 8, n);
+    int c = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows, ++c) {
+        const int b = c & 1;
+        const int64_t nr = std::min(rows, n - r0);
+        cudaStream_t st = p->streams[b];
+        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
+        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * K * 8)) != PCQ_OK) return rc;
+        PCQ_CUDA(cudaMemcpy2DAsync(p->d_stage[b], (size_t)s * 8, x + r0 * ldx, (size_t)ldx * 8,
+                                   (size_t)s * 8, (size_t)nr, cudaMemcpyHostToDevice, st));
+        if ((rc = pcq_launch_bases(p, p->d_stage[b], nr, s, p->d_out[b], K, st)) != PCQ_OK) return rc;
+        PCQ_CUDA(cudaMemcpy2DAsync(a + r0 * lda, (size_t)lda * 8, p->d_out[b], (size_t)K * 8,
+                                   (size_t)K * 8, (size_t)nr, cudaMemcpyDeviceToHost, st));
+    }
+    PCQ_CUDA(cudaStreamSynchronize(p->streams[0]));
+    PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));
+    return PCQ_OK;
+}
+
+int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m,
+                double* y, int64_t ldy, int mode) {
+    if (!p || n < 0 || m < 0 || (n > 0 && m > 0 && (!x || !cf || !y)) || ldx < p->sdim || ldy < m) {
+        pcq_set_error("eval_pc: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    if (n == 0 || m == 0) return PCQ_OK;
+    DeviceGuard guard(p->device);
+    int rc = ensure_streams(p);
+    if (rc != PCQ_OK) return rc;
+    const int K = p->nterms, s = p->sdim;
+    if ((rc = pcq_ensure_dev(&p->d_misc, &p->misc_bytes, (size_t)m * K * 8)) != PCQ_OK) return rc;
+    PCQ_CUDA(cudaMemcpyAsync(p->d_misc, cf, (size_t)m * K * 8, cudaMemcpyHostToDevice, p->streams[0]));
+    PCQ_CUDA(cudaEventRecord(p->events[0], p->streams[0]));
+    PCQ_CUDA(cudaStreamWaitEvent(p->streams[1], p->events[0], 0));
+    const int64_t rows = chunk_rows((int64_t)(s + m) * 8, n);
+    int c = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows, ++c) {
+        const int b = c & 1;
+        const int64_t nr = std::min(rows, n - r0);
+        cudaStream_t st = p->streams[b];
+        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
+        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * m * 8)) != PCQ_OK) return rc;
+        PCQ_CUDA(cudaMemcpy2DAsync(p->d_stage[b], (size_t)s * 8, x + r0 * ldx, (size_t)ldx * 8,
+                                   (size_t)s * 8, (size_t)nr, cudaMemcpyHostToDevice, st));
+        if ((rc = pcq_launch_evalpc(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], m, mode, st)) != PCQ_OK)
+            return rc;
+        PCQ_CUDA(cudaMemcpy2DAsync(y + r0 * ldy, (size_t)ldy * 8, p->d_out[b], (size_t)m * 8,
+                                   (size_t)m * 8, (size_t)nr, cudaMemcpyDeviceToHost, st));
+    }
+    PCQ_CUDA(cudaStreamSynchronize(p->streams[0]));
+    PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));
+    return PCQ_OK;
+}
+
+int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
+                  int m, double* s_host) {
+    if (!p || n < 0 || m < 0 || !s_host || (n > 0 && !x) || (n > 0 && m > 0 && !y) ||
+        ldx < p->sdim || (m > 0 && ldy < m)) {
+        pcq_set_error("suffstats: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    int rc = ensure_streams(p);
+    if (rc != PCQ_OK) return rc;
+    const int s = p->sdim;
+    const int64_t L = (int64_t)p->nterms + m + 1;
+    if ((rc = pcq_ensure_dev(&p->d_misc, &p->misc_bytes, (size_t)L * L * 8)) != PCQ_OK) return rc;
+    // copies go on stream 1 / 0 alternately, all Gram launches are ordered on stream 0 through
+    // events (they accumulate into the same S)
+    cudaStream_t sk = p->streams[0];
+    if (n == 0) {
+        if ((rc = pcq_launch_gram(p, p->num_sms, p->smem_optin, nullptr, 0, s, nullptr, 0, 0, nullptr,
+                                  std::max(m, 1), m, p->d_misc, 0, &p->d_ws, &p->ws_bytes, sk)) != PCQ_OK)
+            return rc;
+    }
+    const int64_t rows = chunk_rows((int64_t)(s + m) * 8, n);
+    int c = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows, ++c) {
+        const int b = c & 1;
+        const int64_t nr = std::min(rows, n - r0);
+        cudaStream_t sc = p->streams[1];
+        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
+        if (m > 0 && (rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * m * 8)) != PCQ_OK) return rc;
+        // buffer b was last read by the Gram launch of chunk c-2
+        if (c >= 2) PCQ_CUDA(cudaStreamWaitEvent(sc, p->events[b], 0));
+        PCQ_CUDA(cudaMemcpy2DAsync(p->d_stage[b], (size_t)s * 8, x + r0 * ldx, (size_t)ldx * 8,
+                                   (size_t)s * 8, (size_t)nr, cudaMemcpyHostToDevice, sc));
+        if (m > 0)
+            PCQ_CUDA(cudaMemcpy2DAsync(p->d_out[b], (size_t)m * 8, y + r0 * ldy, (size_t)ldy * 8,
+                                       (size_t)m * 8, (size_t)nr, cudaMemcpyHostToDevice, sc));
+        cudaEvent_t copied;
+        PCQ_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+        PCQ_CUDA(cudaEventRecord(copied, sc));
+        PCQ_CUDA(cudaStreamWaitEvent(sk, copied, 0));
+        PCQ_CUDA(cudaEventDestroy(copied));
+        if ((rc = pcq_launch_gram(p, p->num_sms, p->smem_optin, p->d_stage[b], nr, s, nullptr, 0, 0,
+                                  p->d_out[b], std::max(m, 1), m, p->d_misc, c > 0, &p->d_ws,
+                                  &p->ws_bytes, sk)) != PCQ_OK)
+            return rc;
+        PCQ_CUDA(cudaEventRecord(p->events[b], sk));
+    }
+    PCQ_CUDA(cudaMemcpyAsync(s_host, p->d_misc, (size_t)L * L * 8, cudaMemcpyDeviceToHost, sk));
+    PCQ_CUDA(cudaStreamSynchronize(sk));
+    PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));
+    return PCQ_OK;
+}
+
+int pcq_gram(int device, const double* a, int64_t n, int64_t lda, int kcols, const double* y,
+             int64_t ldy, int m, double* s_host) {
+    if (device < 0 || device >= 64 || n < 0 || kcols <= 0 || m < 0 || !s_host || (n > 0 && !a) ||
+        (n > 0 && m > 0 && !y) || lda < kcols || (m > 0 && ldy < m)) {
+        pcq_set_error("gram: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) { pcq_set_error("gram: cudaSetDevice(%d) failed", device); return PCQ_ERR_NODEV; }
+    GramCtx& c = g_gram_ctx[device];
+    const int64_t L = (int64_t)kcols + m + 1;
+    int rc;
+    if ((rc = pcq_ensure_dev(&c.s, &c.s_bytes, (size_t)L * L * 8)) != PCQ_OK) return rc;
+    const int64_t rows = chunk_rows((int64_t)(kcols + m) * 8, n);
+    if (n == 0) {
+        if ((rc = pcq_gram_dev(device, nullptr, 0, lda, kcols, nullptr, ldy, m, c.s, 0, nullptr)) != PCQ_OK) return rc;
+    }
+    int ci = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows, ++ci) {
+        const int64_t nr = std::min(rows, n - r0);
+        if ((rc = pcq_ensure_dev(&c.stage[0], &c.stage_bytes[0], (size_t)rows * kcols * 8)) != PCQ_OK) return rc;
+        if (m > 0 && (rc = pcq_ensure_dev(&c.ys[0], &c.ys_bytes[0], (size_t)rows * m * 8)) != PCQ_OK) return rc;
+        PCQ_CUDA(cudaMemcpy2D(c.stage[0], (size_t)kcols * 8, a + r0 * lda, (size_t)lda * 8,
+                              (size_t)kcols * 8, (size_t)nr, cudaMemcpyHostToDevice));
+        if (m > 0)
+            PCQ_CUDA(cudaMemcpy2D(c.ys[0], (size_t)m * 8, y + r0 * ldy, (size_t)ldy * 8, (size_t)m * 8,
+                                  (size_t)nr, cudaMemcpyHostToDevice));
+        if ((rc = pcq_gram_dev(device, c.stage[0], nr, kcols, kcols, c.ys[0], std::max(m, 1), m, c.s,
+                               ci > 0, nullptr)) != PCQ_OK)
+            return rc;
+    }
+    PCQ_CUDA(cudaMemcpy(s_host, c.s, (size_t)L * L * 8, cudaMemcpyDeviceToHost));
+    return PCQ_OK;
+}
+
+}  // extern "C"

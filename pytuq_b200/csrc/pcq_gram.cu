@@ -1,0 +1,370 @@
+// K3 / K4: sufficient statistics S = sum_n z_n z_n^T on the FP64 tensor pipe (DMMA) for sm_100a.
+//
+//   z_n = [ Psi(x_n) (K) | y_n (M) | 1 ],  L = K + M + 1
+//   S[:K,:K] = A^T A (anl.fita lreg/anl.py:78, bcs_fit lreg/bcs.py:84,95,100)
+//   S[:K,K:K+M] = A^T Y (lreg/anl.py:83, lreg/bcs.py:83),  S[K:,K:] = Y^T Y, sums, N
+//
+// Work decomposition (stream-K over the upper triangle):
+//   the L x L output is cut into 128 x 128 tiles, only tiles (I <= J) are computed; the
+//   sample axis is cut into blocks of GRAM_SB samples; the ntri * nblk (tile, block)
+//   units are laid out tile-major and divided evenly and contiguously among the CTAs
+//   (one CTA per SM).  A CTA therefore works on at most two partial tiles plus complete
+//   tiles in between.  Partial tiles go to a workspace and are summed in CTA order by a
+//   fix-up kernel (deterministic, no atomics); a mirror kernel fills the lower triangle.
+// Per CTA (256 threads, 8 warps as 4 x 2, warp tile 32 x 64, 64 accumulators per thread):
+//   stage it+1: the 1-D recurrences of KT samples go to a shared slot table, then each
+//   thread generates one column of the I or J operand tile for those samples (A is never
+//   written to HBM); stage it: mma.sync.m8n8k4.f64 over the previous stage's tiles.
+//   Operand tiles and slot tables are double buffered: one __syncthreads per stage.
+#include "pcq_internal.cuh"
+
+namespace {
+
+constexpr int GT = 128;          // tile edge (terms)
+constexpr int KT = 16;           // samples per pipeline stage
+constexpr int LDT = GT + 4;      // padded operand row: conflict-free DMMA fragment loads
+constexpr int G_THREADS = 256;
+constexpr int GRAM_SB = 64;      // samples per scheduling unit (multiple of KT)
+constexpr int XPF = 4;           // x values prefetched per thread per stage
+
+struct GramParams {
+    const double* x; int64_t ldx;
+    const double* a; int64_t lda;
+    const double* y; int64_t ldy;
+    int kb;            // number of basis columns (K, or kcols of a materialised A)
+    int m;
+    int L;             // kb + m + 1
+    int ntile;         // ceil(L / GT)
+    int64_t n;
+    int64_t nblk;      // ceil(n / GRAM_SB)
+    int64_t total;     // ntri * nblk
+    int sdim, pmax, nslots, width;
+    const double* rec_a; const double* rec_b; const double* p1;
+    const unsigned long long* desc4; const uint16_t* descw;
+    double* s_out; int accumulate;
+    double* ws;        // [grid][2][GT*GT]
+};
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void tile_decode(int64_t t, int ntile, int& I, int& J) {
+    int i = 0;
+    int64_t rem = t;
+    while (rem >= (int64_t)(ntile - i)) { rem -= (ntile - i); ++i; }
+    I = i;
+    J = i + (int)rem;
+}
+
+template <int W, bool FUSED>
+__global__ void __launch_bounds__(G_THREADS, 1) pcq_gram_kernel(GramParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: op[2 stages][2 operands][KT][LDT] | tab[2 stages][KT][nslots]
+    double* op = reinterpret_cast<double*>(smem_raw);
+    double* tab = op + 2 * 2 * KT * LDT;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int g = lane >> 2;      // groupID
+    const int tig = lane & 3;     // thread in group
+    const int wm = warp & 3;      // 4 warps along M (32 rows each)
+    const int wn = warp >> 2;     // 2 warps along N (64 cols each)
+    const int half = tid >> 7;    // which operand tile this thread generates
+    const int col = tid & 127;
+    const int s = P.sdim;
+
+    const int64_t G = gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * P.total / G;
+    const int64_t hi = ((int64_t)blockIdx.x + 1) * P.total / G;
+    const int64_t first_tile = (hi > lo) ? lo / P.nblk : -1;
+
+    int64_t u = lo;
+    while (u < hi) {
+        const int64_t t = u / P.nblk;
+        const int64_t b0 = u - t * P.nblk;
+        const int64_t seg_end = min(hi, (t + 1) * P.nblk);
+        const int64_t nb = seg_end - u;
+        const int64_t sbeg = b0 * GRAM_SB;
+        const int64_t send = min(P.n, (b0 + nb) * GRAM_SB);
+        int I, J;
+        tile_decode(t, P.ntile, I, J);
+        const bool diag = (I == J);
+
+        // this thread's generated column
+        const int gc = ((half == 0 || diag) ? I : J) * GT + col;
+        int kind;   // 0 basis, 1 y, 2 ones, 3 zero padding
+        if (gc < P.kb) kind = 0;
+        else if (gc < P.kb + P.m) kind = 1;
+        else if (gc == P.kb + P.m) kind = 2;
+        else kind = 3;
+        unsigned long long mydesc = 0;
+        if (FUSED && W > 0 && kind == 0) mydesc = P.desc4[gc];
+        const int rstart = diag ? half : 0;
+        const int rstep = diag ? 2 : 1;
+        double* opw_base = op + (size_t)((diag ? 0 : half) * KT) * LDT + col;
+
+        double acc[4][8][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+        const int nst = (int)((send - sbeg + KT - 1) / KT);
+        const int npairs = KT * s;
+
+        auto load_x = [&](int st, double (&xr)[XPF]) {
+            if (!FUSED) return;
+            const int64_t n0 = sbeg + (int64_t)st * KT;
+#pragma unroll
+            for (int j = 0; j < XPF; ++j) {
+                const int idx = tid + j * G_THREADS;
+                xr[j] = 0.0;
+                if (idx < npairs && st < nst) {
+                    const int r = idx / s;
+                    const int i = idx - r * s;
+                    if (n0 + r < send) xr[j] = P.x[(n0 + r) * P.ldx + i];
+                }
+            }
+        };
+        auto build_tables = [&](int st, const double (&xr)[XPF]) {
+            if (!FUSED) return;
+            double* T = tab + (size_t)(st & 1) * KT * P.nslots;
+            const int64_t n0 = sbeg + (int64_t)st * KT;
+#pragma unroll
+            for (int j = 0; j < XPF; ++j) {
+                const int idx = tid + j * G_THREADS;
+                if (idx < npairs) {
+                    const int r = idx / s;
+                    const int i = idx - r * s;
+                    double* tr = T + (size_t)r * P.nslots;
+                    if (i == 0) tr[0] = 1.0;
+                    pcq_fill_1d(xr[j], i, s, P.pmax, P.rec_a, P.rec_b, P.p1, tr, 1);
+                }
+            }
+            for (int idx = tid + XPF * G_THREADS; idx < npairs; idx += G_THREADS) {
+                const int r = idx / s;
+                const int i = idx - r * s;
+                double* tr = T + (size_t)r * P.nslots;
+                if (i == 0) tr[0] = 1.0;
+                const double xv = (n0 + r < send) ? P.x[(n0 + r) * P.ldx + i] : 0.0;
+                pcq_fill_1d(xv, i, s, P.pmax, P.rec_a, P.rec_b, P.p1, tr, 1);
+            }
+        };
+        auto generate = [&](int st) {
+            const double* T = tab + (size_t)(st & 1) * KT * P.nslots;
+            double* o = opw_base + (size_t)(st & 1) * 2 * KT * LDT;
+            const int64_t n0 = sbeg + (int64_t)st * KT;
+#pragma unroll 4
+            for (int r = rstart; r < KT; r += rstep) {
+                const bool live = (n0 + r) < send;
+                double v;
+                if (kind == 0) {
+                    if (FUSED) {
+                        if (W > 0) v = pcq_term4<W>(T + (size_t)r * P.nslots, 1, mydesc);
+                        else v = pcq_termw(T + (size_t)r * P.nslots, 1,
+                                           P.descw + (size_t)gc * P.width, P.width);
+                    } else {
+                        v = live ? P.a[(n0 + r) * P.lda + gc] : 0.0;
+                    }
+                } else if (kind == 1) {
+                    v = live ? P.y[(n0 + r) * P.ldy + (gc - P.kb)] : 0.0;
+                } else if (kind == 2) {
+                    v = 1.0;
+                } else {
+                    v = 0.0;
+                }
+                o[(size_t)r * LDT] = live ? v : 0.0;
+            }
+        };
+        auto mma_stage = [&](int st) {
+            const double* oa = op + (size_t)(st & 1) * 2 * KT * LDT;
+            const double* ob = oa + (diag ? 0 : KT * LDT);
+            const double* pa = oa + (size_t)tig * LDT + wm * 32 + g;
+            const double* pb = ob + (size_t)tig * LDT + wn * 64 + g;
+#pragma unroll
+            for (int kk = 0; kk < KT; kk += 4) {
+                double af[4], bf[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] = pa[(size_t)kk * LDT + i * 8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bf[j] = pb[(size_t)kk * LDT + j * 8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        };
+
+        __syncthreads();   // previous segment's MMA readers are done with op / tab
+        double xr[XPF];
+        load_x(0, xr);
+        build_tables(0, xr);
+        load_x(1, xr);
+        __syncthreads();
+        generate(0);
+        for (int it = 0; it < nst; ++it) {
+            if (it + 1 < nst) {
+                build_tables(it + 1, xr);
+                load_x(it + 2, xr);
+            }
+            __syncthreads();
+            if (it + 1 < nst) generate(it + 1);
+            mma_stage(it);
+        }
+
+        // flush: complete tiles go straight to S, partial ones to this CTA's workspace slot
+        const bool complete = (nb == P.nblk);
+        if (complete) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = I * GT + wm * 32 + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = J * GT + wn * 64 + j * 8 + 2 * tig;
+                    if (row < P.L) {
+                        double* dst = P.s_out + (size_t)row * P.L + c;
+                        if (c < P.L) dst[0] = (P.accumulate ? dst[0] : 0.0) + acc[i][j][0];
+                        if (c + 1 < P.L) dst[1] = (P.accumulate ? dst[1] : 0.0) + acc[i][j][1];
+                    }
+                }
+            }
+        } else {
+            const int slot = (t == first_tile) ? 0 : 1;
+            double* w = P.ws + ((size_t)blockIdx.x * 2 + slot) * GT * GT;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = wm * 32 + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = wn * 64 + j * 8 + 2 * tig;
+                    *reinterpret_cast<double2*>(w + (size_t)row * GT + c) =
+                        make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+            }
+        }
+        u = seg_end;
+    }
+}
+
+// sums the partial tiles of every tile that was split across CTAs, in CTA order
+__global__ void __launch_bounds__(256) pcq_gram_fixup_kernel(GramParams P, int grid_main) {
+    const int64_t t = blockIdx.x;
+    const int64_t G = grid_main;
+    const int64_t u0 = t * P.nblk;
+    const int64_t u1 = (t + 1) * P.nblk - 1;
+    const int64_t c_first = ((u0 + 1) * G - 1) / P.total;
+    const int64_t c_last = ((u1 + 1) * G - 1) / P.total;
+    if (c_first == c_last) return;   // complete tile, already written by its owner
+    int I, J;
+    tile_decode(t, P.ntile, I, J);
+    for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < GT * GT; e += blockDim.x * gridDim.y) {
+        const int r = e / GT;
+        const int c = e - r * GT;
+        const int row = I * GT + r;
+        const int cc = J * GT + c;
+        if (row >= P.L || cc >= P.L) continue;
+        double sum = 0.0;
+        for (int64_t cta = c_first; cta <= c_last; ++cta) {
+            const int64_t lo = cta * P.total / G;
+            const int slot = (lo / P.nblk == t) ? 0 : 1;
+            sum += P.ws[((size_t)cta * 2 + slot) * GT * GT + e];
+        }
+        double* dst = P.s_out + (size_t)row * P.L + cc;
+        *dst = (P.accumulate ? *dst : 0.0) + sum;
+    }
+}
+
+// lower triangle <- upper triangle
+__global__ void __launch_bounds__(256) pcq_gram_mirror_kernel(double* s, int L) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;   // source blocks: upper triangle (incl. diagonal blocks)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int row = bi * 32 + r, c = bj * 32 + tx;
+        tile[r][tx] = (row < L && c < L) ? s[(size_t)row * L + c] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int row = bj * 32 + r, c = bi * 32 + tx;   // transposed destination
+        if (row < L && c < L && row > c) s[(size_t)row * L + c] = tile[tx][r];
+    }
+}
+
+template <int W, bool FUSED>
+int launch_gram_t(const GramParams& P0, int num_sms, size_t smem_optin, double** ws,
+                  size_t* ws_bytes, cudaStream_t st) {
+    GramParams P = P0;
+    const size_t smem = (size_t)(2 * 2 * KT * LDT + (FUSED ? 2 * KT * P.nslots : 0)) * sizeof(double);
+    if (smem > smem_optin) {
+        pcq_set_error("suffstats: %zu bytes of shared memory needed, %zu available", smem, smem_optin);
+        return PCQ_ERR_UNSUPPORTED;
+    }
+    auto kern = pcq_gram_kernel<W, FUSED>;
+    PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid64 = P.total < num_sms ? P.total : num_sms;
+    const int grid = (int)grid64;
+    const size_t need = (size_t)grid * 2 * GT * GT * sizeof(double);
+    int rc = pcq_ensure_dev(ws, ws_bytes, need);
+    if (rc != PCQ_OK) return rc;
+    P.ws = *ws;
+    kern<<<grid, G_THREADS, smem, st>>>(P);
+    PCQ_LAUNCH_CHECK("pcq_gram_kernel");
+    const int ntri = P.ntile * (P.ntile + 1) / 2;
+    pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
+    PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
+    const int nb32 = (P.L + 31) / 32;
+    pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
+    PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    return PCQ_OK;
+}
+
+__global__ void pcq_fill_kernel(double* p, size_t n, double v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+}  // namespace
+
+int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n,
+                    int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,
+                    int64_t ldy, int m, double* s, int accumulate, double** ws,
+                    size_t* ws_bytes, cudaStream_t st) {
+    GramParams P;
+    memset(&P, 0, sizeof(P));
+    const bool fused = (a == nullptr);
+    P.x = x; P.ldx = ldx; P.a = a; P.lda = lda; P.y = y; P.ldy = ldy;
+    P.kb = fused ? p->nterms : kcols;
+    P.m = m;
+    P.L = P.kb + m + 1;
+    P.ntile = (P.L + GT - 1) / GT;
+    P.n = n;
+    P.s_out = s; P.accumulate = accumulate;
+    if (n == 0) {
+        if (!accumulate) {
+            pcq_fill_kernel<<<256, 256, 0, st>>>(s, (size_t)P.L * P.L, 0.0);
+            PCQ_LAUNCH_CHECK("pcq_fill_kernel");
+        }
+        return PCQ_OK;
+    }
+    P.nblk = (n + GRAM_SB - 1) / GRAM_SB;
+    P.total = (int64_t)(P.ntile * (P.ntile + 1) / 2) * P.nblk;
+    if (fused) {
+        P.sdim = p->sdim; P.pmax = p->pmax; P.nslots = p->nslots; P.width = p->width;
+        P.rec_a = p->d_rec_a; P.rec_b = p->d_rec_b; P.p1 = p->d_p1;
+        P.desc4 = p->d_desc4; P.descw = p->d_descw;
+        switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
+            case 1: return launch_gram_t<1, true>(P, num_sms, smem_optin, ws, ws_bytes, st);
+            case 2: return launch_gram_t<2, true>(P, num_sms, smem_optin, ws, ws_bytes, st);
+            case 3: return launch_gram_t<3, true>(P, num_sms, smem_optin, ws, ws_bytes, st);
+            case 4: return launch_gram_t<4, true>(P, num_sms, smem_optin, ws, ws_bytes, st);
+            default: return launch_gram_t<0, true>(P, num_sms, smem_optin, ws, ws_bytes, st);
+        }
+    }
+    return launch_gram_t<0, false>(P, num_sms, smem_optin, ws, ws_bytes, st);
+}

@@ -1,0 +1,168 @@
+"""Linear-regression base class and least squares on GPU-computed sufficient statistics.
+
+Drop-in for the reference's ``lreg/lreg.py`` (``lreg`` 12-306, ``lsq`` 310-339): same
+attributes after a fit (``cf, cf_cov, used, datavar, fitted``) and same methods.  What
+changes is where the O(N K^2) work happens:
+
+* ``fit(x, y)`` with a PC basis evaluator never materialises the design matrix: the fused
+  kernel K3 reduces (x, y) to S = [A|y|1]^T [A|y|1] on the device (include/pcq.h) and the
+  fitter works on the K x K statistics;
+* ``fita(Amat, y)`` with a caller-supplied matrix reduces it with the DMMA Gram kernel K4.
+
+The K x K factorisation itself is host LAPACK (it is not sample-parallel).
+"""
+import sys
+
+import numpy as np
+from scipy.linalg import cho_factor, cho_solve
+
+from ..fit.fit import fitbase
+from .stats import SuffStats
+
+
+class PCBasisEvaluator:
+    """Basis evaluator ``(x, pars) -> pars[0].evalBases(x, jdim)`` that ``lreg`` recognises:
+    fits through it take the fused no-A path.  Same call convention as the closure the
+    reference installs in surrogates/pce.py:378-382."""
+
+    def __init__(self, jdim=0):
+        self.jdim = jdim
+
+    def __call__(self, x, pars):
+        return pars[0].evalBases(x, self.jdim)
+
+
+def solve_normal(G, b):
+    """Solves G c = b for symmetric positive (semi)definite G.
+
+    Jacobi-scaled Cholesky; when G is numerically singular the minimum-norm solution on
+    the retained eigen-space is returned instead (the closest normal-equation analogue of
+    the reference's SVD least squares with cond=1e-13, lreg/lreg.py:335 -- see DESIGN.md
+    for the conditioning limit of that equivalence)."""
+    d = np.sqrt(np.clip(np.diag(G), 0.0, None))
+    d[d == 0.0] = 1.0
+    scale = d if b.ndim == 1 else d[:, None]
+    Gs = G / np.outer(d, d)
+    try:
+        fac = cho_factor(Gs, lower=True, check_finite=False)
+        piv = np.abs(np.diag(fac[0]))
+        if piv.min() > 1.0e-6 * piv.max():          # cond(Gs) well below 1e12: Cholesky is safe
+            c = cho_solve(fac, b / scale, check_finite=False)
+            if np.all(np.isfinite(c)):
+                return c / scale
+    except np.linalg.LinAlgError:
+        pass
+    # (near-)singular: minimum-norm solution in the original variables, like an SVD solve
+    lam, V = np.linalg.eigh(G)
+    keep = lam > lam[-1] * max(G.shape[0], 10) * 1.0e-14
+    return (V[:, keep] / lam[keep]) @ (V[:, keep].T @ b)
+
+
+class lreg(fitbase):
+    """Base class for linear regression (attributes as in lreg/lreg.py:12-34)."""
+
+    def __init__(self):
+        super().__init__()
+        self.cf = None
+        self.cf_cov = None
+        self.datavar = 0.0
+        self.basisEvaluatorSet = False
+        self.used = None
+
+    def setBasisEvaluator(self, basiseval, basisevalpars):
+        self.basisEval = basiseval
+        self.basisEvalPars = basisevalpars
+        self.basisEvaluatorSet = True
+
+    # -- fitting ------------------------------------------------------------------------
+    def _fit_stats(self, stats):
+        """Fit from sufficient statistics of one output (SuffStats with M = 1)."""
+        raise NotImplementedError("Fitting not implemented in the base class.")
+
+    def fita(self, Amat, y):
+        r"""Fit given a materialised design matrix (N, K) and data (N,): K4 + _fit_stats."""
+        self._fit_stats(SuffStats.from_matrix(Amat, y))
+
+    def fit(self, x, y):
+        r"""Fit with (x, y) pairs through the basis evaluator (lreg/lreg.py:62-71)."""
+        assert(self.basisEvaluatorSet)
+        if isinstance(self.basisEval, PCBasisEvaluator):
+            stats = SuffStats.from_pc(self.basisEvalPars[0], x, y, self.basisEval.jdim)
+            self._fit_stats(stats)
+        else:
+            Amat = self.basisEval(x, self.basisEvalPars)
+            self.fita(Amat, y)
+
+    def print_coefs(self):
+        assert(self.fitted)
+        print(self.cf)
+
+    # -- prediction (host-side glue on an evaluated basis; SURVEY.md row f1 is the fused form) --
+    def predict(self, x, msc=0, pp=False):
+        assert(self.basisEvaluatorSet)
+        Amat = self.basisEval(x, self.basisEvalPars)
+        return self.predicta(Amat, msc=msc, pp=pp)
+
+    def predict_samples(self, x, nsamples=100):
+        assert(self.basisEvaluatorSet)
+        Amat = self.basisEval(x, self.basisEvalPars)
+        return self.predicta_samples(Amat, nsamples=nsamples)
+
+    def predicta(self, Amat, msc=0, pp=False):
+        r"""(mean, variance | None, covariance | None) for an evaluated basis (lreg/lreg.py:112-143)."""
+        assert(self.fitted)
+        ypred = Amat @ self.cf
+        ypred_var = ypred_cov = None
+        if msc == 2:
+            ypred_cov = (Amat @ self.cf_cov) @ Amat.T + int(pp) * self.datavar * np.eye(Amat.shape[0])
+            ypred_var = np.diag(ypred_cov)
+        elif msc == 1:
+            try:
+                ypred_var = self.compute_stdev(Amat, method='chol') ** 2
+            except np.linalg.LinAlgError:
+                ypred_var = self.compute_stdev(Amat, method='svd') ** 2
+            ypred_var += int(pp) * self.datavar
+        elif msc != 0:
+            print(f"msc={msc}, but needs to be 0,1, or 2. Exiting.")
+            sys.exit()
+        return ypred, ypred_var, ypred_cov
+
+    def predicta_samples(self, Amat, nsamples=100):
+        assert(self.fitted)
+        assert(self.cf_cov is not None)
+        return Amat @ np.random.multivariate_normal(self.cf, self.cf_cov, nsamples).T
+
+    def compute_stdev(self, Amat, method="chol"):
+        r"""Pushed-forward standard deviation sqrt(diag(A C A^T)) (lreg/lreg.py:164-198)."""
+        assert(self.cf_cov is not None)
+        C = self.cf_cov
+        if method == "chol":
+            return np.linalg.norm(Amat @ np.linalg.cholesky(C), axis=1)
+        if method == "choleye":
+            shift = abs(np.linalg.eigvalsh(C)[0]) + 1e-14
+            return np.linalg.norm(Amat @ np.linalg.cholesky(C + shift * np.eye(C.shape[0])), axis=1)
+        if method == "svd":
+            u, s, _ = np.linalg.svd(C, hermitian=True)
+            return np.linalg.norm((Amat @ u) @ np.sqrt(np.diag(s)), axis=1)
+        if method == "loop":
+            return np.sqrt(np.einsum('ij,ij->i', Amat @ C, Amat))
+        if method == "fullcov":
+            return np.sqrt(np.diag((Amat @ C) @ Amat.T))
+        return np.zeros(Amat.shape[0])
+
+
+class lsq(lreg):
+    """Least squares.  The reference solves min ||A c - y|| with an SVD of the N x K matrix
+    (scipy gelsd, lreg/lreg.py:328-339); here the sample axis is reduced on the GPU and the
+    K x K normal equations are solved, which agrees to ~1e-14 for the well-conditioned
+    bases of the PC path (cond(G) ~ 10..100)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def _fit_stats(self, stats):
+        K = stats.K
+        self.cf = solve_normal(stats.G, stats.b(0))
+        self.cf_cov = np.zeros((K, K))
+        self.fitted = True
+        self.used = np.arange(K)

@@ -1,0 +1,93 @@
+"""Sufficient statistics of a linear regression, computed on the GPU (K3 / K4).
+
+Every fitter on the path needs only  G = A^T A,  b = A^T y,  y^T y,  sum(y)  and N
+(anl: lreg/anl.py:78-99; bcs_fit: lreg/bcs.py:79-100,166-193,229; lsq through the normal
+equations).  libpcq returns them packed in one symmetric matrix
+
+    S = sum_n z_n z_n^T ,   z_n = [ A[n,:] (K) | y_n (M) | 1 ]
+
+so the sample axis is reduced in one streaming pass, shards over samples with a single
+all-reduce of S, and A is never materialised on the fused path.
+"""
+import numpy as np
+
+from .. import _native, device as _device
+
+
+class SuffStats:
+    """View of the packed statistics matrix S ((K+M+1) x (K+M+1), float64)."""
+
+    def __init__(self, S, nbasis, nout):
+        self.S = S
+        self.K = int(nbasis)
+        self.M = int(nout)
+        assert S.shape == (self.K + self.M + 1, self.K + self.M + 1)
+
+    # --- accessors -------------------------------------------------------------------
+    @property
+    def G(self):
+        return self.S[:self.K, :self.K]
+
+    @property
+    def n(self):
+        return float(self.S[-1, -1])
+
+    def b(self, j=0):
+        return self.S[:self.K, self.K + j]
+
+    def B(self):
+        return self.S[:self.K, self.K:self.K + self.M]
+
+    def yty(self, j=0):
+        return float(self.S[self.K + j, self.K + j])
+
+    def ysum(self, j=0):
+        return float(self.S[self.K + j, -1])
+
+    def colsum(self):
+        return self.S[:self.K, -1]
+
+    def yvar(self, j=0):
+        """Population variance of y_j (np.std(y)**2 in lreg/bcs.py:79)."""
+        n = self.n
+        mean = self.ysum(j) / n
+        return max(self.yty(j) / n - mean * mean, 0.0)
+
+    def rss(self, cf, used=None, j=0):
+        """sum_n (y_n - A[n,used] cf)^2 = y^T y - 2 cf^T b_used + cf^T G_used cf."""
+        if used is None:
+            used = np.arange(self.K)
+        Gu = self.G[np.ix_(used, used)]
+        bu = self.b(j)[used]
+        return self.yty(j) - 2.0 * float(cf @ bu) + float(cf @ (Gu @ cf))
+
+    def select(self, j):
+        """Statistics of output j alone (M = 1)."""
+        idx = np.concatenate([np.arange(self.K), [self.K + j, self.K + self.M]])
+        return SuffStats(np.ascontiguousarray(self.S[np.ix_(idx, idx)]), self.K, 1)
+
+    # --- constructors -------------------------------------------------------------------
+    @classmethod
+    def from_pc(cls, pcrv, x, y=None, jdim=0):
+        """Fused path (K3): statistics of the jdim-th PC basis at germ points x, no A."""
+        from ..parallel import suffstats_pc
+        return suffstats_pc(pcrv, x, y, jdim)
+
+    @classmethod
+    def from_matrix(cls, Amat, y=None):
+        """Materialised path (K4): statistics of a design matrix handed over by the caller
+        (lreg.fita(Amat, y), lreg/lreg.py:48-59)."""
+        _device.require_device()
+        A = np.ascontiguousarray(Amat, dtype=np.float64)
+        N, K = A.shape
+        if y is None:
+            Y, M = None, 0
+        else:
+            Y = np.ascontiguousarray(y, dtype=np.float64).reshape(N, -1)
+            M = Y.shape[1]
+        L = K + M + 1
+        S = np.empty((L, L))
+        st = _native.lib().pcq_gram(_device.current_device(), _native.ptr(A), N, K, K,
+                                    _native.ptr(Y), max(M, 1), M, _native.ptr(S))
+        _native.check(st, "pcq_gram")
+        return cls(S, K, M)

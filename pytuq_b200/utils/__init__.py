@@ -1,0 +1,2 @@
+"""Host-side utilities of the PC path (multi-index tables)."""
+from .mindex import get_mi, get_npc, encode_mindex, micf_join, mi_addfront, mi_addfront_cons  # noqa: F401

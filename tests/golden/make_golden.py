@@ -1,0 +1,201 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (PyTUQ) in this container.
+
+Run once, here (needs /root/reference; the GPU box does not have it):
+
+    python tests/golden/make_golden.py
+
+matplotlib is absent from the image and PyTUQ imports it at module import time
+(func/func.py:7, utils/plotting.py:13-16, lreg/lreg.py:6), so it is stubbed in
+sys.modules before the import.  Nothing on the arithmetic path touches matplotlib.
+The committed .npz files are what tests/ compares the oracle and the CUDA path with.
+"""
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+
+REF = os.environ.get("PYTUQ_REF", "/root/reference/src")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.lines",
+                 "matplotlib.patches", "matplotlib.ticker", "matplotlib.cm", "matplotlib.gridspec",
+                 "matplotlib.collections", "matplotlib.tri", "mpl_toolkits", "mpl_toolkits.mplot3d",
+                 "mpl_toolkits.axes_grid1"):
+        sys.modules.setdefault(name, MagicMock())
+    sys.path.insert(0, REF)
+    from pytuq.rv.pcrv import PCRV, PC1d                      # noqa
+    from pytuq.utils.mindex import get_mi, get_npc            # noqa
+    from pytuq.lreg.lreg import lsq                           # noqa
+    from pytuq.lreg.anl import anl                            # noqa
+    from pytuq.lreg.bcs import bcs, bcs_fit                   # noqa
+    from pytuq.workflows.fits import pc_fit                   # noqa
+    from pytuq.surrogates.pce import PCE                      # noqa
+    return dict(PCRV=PCRV, PC1d=PC1d, get_mi=get_mi, get_npc=get_npc, lsq=lsq, anl=anl,
+                bcs=bcs, bcs_fit=bcs_fit, pc_fit=pc_fit, PCE=PCE)
+
+
+def germ(rng, fam, shape):
+    return rng.uniform(-1, 1, shape) if fam in ("LU", "nLU") else rng.standard_normal(shape)
+
+
+def main():
+    R = import_reference()
+    PCRV, PC1d, get_mi = R["PCRV"], R["PC1d"], R["get_mi"]
+    out = {}
+
+    # --- 1-D families -------------------------------------------------------------------
+    rng = np.random.default_rng(101)
+    d1 = {}
+    for fam in ("LU", "nLU", "HG", "nHG"):
+        x = germ(rng, fam, 48)
+        x[:3] = [0.0, 0.45, -0.45]
+        vals = PC1d(fam)(x, 7)
+        d1[f"{fam}_x"] = x
+        d1[f"{fam}_vals"] = np.array(vals)
+        d1[f"{fam}_normsq"] = np.array([PC1d(fam).normsq(n) for n in range(8)])
+        d1[f"{fam}_a"] = np.array([float(PC1d(fam).a(n)) for n in range(1, 8)])
+        d1[f"{fam}_b"] = np.array([float(PC1d(fam).b(n)) for n in range(1, 8)])
+    np.savez_compressed(os.path.join(HERE, "pc1d.npz"), **d1)
+
+    # --- multi-indices -------------------------------------------------------------------
+    dmi = {}
+    for (p, d) in [(0, 3), (1, 4), (2, 3), (3, 2), (3, 5), (4, 3), (2, 10), (5, 2), (3, 7)]:
+        dmi[f"mi_{p}_{d}"] = get_mi(p, d)
+    dmi["npc"] = np.array([[p, d, R["get_npc"](p, d)] for p in range(6) for d in range(1, 52, 7)])
+    np.savez_compressed(os.path.join(HERE, "mindex.npz"), **dmi)
+
+    # --- evalBases / evalPC / moments / Sobol ---------------------------------------------
+    cases = {}
+
+    def add_case(name, pctype, mis, nx, seed, strided=False):
+        rng = np.random.default_rng(seed)
+        sdim = mis[0].shape[1]
+        types = [pctype] * sdim if isinstance(pctype, str) else pctype
+        cols = [germ(rng, t, nx) for t in types]
+        x = np.stack(cols, axis=1)
+        if strided:
+            x = np.asfortranarray(x)
+        cfs = [rng.standard_normal(m.shape[0]) / (1.0 + m.sum(axis=1)) ** 2 for m in mis]
+        pc = PCRV(len(mis), sdim, pctype, mi=[m.copy() for m in mis], cfs=[c.copy() for c in cfs])
+        cases[f"{name}__x"] = np.ascontiguousarray(x)
+        cases[f"{name}__types"] = np.array(types)
+        cases[f"{name}__npdim"] = np.array(len(mis))
+        for j, (m, c) in enumerate(zip(mis, cfs)):
+            cases[f"{name}__mi{j}"] = m
+            cases[f"{name}__cf{j}"] = c
+            cases[f"{name}__A{j}"] = pc.evalBases(x, j)
+            cases[f"{name}__normsq{j}"] = pc.evalBasesNormsSq(j)
+        cases[f"{name}__y"] = pc.evalPC(x)
+        cases[f"{name}__mean"] = pc.computeMean()
+        cases[f"{name}__var"] = pc.computeVar()
+        cases[f"{name}__main"] = pc.computeSens()
+        cases[f"{name}__total"] = pc.computeTotSens()
+        if sdim <= 12:
+            cases[f"{name}__joint"] = pc.computeJointSens()
+        cases[f"{name}__group01"] = pc.computeGroupSens([0, 1]) if sdim > 2 else np.zeros(len(mis))
+
+    for fam in ("LU", "nLU", "HG", "nHG"):
+        add_case(f"fam_{fam}", fam, [get_mi(4, 3)], 40, 7)
+    add_case("mixed", ["LU", "HG", "nLU", "nHG"], [get_mi(3, 4), get_mi(2, 4)], 33, 8, strided=True)
+    add_case("c1_lu_d10p4", "LU", [get_mi(4, 10)], 24, 1)
+    add_case("c2_hg_d20p3", "HG", [get_mi(3, 20)], 20, 2)
+    add_case("c3_lu_d50p2", "LU", [get_mi(2, 50)], 12, 3)
+    add_case("c4_hg_d20p4", "HG", [get_mi(4, 20)], 6, 4)
+    add_case("d1_p6", "LU", [get_mi(6, 1)], 17, 5)
+    add_case("p0_const", "HG", [get_mi(0, 3)], 9, 6)
+    # general multi-index: not downward closed, duplicate rows, dense rows (width 6 > 4)
+    rng = np.random.default_rng(9)
+    gen = rng.integers(0, 4, size=(37, 6))
+    gen[5] = gen[11]
+    gen[0] = 0
+    add_case("general_dense", ["LU", "HG", "LU", "nLU", "HG", "nHG"], [gen, gen[::2].copy()], 29, 10)
+    # single-dimension growth only (width 1)
+    w1 = np.zeros((9, 3), dtype=int)
+    w1[1:4, 0] = [1, 2, 3]; w1[4:7, 1] = [1, 2, 3]; w1[7:9, 2] = [1, 2]
+    add_case("width1", "HG", [w1], 21, 11)
+    np.savez_compressed(os.path.join(HERE, "pcrv_cases.npz"), **cases)
+
+    # --- fitters ---------------------------------------------------------------------------
+    fits = {}
+
+    def fit_case(name, pctype, order, dim, N, seed, noise, sparse=0):
+        rng = np.random.default_rng(seed)
+        mi = get_mi(order, dim)
+        K = mi.shape[0]
+        x = germ(rng, pctype, (N, dim))
+        pc = PCRV(1, dim, pctype, mi=mi)
+        A = pc.evalBases(x, 0)
+        if sparse:
+            c = np.zeros(K)
+            sup = rng.choice(K, sparse, replace=False)
+            c[sup] = rng.standard_normal(sparse)
+        else:
+            c = rng.standard_normal(K) / (1.0 + mi.sum(axis=1)) ** 2
+        y = A @ c + noise * rng.standard_normal(N)
+        fits[f"{name}__x"] = x
+        fits[f"{name}__y"] = y
+        fits[f"{name}__mi"] = mi
+        fits[f"{name}__type"] = np.array(pctype)
+        fits[f"{name}__ctrue"] = c
+        l = R["lsq"](); l.fita(A, y)
+        fits[f"{name}__lsq_cf"] = l.cf
+        a = R["anl"](); a.fita(A, y)
+        fits[f"{name}__anl_cf"] = a.cf
+        fits[f"{name}__anl_cov"] = a.cf_cov
+        fits[f"{name}__anl_datavar"] = np.array(a.datavar)
+        a2 = R["anl"](datavar=0.01, prior_var=2.0, cov_nugget=1e-8); a2.fita(A, y)
+        fits[f"{name}__anlp_cf"] = a2.cf
+        fits[f"{name}__anlp_cov"] = a2.cf_cov
+        a3 = R["anl"](method="vi"); a3.fita(A, y)
+        fits[f"{name}__anlvi_cov_diag"] = np.diag(a3.cf_cov)
+        for eta in (1e-3, 1e-8):
+            b = R["bcs"](eta=eta); b.fita(A, y)
+            tag = f"{name}__bcs{eta:g}"
+            fits[f"{tag}_cf"] = b.cf
+            fits[f"{tag}_used"] = np.asarray(b.used)
+            fits[f"{tag}_datavar"] = np.asarray(b.datavar)
+            fits[f"{tag}_cov"] = b.cf_cov
+        # prediction with variance on a few fresh points (lreg.predicta msc=1)
+        xt = germ(rng, pctype, (11, dim))
+        At = pc.evalBases(xt, 0)
+        mean, var, _ = a.predicta(At, msc=1)
+        fits[f"{name}__xt"] = xt
+        fits[f"{name}__anl_pred_mean"] = mean
+        fits[f"{name}__anl_pred_var"] = var
+
+    fit_case("lu_d3p3", "LU", 3, 3, 400, 21, 1e-2)
+    fit_case("hg_d5p3", "HG", 3, 5, 900, 22, 1e-2)
+    fit_case("lu_d8p2_sparse", "LU", 2, 8, 700, 23, 1e-2, sparse=6)
+    fit_case("nlu_d4p4", "nLU", 4, 4, 1200, 24, 5e-3)
+    np.savez_compressed(os.path.join(HERE, "fits.npz"), **fits)
+
+    # --- workflow: pc_fit with two outputs + Sobol -------------------------------------------
+    wf = {}
+    rng = np.random.default_rng(31)
+    x = rng.uniform(-1, 1, (600, 4))
+    ymat = np.stack([np.sin(x[:, 0]) + 0.3 * x[:, 1] * x[:, 2], x[:, 3] ** 2 + 0.1 * x[:, 0]], axis=1)
+    import io, contextlib
+    for method in ("lsq", "anl", "bcs"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            pc, lregs = R["pc_fit"](x, ymat, order=3, pctype="LU", method=method)
+        for j in range(2):
+            wf[f"{method}__cf{j}"] = pc.coefs[j]
+            wf[f"{method}__mi{j}"] = pc.mindices[j]
+        wf[f"{method}__main"] = pc.computeSens()
+        wf[f"{method}__total"] = pc.computeTotSens()
+        wf[f"{method}__eval"] = pc.function(x[:16])
+    wf["x"] = x
+    wf["y"] = ymat
+    np.savez_compressed(os.path.join(HERE, "workflow.npz"), **wf)
+
+    for f in ("pc1d", "mindex", "pcrv_cases", "fits", "workflow"):
+        p = os.path.join(HERE, f + ".npz")
+        print(f"{f}.npz  {os.path.getsize(p) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

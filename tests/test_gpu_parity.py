@@ -1,0 +1,379 @@
+"""Parity of the CUDA path (through the C-ABI / ctypes shim) against the reference's golden
+vectors and the CPU oracle.  Bit-exact for basis values and exact-mode evalPC; 1e-12 for the
+tensor-pipe statistics (BLAS-order sums have no defined order in the reference either);
+1e-10 for fitted coefficients and Sobol indices (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_cases, case_mis_cfs, case_types
+from oracle import pc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pcrv(case):
+    from pytuq_b200.rv.pcrv import PCRV
+    mis, cfs = case_mis_cfs(case)
+    return PCRV(len(mis), mis[0].shape[1], case_types(case), mi=[m.copy() for m in mis],
+                cfs=[c.copy() for c in cfs])
+
+
+def rel_err(a, b):
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return np.max(np.abs(a - b)) / scale
+
+
+# ----------------------------------------------------------------------------- K1
+def test_k1_evalbases_bitexact_vs_reference(pcrv_cases):
+    for name, c in pcrv_cases.items():
+        pc = _pcrv(c)
+        for j in range(pc.pdim):
+            A = pc.evalBases(c["x"], j)
+            assert A.flags["C_CONTIGUOUS"] and A.dtype == np.float64
+            assert np.array_equal(A, c[f"A{j}"]), (name, j)
+
+
+def test_k1_pc1d_call_bitexact():
+    from pytuq_b200.rv.pcrv import PC1d
+    g = load_golden("pc1d")
+    for fam in orc.FAMILIES:
+        vals = PC1d(fam)(g[f"{fam}_x"], 7)
+        assert len(vals) == 8 and np.array_equal(np.array(vals), g[f"{fam}_vals"]), fam
+        assert np.array_equal(np.array(PC1d(fam)(g[f"{fam}_x"], 0)), g[f"{fam}_vals"][:1])
+        assert np.array_equal(np.array(PC1d(fam)(g[f"{fam}_x"], 1)), g[f"{fam}_vals"][:2])
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 1000, 4099])
+def test_k1_ragged_sizes_vs_oracle(n):
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(n)
+    for (fam, p, d) in [("LU", 4, 10), ("HG", 3, 20), ("nLU", 2, 50), ("nHG", 5, 3)]:
+        mi = orc.get_mi(p, d)
+        x = rng.uniform(-1, 1, (n, d)) if fam.endswith("LU") else rng.standard_normal((n, d))
+        nn = min(n, 64)   # the oracle's Python loop is slow: check head and tail rows
+        A = PCRV(1, d, fam, mi=mi).evalBases(x, 0)
+        assert np.array_equal(A[:nn], orc.eval_bases(x[:nn], mi, fam))
+        assert np.array_equal(A[-nn:], orc.eval_bases(x[-nn:], mi, fam))
+
+
+def test_k1_input_forms():
+    """F-order, strided and integer inputs behave like the reference."""
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(3)
+    mi = orc.get_mi(3, 4)
+    pc = PCRV(1, 4, "LU", mi=mi)
+    x = rng.uniform(-1, 1, (50, 4))
+    ref = orc.eval_bases(x, mi, "LU")
+    assert np.array_equal(pc.evalBases(np.asfortranarray(x), 0), ref)
+    big = rng.uniform(-1, 1, (100, 8))
+    big[::2, ::2] = x
+    assert np.array_equal(pc.evalBases(big[::2, ::2], 0), ref)
+    xi = rng.integers(-1, 2, (20, 4))
+    assert np.array_equal(pc.evalBases(xi, 0), orc.eval_bases(xi.astype(float), mi, "LU"))
+    with pytest.raises(AssertionError):
+        pc.evalBases(x[:, :3], 0)
+    with pytest.raises(AssertionError):
+        pc.evalBases(x, 1)
+    assert pc.evalBases(x[:0], 0).shape == (0, mi.shape[0])
+
+
+def test_k1_stale_maxord_raises_indexerror():
+    from pytuq_b200.rv.pcrv import PCRV
+    pc = PCRV(1, 3, "LU", mi=orc.get_mi(2, 3))
+    pc.setMiCfs(orc.get_mi(3, 3))          # grown after construction: reference raises IndexError
+    with pytest.raises(IndexError):
+        pc.evalBases(np.zeros((2, 3)), 0)
+    pc.setMiCfs(orc.get_mi(1, 3))          # shrinking is fine
+    assert pc.evalBases(np.zeros((2, 3)), 0).shape == (2, 4)
+
+
+def test_k1_device_pointers_with_leading_dimensions():
+    """_dev entry point, ldx > s and lda > K (also exercises the unaligned-row store path)."""
+    import torch
+    from pytuq_b200 import _native
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(5)
+    for (p, d) in [(3, 5), (2, 6), (4, 3)]:
+        mi = orc.get_mi(p, d)
+        K = mi.shape[0]
+        pc = PCRV(1, d, "HG", mi=mi)
+        plan = pc._plan(mi)
+        n, ldx, lda = 77, d + 3, K + 5
+        xh = rng.standard_normal((n, ldx))
+        xd = torch.from_numpy(xh).cuda()
+        ad = torch.full((n, lda), -7.0, dtype=torch.float64, device="cuda")
+        st = _native.lib().pcq_eval_bases_dev(plan.handle, xd.data_ptr(), n, ldx, ad.data_ptr(), lda,
+                                              torch.cuda.current_stream().cuda_stream)
+        _native.check(st)
+        torch.cuda.synchronize()
+        got = ad.cpu().numpy()
+        assert np.array_equal(got[:, :K], orc.eval_bases(xh[:, :d].copy(), mi, "HG"))
+        assert np.all(got[:, K:] == -7.0)
+
+
+# ----------------------------------------------------------------------------- K2
+def test_k2_evalpc_bitexact_vs_reference(pcrv_cases):
+    for name, c in pcrv_cases.items():
+        pc = _pcrv(c)
+        y = pc.evalPC(c["x"])
+        assert y.shape == c["y"].shape
+        assert np.array_equal(y, c["y"]), name
+        yf = pc.evalPC(c["x"], exact=False)
+        assert rel_err(yf, c["y"]) < 1e-13, name
+        pc.setFunction()
+        assert np.array_equal(pc.function(c["x"]), c["y"]), name
+
+
+def test_k2_many_outputs_and_sizes():
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(11)
+    mi = orc.get_mi(3, 6)
+    K = mi.shape[0]
+    for M in (1, 3, 4, 9):
+        cfs = rng.standard_normal((M, K))
+        pc = PCRV(M, 6, "LU", mi=mi, cfs=cfs)
+        for n in (1, 31, 129, 700):
+            x = rng.uniform(-1, 1, (n, 6))
+            ref = orc.eval_pc(x, [mi] * M, list(cfs), "LU")
+            assert np.array_equal(pc.evalPC(x), ref), (M, n)
+            assert rel_err(pc.evalPC(x, exact=False), ref) < 1e-13
+
+
+# ----------------------------------------------------------------------------- K3 / K4
+@pytest.mark.parametrize("fam,p,d,n,M", [("LU", 3, 5, 5000, 1), ("HG", 3, 5, 4097, 3), ("nLU", 2, 8, 333, 0),
+                                         ("LU", 4, 10, 2500, 1), ("HG", 3, 20, 3000, 2), ("LU", 2, 50, 1500, 1),
+                                         ("nHG", 4, 3, 63, 1), ("LU", 1, 2, 1, 1)])
+def test_k3_suffstats_vs_oracle(fam, p, d, n, M):
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(p * 100 + d)
+    mi = orc.get_mi(p, d)
+    x = rng.uniform(-1, 1, (n, d)) if fam.endswith("LU") else rng.standard_normal((n, d))
+    Y = rng.standard_normal((n, M)) if M else None
+    pc = PCRV(1, d, fam, mi=mi)
+    st = pc.suffStats(x, Y, 0)
+    A = pc.evalBases(x, 0)
+    ref = orc.suffstats(A, Y if M else np.zeros((n, 0)))
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert np.max(np.abs(st.S - ref) / np.maximum(scale, 1e-300)) < 1e-12
+    assert np.array_equal(st.S, st.S.T)
+    assert st.n == n
+
+
+def test_k3_general_multiindex_and_accumulate(pcrv_cases):
+    import torch
+    from pytuq_b200 import _native
+    c = pcrv_cases["general_dense"]
+    pc = _pcrv(c)
+    x = np.tile(c["x"], (9, 1))
+    y = np.arange(x.shape[0], dtype=float) / 7.0
+    st = pc.suffStats(x, y, 0)
+    ref = orc.suffstats(np.tile(c["A0"], (9, 1)), y)
+    assert rel_err(st.S, ref) < 1e-12
+    # accumulate flag of the device entry point: two halves add up to the whole
+    plan = pc._plan(pc.mindices[0])
+    L = int(_native.lib().pcq_suffstats_dim(plan.handle, 1))
+    assert L == st.S.shape[0]
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.from_numpy(y).cuda()
+    sd = torch.empty((L, L), dtype=torch.float64, device="cuda")
+    h = x.shape[0] // 2 + 3
+    stream = torch.cuda.current_stream().cuda_stream
+    _native.check(_native.lib().pcq_suffstats_dev(plan.handle, xd.data_ptr(), h, x.shape[1], yd.data_ptr(), 1, 1,
+                                                  sd.data_ptr(), 0, stream))
+    _native.check(_native.lib().pcq_suffstats_dev(plan.handle, xd[h:].data_ptr(), x.shape[0] - h, x.shape[1],
+                                                  yd[h:].data_ptr(), 1, 1, sd.data_ptr(), 1, stream))
+    torch.cuda.synchronize()
+    assert rel_err(sd.cpu().numpy(), ref) < 1e-12
+
+
+def test_k4_gram_of_materialised_matrix():
+    from pytuq_b200.lreg.stats import SuffStats
+    rng = np.random.default_rng(8)
+    for (n, K, M) in [(1000, 37, 1), (513, 130, 2), (64, 300, 0), (5, 3, 1)]:
+        A = rng.standard_normal((n, K))
+        Y = rng.standard_normal((n, M)) if M else None
+        st = SuffStats.from_matrix(A, Y)
+        ref = orc.suffstats(A, Y if M else np.zeros((n, 0)))
+        assert rel_err(st.S, ref) < 1e-12, (n, K, M)
+
+
+# ----------------------------------------------------------------------------- K5
+def test_k5_germ_stream_and_propagation():
+    import torch
+    from pytuq_b200 import _native
+    from pytuq_b200.rv.pcrv import PCRV
+    mi = orc.get_mi(3, 5)
+    types = ["LU", "HG", "HG", "nLU", "nHG"]
+    rng = np.random.default_rng(2)
+    cfs = rng.standard_normal((2, mi.shape[0]))
+    pc = PCRV(2, 5, types, mi=mi, cfs=cfs)
+    kinds = pc._germ_kinds()
+    assert kinds.tolist() == [0, 1, 1, 0, 1]
+    n, seed, first = 4001, 12345, 1000
+    plan = pc._plan(mi)
+    xd = torch.empty((n, 5), dtype=torch.float64, device="cuda")
+    _native.check(_native.lib().pcq_sample_germ_dev(plan.handle, seed, first, n, _native.ptr(kinds),
+                                                    xd.data_ptr(), 5, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    x = xd.cpu().numpy()
+    ref = orc.germ_philox(seed, first, n, kinds)
+    assert np.array_equal(x[:, [0, 3]], ref[:, [0, 3]])          # uniform dims: exact
+    assert np.max(np.abs(x - ref)) < 1e-13                          # normal dims: libm-level
+    out = pc.propagate(n, seed=seed, exact=True, return_samples=True, first_index=first)
+    yref = orc.eval_pc(x, [mi, mi], list(cfs), types)
+    assert np.array_equal(out["samples"], pc.evalPC(x))
+    assert rel_err(out["samples"], yref) < 1e-13
+    np.testing.assert_allclose(out["sum"], yref.sum(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(out["sumsq"], (yref ** 2).sum(axis=0), rtol=1e-12)
+    assert np.array_equal(out["min"], out["samples"].min(axis=0))
+    assert np.array_equal(out["max"], out["samples"].max(axis=0))
+    fast = pc.propagate(n, seed=seed, first_index=first)
+    np.testing.assert_allclose(fast["mean"], out["mean"], rtol=1e-11, atol=1e-13)
+
+
+# ----------------------------------------------------------------------------- fitters and workflows
+def test_fitters_vs_reference(fit_cases):
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import lsq, anl, bcs, PCBasisEvaluator
+    for name, c in fit_cases.items():
+        fam = str(c["type"])
+        mi = c["mi"]
+        pc = PCRV(1, mi.shape[1], fam, mi=mi)
+        x, y = c["x"], c["y"]
+
+        def fused(fitter):
+            fitter.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+            fitter.fit(x, y)
+            return fitter
+
+        A = pc.evalBases(x, 0)
+        for make in (lambda f: fused(f), lambda f: (f.fita(A, y), f)[1]):
+            l = make(lsq())
+            np.testing.assert_allclose(l.cf, c["lsq_cf"], rtol=1e-10, atol=1e-12)
+            assert np.array_equal(l.used, np.arange(mi.shape[0])) and not l.cf_cov.any()
+            a = make(anl())
+            np.testing.assert_allclose(a.cf, c["anl_cf"], rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(a.datavar, c["anl_datavar"], rtol=1e-8)
+            np.testing.assert_allclose(a.cf_cov, c["anl_cov"], rtol=1e-8, atol=1e-16)
+            ap = make(anl(datavar=0.01, prior_var=2.0, cov_nugget=1e-8))
+            np.testing.assert_allclose(ap.cf, c["anlp_cf"], rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(ap.cf_cov, c["anlp_cov"], rtol=1e-9, atol=1e-18)
+            av = make(anl(method="vi"))
+            np.testing.assert_allclose(np.diag(av.cf_cov), c["anlvi_cov_diag"], rtol=1e-8)
+            for tag in ("bcs0.001", "bcs1e-08"):
+                b = make(bcs(eta=float(tag[3:])))
+                assert np.array_equal(b.used, c[f"{tag}_used"]), (name, tag)
+                np.testing.assert_allclose(b.cf, c[f"{tag}_cf"], rtol=1e-10, atol=1e-12)
+                assert np.shape(b.datavar) == (1,)
+                np.testing.assert_allclose(b.datavar, c[f"{tag}_datavar"], rtol=1e-7)
+                np.testing.assert_allclose(b.cf_cov, c[f"{tag}_cov"], rtol=1e-7, atol=1e-18)
+        mean, var, _ = a.predict(c["xt"], msc=1)
+        np.testing.assert_allclose(mean, c["anl_pred_mean"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(var, c["anl_pred_var"], rtol=1e-7)
+
+
+def test_pc_fit_workflow_vs_reference():
+    import contextlib, io
+    from pytuq_b200.workflows.fits import pc_fit
+    g = load_golden("workflow")
+    x, y = g["x"], g["y"]
+    for method in ("lsq", "anl", "bcs"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            pc, lregs = pc_fit(x, y, order=3, pctype="LU", method=method)
+        assert len(lregs) == 2
+        for j in range(2):
+            assert np.array_equal(pc.mindices[j], g[f"{method}__mi{j}"]), method
+            np.testing.assert_allclose(pc.coefs[j], g[f"{method}__cf{j}"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(pc.computeSens(), g[f"{method}__main"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(pc.computeTotSens(), g[f"{method}__total"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(pc.function(x[:16]), g[f"{method}__eval"], rtol=1e-10, atol=1e-12)
+
+
+def test_pce_and_pcsobol():
+    import contextlib, io
+    from pytuq_b200.surrogates.pce import PCE
+    from pytuq_b200.gsa.gsa import PCSobol
+    rng = np.random.default_rng(17)
+    x = rng.uniform(-1, 1, (300, 3))
+    y = 1.0 + 2.0 * x[:, 0] + 0.5 * x[:, 1] * x[:, 2] + x[:, 0] ** 2
+    pce = PCE(3, 2, "LU")
+    pce.set_training_data(x, y)
+    cf = pce.build(regression="lsq")
+    assert pce.get_pc_terms() == [10]
+    out = pce.evaluate(x)
+    np.testing.assert_allclose(out["Y_eval"], y, atol=1e-10)
+    assert out["Y_eval_std"] is None
+    pce.build(regression="anl")
+    assert pce.evaluate(x[:7])["Y_eval_std"].shape == (7,)
+    cfb = pce.build(regression="bcs", eta=1e-6)
+    assert len(cfb) == len(pce.lreg.used) <= 10
+    np.testing.assert_allclose(pce.evaluate(x)["Y_eval"], y, atol=1e-5)
+    eta = pce.build(regression="bcs", eta=[1e-2, 1e-6], nfolds=2)
+    assert pce.lreg.eta in (1e-2, 1e-6)
+    # PC Sobol on a seeded germ: same numpy stream as the reference, indices vs the oracle fit
+    with contextlib.redirect_stdout(io.StringIO()):
+        dom = np.array([[-1., 1.], [0., 2.], [-3., 3.]])
+        sob = PCSobol(dom, pctype="LU", order=3)
+        np.random.seed(5)
+        xs = sob.sample(500)
+        ys = xs[:, 0] + 0.3 * xs[:, 1] ** 2 + 0.1 * xs[:, 0] * xs[:, 2]
+        sens = sob.compute(ys)
+    mi = orc.get_mi(3, 3)
+    cf_ref = orc.lsq_fit(orc.eval_bases(sob.germ_sam, mi, "LU"), ys)
+    np.testing.assert_allclose(sens["main"], orc.sobol_main(mi, cf_ref, "LU"), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(sens["total"], orc.sobol_total(mi, cf_ref, "LU"), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(sens["jointt"], orc.sobol_joint(mi, cf_ref, "LU"), rtol=1e-10, atol=1e-13)
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_full_size_c2_properties():
+    """BASELINE config 2 at full size (HG, d=20, p=3, K=1771, N=1e6): size-independent checks."""
+    import torch
+    from pytuq_b200 import _native
+    from pytuq_b200.rv.pcrv import PCRV
+    d, p, n = 20, 3, 1_000_000
+    mi = orc.get_mi(p, d)
+    K = mi.shape[0]
+    pc = PCRV(1, d, "HG", mi=mi)
+    plan = pc._plan(mi)
+    lib = _native.lib()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn((n, d), dtype=torch.float64, device="cuda", generator=g)
+    c = torch.randn(K, dtype=torch.float64, device="cuda", generator=g) / (1.0 + torch.from_numpy(mi.sum(1)).cuda()) ** 2
+    stream = torch.cuda.current_stream().cuda_stream
+    y = torch.empty((n, 1), dtype=torch.float64, device="cuda")
+    _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n, d, c.data_ptr(), 1, y.data_ptr(), 1, 0, stream))
+    L = K + 2
+    S = torch.empty((L, L), dtype=torch.float64, device="cuda")
+    _native.check(lib.pcq_suffstats_dev(plan.handle, x.data_ptr(), n, d, y.data_ptr(), 1, 1, S.data_ptr(), 0, stream))
+    # (1) linearity over the sample axis: halves accumulate to the whole
+    S2 = torch.empty_like(S)
+    h = 499_999
+    _native.check(lib.pcq_suffstats_dev(plan.handle, x.data_ptr(), h, d, y.data_ptr(), 1, 1, S2.data_ptr(), 0, stream))
+    _native.check(lib.pcq_suffstats_dev(plan.handle, x[h:].data_ptr(), n - h, d, y[h:].data_ptr(), 1, 1, S2.data_ptr(), 1, stream))
+    torch.cuda.synchronize()
+    Sh, S2h = S.cpu().numpy(), S2.cpu().numpy()
+    dg = np.sqrt(np.outer(np.diag(Sh), np.diag(Sh)))
+    assert np.max(np.abs(Sh - S2h) / dg) < 1e-12
+    assert Sh[-1, -1] == n and Sh[0, 0] == n and np.array_equal(Sh, Sh.T)
+    # (2) noiseless data: the normal equations recover the coefficients that generated y
+    from pytuq_b200.lreg.lreg import solve_normal
+    cf = solve_normal(Sh[:K, :K], Sh[:K, K])
+    np.testing.assert_allclose(cf, c.cpu().numpy(), rtol=0, atol=1e-10)
+    # (3) K1 rows agree with the statistics: A^T 1 column and a block of A^T A from a 64k-row slab
+    m = 65536
+    A = torch.empty((m, K), dtype=torch.float64, device="cuda")
+    _native.check(lib.pcq_eval_bases_dev(plan.handle, x.data_ptr(), m, d, A.data_ptr(), K, stream))
+    Sm = torch.empty_like(S)
+    _native.check(lib.pcq_suffstats_dev(plan.handle, x.data_ptr(), m, d, y.data_ptr(), 1, 1, Sm.data_ptr(), 0, stream))
+    torch.cuda.synchronize()
+    Gm = (A.T @ A).cpu().numpy()
+    Smh = Sm.cpu().numpy()
+    dgm = np.sqrt(np.outer(np.diag(Gm), np.diag(Gm)))
+    assert np.max(np.abs(Smh[:K, :K] - Gm) / dgm) < 1e-12
+    np.testing.assert_allclose(Smh[:K, K], (A.T @ y[:m, 0]).cpu().numpy(), rtol=1e-10, atol=1e-7)
+    # (4) evalPC equals A @ c on the slab (sequential vs BLAS order: tolerance)
+    np.testing.assert_allclose((A @ c).cpu().numpy(), y[:m, 0].cpu().numpy(), rtol=1e-11, atol=1e-11)
+    # oracle spot check on rows from the far end of the array
+    idx = [0, 1, m - 1]
+    assert np.array_equal(A[idx].cpu().numpy(), orc.eval_bases(x[idx].cpu().numpy(), mi, "HG"))

@@ -1,0 +1,130 @@
+"""Pins the CPU oracle (oracle/pc_oracle.py) to the reference: golden vectors produced by the
+unmodified PyTUQ (tests/golden/make_golden.py) and the known-answer vectors of SURVEY.md
+Appendix A.  Bit-exact where the arithmetic order is defined, 1e-12 for LAPACK solves."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_cases, case_mis_cfs, case_types
+from oracle import pc_oracle as orc
+
+
+def test_pc1d_families_bitexact():
+    g = load_golden("pc1d")
+    for fam in orc.FAMILIES:
+        x = g[f"{fam}_x"]
+        vals = np.array(orc.pc1d(fam, x, 7))
+        assert np.array_equal(vals, g[f"{fam}_vals"]), fam
+        assert np.array_equal([orc.normsq_1d(fam, n) for n in range(8)], g[f"{fam}_normsq"])
+        assert np.array_equal([float(orc.rec_a(fam, n)) for n in range(1, 8)], g[f"{fam}_a"])
+        assert np.array_equal([float(orc.rec_b(fam, n)) for n in range(1, 8)], g[f"{fam}_b"])
+
+
+def test_appendix_a_known_answers():
+    x = np.array([0.45])
+    expect = {
+        "LU": [1, 0.45, -0.19624999999999998, -0.44718749999999996, -0.20497265625, 0.19172214843750002],
+        "nLU": [1, 0.7794228634059948, -0.43882834058433373, -1.1831469144166966, -0.61491796875, 0.63587043036801],
+        "HG": [1, 0.45, -0.7975, -1.258875, 1.82600625, 5.8572028125],
+        "nHG": [1, 0.45, -0.39875, -0.20981249999999999, 0.07608359375, 0.0488100234375],
+    }
+    for fam, ref in expect.items():
+        got = [float(v[0]) for v in orc.pc1d(fam, x, 5)]
+        np.testing.assert_allclose(got, ref, rtol=1e-15, atol=0)
+    mi = orc.get_mi(2, 3)
+    assert ["".join(map(str, r)) for r in mi] == "000,100,010,001,200,110,101,020,011,002".split(",")
+    assert orc.get_mi(3, 2).T.tolist() == [[0, 1, 0, 2, 1, 0, 3, 2, 1, 0], [0, 0, 1, 0, 1, 2, 0, 1, 2, 3]]
+    X = np.array([[0.1, -0.2, 0.3], [0.5, 0.6, -0.7]])
+    A = orc.eval_bases(X, mi, "LU")
+    np.testing.assert_allclose(A[0], [1, 0.1, -0.2, 0.3, -0.485, -0.02, 0.03, -0.44, -0.06, -0.365], rtol=2e-15)
+    A = orc.eval_bases(X, mi, "HG")
+    np.testing.assert_allclose(A[1], [1, 0.5, 0.6, -0.7, -0.75, 0.3, -0.35, -0.64, -0.42, -0.51], rtol=2e-15)
+    types = ["LU", "HG", "nLU"]
+    cfs = np.arange(20.).reshape(2, 10) / 10
+    y = orc.eval_pc(X, [mi, mi], [cfs[0], cfs[1]], types)
+    np.testing.assert_allclose(y, [[-1.5366252821545485, -2.4501363758983747],
+                                   [-1.0145020332808654, -1.400140745694665]], rtol=1e-15)
+    np.testing.assert_allclose(orc.norms_sq(mi, types), [1, 1 / 3, 1, 1, 0.2, 1 / 3, 1 / 3, 2, 1, 1], rtol=1e-15)
+    np.testing.assert_allclose([orc.pc_var(mi, c, types) for c in cfs], [2.7986666666666666, 18.158666666666665], rtol=1e-15)
+    np.testing.assert_allclose(orc.sobol_main(mi, cfs[0], types),
+                               [0.0126250595521677, 0.36445926631729386, 0.3215817055740829], rtol=1e-14)
+    np.testing.assert_allclose(orc.sobol_total(mi, cfs[1], types),
+                               [0.13209486746457158, 0.6173360746016594, 0.5172920185035613], rtol=1e-14)
+    for (p, d, n) in [(4, 10, 1001), (3, 20, 1771), (2, 50, 1326), (4, 20, 10626), (3, 30, 5456)]:
+        assert orc.get_npc(p, d) == n
+
+
+def test_get_mi_matches_reference():
+    g = load_golden("mindex")
+    for key in g.files:
+        if key.startswith("mi_"):
+            _, p, d = key.split("_")
+            got = orc.get_mi(int(p), int(d))
+            assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key
+    for p, d, n in g["npc"]:
+        assert orc.get_npc(int(p), int(d)) == n
+
+
+def test_eval_bases_and_pc_bitexact(pcrv_cases):
+    for name, c in pcrv_cases.items():
+        mis, cfs = case_mis_cfs(c)
+        types = case_types(c)
+        max_ord = np.max([m.max(axis=0) for m in mis], axis=0)
+        for j, mi in enumerate(mis):
+            A = orc.eval_bases(c["x"], mi, types, max_ord)
+            assert np.array_equal(A, c[f"A{j}"]), (name, j)
+            assert np.array_equal(orc.norms_sq(mi, types), c[f"normsq{j}"]), (name, j)
+        y = orc.eval_pc(c["x"], mis, cfs, types, max_ord)
+        assert np.array_equal(y, c["y"]), name
+
+
+def test_moments_and_sobol_bitexact(pcrv_cases):
+    for name, c in pcrv_cases.items():
+        mis, cfs = case_mis_cfs(c)
+        types = case_types(c)
+        for j, (mi, cf) in enumerate(zip(mis, cfs)):
+            assert orc.pc_mean(mi, cf) == c["mean"][j], name
+            assert orc.pc_var(mi, cf, types) == c["var"][j], name
+            assert np.array_equal(orc.sobol_main(mi, cf, types), c["main"][j]), name
+            assert np.array_equal(orc.sobol_total(mi, cf, types), c["total"][j]), name
+            if "joint" in c:
+                assert np.array_equal(orc.sobol_joint(mi, cf, types), c["joint"][j]), name
+            if mi.shape[1] > 2:
+                assert orc.sobol_group(mi, cf, types, [0, 1]) == c["group01"][j], name
+
+
+def test_fitters_match_reference(fit_cases):
+    for name, c in fit_cases.items():
+        A = orc.eval_bases(c["x"], c["mi"], str(c["type"]))
+        y = c["y"]
+        np.testing.assert_allclose(orc.lsq_fit(A, y), c["lsq_cf"], rtol=1e-12, atol=1e-14)
+        cf, cov, dv = orc.anl_fit(A, y)
+        np.testing.assert_allclose(cf, c["anl_cf"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(cov, c["anl_cov"], rtol=1e-10, atol=1e-18)
+        np.testing.assert_allclose(dv, c["anl_datavar"], rtol=1e-12)
+        cf, cov, _ = orc.anl_fit(A, y, datavar=0.01, prior_var=2.0, cov_nugget=1e-8)
+        np.testing.assert_allclose(cf, c["anlp_cf"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(cov, c["anlp_cov"], rtol=1e-10, atol=1e-18)
+        _, cov, _ = orc.anl_fit(A, y, method="vi")
+        np.testing.assert_allclose(np.diag(cov), c["anlvi_cov_diag"], rtol=1e-12)
+        for tag in ("bcs0.001", "bcs1e-08"):
+            eta = float(tag[3:])
+            w, err, used, s2, Sig = orc.bcs_fit(A, y, eta=eta)
+            assert np.array_equal(used, c[f"{tag}_used"]), (name, tag)
+            np.testing.assert_allclose(w, c[f"{tag}_cf"], rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(s2, c[f"{tag}_datavar"], rtol=1e-12)
+            np.testing.assert_allclose(Sig, c[f"{tag}_cov"], rtol=1e-10, atol=1e-20)
+
+
+def test_philox_known_answer():
+    # Random123 known-answer test: counter = key = 0 and the all-ones / pi vectors
+    out = orc.philox4x32_10((0, 0, 0, 0), (0, 0))
+    assert [int(v) for v in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    out = orc.philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff))
+    assert [int(v) for v in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    out = orc.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0))
+    assert [int(v) for v in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    x = orc.germ_philox(4, 0, 20000, [0, 1, 1, 0, 1])
+    assert x.shape == (20000, 5)
+    assert abs(x[:, 0].mean()) < 0.02 and abs(x[:, 0].var() - 1 / 3) < 0.01
+    assert abs(x[:, 1].mean()) < 0.03 and abs(x[:, 1].var() - 1) < 0.04
+    assert abs(np.corrcoef(x[:, 1], x[:, 2])[0, 1]) < 0.03
