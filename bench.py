@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Headline benchmark of the PC hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): BASELINE config 2/"target" -- Hermite PCE, d=20, order 3
+(K=1771 terms), basis evaluation + least-squares fit; 1.25e6 synthetic Gaussian samples
+per GPU (10M at 8 GPUs), weak scaling over the sample axis.
+
+A step = one pass of the hot path over the rank's sample block:
+    fused basis-evaluation + Gram/A^T y statistics (K3, DMMA)  ->  one all-reduce of the
+    packed statistics (N>1)  ->  K x K normal-equation solve  ->  coefficients.
+`value` is basis evaluations (samples x terms) per second for that whole step with x, y
+already resident in HBM; `e2e` is the same metric through the public API
+(`lsq.fit(x, y)` with numpy host arrays: H2D of x, y and D2H of the statistics inside the
+timed region).  `roofline` is for the dominant kernel (K3) against the FP64 tensor (DMMA)
+peak measured live on the same GPU (MEASURED_PEAKS.json has no FP64 number); the K1
+(materialised A) and K2 (evalPC) kernels are reported in `kernels` with their own roofs.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, P, FAMILY = 20, 3, "HG"
+N_PER_GPU = 1_250_000
+WORKLOAD = "C2 Hermite PCE d=20 p=3 K=1771, basis eval + lstsq fit, 1.25e6 Gaussian samples per GPU (10M at 8 GPUs)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--cpu-samples", type=int, default=20000,
+                    help="rows of the workload the CPU baseline is timed on")
+    ap.add_argument("--no-extras", action="store_true", help="skip K1/K2/peak side measurements")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1])); power.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_reference_pass(x, y, mi):
+    """One pass of the reference's algorithm on the host: evalBases (Python loop over K x s,
+    rv/pcrv.py:413-442) + lsq.fita (scipy gelsd, lreg/lreg.py:328-339)."""
+    from oracle import pc_oracle as orc
+    t0 = time.perf_counter()
+    A = orc.eval_bases(x, mi, FAMILY)
+    t1 = time.perf_counter()
+    cf = orc.lsq_fit(A, y)
+    t2 = time.perf_counter()
+    return cf, t1 - t0, t2 - t1
+
+
+def synth_host(n, seed, mi):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, D))
+    c_true = rng.standard_normal(mi.shape[0]) / (1.0 + mi.sum(axis=1)) ** 2
+    return rng, x, c_true
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot
+    travel to the GPU box) on a bounded sample of the same workload, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pc_oracle as orc
+    mi = orc.get_mi(P, D)
+    K = mi.shape[0]
+    n = args.cpu_samples
+    _, x, c_true = synth_host(n, 2, mi)
+    rng = np.random.default_rng(99)
+    A = orc.eval_bases(x, mi, FAMILY)               # untimed: only to synthesise the targets
+    yfull = A @ c_true + 1e-2 * rng.standard_normal(n)
+    del A
+    times = []
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    for it in range(warm + steps):
+        cf, tb, tf = cpu_reference_pass(x, yfull, mi)
+        if it >= warm:
+            times.append((tb, tf))
+    tb = float(np.mean([t[0] for t in times])); tf = float(np.mean([t[1] for t in times]))
+    value = n * K / (tb + tf)
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": "pc_basis_evals_per_s", "value": value, "unit": "basis evals/s (samples*terms)",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * (tb + tf),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{n} rows of the workload per step"},
+        "fit_seconds": tf, "basis_seconds": tb,
+        "cpu_baseline": {"value": value, "unit": "basis evals/s (samples*terms)", "cores": cores, "kind": "port",
+                         "sample": f"oracle port of evalBases+lsq.fita on {n} rows (basis {tb:.2f}s single-threaded "
+                                   f"numpy loop, lstsq {tf:.2f}s on {cores} BLAS threads)"},
+        "e2e": {"value": value, "unit": "basis evals/s (samples*terms)", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from pytuq_b200 import _native, device as pdev
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.utils.mindex import get_mi
+    from pytuq_b200.lreg import lsq, PCBasisEvaluator
+    from pytuq_b200.lreg.lreg import solve_normal
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    pdev.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _native.lib()
+    dev = torch.device("cuda", local)
+
+    mi = get_mi(P, D)
+    K = mi.shape[0]
+    n = args.samples_per_gpu
+    pc = PCRV(1, D, FAMILY, mi=mi)
+    plan = pc._plan(mi, dev=local)
+
+    # synthetic inputs, generated on the device for the HBM-resident arm
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    x = torch.randn((n, D), dtype=torch.float64, device=dev, generator=g)
+    gc = torch.Generator(device=dev).manual_seed(7)
+    c_true = torch.randn(K, dtype=torch.float64, device=dev, generator=gc) / \
+        (1.0 + torch.from_numpy(mi.sum(axis=1)).to(dev)) ** 2
+    y = torch.empty((n, 1), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n, D, c_true.data_ptr(), 1, y.data_ptr(), 1, 1, stream))
+    y += 1e-2 * torch.randn((n, 1), dtype=torch.float64, device=dev, generator=g)
+    L = K + 2
+    S = torch.empty((L, L), dtype=torch.float64, device=dev)
+    S_host = torch.empty((L, L), dtype=torch.float64).pin_memory()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step():
+        """K3 -> (all-reduce) -> D2H of S -> host solve.  Returns (cf, ms of K3, ms of all-reduce, s of solve)."""
+        ev[0].record()
+        _native.check(lib.pcq_suffstats_dev(plan.handle, x.data_ptr(), n, D, y.data_ptr(), 1, 1, S.data_ptr(), 0, stream))
+        ev[1].record()
+        if world > 1:
+            dist.all_reduce(S, op=dist.ReduceOp.SUM)
+        ev[2].record()
+        S_host.copy_(S, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        t0 = time.perf_counter()
+        Sh = S_host.numpy()
+        cf = solve_normal(Sh[:K, :K], Sh[:K, K])
+        t1 = time.perf_counter()
+        return cf, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), t1 - t0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        cf, *_ = step()
+    sampler = ClockSampler(local)
+    launches0 = lib.pcq_launch_count()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_start = time.perf_counter()
+    k3_ms, ar_ms, solve_s = [], [], []
+    for _ in range(args.steps):
+        cf, a, b, c = step()
+        k3_ms.append(a); ar_ms.append(b); solve_s.append(c)
+    barrier()
+    elapsed = time.perf_counter() - t_start
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.pcq_launch_count() - launches0
+    tmax = torch.tensor([elapsed, float(np.mean(k3_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    elapsed, k3_mean_ms = float(tmax[0]), float(tmax[1])
+    ms_per_step = 1e3 * elapsed / args.steps
+    total_evals = float(n) * world * K
+    value = total_evals / (elapsed / args.steps)
+    err = float(np.max(np.abs(cf - c_true.cpu().numpy())))
+
+    # ---------------- end to end through the public API (host numpy in, coefficients out)
+    xh = x.cpu().numpy()
+    yh = y.cpu().numpy()[:, 0].copy()
+    fitter = lsq()
+    fitter.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+
+    def e2e_step():
+        if world > 1:
+            from pytuq_b200.parallel import suffstats_pc
+            st = suffstats_pc(pc, xh, yh, 0, distributed=True)
+            fitter._fit_stats(st)
+        else:
+            fitter.fit(xh, yh)
+        return fitter.cf
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        cf_e2e = e2e_step()
+    barrier()
+    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = total_evals / float(e2e_t[0])
+    e2e_err = float(np.max(np.abs(cf_e2e - cf)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel + side kernels (rank 0)
+    flops = float(n) * K * (K + 1) + 2.0 * n * K * 1 + 2.0 * n * 1
+    achieved = flops / (k3_mean_ms * 1e-3) / 1e12
+    peaks = {}
+    kernels = {}
+    if not args.no_extras:
+        for kind, name in ((1, "fp64_dmma_tflops"), (0, "fp64_dfma_tflops"), (2, "hbm_copy_gbs")):
+            best = 0.0
+            for _ in range(2):
+                v = ctypes.c_double()
+                _native.check(lib.pcq_measure_peak(local, kind, ctypes.byref(v)))
+                best = max(best, v.value)
+            peaks[name] = best
+        # K1: materialised design matrix, device resident (N*K*8 bytes must fit: use 2^19 rows = 7.4 GB)
+        n1 = 1 << 19
+        A = torch.empty((n1, K), dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for it in range(6):
+            e0.record()
+            _native.check(lib.pcq_eval_bases_dev(plan.handle, x.data_ptr(), n1, D, A.data_ptr(), K, stream))
+            e1.record(); e1.synchronize()
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1))
+        k1_ms = float(np.mean(ts))
+        k1_bytes = 8.0 * n1 * (D + K)
+        kernels["K1_evalBases"] = {"rows": n1, "ms": k1_ms, "evals_per_s": n1 * K / (k1_ms * 1e-3),
+                                   "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9, "bound": "hbm"}
+        del A
+        # K2: surrogate evaluation without A (exact and fast modes)
+        yy = torch.empty((n, 1), dtype=torch.float64, device=dev)
+        for mode, tag in ((0, "K2_evalPC_exact"), (1, "K2_evalPC_fast")):
+            ts = []
+            for it in range(5):
+                e0.record()
+                _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n, D, c_true.data_ptr(), 1,
+                                                  yy.data_ptr(), 1, mode, stream))
+                e1.record(); e1.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            ms = float(np.mean(ts))
+            fl = n * (4.0 * D * (P - 1) + 3.0 * K)
+            kernels[tag] = {"rows": n, "ms": ms, "samples_per_s": n / (ms * 1e-3),
+                            "TFLOPs_algorithmic": fl / (ms * 1e-3) / 1e12, "bound": "fp64"}
+    peak = peaks.get("fp64_dmma_tflops")
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if "K1_evalBases" in kernels:
+        hb = mp.get("hbm_gbs", 6650.0)
+        kernels["K1_evalBases"]["frac_of_hbm_peak"] = kernels["K1_evalBases"]["GBps"] / hb
+        kernels["K1_evalBases"]["hbm_peak_GBps"] = hb
+        kernels["K1_evalBases"]["hbm_peak_source"] = "MEASURED_PEAKS.json" if "hbm_gbs" in mp else "fallback"
+    if peaks.get("fp64_dfma_tflops"):
+        for tag in ("K2_evalPC_exact", "K2_evalPC_fast"):
+            if tag in kernels:
+                kernels[tag]["frac_of_fp64_peak"] = kernels[tag]["TFLOPs_algorithmic"] / peaks["fp64_dfma_tflops"]
+
+    # ---------------- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1:
+        from oracle import pc_oracle as orc
+        nc = args.cpu_samples
+        xc = xh[:nc]
+        yc = yh[:nc]
+        _, tb, tf = cpu_reference_pass(xc, yc, mi)
+        cores = host_threads()
+        cpu = {"value": nc * K / (tb + tf), "unit": "basis evals/s (samples*terms)", "cores": cores, "kind": "port",
+               "sample": f"oracle port (numpy restatement of PCRV.evalBases + lsq.fita) on the first {nc} rows: "
+                         f"basis {tb:.2f} s (single-threaded numpy loop), lstsq {tf:.2f} s ({cores} BLAS threads)",
+               "basis_evals_per_s": nc * K / tb, "fit_seconds": tf}
+
+    line = {
+        "metric": "pc_basis_evals_per_s", "value": value, "unit": "basis evals/s (samples*terms)",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "samples_per_gpu": n, "terms": K, "dim": D, "order": P,
+                   "parallelism": f"sample-sharded x{world}, one all-reduce of the packed statistics",
+                   "l2": "inputs (x,y = %.0f MB per GPU) larger than the 126 MB L2; no explicit flush" % ((n * (D + 1) * 8) / 1e6)},
+        "fit_seconds": ms_per_step * 1e-3,
+        "breakdown_ms": {"k3_suffstats": k3_mean_ms, "allreduce": float(np.mean(ar_ms)),
+                         "host_solve": 1e3 * float(np.mean(solve_s))},
+        "max_abs_coef_error_vs_truth": err,
+        "roofline": {"bound": "tensor", "kernel": "pcq_gram_kernel (K3, fused basis + DMMA SYRK)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": (achieved / peak) if peak else None, "traffic": None,
+                     "algorithmic_flops_per_launch": flops,
+                     "peak_source": "FP64 DMMA m8n8k4 register-chain micro-benchmark run live on this GPU "
+                                    "(pcq_measure_peak); MEASURED_PEAKS.json has no FP64 figure"},
+        "peaks_measured_live": peaks,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "basis evals/s (samples*terms)",
+                "h2d_bytes_per_step": int(n * (D + 1) * 8), "d2h_bytes_per_step": int(L * L * 8),
+                "api": "pytuq_b200.lreg.lsq.fit(x, y) with numpy host arrays",
+                "max_abs_coef_diff_vs_resident": e2e_err},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -267,6 +267,7 @@ def test_fitters_vs_reference(fit_cases):
                 assert np.shape(b.datavar) == (1,)
                 np.testing.assert_allclose(b.datavar, c[f"{tag}_datavar"], rtol=1e-7)
                 np.testing.assert_allclose(b.cf_cov, c[f"{tag}_cov"], rtol=1e-7, atol=1e-18)
+        a = fused(anl())
         mean, var, _ = a.predict(c["xt"], msc=1)
         np.testing.assert_allclose(mean, c["anl_pred_mean"], rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(var, c["anl_pred_var"], rtol=1e-7)
