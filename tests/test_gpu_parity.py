@@ -308,7 +308,11 @@ def test_pce_and_pcsobol():
     assert pce.evaluate(x[:7])["Y_eval_std"].shape == (7,)
     cfb = pce.build(regression="bcs", eta=1e-6)
     assert len(cfb) == len(pce.lreg.used) <= 10
-    np.testing.assert_allclose(pce.evaluate(x)["Y_eval"], y, atol=1e-5)
+    mi2 = orc.get_mi(2, 3)
+    wref, _, uref, _, _ = orc.bcs_fit(orc.eval_bases(x, mi2, "LU"), y, eta=1e-6)
+    assert np.array_equal(pce.lreg.used, uref)
+    np.testing.assert_allclose(cfb, wref, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(pce.evaluate(x)["Y_eval"], orc.eval_bases(x, mi2[uref], "LU") @ wref, rtol=1e-9, atol=1e-10)
     eta = pce.build(regression="bcs", eta=[1e-2, 1e-6], nfolds=2)
     assert pce.lreg.eta in (1e-2, 1e-6)
     # PC Sobol on a seeded germ: same numpy stream as the reference, indices vs the oracle fit
