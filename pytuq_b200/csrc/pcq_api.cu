@@ -132,10 +132,17 @@ int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms, const int3
         }
         width = std::max(width, nnz);
     }
+    // Canonical descriptor: W slots, padding (slot 0 = 1.0) FIRST, then the non-zero orders in
+    // ascending dimension.  1.0 * a * b rounds exactly like a * b, so the value is unchanged, and
+    // neighbouring terms of graded sets then share their first W-1 slots ("prefix"): flag bit 0 of
+    // term k says that its prefix differs from term k-1's (K2 reloads the prefix only then).
     std::vector<uint16_t> descw((size_t)nterms * width, 0);
     std::vector<unsigned long long> desc4(nterms, 0ull);
+    std::vector<uint8_t> flags(nterms, 1);
     for (int k = 0; k < nterms; ++k) {
-        int j = 0;
+        int nnz = 0;
+        for (int i = 0; i < sdim; ++i) nnz += (mi[(size_t)k * sdim + i] > 0);
+        int j = width - nnz;
         for (int i = 0; i < sdim; ++i) {
             const int o = mi[(size_t)k * sdim + i];
             if (o > 0) descw[(size_t)k * width + j++] = (uint16_t)(1 + (o - 1) * sdim + i);
@@ -144,6 +151,12 @@ int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms, const int3
             unsigned long long d = 0;
             for (int q = 0; q < width; ++q) d |= (unsigned long long)descw[(size_t)k * width + q] << (16 * q);
             desc4[k] = d;
+        }
+        if (k > 0) {
+            bool same = true;
+            for (int q = 0; q + 1 < width; ++q)
+                same = same && descw[(size_t)k * width + q] == descw[(size_t)(k - 1) * width + q];
+            flags[k] = same ? 0 : 1;
         }
     }
     // downward-closed check (informational; lets callers pick parent-product algorithms)
@@ -178,6 +191,7 @@ int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms, const int3
     if (rc == PCQ_OK) rc = dev_upload(&p->d_p1, p1_scale, (size_t)sdim);
     if (rc == PCQ_OK) rc = dev_upload(&p->d_descw, descw.data(), descw.size());
     if (rc == PCQ_OK) rc = dev_upload(&p->d_desc4, desc4.data(), desc4.size());
+    if (rc == PCQ_OK) rc = dev_upload(&p->d_flags, flags.data(), flags.size());
     if (rc == PCQ_OK) {
         std::vector<int> zeros(sdim, 0);
         rc = dev_upload(&p->d_kinds, zeros.data(), zeros.size());
@@ -191,7 +205,7 @@ int pcq_plan_destroy(pcq_plan* p) {
     if (!p) return PCQ_OK;
     DeviceGuard guard(p->device);
     cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
-    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_ws); cudaFree(p->d_misc);
+    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc);
     for (int i = 0; i < 2; ++i) {
         cudaFree(p->d_stage[i]); cudaFree(p->d_out[i]);
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);

@@ -10,6 +10,7 @@
 //     free), descriptors and coefficients are warp-uniform loads.
 #include "pcq_internal.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 
 namespace {
@@ -114,287 +115,95 @@ int launch_bases_w(pcq_plan* p, const BasesParams& P, cudaStream_t st) {
     return PCQ_OK;
 }
 
-// ---------------------------------------------------------------------------- K2 / K5
-struct EvalParams {
-    const double* x;
-    const double* cf;   // M x K
-    double* y;          // may be null in germ mode
-    int64_t n, ldx, ldy;
-    int sdim, nterms, pmax, nslots, width, m;
-    const double* rec_a;
-    const double* rec_b;
-    const double* p1;
-    const unsigned long long* desc4;
-    const uint16_t* descw;
-    // germ mode (K5)
-    unsigned long long seed;
-    int64_t first_index;
-    const int* germ_kind;   // device, s entries: 0 uniform(-1,1), 1 normal(0,1)
-    double* part;           // [grid*warps][m][4] partial (sum, sumsq, min, max)
-};
 
-// Philox4x32-10 (Salmon et al., SC'11), counter-based: the draw for (sample, dim pair) is a
-// pure function of (seed, global sample index, pair index), so shards of one logical
-// stream can be generated independently on different GPUs.
-__device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2,
-                                              unsigned int c3, unsigned int k0, unsigned int k1,
-                                              unsigned int (&out)[4]) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const unsigned int n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
+// ------------------------------------------------------------------------------------------------
+// K1 v2: the term descriptors live in registers.  A CTA owns 16 consecutive rows; the slot table
+// is laid out [slot][row] (stride 17 doubles) so that with the row loop unrolled every gather is
+// register + immediate; each warp walks 64-term chunks (two terms per lane), loads the two
+// descriptors once and produces the chunk for all 16 rows: shared-memory traffic per value is the
+// W gathers only.
+constexpr int K1_TS = K1_ROWS + 1;
 
-// two germ values for dimensions (2*pair, 2*pair+1) of global sample `gidx`
-__device__ __forceinline__ void pcq_germ_pair(unsigned long long seed, unsigned long long gidx,
-                                              unsigned int pair, int kind0, int kind1,
-                                              double& z0, double& z1) {
-    unsigned int r[4];
-    philox4x32_10((unsigned int)gidx, (unsigned int)(gidx >> 32), pair, 0x50435121u,
-                  (unsigned int)seed, (unsigned int)(seed >> 32), r);
-    const unsigned long long a = ((unsigned long long)r[1] << 32) | r[0];
-    const unsigned long long b = ((unsigned long long)r[3] << 32) | r[2];
-    const double u0 = (double)(a >> 11) * 0x1.0p-53;   // [0,1)
-    const double u1 = (double)(b >> 11) * 0x1.0p-53;
-    // Box-Muller on (1-u0) in (0,1] and u1
-    const double rad = sqrt(-2.0 * log(1.0 - u0));
-    double sn, cs;
-    sincospi(2.0 * u1, &sn, &cs);
-    z0 = kind0 ? rad * cs : 2.0 * u0 - 1.0;
-    z1 = kind1 ? rad * sn : 2.0 * u1 - 1.0;
-}
-
-// W = 0: generic width from descw.  MB outputs per pass.  FAST: shared basis product + FMA.
-// GERM: x comes from the Philox stream and per-output power sums are reduced (K5).
-template <int W, int MB, bool FAST, int THREADS, bool GERM>
-__global__ void __launch_bounds__(THREADS) pcq_evalpc_kernel(EvalParams P) {
+template <int W>
+__global__ void __launch_bounds__(K1_THREADS) pcq_bases2_kernel(BasesParams P, int vec_ok) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tab = reinterpret_cast<double*>(smem_raw);   // [nslots][THREADS]
+    double* tab = reinterpret_cast<double*>(smem_raw);     // [nslots][K1_TS]
     const int tid = threadIdx.x;
-    const int s = P.sdim;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    constexpr int NWARPS = K1_THREADS / 32;
     const int K = P.nterms;
-    double* mytab = tab + tid;
-    constexpr int WW = W > 0 ? W : 1;
-    double* mypart = nullptr;
-    if (GERM) mypart = P.part + ((size_t)blockIdx.x * (THREADS / 32) + (tid >> 5)) * P.m * 4;
-    bool first_iter = true;
+    const int s = P.sdim;
+    const int nchunks = (K + 63) / 64;
+    const bool lda_odd = (P.lda & 1) != 0;
 
-    const int64_t nblocks = (P.n + THREADS - 1) / THREADS;
+    const int64_t nblocks = (P.n + K1_ROWS - 1) / K1_ROWS;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        const int64_t n = blk * THREADS + tid;
-        const bool live = n < P.n;
-        // each thread only ever touches its own column of the table: no barrier needed
-        mytab[0] = 1.0;
-        if (GERM) {
-            for (int i = 0; i < s; i += 2) {
-                double z0, z1;
-                const int k0 = P.germ_kind[i];
-                const int k1 = (i + 1 < s) ? P.germ_kind[i + 1] : 0;
-                pcq_germ_pair(P.seed, (unsigned long long)(P.first_index + n), (unsigned int)(i >> 1),
-                              k0, k1, z0, z1);
-                pcq_fill_1d(z0, i, s, P.pmax, P.rec_a, P.rec_b, P.p1, mytab, THREADS);
-                if (i + 1 < s)
-                    pcq_fill_1d(z1, i + 1, s, P.pmax, P.rec_a, P.rec_b, P.p1, mytab, THREADS);
-            }
-        } else {
-            for (int i = 0; i < s; ++i) {
-                const double xv = live ? P.x[n * P.ldx + i] : 0.0;
-                pcq_fill_1d(xv, i, s, P.pmax, P.rec_a, P.rec_b, P.p1, mytab, THREADS);
-            }
+        const int64_t n0 = blk * K1_ROWS;
+        const int rows = (int)min((int64_t)K1_ROWS, P.n - n0);
+        __syncthreads();   // previous iteration's readers are done with tab
+        for (int idx = tid; idx < K1_ROWS * s; idx += K1_THREADS) {
+            const int r = idx / s;
+            const int i = idx - r * s;
+            if (i == 0) tab[r] = 1.0;
+            const double xv = (r < rows) ? P.x[(n0 + r) * P.ldx + i] : 0.0;
+            pcq_fill_1d(xv, i, s, P.pmax, P.rec_a, P.rec_b, P.p1, tab + r, K1_TS);
         }
-        for (int m0 = 0; m0 < P.m; m0 += MB) {
-            double acc[MB];
+        __syncthreads();
+        for (int c = warp; c < nchunks; c += NWARPS) {
+            const int k = c * 64 + 2 * lane;
+            const bool v0 = k < K, v1 = k + 1 < K;
+            const unsigned long long d0 = v0 ? __ldg(P.desc4 + k) : 0ull;
+            const unsigned long long d1 = v1 ? __ldg(P.desc4 + k + 1) : 0ull;
+            int o0[W], o1[W];
 #pragma unroll
-            for (int j = 0; j < MB; ++j) acc[j] = 0.0;
-            const double* cfp[MB];
-#pragma unroll
-            for (int j = 0; j < MB; ++j) cfp[j] = P.cf + (size_t)min(m0 + j, P.m - 1) * K;
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                if constexpr (W > 0) {
-                    const unsigned long long d = __ldg(P.desc4 + k);
-                    double f[WW];
-                    f[0] = mytab[(size_t)(d & 0xffffull) * THREADS];
-                    if constexpr (W >= 2) f[1] = mytab[(size_t)((d >> 16) & 0xffffull) * THREADS];
-                    if constexpr (W >= 3) f[2] = mytab[(size_t)((d >> 32) & 0xffffull) * THREADS];
-                    if constexpr (W >= 4) f[3] = mytab[(size_t)((d >> 48) & 0xffffull) * THREADS];
-                    if constexpr (FAST) {
-                        double psi = f[0];
-#pragma unroll
-                        for (int q = 1; q < W; ++q) psi = __dmul_rn(psi, f[q]);
-#pragma unroll
-                        for (int j = 0; j < MB; ++j) acc[j] = __fma_rn(__ldg(cfp[j] + k), psi, acc[j]);
-                    } else {
-                        // rv/pcrv.py:492-495: prd = cf[k]; prd *= phi_i (i ascending); val += prd
-#pragma unroll
-                        for (int j = 0; j < MB; ++j) {
-                            double prd = __ldg(cfp[j] + k);
-#pragma unroll
-                            for (int q = 0; q < W; ++q) prd = __dmul_rn(prd, f[q]);
-                            acc[j] = __dadd_rn(acc[j], prd);
-                        }
-                    }
-                } else {
-                    const uint16_t* dw = P.descw + (size_t)k * P.width;
-                    if constexpr (FAST) {
-                        const double psi = pcq_termw(mytab, THREADS, dw, P.width);
-#pragma unroll
-                        for (int j = 0; j < MB; ++j) acc[j] = __fma_rn(__ldg(cfp[j] + k), psi, acc[j]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < MB; ++j) {
-                            double prd = __ldg(cfp[j] + k);
-                            for (int q = 0; q < P.width; ++q)
-                                prd = __dmul_rn(prd, mytab[(size_t)__ldg(dw + q) * THREADS]);
-                            acc[j] = __dadd_rn(acc[j], prd);
-                        }
-                    }
-                }
+            for (int q = 0; q < W; ++q) {
+                o0[q] = (int)((d0 >> (16 * q)) & 0xffffull) * K1_TS;
+                o1[q] = (int)((d1 >> (16 * q)) & 0xffffull) * K1_TS;
             }
-            if (live && P.y != nullptr) {
+            double* out = P.a + n0 * P.lda + k;
 #pragma unroll
-                for (int j = 0; j < MB; ++j)
-                    if (m0 + j < P.m) P.y[n * P.ldy + m0 + j] = acc[j];
-            }
-            if constexpr (GERM) {
-                // warp-shuffle reduction of (sum, sum of squares, min, max); lane 0 keeps the
-                // warp's running partial in its private workspace row (no atomics)
+            for (int r = 0; r < K1_ROWS; ++r) {
+                if (r < rows) {
+                    double a = tab[o0[0] + r], b = tab[o1[0] + r];
 #pragma unroll
-                for (int j = 0; j < MB; ++j) {
-                    double v1 = live ? acc[j] : 0.0;
-                    double v2 = live ? acc[j] * acc[j] : 0.0;
-                    double mn = live ? acc[j] : INFINITY;
-                    double mx = live ? acc[j] : -INFINITY;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-                        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-                        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    for (int q = 1; q < W; ++q) {
+                        a = __dmul_rn(a, tab[o0[q] + r]);
+                        b = __dmul_rn(b, tab[o1[q] + r]);
                     }
-                    if ((tid & 31) == 0 && m0 + j < P.m) {
-                        double* q = mypart + (size_t)(m0 + j) * 4;
-                        if (first_iter) { q[0] = v1; q[1] = v2; q[2] = mn; q[3] = mx; }
-                        else { q[0] += v1; q[1] += v2; q[2] = fmin(q[2], mn); q[3] = fmax(q[3], mx); }
+                    double* dst = out + (size_t)r * P.lda;
+                    // n0 is a multiple of 16 and k is even: the pair is 16-byte aligned unless the
+                    // leading dimension is odd and the row is odd
+                    if (vec_ok && v1 && !(lda_odd && (r & 1))) {
+                        __stcs(reinterpret_cast<double2*>(dst), make_double2(a, b));
+                    } else {
+                        if (v0) __stcs(dst, a);
+                        if (v1) __stcs(dst + 1, b);
                     }
                 }
             }
         }
-        first_iter = false;
-    }
-    if constexpr (GERM) {
-        // CTAs (or warps) that never ran an iteration still own a workspace row
-        if (first_iter && (tid & 31) == 0) {
-            for (int j = 0; j < P.m; ++j) {
-                double* q = mypart + (size_t)j * 4;
-                q[0] = 0.0; q[1] = 0.0; q[2] = INFINITY; q[3] = -INFINITY;
-            }
-        }
     }
 }
 
-// fixed-order reduction of the per-warp partials -> sums[m][4]
-__global__ void pcq_prop_reduce_kernel(const double* part, int nrows, int m, double* sums) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    double s1 = 0.0, s2 = 0.0, mn = INFINITY, mx = -INFINITY;
-    for (int r = 0; r < nrows; ++r) {
-        const double* q = part + ((size_t)r * m + j) * 4;
-        s1 += q[0]; s2 += q[1]; mn = fmin(mn, q[2]); mx = fmax(mx, q[3]);
-    }
-    sums[j * 4 + 0] = s1; sums[j * 4 + 1] = s2; sums[j * 4 + 2] = mn; sums[j * 4 + 3] = mx;
-}
-
-__global__ void pcq_germ_kernel(unsigned long long seed, int64_t first, int64_t n, int s,
-                                const int* kind, double* x, int64_t ldx) {
-    const int npair = (s + 1) / 2;
-    const int64_t total = n * npair;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = idx / npair;
-        const int pr = (int)(idx - r * npair);
-        const int i = 2 * pr;
-        double z0, z1;
-        pcq_germ_pair(seed, (unsigned long long)(first + r), (unsigned int)pr, kind[i],
-                      (i + 1 < s) ? kind[i + 1] : 0, z0, z1);
-        x[r * ldx + i] = z0;
-        if (i + 1 < s) x[r * ldx + i + 1] = z1;
-    }
-}
-
-template <int W, int MB, bool FAST, int THREADS, bool GERM>
-int launch_evalpc_t(pcq_plan* p, EvalParams P, cudaStream_t st, double* sums) {
-    const size_t smem = (size_t)p->nslots * THREADS * sizeof(double);
-    auto kern = pcq_evalpc_kernel<W, MB, FAST, THREADS, GERM>;
+template <int W>
+int launch_bases2_w(pcq_plan* p, const BasesParams& P, cudaStream_t st, bool* handled) {
+    const size_t smem = (size_t)p->nslots * K1_TS * sizeof(double);
+    *handled = false;
+    if (smem > p->smem_optin || getenv("PCQ_K1_V1")) return PCQ_OK;
+    *handled = true;
+    auto kern = pcq_bases2_kernel<W>;
     PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    PCQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    PCQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
     if (occ < 1) occ = 1;
-    const int64_t nblocks = (P.n + THREADS - 1) / THREADS;
+    const int64_t nblocks = (P.n + K1_ROWS - 1) / K1_ROWS;
     const int64_t cap = (int64_t)p->num_sms * occ;
     const int grid = (int)(nblocks < cap ? nblocks : cap);
-    if (GERM) {
-        const int nrows = grid * (THREADS / 32);
-        int rc = pcq_ensure_dev(&p->d_ws, &p->ws_bytes, (size_t)nrows * P.m * 4 * sizeof(double));
-        if (rc != PCQ_OK) return rc;
-        P.part = p->d_ws;
-        kern<<<grid, THREADS, smem, st>>>(P);
-        PCQ_LAUNCH_CHECK("pcq_evalpc_kernel<germ>");
-        pcq_prop_reduce_kernel<<<(P.m + 127) / 128, 128, 0, st>>>(P.part, nrows, P.m, sums);
-        PCQ_LAUNCH_CHECK("pcq_prop_reduce_kernel");
-        return PCQ_OK;
-    }
-    kern<<<grid, THREADS, smem, st>>>(P);
-    PCQ_LAUNCH_CHECK("pcq_evalpc_kernel");
+    const int vec_ok = (reinterpret_cast<uintptr_t>(P.a) & 15) == 0;
+    kern<<<grid, K1_THREADS, smem, st>>>(P, vec_ok);
+    PCQ_LAUNCH_CHECK("pcq_bases2_kernel");
     return PCQ_OK;
-}
-
-template <int W, int MB, bool FAST, bool GERM>
-int launch_evalpc_threads(pcq_plan* p, const EvalParams& P, cudaStream_t st, double* sums) {
-    // the [slot][lane] table costs nslots*8 bytes per thread; pick the widest CTA that
-    // still leaves room for two CTAs per SM
-    const size_t per_thread = (size_t)p->nslots * sizeof(double);
-    const size_t budget = p->smem_optin;
-    if (per_thread * 128 * 2 <= budget) return launch_evalpc_t<W, MB, FAST, 128, GERM>(p, P, st, sums);
-    if (per_thread * 64 <= budget) return launch_evalpc_t<W, MB, FAST, 64, GERM>(p, P, st, sums);
-    if (per_thread * 32 <= budget) return launch_evalpc_t<W, MB, FAST, 32, GERM>(p, P, st, sums);
-    pcq_set_error("evalPC: %d table slots per sample do not fit shared memory", p->nslots);
-    return PCQ_ERR_UNSUPPORTED;
-}
-
-template <int W, bool GERM>
-int launch_evalpc_w(pcq_plan* p, const EvalParams& P, int mode, cudaStream_t st, double* sums) {
-    const bool fast = mode != 0;
-    if (P.m >= 4) {
-        return fast ? launch_evalpc_threads<W, 4, true, GERM>(p, P, st, sums)
-                    : launch_evalpc_threads<W, 4, false, GERM>(p, P, st, sums);
-    }
-    return fast ? launch_evalpc_threads<W, 1, true, GERM>(p, P, st, sums)
-                : launch_evalpc_threads<W, 1, false, GERM>(p, P, st, sums);
-}
-
-template <bool GERM>
-int launch_evalpc_any(pcq_plan* p, const EvalParams& P, int mode, cudaStream_t st, double* sums) {
-    switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
-        case 1: return launch_evalpc_w<1, GERM>(p, P, mode, st, sums);
-        case 2: return launch_evalpc_w<2, GERM>(p, P, mode, st, sums);
-        case 3: return launch_evalpc_w<3, GERM>(p, P, mode, st, sums);
-        case 4: return launch_evalpc_w<4, GERM>(p, P, mode, st, sums);
-        default: return launch_evalpc_w<0, GERM>(p, P, mode, st, sums);
-    }
-}
-
-void fill_eval_params(pcq_plan* p, EvalParams& P) {
-    memset(&P, 0, sizeof(P));
-    P.sdim = p->sdim; P.nterms = p->nterms; P.pmax = p->pmax; P.nslots = p->nslots;
-    P.width = p->width;
-    P.rec_a = p->d_rec_a; P.rec_b = p->d_rec_b; P.p1 = p->d_p1;
-    P.desc4 = p->d_desc4; P.descw = p->d_descw;
 }
 
 }  // namespace
@@ -408,6 +217,16 @@ int pcq_launch_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, doubl
     P.width = p->width;
     P.rec_a = p->d_rec_a; P.rec_b = p->d_rec_b; P.p1 = p->d_p1;
     P.desc4 = p->d_desc4; P.descw = p->d_descw;
+    bool handled = false;
+    int rc = PCQ_OK;
+    switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
+        case 1: rc = launch_bases2_w<1>(p, P, st, &handled); break;
+        case 2: rc = launch_bases2_w<2>(p, P, st, &handled); break;
+        case 3: rc = launch_bases2_w<3>(p, P, st, &handled); break;
+        case 4: rc = launch_bases2_w<4>(p, P, st, &handled); break;
+        default: break;
+    }
+    if (handled || rc != PCQ_OK) return rc;
     switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
         case 1: return launch_bases_w<1>(p, P, st);
         case 2: return launch_bases_w<2>(p, P, st);
@@ -415,48 +234,4 @@ int pcq_launch_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, doubl
         case 4: return launch_bases_w<4>(p, P, st);
         default: return launch_bases_w<0>(p, P, st);
     }
-}
-
-int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf,
-                      int m, double* y, int64_t ldy, int mode, cudaStream_t st) {
-    if (n == 0 || m == 0) return PCQ_OK;
-    EvalParams P;
-    fill_eval_params(p, P);
-    P.x = x; P.cf = cf; P.y = y; P.n = n; P.ldx = ldx; P.ldy = ldy; P.m = m;
-    return launch_evalpc_any<false>(p, P, mode, st, nullptr);
-}
-
-static int upload_kinds(pcq_plan* p, const int32_t* germ_kind, const int** dev, cudaStream_t st) {
-    PCQ_CUDA(cudaMemcpyAsync(p->d_kinds, germ_kind, (size_t)p->sdim * sizeof(int),
-                             cudaMemcpyHostToDevice, st));
-    *dev = p->d_kinds;
-    return PCQ_OK;
-}
-
-int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
-                         const int32_t* germ_kind, const double* cf, int m, double* sums,
-                         double* y, int64_t ldy, int mode, cudaStream_t st) {
-    if (m == 0) return PCQ_OK;
-    EvalParams P;
-    fill_eval_params(p, P);
-    const int* dkind = nullptr;
-    int rc = upload_kinds(p, germ_kind, &dkind, st);
-    if (rc != PCQ_OK) return rc;
-    P.cf = cf; P.y = y; P.n = n; P.ldy = ldy; P.m = m;
-    P.seed = seed; P.first_index = first; P.germ_kind = dkind;
-    return launch_evalpc_any<true>(p, P, mode, st, sums);
-}
-
-int pcq_launch_germ(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
-                    const int32_t* germ_kind, double* x, int64_t ldx, cudaStream_t st) {
-    if (n == 0) return PCQ_OK;
-    const int* dkind = nullptr;
-    int rc = upload_kinds(p, germ_kind, &dkind, st);
-    if (rc != PCQ_OK) return rc;
-    const int64_t total = n * ((p->sdim + 1) / 2);
-    const int64_t want = (total + 255) / 256;
-    const int64_t cap = (int64_t)p->num_sms * 8;
-    pcq_germ_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(seed, first, n, p->sdim, dkind, x, ldx);
-    PCQ_LAUNCH_CHECK("pcq_germ_kernel");
-    return PCQ_OK;
 }

@@ -31,9 +31,10 @@ struct pcq_plan {
     double* d_rec_b = nullptr;    // (pmax+1) x s
     double* d_p1 = nullptr;       // s
     int* d_kinds = nullptr;       // s, germ kinds of the last propagate call
-    // term descriptors: W slot indices per term, ascending dimension, padded with slot 0
+    // term descriptors: W slot indices per term: padding (slot 0) first, then ascending dimension
     unsigned long long* d_desc4 = nullptr;  // K packed 4 x uint16 (valid when width <= 4)
     uint16_t* d_descw = nullptr;            // K x width (always valid)
+    uint8_t* d_flags = nullptr;             // K, bit 0: first W-1 slots differ from the previous term's
 
     // Gram workspace (lazily grown)
     double* d_ws = nullptr;

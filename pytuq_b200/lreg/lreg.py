@@ -14,7 +14,7 @@ The K x K factorisation itself is host LAPACK (it is not sample-parallel; SURVEY
 import sys
 
 import numpy as np
-from scipy.linalg import cho_factor, cho_solve
+from scipy.linalg.lapack import dpotrf, dpotrs
 
 from ..fit.fit import fitbase
 from .stats import SuffStats
@@ -35,23 +35,23 @@ class PCBasisEvaluator:
 def solve_normal(G, b):
     """Solves G c = b for symmetric positive (semi)definite G.
 
-    Jacobi-scaled Cholesky; when G is numerically singular the minimum-norm solution on
-    the retained eigen-space is returned instead (the closest normal-equation analogue of
-    the reference's SVD least squares with cond=1e-13, lreg/lreg.py:335 -- see DESIGN.md
-    for the conditioning limit of that equivalence)."""
-    d = np.sqrt(np.clip(np.diag(G), 0.0, None))
-    d[d == 0.0] = 1.0
-    scale = d if b.ndim == 1 else d[:, None]
-    Gs = G / np.outer(d, d)
-    try:
-        fac = cho_factor(Gs, lower=True, check_finite=False)
-        piv = np.abs(np.diag(fac[0]))
-        if piv.min() > 1.0e-6 * piv.max():          # cond(Gs) well below 1e12: Cholesky is safe
-            c = cho_solve(fac, b / scale, check_finite=False)
-            if np.all(np.isfinite(c)):
-                return c / scale
-    except np.linalg.LinAlgError:
-        pass
+    Plain LAPACK Cholesky (dpotrf/dpotrs): its backward error is invariant under diagonal scaling,
+    so no explicit equilibration pass over the K x K matrix is needed; conditioning is judged on the
+    scaled pivots L_ii / sqrt(G_ii).  When G is numerically singular the minimum-norm solution on
+    the retained eigen-space is returned instead (the closest normal-equation analogue of the
+    reference's SVD least squares with cond=1e-13, lreg/lreg.py:335 -- see DESIGN.md for the
+    conditioning limit of that equivalence)."""
+    diag = np.diag(G)
+    if diag.size and np.all(diag > 0.0) and np.all(np.isfinite(diag)):
+        # G is symmetric: the transpose of a C-ordered copy is the same matrix in Fortran order
+        fac = np.array(G, dtype=np.float64, order="C").T
+        L, info = dpotrf(fac, lower=0, overwrite_a=1, clean=0)
+        if info == 0:
+            piv = np.abs(np.diag(L)) / np.sqrt(diag)
+            if piv.min() > 1.0e-6:                    # cond of the equilibrated G well below 1e12
+                c, info2 = dpotrs(L, np.asfortranarray(b), lower=0)
+                if info2 == 0 and np.all(np.isfinite(c)):
+                    return np.ascontiguousarray(c) if c.ndim == 2 else c
     # (near-)singular: minimum-norm solution in the original variables, like an SVD solve
     lam, V = np.linalg.eigh(G)
     keep = lam > lam[-1] * max(G.shape[0], 10) * 1.0e-14
