@@ -50,6 +50,21 @@ int64_t chunk_rows(int64_t bytes_per_row, int64_t n) {
     return std::min(r, std::max<int64_t>(n, 1));
 }
 
+
+// host <-> device copy of `rows` rows of `width` doubles; flat when both sides are contiguous
+// (2-D copies from pageable memory are staged row by row and are several times slower)
+int copy_rows(double* dst, int64_t ld_dst, const double* src, int64_t ld_src, int64_t width, int64_t rows,
+              cudaMemcpyKind kind, cudaStream_t st) {
+    if (rows == 0 || width == 0) return PCQ_OK;
+    if (ld_dst == width && ld_src == width) {
+        PCQ_CUDA(cudaMemcpyAsync(dst, src, (size_t)rows * width * 8, kind, st));
+    } else {
+        PCQ_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld_dst * 8, src, (size_t)ld_src * 8, (size_t)width * 8,
+                                   (size_t)rows, kind, st));
+    }
+    return PCQ_OK;
+}
+
 int ensure_streams(pcq_plan* p) {
     for (int i = 0; i < 2; ++i) {
         if (!p->streams[i]) PCQ_CUDA(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
@@ -336,11 +351,9 @@ int pcq_eval_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double*
         cudaStream_t st = p->streams[b];
         if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
         if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * K * 8)) != PCQ_OK) return rc;
-        PCQ_CUDA(cudaMemcpy2DAsync(p->d_stage[b], (size_t)s * 8, x + r0 * ldx, (size_t)ldx * 8,
-                                   (size_t)s * 8, (size_t)nr, cudaMemcpyHostToDevice, st));
+        if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
         if ((rc = pcq_launch_bases(p, p->d_stage[b], nr, s, p->d_out[b], K, st)) != PCQ_OK) return rc;
-        PCQ_CUDA(cudaMemcpy2DAsync(a + r0 * lda, (size_t)lda * 8, p->d_out[b], (size_t)K * 8,
-                                   (size_t)K * 8, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        if ((rc = copy_rows(a + r0 * lda, lda, p->d_out[b], K, K, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return rc;
     }
     PCQ_CUDA(cudaStreamSynchronize(p->streams[0]));
     PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));
@@ -370,12 +383,10 @@ int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const doub
         cudaStream_t st = p->streams[b];
         if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
         if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * m * 8)) != PCQ_OK) return rc;
-        PCQ_CUDA(cudaMemcpy2DAsync(p->d_stage[b], (size_t)s * 8, x + r0 * ldx, (size_t)ldx * 8,
-                                   (size_t)s * 8, (size_t)nr, cudaMemcpyHostToDevice, st));
+        if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
         if ((rc = pcq_launch_evalpc(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], m, mode, st)) != PCQ_OK)
             return rc;
-        PCQ_CUDA(cudaMemcpy2DAsync(y + r0 * ldy, (size_t)ldy * 8, p->d_out[b], (size_t)m * 8,
-                                   (size_t)m * 8, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        if ((rc = copy_rows(y + r0 * ldy, ldy, p->d_out[b], m, m, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return rc;
     }
     PCQ_CUDA(cudaStreamSynchronize(p->streams[0]));
     PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));
@@ -413,11 +424,8 @@ int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const do
         if (m > 0 && (rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * m * 8)) != PCQ_OK) return rc;
         // buffer b was last read by the Gram launch of chunk c-2
         if (c >= 2) PCQ_CUDA(cudaStreamWaitEvent(sc, p->events[b], 0));
-        PCQ_CUDA(cudaMemcpy2DAsync(p->d_stage[b], (size_t)s * 8, x + r0 * ldx, (size_t)ldx * 8,
-                                   (size_t)s * 8, (size_t)nr, cudaMemcpyHostToDevice, sc));
-        if (m > 0)
-            PCQ_CUDA(cudaMemcpy2DAsync(p->d_out[b], (size_t)m * 8, y + r0 * ldy, (size_t)ldy * 8,
-                                       (size_t)m * 8, (size_t)nr, cudaMemcpyHostToDevice, sc));
+        if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, sc)) != PCQ_OK) return rc;
+        if (m > 0 && (rc = copy_rows(p->d_out[b], m, y + r0 * ldy, ldy, m, nr, cudaMemcpyHostToDevice, sc)) != PCQ_OK) return rc;
         cudaEvent_t copied;
         PCQ_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
         PCQ_CUDA(cudaEventRecord(copied, sc));

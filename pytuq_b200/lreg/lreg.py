@@ -32,23 +32,53 @@ class PCBasisEvaluator:
         return pars[0].evalBases(x, self.jdim)
 
 
-def solve_normal(G, b):
-    """Solves G c = b for symmetric positive (semi)definite G.
+def _scaled_pivots_ok(diagG, diagL):
+    # cond of the equilibrated G well below 1e12: pivots L_ii / sqrt(G_ii) stay away from 0
+    return bool((diagL.abs() / diagG.sqrt()).min() > 1.0e-6)
 
-    Plain LAPACK Cholesky (dpotrf/dpotrs): its backward error is invariant under diagonal scaling,
-    so no explicit equilibration pass over the K x K matrix is needed; conditioning is judged on the
-    scaled pivots L_ii / sqrt(G_ii).  When G is numerically singular the minimum-norm solution on
-    the retained eigen-space is returned instead (the closest normal-equation analogue of the
-    reference's SVD least squares with cond=1e-13, lreg/lreg.py:335 -- see DESIGN.md for the
-    conditioning limit of that equivalence)."""
-    diag = np.diag(G)
-    if diag.size and np.all(diag > 0.0) and np.all(np.isfinite(diag)):
-        # G is symmetric: the transpose of a C-ordered copy is the same matrix in Fortran order
-        fac = np.array(G, dtype=np.float64, order="C").T
-        L, info = dpotrf(fac, lower=0, overwrite_a=1, clean=0)
-        if info == 0:
-            piv = np.abs(np.diag(L)) / np.sqrt(diag)
-            if piv.min() > 1.0e-6:                    # cond of the equilibrated G well below 1e12
+
+def solve_normal_device(G_t, B_t):
+    """Cholesky solve of G C = B on the GPU (torch tensors, float64).  The K x K factorisation is not
+    sample-parallel; it is a plain library call (cuSOLVER potrf/potrs through
+    torch.linalg), kept on the device so that only K coefficients travel back to the host.
+    Returns None when G is not numerically positive definite (callers then take the eigen path)."""
+    import torch
+    diag = torch.diagonal(G_t)
+    if not bool(torch.all(diag > 0.0)):
+        return None
+    L, info = torch.linalg.cholesky_ex(G_t)
+    if int(info) != 0 or not _scaled_pivots_ok(diag, torch.diagonal(L)):
+        return None
+    C = torch.cholesky_solve(B_t if B_t.ndim == 2 else B_t[:, None], L)
+    if not bool(torch.all(torch.isfinite(C))):
+        return None
+    return C if B_t.ndim == 2 else C[:, 0]
+
+
+def solve_normal(G, b):
+    """Solves G c = b for symmetric positive (semi)definite G (numpy in / numpy out).
+
+    Cholesky on the GPU; its backward error is invariant under diagonal scaling, so no explicit
+    equilibration pass is needed and conditioning is judged on the scaled pivots.  When G is
+    numerically singular the minimum-norm solution on the retained eigen-space is returned instead
+    (the closest normal-equation analogue of the reference's SVD least squares with cond=1e-13,
+    lreg/lreg.py:335 -- see DESIGN.md for the conditioning limit of that equivalence)."""
+    import torch
+    from .. import device as _device
+    if torch.cuda.is_available():
+        dev = torch.device("cuda", _device.current_device())
+        G_t = torch.from_numpy(np.ascontiguousarray(G, dtype=np.float64)).to(dev)
+        B_t = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64)).to(dev)
+        C = solve_normal_device(G_t, B_t)
+        if C is not None:
+            return C.cpu().numpy()
+    else:
+        # no device (host-logic tests): LAPACK dpotrf/dpotrs with the same acceptance test
+        diag = np.diag(G)
+        if diag.size and np.all(diag > 0.0) and np.all(np.isfinite(diag)):
+            fac = np.array(G, dtype=np.float64, order="C").T    # symmetric: same matrix, Fortran order
+            L, info = dpotrf(fac, lower=0, overwrite_a=1, clean=0)
+            if info == 0 and (np.abs(np.diag(L)) / np.sqrt(diag)).min() > 1.0e-6:
                 c, info2 = dpotrs(L, np.asfortranarray(b), lower=0)
                 if info2 == 0 and np.all(np.isfinite(c)):
                     return np.ascontiguousarray(c) if c.ndim == 2 else c
