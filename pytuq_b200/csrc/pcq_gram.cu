@@ -51,6 +51,7 @@ struct GramParams {
     const unsigned long long* desc4; const uint16_t* descw;
     double* s_out; int accumulate;
     double* ws;        // [grid][2][GT*GT]
+    int mirror;        // fill the lower triangle after this launch
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -330,8 +331,10 @@ int launch_gram_t(const GramParams& P0, int num_sms, size_t smem_optin, double**
     pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
     PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
     const int nb32 = (P.L + 31) / 32;
-    pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
-    PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    if (P.mirror) {
+        pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
+        PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    }
     return PCQ_OK;
 }
 
@@ -620,8 +623,10 @@ int launch_gram_fused(const GramParams& P0, int num_sms, size_t smem_optin, doub
     pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
     PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
     const int nb32 = (P.L + 31) / 32;
-    pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
-    PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    if (P.mirror) {
+        pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
+        PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    }
     return PCQ_OK;
 }
 
@@ -827,8 +832,10 @@ int launch_gram_fused2(const GramParams& P0, int num_sms, size_t smem_optin, dou
     pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
     PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
     const int nb32 = (P.L + 31) / 32;
-    pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
-    PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    if (P.mirror) {
+        pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
+        PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    }
     return PCQ_OK;
 }
 
@@ -1115,8 +1122,10 @@ int launch_gram_ws(const GramParams& P0, int num_sms, size_t smem_optin, double*
     pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
     PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
     const int nb32 = (P.L + 31) / 32;
-    pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
-    PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    if (P.mirror) {
+        pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
+        PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    }
     return PCQ_OK;
 }
 
@@ -1139,12 +1148,13 @@ __global__ void pcq_fill_kernel(double* p, size_t n, double v) {
 
 }  // namespace
 
-int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n,
-                    int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,
-                    int64_t ldy, int m, double* s, int accumulate, double** ws,
-                    size_t* ws_bytes, cudaStream_t st) {
+static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n,
+                            int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,
+                            int64_t ldy, int m, double* s, int accumulate, int mirror, double** ws,
+                            size_t* ws_bytes, cudaStream_t st) {
     GramParams P;
     memset(&P, 0, sizeof(P));
+    P.mirror = mirror;
     const bool fused = (a == nullptr);
     P.x = x; P.ldx = ldx; P.a = a; P.lda = lda; P.y = y; P.ldy = ldy;
     P.kb = fused ? p->nterms : kcols;
@@ -1212,4 +1222,33 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
         }
     }
     return launch_gram_t<0, false>(P, num_sms, smem_optin, ws, ws_bytes, st);
+}
+
+// Every sample block is read by all ntri output tiles.  With one launch over all samples the tiles
+// reach a given block at different times and x is re-read from HBM ~ntri times (ncu, r01: 18.8 GB for
+// 210 MB of input).  Processing the samples in L2-sized chunks (default 48 MB of x/y per launch,
+// accumulating into S) keeps each chunk L2-resident while the tiles sweep it.
+int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n,
+                    int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,
+                    int64_t ldy, int m, double* s, int accumulate, double** ws,
+                    size_t* ws_bytes, cudaStream_t st) {
+    if (n == 0)
+        return launch_gram_once(p, num_sms, smem_optin, x, 0, ldx, a, lda, kcols, y, ldy, m, s, accumulate, 1,
+                                ws, ws_bytes, st);
+    const bool fused = (a == nullptr);
+    const int64_t row_bytes = 8 * (int64_t)((fused ? p->sdim : kcols) + m);
+    const char* env = getenv("PCQ_GRAM_CHUNK_MB");
+    const int64_t target = (int64_t)(env ? atoi(env) : 48) << 20;
+    int64_t rows = target > 0 ? target / row_bytes : n;
+    rows = (rows / GRAM_SB) * GRAM_SB;
+    if (rows < 8192) rows = 8192;
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t nr = (n - r0 < rows) ? n - r0 : rows;
+        const int last = (r0 + nr >= n);
+        int rc = launch_gram_once(p, num_sms, smem_optin, fused ? x + r0 * ldx : nullptr, nr, ldx,
+                                  fused ? nullptr : a + r0 * lda, lda, kcols, y ? y + r0 * ldy : nullptr, ldy, m,
+                                  s, accumulate || r0 > 0, last, ws, ws_bytes, st);
+        if (rc != PCQ_OK) return rc;
+    }
+    return PCQ_OK;
 }

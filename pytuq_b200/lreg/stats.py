@@ -83,7 +83,8 @@ class SuffStats:
         if y is None:
             Y, M = None, 0
         else:
-            Y = np.ascontiguousarray(y, dtype=np.float64).reshape(N, -1)
+            Y = np.ascontiguousarray(y, dtype=np.float64)
+            Y = Y.reshape(N, Y.shape[1] if Y.ndim == 2 else 1)
             M = Y.shape[1]
         L = K + M + 1
         S = np.empty((L, L))

@@ -59,7 +59,8 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
     if y is None:
         Y, M = None, 0
     else:
-        Y = np.ascontiguousarray(y, dtype=np.float64).reshape(N, -1)
+        Y = np.ascontiguousarray(y, dtype=np.float64)
+        Y = Y.reshape(N, Y.shape[1] if Y.ndim == 2 else 1)
         M = Y.shape[1]
     plan = pcrv._plan(mindex)
     K = mindex.shape[0]

@@ -142,7 +142,8 @@ def test_k2_many_outputs_and_sizes():
 # ----------------------------------------------------------------------------- K3 / K4
 @pytest.mark.parametrize("fam,p,d,n,M", [("LU", 3, 5, 5000, 1), ("HG", 3, 5, 4097, 3), ("nLU", 2, 8, 333, 0),
                                          ("LU", 4, 10, 2500, 1), ("HG", 3, 20, 3000, 2), ("LU", 2, 50, 1500, 1),
-                                         ("nHG", 4, 3, 63, 1), ("LU", 1, 2, 1, 1)])
+                                         ("nHG", 4, 3, 63, 1), ("LU", 1, 2, 1, 1), ("LU", 3, 5, 777, 40),
+                                         ("HG", 2, 6, 1234, 70), ("LU", 6, 1, 100, 1), ("LU", 0, 3, 50, 2)])
 def test_k3_suffstats_vs_oracle(fam, p, d, n, M):
     from pytuq_b200.rv.pcrv import PCRV
     rng = np.random.default_rng(p * 100 + d)
@@ -184,6 +185,39 @@ def test_k3_general_multiindex_and_accumulate(pcrv_cases):
                                                   yd[h:].data_ptr(), 1, 1, sd.data_ptr(), 1, stream))
     torch.cuda.synchronize()
     assert rel_err(sd.cpu().numpy(), ref) < 1e-12
+
+
+def test_empty_inputs():
+    from pytuq_b200.rv.pcrv import PCRV
+    mi = orc.get_mi(2, 3)
+    pc = PCRV(2, 3, "LU", mi=mi, cfs=np.ones((2, mi.shape[0])))
+    assert pc.evalPC(np.zeros((0, 3))).shape == (0, 2)
+    st = pc.suffStats(np.zeros((0, 3)), np.zeros((0, 1)), 0)
+    assert st.S.shape == (12, 12) and not st.S.any()
+
+
+def test_k3_large_orders_and_dims_fall_back_cleanly():
+    """Shapes outside the packed fast path: width > 4 (generic descriptors) and a table too large for
+    the pipelined kernel's double buffers."""
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(21)
+    mi = rng.integers(0, 3, size=(50, 7))          # up to 7 non-zero orders per term
+    x = rng.uniform(-1, 1, (300, 7))
+    y = rng.standard_normal(300)
+    pc = PCRV(1, 7, "LU", mi=mi)
+    st = pc.suffStats(x, y, 0)
+    assert rel_err(st.S, orc.suffstats(orc.eval_bases(x, mi, "LU"), y)) < 1e-12
+    d = 120                                         # 1 + 2*120 = 241 slots
+    mi = orc.get_mi(2, d)[:400]
+    x = rng.uniform(-1, 1, (200, d))
+    pc = PCRV(1, d, "LU", mi=mi)
+    A = pc.evalBases(x, 0)
+    assert np.array_equal(A[:20], orc.eval_bases(x[:20], mi, "LU", np.full(d, 2)))
+    st = pc.suffStats(x, None, 0)
+    assert rel_err(st.S, orc.suffstats(A, np.zeros((200, 0)))) < 1e-12
+    cf = rng.standard_normal(400)
+    pc.setCfs(cf)
+    assert rel_err(pc.evalPC(x)[:, 0], A @ cf) < 1e-12
 
 
 def test_k4_gram_of_materialised_matrix():

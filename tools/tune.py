@@ -31,7 +31,7 @@ def setenv(**kw):
 
 
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["k1", "k2", "k3"]
-shapes = [("C2", "HG", 20, 3, 1_000_000), ("C1", "LU", 10, 4, 1_000_000), ("C3", "LU", 50, 2, 500_000),
+shapes = [("C2", "HG", 20, 3, 1_250_000 if "k3chunk" in which else 1_000_000), ("C1", "LU", 10, 4, 1_000_000), ("C3", "LU", 50, 2, 500_000),
           ("C4", "HG", 20, 4, 200_000), ("C5", "LU", 30, 3, 200_000)]
 for name, fam, d, p, n in shapes:
     mi = get_mi(p, d)
@@ -65,6 +65,15 @@ for name, fam, d, p, n in shapes:
             setenv(PCQ_K2_CFG=None)
             ms = timeit(lambda: _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n, d, c.data_ptr(), 1, y.data_ptr(), 1, mode, st)))
             print(f"{name} K2 mode{mode} auto: {ms:8.3f} ms", flush=True)
+    if "k3chunk" in which and name == "C2":
+        S = torch.empty((K + 2, K + 2), dtype=torch.float64, device="cuda")
+        for mb in (0, 24, 48, 96):
+            setenv(PCQ_GRAM_CHUNK_MB=mb)
+            ms = timeit(lambda: _native.check(lib.pcq_suffstats_dev(plan.handle, x.data_ptr(), n, d, y.data_ptr(), 1, 1, S.data_ptr(), 0, st)), reps=3, warm=1)
+            fl = float(n) * K * (K + 1) + 2.0 * n * K + 2.0 * n
+            print(f"{name} K3 chunk={mb}MB: n={n} {ms:8.3f} ms  {fl / ms / 1e9:6.2f} TFLOP/s(alg)", flush=True)
+        setenv(PCQ_GRAM_CHUNK_MB=None)
+        del S
     if "k3only" in which:
         S = torch.empty((K + 2, K + 2), dtype=torch.float64, device="cuda")
         n3 = min(n, 400_000 if K < 3000 else 60_000)
