@@ -13,8 +13,8 @@ A step = one pass of the hot path over the rank's sample block:
     library call: the factorisation is not sample-parallel)  ->  coefficients.
 `value` is basis evaluations (samples x terms) per second for that whole step with x, y
 already resident in HBM; `e2e` is the same metric through the public API
-(`lsq.fit(x, y)` with numpy host arrays: H2D of x, y and D2H of the statistics inside the
-timed region).  `roofline` is for the dominant kernel (K3) against the FP64 tensor (DMMA)
+(`lsq.fit(x, y)` with numpy host arrays: pinned double-buffered H2D of x, y and D2H of the
+coefficients inside the timed region).  `roofline` is for the dominant kernel (K3) against the FP64 tensor (DMMA)
 peak measured live on the same GPU (MEASURED_PEAKS.json has no FP64 number); the K1
 (materialised A) and K2 (evalPC) kernels are reported in `kernels` with their own roofs.
 """
@@ -227,7 +227,6 @@ def main():
         if world > 1:
             dist.all_reduce(S, op=dist.ReduceOp.SUM)
         ev[2].record()
-        t0 = time.perf_counter()
         C = solve_normal_device(S[:K, :K], S[:K, K])          # cuSOLVER potrf/potrs on the device
         if C is None:                                        # not positive definite: host eigen path
             S_host.copy_(S)
@@ -235,8 +234,9 @@ def main():
             cf = solve_normal(Sh[:K, :K], Sh[:K, K])
         else:
             cf = C.cpu().numpy()                             # D2H of K doubles; syncs the stream
-        t1 = time.perf_counter()
-        return cf, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), t1 - t0
+        ev[3].record()
+        ev[3].synchronize()
+        return cf, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), 1e-3 * ev[2].elapsed_time(ev[3])
 
     def barrier():
         if world > 1:
@@ -404,7 +404,7 @@ def main():
         "kernels": kernels,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "basis evals/s (samples*terms)",
-                "h2d_bytes_per_step": int(n * (D + 1) * 8 + (K * K + K) * 8), "d2h_bytes_per_step": int(L * L * 8 + K * 8),
+                "h2d_bytes_per_step": int(n * (D + 1) * 8), "d2h_bytes_per_step": int(K * 8),
                 "api": "pytuq_b200.lreg.lsq.fit(x, y) with numpy host arrays",
                 "max_abs_coef_diff_vs_resident": e2e_err},
         "gpu_launches": int(launches),

@@ -192,7 +192,13 @@ class lsq(lreg):
 
     def _fit_stats(self, stats):
         K = stats.K
-        self.cf = solve_normal(stats.G, stats.b(0))
+        cf = None
+        sysdev = stats.dev_system()
+        if sysdev is not None:             # statistics still on the device: solve there, bring back K doubles
+            C = solve_normal_device(sysdev[0], sysdev[1][:, 0])
+            if C is not None:
+                cf = C.cpu().numpy()
+        self.cf = cf if cf is not None else solve_normal(stats.G, stats.b(0))
         self.cf_cov = np.zeros((K, K))
         self.fitted = True
         self.used = np.arange(K)

@@ -15,13 +15,32 @@ from .. import _native, device as _device
 
 
 class SuffStats:
-    """View of the packed statistics matrix S ((K+M+1) x (K+M+1), float64)."""
+    """View of the packed statistics matrix S ((K+M+1) x (K+M+1), float64).
 
-    def __init__(self, S, nbasis, nout):
-        self.S = S
+    The matrix may live on the device (``S_dev``, a torch tensor produced by the fused path): the
+    least-squares solve then runs on the GPU and only K coefficients come back; the host copy ``S`` is
+    made lazily (once, shared by all per-output views) for the fitters that work on K x K slices with
+    numpy (anl, bcs).  ``select(j)`` is a zero-copy view exposing one output."""
+
+    def __init__(self, S, nbasis, nout, S_dev=None, cols=None, parent=None):
+        self._S = S
+        self.S_dev = S_dev
         self.K = int(nbasis)
-        self.M = int(nout)
-        assert S.shape == (self.K + self.M + 1, self.K + self.M + 1)
+        self._Mall = int(nout)                       # outputs held by the packed matrix
+        self.cols = list(range(self._Mall)) if cols is None else list(cols)
+        self.M = len(self.cols)                      # outputs this view exposes
+        self._parent = parent
+        shape = tuple(S.shape) if S is not None else tuple(S_dev.shape)
+        assert shape == (self.K + self._Mall + 1, self.K + self._Mall + 1)
+
+    @property
+    def S(self):
+        if self._S is None:
+            self._S = self._parent.S if self._parent is not None else self.S_dev.cpu().numpy()
+        return self._S
+
+    def _col(self, j):
+        return self.K + self.cols[j]
 
     # --- accessors -------------------------------------------------------------------
     @property
@@ -33,16 +52,16 @@ class SuffStats:
         return float(self.S[-1, -1])
 
     def b(self, j=0):
-        return self.S[:self.K, self.K + j]
+        return self.S[:self.K, self._col(j)]
 
     def B(self):
-        return self.S[:self.K, self.K:self.K + self.M]
+        return self.S[:self.K, [self._col(j) for j in range(self.M)]]
 
     def yty(self, j=0):
-        return float(self.S[self.K + j, self.K + j])
+        return float(self.S[self._col(j), self._col(j)])
 
     def ysum(self, j=0):
-        return float(self.S[self.K + j, -1])
+        return float(self.S[self._col(j), -1])
 
     def colsum(self):
         return self.S[:self.K, -1]
@@ -62,9 +81,19 @@ class SuffStats:
         return self.yty(j) - 2.0 * float(cf @ bu) + float(cf @ (Gu @ cf))
 
     def select(self, j):
-        """Statistics of output j alone (M = 1)."""
-        idx = np.concatenate([np.arange(self.K), [self.K + j, self.K + self.M]])
-        return SuffStats(np.ascontiguousarray(self.S[np.ix_(idx, idx)]), self.K, 1)
+        """Statistics of output j alone (a view: the shared G is neither copied nor re-downloaded)."""
+        return SuffStats(self._S, self.K, self._Mall, S_dev=self.S_dev, cols=[self.cols[j]], parent=self)
+
+    def dev_system(self):
+        """(G, B) as device tensors for the exposed outputs, or None when the statistics are host-only."""
+        if self.S_dev is None:
+            return None
+        G = self.S_dev[:self.K, :self.K]
+        if self.cols == list(range(self.cols[0], self.cols[0] + self.M)):
+            B = self.S_dev[:self.K, self.K + self.cols[0]:self.K + self.cols[0] + self.M]
+        else:
+            B = self.S_dev[:self.K, [self._col(j) for j in range(self.M)]]
+        return G, B
 
     # --- constructors -------------------------------------------------------------------
     @classmethod

@@ -47,10 +47,29 @@ def allreduce_stats(S):
     return t.numpy()
 
 
+_STAGE_BYTES = 48 << 20        # host chunk = the Gram kernel's L2-sized sample chunk
+_pinned = {}
+
+
+def _pinned_pair(nbytes):
+    """Two reusable pinned staging buffers (double buffering of the H2D pipeline)."""
+    import torch
+    bufs = _pinned.get("bufs")
+    if bufs is None or bufs[0].numel() * 8 < nbytes:
+        n = max(int(nbytes) // 8, 1)
+        bufs = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+        _pinned["bufs"] = bufs
+    return bufs
+
+
 def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
-    """K3 through the host-pointer C-ABI.  With ``distributed=True`` every rank passes its
-    own row block (x, y) and receives the statistics of the union."""
+    """K3 on host (numpy) inputs: the rows are streamed through two pinned staging buffers in L2-sized
+    chunks (host memcpy and H2D of chunk i+1 overlap the Gram kernel of chunk i), the statistics are
+    accumulated and stay on the device.  With ``distributed=True`` every rank passes its own row
+    block (x, y) and the partial statistics are all-reduced on the device (NCCL)."""
+    import torch
     from .lreg.stats import SuffStats
+    _device.require_device()
     mindex = pcrv.mindices[jdim]
     pcrv._check_orders(mindex)
     xin = np.ascontiguousarray(x, dtype=np.float64)
@@ -62,16 +81,55 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
         Y = np.ascontiguousarray(y, dtype=np.float64)
         Y = Y.reshape(N, Y.shape[1] if Y.ndim == 2 else 1)
         M = Y.shape[1]
-    plan = pcrv._plan(mindex)
+    dev = _device.current_device()
+    tdev = torch.device("cuda", dev)
+    plan = pcrv._plan(mindex, dev=dev)
     K = mindex.shape[0]
     L = K + M + 1
-    S = np.empty((L, L))
-    st = _native.lib().pcq_suffstats(plan.handle, _native.ptr(xin), N, s, _native.ptr(Y), max(M, 1), M,
-                                     _native.ptr(S))
-    _native.check(st, "pcq_suffstats")
-    if distributed:
-        S = allreduce_stats(S)
-    return SuffStats(S, K, M)
+    lib = _native.lib()
+    S_t = torch.empty((L, L), dtype=torch.float64, device=tdev)
+    ncol = s + M
+    rows = max(_STAGE_BYTES // (ncol * 8), 4096)
+    pin = _pinned_pair(rows * ncol * 8)
+    with torch.cuda.device(tdev):
+        main = torch.cuda.current_stream()
+        copy_stream = _pinned.setdefault("stream%d" % dev, torch.cuda.Stream(device=tdev))
+        dbuf = [torch.empty(rows * ncol, dtype=torch.float64, device=tdev) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        if N == 0:
+            _native.check(lib.pcq_suffstats_dev(plan.handle, None, 0, s, None, max(M, 1), M, S_t.data_ptr(), 0,
+                                                main.cuda_stream), "pcq_suffstats_dev")
+        c = 0
+        for r0 in range(0, N, rows):
+            b = c & 1
+            nr = min(rows, N - r0)
+            if c >= 2:
+                consumed[b].synchronize()          # staging buffer b free again (host and device side)
+            hx = pin[b][:nr * s].view(nr, s)
+            np.copyto(hx.numpy(), xin[r0:r0 + nr])
+            if M:
+                hy = pin[b][nr * s:nr * ncol].view(nr, M)
+                np.copyto(hy.numpy(), Y[r0:r0 + nr])
+            with torch.cuda.stream(copy_stream):
+                dbuf[b][:nr * ncol].copy_(pin[b][:nr * ncol], non_blocking=True)
+                copied[b].record(copy_stream)
+            main.wait_event(copied[b])
+            xd = dbuf[b].data_ptr()
+            yd = xd + nr * s * 8 if M else None
+            _native.check(lib.pcq_suffstats_dev(plan.handle, xd, nr, s, yd, max(M, 1), M, S_t.data_ptr(),
+                                                1 if c > 0 else 0, main.cuda_stream), "pcq_suffstats_dev")
+            consumed[b].record(main)
+            copy_stream.wait_event(consumed[b])    # next H2D into buffer b waits for the kernel
+            c += 1
+        if distributed and dist_info()[1] > 1:
+            import torch.distributed as dist
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(S_t, op=dist.ReduceOp.SUM)
+            else:
+                S_t = torch.from_numpy(allreduce_stats(S_t.cpu().numpy())).to(tdev)
+        main.synchronize()
+    return SuffStats(None, K, M, S_dev=S_t)
 
 
 def propagate(pcrv, nsam, seed=0, exact=False, return_samples=False, first_index=0):

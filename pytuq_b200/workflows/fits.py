@@ -38,11 +38,26 @@ def pc_fit(x, y, order=3, pctype='LU', method='anl', **kwargs):
     # one pass over the samples for all outputs
     stats = SuffStats.from_pc(pcrv, x, y, 0)
 
+    # lsq: all outputs share G -> one batched Cholesky solve on the device for the K x M block
+    batched = None
+    if method == 'lsq' and stats.dev_system() is not None:
+        from ..lreg.lreg import solve_normal_device
+        G_t, B_t = stats.dev_system()
+        C = solve_normal_device(G_t, B_t)
+        if C is not None:
+            batched = C.cpu().numpy()
+
     mindices_list, cfs_list, lregs = [], [], []
     for iout in range(nout):
         print(f"Fitting output {iout+1} / {nout}")
         lreg = _make_fitter(method, kwargs)
-        lreg._fit_stats(stats.select(iout))
+        if batched is not None:
+            lreg.cf = np.ascontiguousarray(batched[:, iout])
+            lreg.cf_cov = np.zeros((mindex.shape[0], mindex.shape[0]))
+            lreg.used = np.arange(mindex.shape[0])
+            lreg.fitted = True
+        else:
+            lreg._fit_stats(stats.select(iout))
         mindices_list.append(mindex[lreg.used, :])
         cfs_list.append(lreg.cf)
         lregs.append(lreg)

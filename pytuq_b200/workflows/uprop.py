@@ -41,7 +41,13 @@ def uprop_regr(in_pc, model, nsam, out_pc):
     assert(ysamples.shape[1] == out_pc.pdim)
     if _shared_basis(out_pc):
         stats = SuffStats.from_pc(out_pc, samples_germ, ysamples, 0)
-        sol = solve_normal(stats.G, stats.B())
+        sol = None
+        if stats.dev_system() is not None:
+            from ..lreg.lreg import solve_normal_device
+            C = solve_normal_device(*stats.dev_system())
+            sol = C.cpu().numpy() if C is not None else None
+        if sol is None:
+            sol = solve_normal(stats.G, stats.B())
         out_cfs_all = [np.ascontiguousarray(sol[:, odim]) for odim in range(out_pc.pdim)]
     else:
         out_cfs_all = []
