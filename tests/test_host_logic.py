@@ -216,7 +216,11 @@ def test_workflow_pieces_on_statistics():
     for j in range(3):
         sj = st.select(j)
         ref = orc.suffstats(A, Y[:, j])
-        np.testing.assert_allclose(sj.S, ref, rtol=1e-14)
+        assert sj.M == 1 and sj.K == 5 and sj.S is st.S          # a view, nothing copied
+        np.testing.assert_allclose(sj.G, ref[:5, :5], rtol=1e-14)
+        np.testing.assert_allclose(sj.b(0), ref[:5, 5], rtol=1e-14)
+        np.testing.assert_allclose([sj.yty(0), sj.ysum(0), sj.n], [ref[5, 5], ref[5, 6], ref[6, 6]], rtol=1e-14)
+        np.testing.assert_allclose(sj.B()[:, 0], ref[:5, 5], rtol=1e-14)
         assert abs(sj.yvar(0) - np.std(Y[:, j]) ** 2) < 1e-13
         cf = rng.standard_normal(3); used = np.array([0, 2, 4])
         assert abs(sj.rss(cf, used) - np.sum((Y[:, j] - A[:, used] @ cf) ** 2)) < 1e-11
