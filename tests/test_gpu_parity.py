@@ -364,6 +364,42 @@ def test_pce_and_pcsobol():
     np.testing.assert_allclose(sens["jointt"], orc.sobol_joint(mi, cf_ref, "LU"), rtol=1e-10, atol=1e-13)
 
 
+def test_randomized_shapes_all_kernels():
+    """Random (families, dimension, order, N, outputs) combinations, including truncated / shuffled
+    multi-index sets and ragged N: K1 and K2 bit-exact, K3 / K4 1e-12 against the oracle."""
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg.stats import SuffStats
+    rng = np.random.default_rng(2024)
+    fams = list(orc.FAMILIES)
+    for trial in range(36):
+        d = int(rng.integers(1, 9))
+        p = int(rng.integers(0, 5 if d > 4 else 7))
+        mi = orc.get_mi(p, d)
+        if mi.shape[0] > 3 and trial % 3 == 0:          # general sets: subset, shuffled, with a duplicate
+            keep = rng.permutation(mi.shape[0])[: max(2, mi.shape[0] // 2)]
+            mi = mi[keep]
+            mi = np.vstack([mi, mi[:1]])
+        types = [fams[int(rng.integers(0, 4))] for _ in range(d)]
+        n = int(rng.choice([1, 3, 15, 16, 17, 31, 64, 65, 255, 1000, 2049]))
+        M = int(rng.choice([0, 1, 1, 2, 5]))
+        x = np.stack([rng.uniform(-1, 1, n) if t.endswith("LU") else rng.standard_normal(n) for t in types], axis=1)
+        Y = rng.standard_normal((n, M)) if M else None
+        pdim = max(M, 1)
+        cfs = rng.standard_normal((pdim, mi.shape[0]))
+        pc = PCRV(pdim, d, types, mi=mi, cfs=cfs)
+        max_ord = mi.max(axis=0)
+        A = pc.evalBases(x, 0)
+        ref = orc.eval_bases(x, mi, types, max_ord)
+        assert np.array_equal(A, ref), (trial, d, p, n)
+        assert np.array_equal(pc.evalPC(x), orc.eval_pc(x, [mi] * pdim, list(cfs), types, max_ord)), (trial, d, p, n)
+        Sref = orc.suffstats(ref, Y if M else np.zeros((n, 0)))
+        scale = np.sqrt(np.outer(np.diag(Sref), np.diag(Sref))) + 1e-300
+        S3 = pc.suffStats(x, Y, 0).S
+        assert np.max(np.abs(S3 - Sref) / scale) < 1e-12, (trial, d, p, n, M)
+        S4 = SuffStats.from_matrix(ref, Y).S
+        assert np.max(np.abs(S4 - Sref) / scale) < 1e-12, (trial, d, p, n, M)
+
+
 # ----------------------------------------------------------------------------- full-size properties
 def test_full_size_c2_properties():
     """BASELINE config 2 at full size (HG, d=20, p=3, K=1771, N=1e6): size-independent checks."""
