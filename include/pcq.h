@@ -95,6 +95,10 @@ int pcq_eval_bases(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
  *   terms summed sequentially in k order — bit-identical to the reference.
  * mode 1 (fast): one basis product per term shared by all outputs and fused
  *   multiply-adds; differs from mode 0 by rounding only.
+ * mode | 2 (quadratic form): instead of the M outputs, y[n] = sum_m (output m)^2 is stored
+ *   (one column, ldy >= 1).  With cf = F^T, F a factor of the coefficient covariance
+ *   (cf_cov = F F^T), this is the pushed-forward variance || Psi(x_n) F ||^2 of
+ *   lreg.compute_stdev / predicta(msc=1) (lreg/lreg.py:112-143,164-198) without forming A.
  *   cf  M x K (row m = coefficients of output m), y  N x M with leading dimension ldy
  */
 int pcq_eval_pc_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,

@@ -257,7 +257,8 @@ int pcq_eval_bases_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, dou
 
 int pcq_eval_pc_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m,
                     double* y, int64_t ldy, int mode, void* stream) {
-    if (!p || n < 0 || m < 0 || (n > 0 && m > 0 && (!x || !cf || !y)) || ldx < p->sdim || ldy < m) {
+    if (!p || n < 0 || m < 0 || (n > 0 && m > 0 && (!x || !cf || !y)) || ldx < p->sdim ||
+        ldy < ((mode & 2) ? 1 : m)) {
         pcq_set_error("eval_pc: bad argument");
         return PCQ_ERR_ARG;
     }
@@ -362,7 +363,7 @@ int pcq_eval_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double*
 
 int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m,
                 double* y, int64_t ldy, int mode) {
-    if (!p || n < 0 || m < 0 || (n > 0 && m > 0 && (!x || !cf || !y)) || ldx < p->sdim || ldy < m) {
+    if (!p || n < 0 || m < 0 || (n > 0 && m > 0 && (!x || !cf || !y)) || ldx < p->sdim || ldy < ((mode & 2) ? 1 : m)) {
         pcq_set_error("eval_pc: bad argument");
         return PCQ_ERR_ARG;
     }
@@ -375,18 +376,19 @@ int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const doub
     PCQ_CUDA(cudaMemcpyAsync(p->d_misc, cf, (size_t)m * K * 8, cudaMemcpyHostToDevice, p->streams[0]));
     PCQ_CUDA(cudaEventRecord(p->events[0], p->streams[0]));
     PCQ_CUDA(cudaStreamWaitEvent(p->streams[1], p->events[0], 0));
-    const int64_t rows = chunk_rows((int64_t)(s + m) * 8, n);
+    const int mo = (mode & 2) ? 1 : m;          // output columns per sample
+    const int64_t rows = chunk_rows((int64_t)(s + mo) * 8, n);
     int c = 0;
     for (int64_t r0 = 0; r0 < n; r0 += rows, ++c) {
         const int b = c & 1;
         const int64_t nr = std::min(rows, n - r0);
         cudaStream_t st = p->streams[b];
         if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
-        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * m * 8)) != PCQ_OK) return rc;
+        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * mo * 8)) != PCQ_OK) return rc;
         if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
-        if ((rc = pcq_launch_evalpc(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], m, mode, st)) != PCQ_OK)
+        if ((rc = pcq_launch_evalpc(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], mo, mode, st)) != PCQ_OK)
             return rc;
-        if ((rc = copy_rows(y + r0 * ldy, ldy, p->d_out[b], m, m, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return rc;
+        if ((rc = copy_rows(y + r0 * ldy, ldy, p->d_out[b], mo, mo, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return rc;
     }
     PCQ_CUDA(cudaStreamSynchronize(p->streams[0]));
     PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));

@@ -28,6 +28,7 @@ struct EvalParams {
     const unsigned long long* desc4;
     const uint16_t* descw;
     const uint8_t* flags;
+    int sumsq;              // 1: y[n] = sum_m (output m)^2 instead of the M outputs (quadratic forms)
     // germ mode (K5)
     unsigned long long seed;
     int64_t first_index;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(THREADS) pcq_evalpc_kernel(EvalParams P) {
                 pcq_fill_1d(xv, i, s, P.pmax, P.rec_a, P.rec_b, P.p1, mytab, THREADS);
             }
         }
+        double vsq1 = 0.0;
         for (int m0 = 0; m0 < P.m; m0 += MB) {
             double acc[MB];
 #pragma unroll
@@ -158,7 +160,11 @@ __global__ void __launch_bounds__(THREADS) pcq_evalpc_kernel(EvalParams P) {
                     }
                 }
             }
-            if (live && P.y != nullptr) {
+            if (P.sumsq) {
+#pragma unroll
+                for (int j = 0; j < MB; ++j)
+                    if (m0 + j < P.m) vsq1 = __fma_rn(acc[j], acc[j], vsq1);
+            } else if (live && P.y != nullptr) {
 #pragma unroll
                 for (int j = 0; j < MB; ++j)
                     if (m0 + j < P.m) P.y[n * P.ldy + m0 + j] = acc[j];
@@ -187,6 +193,7 @@ __global__ void __launch_bounds__(THREADS) pcq_evalpc_kernel(EvalParams P) {
                 }
             }
         }
+        if (P.sumsq && live && P.y != nullptr) P.y[n * P.ldy] = vsq1;
         first_iter = false;
     }
     if constexpr (GERM) {
@@ -279,6 +286,9 @@ __global__ void __launch_bounds__(THREADS) pcq_evalpc2_kernel(EvalParams P) {
                 }
             }
         }
+        double vsq[SPT];
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) vsq[q] = 0.0;
         for (int m0 = 0; m0 < P.m; m0 += MB) {
             double acc[MB][SPT];
 #pragma unroll
@@ -352,7 +362,13 @@ __global__ void __launch_bounds__(THREADS) pcq_evalpc2_kernel(EvalParams P) {
                     }
                 }
             }
-            if (P.y != nullptr) {
+            if (P.sumsq) {
+#pragma unroll
+                for (int q = 0; q < SPT; ++q)
+#pragma unroll
+                    for (int j = 0; j < MB; ++j)
+                        if (m0 + j < P.m) vsq[q] = __fma_rn(acc[j][q], acc[j][q], vsq[q]);
+            } else if (P.y != nullptr) {
 #pragma unroll
                 for (int q = 0; q < SPT; ++q)
                     if (live[q]) {
@@ -386,6 +402,11 @@ __global__ void __launch_bounds__(THREADS) pcq_evalpc2_kernel(EvalParams P) {
                     }
                 }
             }
+        }
+        if (P.sumsq && P.y != nullptr) {
+#pragma unroll
+            for (int q = 0; q < SPT; ++q)
+                if (live[q]) P.y[nidx[q] * P.ldy] = vsq[q];
         }
         first_iter = false;
     }
@@ -466,7 +487,7 @@ int launch_evalpc2_cfg(pcq_plan* p, const EvalParams& P, cudaStream_t st, double
 
 template <int W, bool GERM>
 int launch_evalpc2_w(pcq_plan* p, const EvalParams& P, int mode, cudaStream_t st, double* sums, bool* handled) {
-    const bool fast = mode != 0;
+    const bool fast = (mode & 1) != 0;
     if (P.m >= 4) {
         return fast ? launch_evalpc2_cfg<W, 4, true, GERM>(p, P, st, sums, handled)
                     : launch_evalpc2_cfg<W, 4, false, GERM>(p, P, st, sums, handled);
@@ -517,7 +538,7 @@ int launch_evalpc_threads(pcq_plan* p, const EvalParams& P, cudaStream_t st, dou
 
 template <int W, bool GERM>
 int launch_evalpc_w(pcq_plan* p, const EvalParams& P, int mode, cudaStream_t st, double* sums) {
-    const bool fast = mode != 0;
+    const bool fast = (mode & 1) != 0;
     if (P.m >= 4) {
         return fast ? launch_evalpc_threads<W, 4, true, GERM>(p, P, st, sums)
                     : launch_evalpc_threads<W, 4, false, GERM>(p, P, st, sums);
@@ -558,6 +579,7 @@ int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, cons
     EvalParams P;
     fill_eval_params(p, P);
     P.x = x; P.cf = cf; P.y = y; P.n = n; P.ldx = ldx; P.ldy = ldy; P.m = m;
+    P.sumsq = (mode & 2) ? 1 : 0;
     return launch_evalpc_any<false>(p, P, mode, st, nullptr);
 }
 

@@ -127,9 +127,38 @@ class lreg(fitbase):
         assert(self.fitted)
         print(self.cf)
 
-    # -- prediction (host-side glue on an evaluated basis; SURVEY.md row f1 is the fused form) --
+    # -- prediction ---------------------------------------------------------------------------
+    def _cov_factor(self):
+        """F with cf_cov = F F^T: Cholesky, or the SVD factor when cf_cov is only semi-definite (the same
+        two routes lreg.predicta takes, lreg/lreg.py:130-134).  None for an all-zero covariance."""
+        C = self.cf_cov
+        if C is None or not np.any(C):
+            return None
+        try:
+            return np.linalg.cholesky(C)
+        except np.linalg.LinAlgError:
+            u, sv, _ = np.linalg.svd(C, hermitian=True)
+            return u * np.sqrt(sv)
+
     def predict(self, x, msc=0, pp=False):
+        r"""Mean (and variance) of the fit at x (lreg/lreg.py:80-94).  With a PC basis evaluator and
+        msc in (0, 1) nothing of size N x K is formed: the mean is an evalPC (K2) and the variance
+        || Psi(x_n) F ||^2, cf_cov = F F^T, is K2's quadratic-form mode."""
         assert(self.basisEvaluatorSet)
+        if isinstance(self.basisEval, PCBasisEvaluator) and msc in (0, 1):
+            assert(self.fitted)
+            pcrv, jdim = self.basisEvalPars[0], self.basisEval.jdim
+            if pcrv.mindices[jdim].shape[0] == self.cf.shape[0]:
+                ypred = pcrv.evalLinearForms(x, self.cf[None, :], jdim)[:, 0]
+                if msc == 0:
+                    return ypred, None, None
+                F = self._cov_factor()
+                if F is None:
+                    ypred_var = np.zeros(ypred.shape[0])
+                else:
+                    ypred_var = pcrv.evalLinearForms(x, np.ascontiguousarray(F.T), jdim, sumsq=True)
+                ypred_var += int(pp) * self.datavar
+                return ypred, ypred_var, None
         Amat = self.basisEval(x, self.basisEvalPars)
         return self.predicta(Amat, msc=msc, pp=pp)
 

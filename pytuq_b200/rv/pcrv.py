@@ -317,6 +317,24 @@ class PCRV(MRV):
                               "pcq_eval_pc")
         return y
 
+    def evalLinearForms(self, x, cfmat, jdim=0, exact=True, sumsq=False):
+        r"""Y[n, m] = sum_k cfmat[m, k] Psi_k(x_n) on the jdim-th basis for M coefficient vectors at once
+        (one K2 launch, A never formed).  With ``sumsq`` the M values are reduced on the device to
+        sum_m Y[n, m]^2 -- the quadratic form Psi(x_n)^T (F F^T) Psi(x_n) for cfmat = F^T, i.e. the
+        pushed-forward variance of a fit with coefficient covariance F F^T."""
+        mindex = self.mindices[jdim]
+        assert(self.sdim == x.shape[1] and cfmat.shape[1] == mindex.shape[0])
+        self._check_orders(mindex)
+        xin = self._as_input(x)
+        cf = np.ascontiguousarray(cfmat, dtype=np.float64)
+        nsam, M = xin.shape[0], cf.shape[0]
+        out = np.zeros((nsam, 1 if sumsq else M))
+        mode = (0 if exact and not sumsq else 1) | (2 if sumsq else 0)
+        _native.check(_native.lib().pcq_eval_pc(self._plan(mindex).handle, _native.ptr(xin), nsam, self.sdim,
+                                                _native.ptr(cf), M, _native.ptr(out), out.shape[1], mode),
+                      "pcq_eval_pc")
+        return out[:, 0] if sumsq else out
+
     def setFunction(self):
         self.function = Function(name='PC Function')
         domain = np.array([p.domain for p in self.PC1ds])

@@ -305,6 +305,17 @@ def test_fitters_vs_reference(fit_cases):
         mean, var, _ = a.predict(c["xt"], msc=1)
         np.testing.assert_allclose(mean, c["anl_pred_mean"], rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(var, c["anl_pred_var"], rtol=1e-7)
+        # fused predict (no design matrix) agrees with predicta on the evaluated basis, incl. pp
+        At = pc.evalBases(c["xt"], 0)
+        m2, v2, _ = a.predicta(At, msc=1, pp=True)
+        m1, v1, _ = a.predict(c["xt"], msc=1, pp=True)
+        np.testing.assert_allclose(m1, m2, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(v1, v2, rtol=1e-9)
+        l = fused(lsq())
+        m0, v0, c0 = l.predict(c["xt"], msc=1)
+        assert not v0.any() and c0 is None
+        np.testing.assert_allclose(m0, At @ l.cf, rtol=1e-12, atol=1e-13)
+        assert l.predict(c["xt"])[1] is None
 
 
 def test_pc_fit_workflow_vs_reference():
