@@ -847,6 +847,273 @@ int launch_gram_fused2_w(const GramParams& P, int num_sms, size_t smem_optin, do
     return launch_gram_fused2<W, 4, 16>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K3 v6: slot tables precomputed per L2-sized chunk and fed to the Gram kernel by TMA.
+//   The recurrences depend on the sample only, yet every one of the ntri tiles rebuilt them, and on
+//   sm_100a those FP64 vector instructions share the pipe with DMMA (profiles/r01_c: ~10 % of the pipe
+//   plus bubbles).  Here a small kernel writes, once per chunk, one blob per 16 samples that is already
+//   in the generator's shared-memory layout [slot][17] (slots: 1, phi..., y..., 0); the Gram kernel then
+//   fetches each stage's blob with ONE cp.async.bulk (TMA, mbarrier complete_tx) two stages ahead:
+//   no recurrences, no x/y prefetch registers and no global-load address arithmetic in the DMMA warps.
+//   The chunk's blobs (518 B per sample at C2) stay L2-resident while the tiles sweep them.
+constexpr int TB_KT = 16;
+constexpr int TB_TS = TB_KT + 1;
+
+__host__ __device__ inline int tb_slots_even(int nslots, int m) { return (nslots + m + 1 + 1) & ~1; }
+
+// one CTA = 8 blobs (128 samples)
+__global__ void __launch_bounds__(256) pcq_tables_kernel(GramParams P, double* blobs, int64_t nblocks16) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* stage = reinterpret_cast<double*>(smem_raw);          // [8][NTe][17]
+    const int NTe = tb_slots_even(P.nslots, P.m);
+    const int blob = NTe * TB_TS;
+    const int s = P.sdim;
+    const int tid = threadIdx.x;
+    for (int64_t b0 = (int64_t)blockIdx.x * 8; b0 < nblocks16; b0 += (int64_t)gridDim.x * 8) {
+        const int nb = (int)min((int64_t)8, nblocks16 - b0);
+        __syncthreads();
+        for (int i = tid; i < nb * blob; i += 256) stage[i] = 0.0;
+        __syncthreads();
+        const int64_t n0 = b0 * TB_KT;
+        // recurrences: one (sample, dim) pair per thread
+        for (int idx = tid; idx < nb * TB_KT * s; idx += 256) {
+            const int sm = idx / s, c = idx - sm * s;
+            const int64_t n = n0 + sm;
+            if (n >= P.n) continue;
+            double* T = stage + (size_t)(sm / TB_KT) * blob + (sm % TB_KT);
+            if (c == 0) T[0] = 1.0;
+            const double v = P.x[n * P.ldx + c];
+            pcq_fill_1d(v, c, s, P.pmax, P.rec_a, P.rec_b, P.p1, T, TB_TS);
+        }
+        for (int idx = tid; idx < nb * TB_KT * P.m; idx += 256) {
+            const int sm = idx / P.m, c = idx - sm * P.m;
+            const int64_t n = n0 + sm;
+            if (n >= P.n) continue;
+            stage[(size_t)(sm / TB_KT) * blob + (size_t)(P.nslots + c) * TB_TS + (sm % TB_KT)] = P.y[n * P.ldy + c];
+        }
+        __syncthreads();
+        double* dst = blobs + (size_t)b0 * blob;
+        for (int i = tid; i < nb * blob; i += 256) dst[i] = stage[i];
+    }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct TmaSmem {
+    double* op;        // [2][2][16][LDT]
+    double* tab;       // [3][NTe][17]
+    uint64_t* bars;    // [3]
+};
+
+template <int W, bool DIAG>
+__device__ __forceinline__ void fused_tma_segment(const GramParams& P, const TmaSmem& sm, const double* blobs,
+                                                  int blob, int I, int J, int64_t blk0, int nst,
+                                                  double (&acc)[4][8][2], int& gbase, uint32_t& phases) {
+    constexpr int KT = TB_KT;
+    constexpr int TS = TB_TS;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int half = tid >> 7, col = tid & 127;
+    const uint32_t blob_bytes = (uint32_t)blob * 8u;
+
+    const int gc = ((half == 0 || DIAG) ? I : J) * GT + col;
+    int off[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) off[q] = 0;
+    if (gc < P.kb) {
+        const unsigned long long d = P.desc4[gc];
+#pragma unroll
+        for (int q = 0; q < W; ++q) off[q] = (int)((d >> (16 * q)) & 0xffffull) * TS;
+    } else if (gc < P.kb + P.m) {
+        off[0] = (P.nslots + gc - P.kb) * TS;
+    } else if (gc > P.kb + P.m) {
+        off[0] = (P.nslots + P.m) * TS;
+    }
+    const int rbase = DIAG ? half : 0;
+
+    auto issue = [&](int st) {          // one elected thread: TMA bulk copy of stage st's blob
+        if (tid == 0 && st < nst) {
+            const int b = (gbase + st) % 3;
+            mbar_expect_tx(sm.bars + b, blob_bytes);
+            tma_bulk_g2s(sm.tab + (size_t)b * blob, blobs + (size_t)(blk0 + st) * blob, blob_bytes, sm.bars + b);
+        }
+    };
+    auto wait_stage = [&](int st) {
+        if (st < nst) {
+            const int b = (gbase + st) % 3;
+            mbar_wait(sm.bars + b, (phases >> b) & 1u);
+            phases ^= (1u << b);
+        }
+    };
+    auto gen_value = [&](const double* Tn, int r) {
+        double v = Tn[off[0] + r];
+#pragma unroll
+        for (int q = 1; q < W; ++q) v = __dmul_rn(v, Tn[off[q] + r]);
+        return v;
+    };
+
+    __syncthreads();   // previous segment's readers are done with op / tab
+    issue(0);
+    issue(1);
+    wait_stage(0);
+    {
+        const double* T0 = sm.tab + (size_t)((gbase + 0) % 3) * blob + rbase;
+        double* o0 = sm.op + (size_t)((DIAG ? 0 : half) * KT) * LDT + col + rbase * LDT;
+#pragma unroll
+        for (int r = 0; r < KT; r += (DIAG ? 2 : 1)) o0[(size_t)r * LDT] = gen_value(T0, r);
+    }
+    __syncthreads();
+
+    for (int it = 0; it < nst; ++it) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        issue(it + 2);             // its buffer was last read by the generator two iterations ago
+        wait_stage(it + 1);
+        const double* Tn = sm.tab + (size_t)((gbase + it + 1) % 3) * blob + rbase;
+        double* on = sm.op + (size_t)nxt * 2 * KT * LDT + (size_t)((DIAG ? 0 : half) * KT) * LDT + col +
+                     rbase * LDT;
+        const double* oa = sm.op + (size_t)cur * 2 * KT * LDT;
+        const double* ob = oa + (DIAG ? 0 : KT * LDT);
+        const double* pa = oa + (size_t)tig * LDT + wm * 32 + g;
+        const double* pb = ob + (size_t)tig * LDT + wn * 64 + g;
+#pragma unroll
+        for (int kk = 0; kk < KT; kk += 4) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = pa[(size_t)kk * LDT + i * 8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bf[j] = pb[(size_t)kk * LDT + j * 8];
+            double gv[4];
+#pragma unroll
+            for (int q = 0; q < (DIAG ? 2 : 4); ++q) {
+                const int r = DIAG ? (kk + 2 * q) : (kk + q);
+                gv[q] = gen_value(Tn, r);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+#pragma unroll
+            for (int q = 0; q < (DIAG ? 2 : 4); ++q) {
+                const int r = DIAG ? (kk + 2 * q) : (kk + q);
+                on[(size_t)r * LDT] = gv[q];
+            }
+        }
+        __syncthreads();
+    }
+    gbase = (gbase + nst) % 3;
+}
+
+template <int W>
+__global__ void __launch_bounds__(G_THREADS, 1) pcq_gram_tma_kernel(GramParams P, const double* blobs) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int NTe = tb_slots_even(P.nslots, P.m);
+    const int blob = NTe * TB_TS;
+    TmaSmem sm;
+    sm.op = reinterpret_cast<double*>(smem_raw);
+    sm.tab = sm.op + 2 * 2 * TB_KT * LDT;
+    sm.bars = reinterpret_cast<uint64_t*>(sm.tab + (size_t)3 * blob);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int b = 0; b < 3; ++b) mbar_init(sm.bars + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3, wm = warp & 3, wn = warp >> 2;
+    const int64_t G = gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * P.total / G;
+    const int64_t hi = ((int64_t)blockIdx.x + 1) * P.total / G;
+    const int64_t first_tile = (hi > lo) ? lo / P.nblk : -1;
+    int gbase = 0;
+    uint32_t phases = 0;
+
+    int64_t u = lo;
+    while (u < hi) {
+        const int64_t t = u / P.nblk;
+        const int64_t b0 = u - t * P.nblk;
+        const int64_t seg_end = min(hi, (t + 1) * P.nblk);
+        const int64_t nb = seg_end - u;
+        const int64_t sbeg = b0 * GRAM_SB;
+        const int64_t send = min(P.n, (b0 + nb) * GRAM_SB);
+        const int nst = (int)((send - sbeg + TB_KT - 1) / TB_KT);
+        int I, J;
+        tile_decode(t, P.ntile, I, J);
+        double acc[4][8][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        if (I == J) fused_tma_segment<W, true>(P, sm, blobs, blob, I, J, sbeg / TB_KT, nst, acc, gbase, phases);
+        else fused_tma_segment<W, false>(P, sm, blobs, blob, I, J, sbeg / TB_KT, nst, acc, gbase, phases);
+        flush_tile(P, acc, I, J, nb == P.nblk, (t == first_tile) ? 0 : 1, wm, wn, g, tig);
+        u = seg_end;
+    }
+}
+
+template <int W>
+int launch_gram_tma(const GramParams& P0, pcq_plan* p, int num_sms, size_t smem_optin, double** ws,
+                    size_t* ws_bytes, cudaStream_t st, bool* handled) {
+    GramParams P = P0;
+    const int NTe = tb_slots_even(P.nslots, P.m);
+    const size_t blob = (size_t)NTe * TB_TS;
+    const size_t smem = ((size_t)2 * 2 * TB_KT * LDT + 3 * blob) * sizeof(double) + 3 * sizeof(uint64_t) + 128;
+    const size_t smem_tab = 8 * blob * sizeof(double);
+    *handled = false;
+    if (smem > smem_optin || smem_tab > smem_optin) return PCQ_OK;
+    *handled = true;
+    const int64_t nblocks16 = (P.n + TB_KT - 1) / TB_KT;
+    int rc = pcq_ensure_dev(&p->d_tabs, &p->tabs_bytes, (size_t)nblocks16 * blob * sizeof(double));
+    if (rc != PCQ_OK) return rc;
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
+    const int64_t want = (nblocks16 + 7) / 8;
+    const int tgrid = (int)(want < (int64_t)num_sms * 2 ? want : (int64_t)num_sms * 2);
+    pcq_tables_kernel<<<tgrid, 256, smem_tab, st>>>(P, p->d_tabs, nblocks16);
+    PCQ_LAUNCH_CHECK("pcq_tables_kernel");
+    auto kern = pcq_gram_tma_kernel<W>;
+    PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)(P.total < num_sms ? P.total : num_sms);
+    rc = pcq_ensure_dev(ws, ws_bytes, (size_t)grid * 2 * GT * GT * sizeof(double));
+    if (rc != PCQ_OK) return rc;
+    P.ws = *ws;
+    kern<<<grid, G_THREADS, smem, st>>>(P, p->d_tabs);
+    PCQ_LAUNCH_CHECK("pcq_gram_tma_kernel");
+    const int ntri = P.ntile * (P.ntile + 1) / 2;
+    pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
+    PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
+    const int nb32 = (P.L + 31) / 32;
+    if (P.mirror) {
+        pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
+        PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
+    }
+    return PCQ_OK;
+}
+
 #if PCQ_BUILD_WS
 // ------------------------------------------------------------------------------------------------
 // K3 v3 (experiment, not built by default: slower, see profiles/r01_c): warp-specialised fused kernel (384 threads: 1 producer warpgroup + 2 consumer warpgroups).
@@ -1192,6 +1459,17 @@ static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const d
             if (handled || rc != PCQ_OK) return rc;
         }
 #endif
+        const char* tmaenv = getenv("PCQ_GRAM_TMA");
+        if (!v1_only && !(tmaenv && atoi(tmaenv) == 0)) {
+            switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
+                case 1: rc = launch_gram_tma<1>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
+                case 2: rc = launch_gram_tma<2>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
+                case 3: rc = launch_gram_tma<3>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
+                case 4: rc = launch_gram_tma<4>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
+                default: break;
+            }
+            if (handled || rc != PCQ_OK) return rc;
+        }
         const char* f2env = getenv("PCQ_GRAM_F2");
         if (!v1_only && f2env && atoi(f2env) == 1) {   // experiment, slower than the staggered v2 (profiles/r01_c)
             switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
@@ -1236,7 +1514,11 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
         return launch_gram_once(p, num_sms, smem_optin, x, 0, ldx, a, lda, kcols, y, ldy, m, s, accumulate, 1,
                                 ws, ws_bytes, st);
     const bool fused = (a == nullptr);
-    const int64_t row_bytes = 8 * (int64_t)((fused ? p->sdim : kcols) + m);
+    const char* tmaenv = getenv("PCQ_GRAM_TMA");
+    const bool use_tma = fused && p->width <= PCQ_MAXW_FAST && !(tmaenv && atoi(tmaenv) == 0) &&
+                         getenv("PCQ_GRAM_V1") == nullptr;
+    const int64_t row_bytes = use_tma ? (int64_t)tb_slots_even(p->nslots, m) * TB_TS * 8 / TB_KT
+                                      : 8 * (int64_t)((fused ? p->sdim : kcols) + m);
     const char* env = getenv("PCQ_GRAM_CHUNK_MB");
     const int64_t target = (int64_t)(env ? atoi(env) : 48) << 20;
     int64_t rows = target > 0 ? target / row_bytes : n;

@@ -36,6 +36,9 @@ struct pcq_plan {
     uint16_t* d_descw = nullptr;            // K x width (always valid)
     uint8_t* d_flags = nullptr;             // K, bit 0: first W-1 slots differ from the previous term's
 
+    // precomputed slot-table blobs of the current Gram chunk (lazily grown)
+    double* d_tabs = nullptr;
+    size_t tabs_bytes = 0;
     // Gram workspace (lazily grown)
     double* d_ws = nullptr;
     size_t ws_bytes = 0;
