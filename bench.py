@@ -348,7 +348,7 @@ def main():
     peak = peaks.get("fp64_dmma_tflops")
     traffic = None
     try:   # DRAM bytes per step of the dominant kernel, from the committed ncu capture of this workload
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_e_k3_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_g_k3_traffic.json")))
         if n == N_PER_GPU:
             traffic = tj["dram_bytes_per_step_main_kernel"]
     except Exception:
@@ -393,10 +393,10 @@ def main():
         "breakdown_ms": {"k3_suffstats": k3_mean_ms, "allreduce": float(np.mean(ar_ms)),
                          "solve_kxk": 1e3 * float(np.mean(solve_s))},
         "max_abs_coef_error_vs_truth": err,
-        "roofline": {"bound": "tensor", "kernel": "pcq_gram_fused_kernel (K3, fused basis + DMMA SYRK; 5 L2-sized chunk launches per step)",
+        "roofline": {"bound": "tensor", "kernel": "pcq_gram_tma_kernel (K3: operands generated on chip from TMA-fed slot tables + DMMA SYRK; 13 L2-sized chunk launches per step)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if peak else None, "traffic": traffic,
-                     "traffic_note": "DRAM read+write bytes of the 5 chunk launches of one step (ncu, profiles/r01_e_k3_traffic.json); algorithmic input bytes = %d" % (8 * n * (D + 1)),
+                     "traffic_note": "DRAM read+write bytes of the 13 chunk launches of one step (ncu, profiles/r01_g_k3_traffic.json); algorithmic input bytes = %d" % (8 * n * (D + 1)),
                      "algorithmic_flops_per_launch": flops,
                      "peak_source": "FP64 DMMA m8n8k4 register-chain micro-benchmark run live on this GPU "
                                     "(pcq_measure_peak); MEASURED_PEAKS.json has no FP64 figure"},
