@@ -124,6 +124,12 @@ int launch_bases_w(pcq_plan* p, const BasesParams& P, cudaStream_t st) {
 // W gathers only.
 constexpr int K1_TS = K1_ROWS + 1;
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 template <int W>
 __global__ void __launch_bounds__(K1_THREADS) pcq_bases2_kernel(BasesParams P, int vec_ok) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -150,26 +156,29 @@ __global__ void __launch_bounds__(K1_THREADS) pcq_bases2_kernel(BasesParams P, i
             pcq_fill_1d(xv, i, s, P.pmax, P.rec_a, P.rec_b, P.p1, tab + r, K1_TS);
         }
         __syncthreads();
+        // 32-bit shared-space addresses + ld.shared: keeps the generic->shared window arithmetic (S2R /
+        // LEA per access, ncu r01-g) out of the inner loop
+        const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
         for (int c = warp; c < nchunks; c += NWARPS) {
             const int k = c * 64 + 2 * lane;
             const bool v0 = k < K, v1 = k + 1 < K;
             const unsigned long long d0 = v0 ? __ldg(P.desc4 + k) : 0ull;
             const unsigned long long d1 = v1 ? __ldg(P.desc4 + k + 1) : 0ull;
-            int o0[W], o1[W];
+            uint32_t o0[W], o1[W];
 #pragma unroll
             for (int q = 0; q < W; ++q) {
-                o0[q] = (int)((d0 >> (16 * q)) & 0xffffull) * K1_TS;
-                o1[q] = (int)((d1 >> (16 * q)) & 0xffffull) * K1_TS;
+                o0[q] = tab_s + (uint32_t)((d0 >> (16 * q)) & 0xffffull) * (K1_TS * 8);
+                o1[q] = tab_s + (uint32_t)((d1 >> (16 * q)) & 0xffffull) * (K1_TS * 8);
             }
             double* out = P.a + n0 * P.lda + k;
 #pragma unroll
             for (int r = 0; r < K1_ROWS; ++r) {
                 if (r < rows) {
-                    double a = tab[o0[0] + r], b = tab[o1[0] + r];
+                    double a = lds_f64(o0[0] + r * 8), b = lds_f64(o1[0] + r * 8);
 #pragma unroll
                     for (int q = 1; q < W; ++q) {
-                        a = __dmul_rn(a, tab[o0[q] + r]);
-                        b = __dmul_rn(b, tab[o1[q] + r]);
+                        a = __dmul_rn(a, lds_f64(o0[q] + r * 8));
+                        b = __dmul_rn(b, lds_f64(o1[q] + r * 8));
                     }
                     double* dst = out + (size_t)r * P.lda;
                     // n0 is a multiple of 16 and k is even: the pair is 16-byte aligned unless the
