@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <set>
+#include <thread>
 
 std::atomic<long long> g_pcq_launches{0};
 
@@ -223,6 +224,7 @@ int pcq_plan_destroy(pcq_plan* p) {
     cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_tabs);
     for (int i = 0; i < 2; ++i) {
         cudaFree(p->d_stage[i]); cudaFree(p->d_out[i]);
+        if (p->h_pin[i]) cudaFreeHost(p->h_pin[i]);
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
         if (p->events[i]) cudaEventDestroy(p->events[i]);
     }
@@ -344,8 +346,41 @@ int pcq_eval_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double*
     int rc = ensure_streams(p);
     if (rc != PCQ_OK) return rc;
     const int K = p->nterms, s = p->sdim;
-    const int64_t rows = chunk_rows((int64_t)K * 8, n);
+    // The result is PCIe bound (8*K bytes per row back to the host).  D2H goes to two pinned staging
+    // buffers at full link speed; the host copies chunk c-1 into the caller's (pageable) array with a few
+    // threads while the GPU computes and ships chunk c.
+    const int64_t rows = std::min<int64_t>(std::max<int64_t>(((int64_t)64 << 20) / ((int64_t)K * 8), 256), n);
+    for (int b = 0; b < 2; ++b) {
+        if (p->pin_bytes[b] < (size_t)rows * K * 8) {
+            if (p->h_pin[b]) cudaFreeHost(p->h_pin[b]);
+            p->h_pin[b] = nullptr; p->pin_bytes[b] = 0;
+            if (cudaHostAlloc((void**)&p->h_pin[b], (size_t)rows * K * 8, cudaHostAllocDefault) != cudaSuccess) {
+                pcq_set_error("eval_bases: pinned staging allocation of %zu bytes failed", (size_t)rows * K * 8);
+                return PCQ_ERR_ALLOC;
+            }
+            p->pin_bytes[b] = (size_t)rows * K * 8;
+        }
+    }
+    auto drain = [&](int b, int64_t r0, int64_t nr) -> int {      // pinned buffer b -> caller rows [r0, r0+nr)
+        PCQ_CUDA(cudaEventSynchronize(p->events[b]));
+        const int nthreads = nr * K * 8 >= (8 << 20) ? 4 : 1;
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) {
+            const int64_t lo = nr * t / nthreads, hi = nr * (t + 1) / nthreads;
+            auto work = [=]() {
+                if (lda == K) {
+                    memcpy(a + (r0 + lo) * lda, p->h_pin[b] + lo * K, (size_t)(hi - lo) * K * 8);
+                } else {
+                    for (int64_t r = lo; r < hi; ++r) memcpy(a + (r0 + r) * lda, p->h_pin[b] + r * K, (size_t)K * 8);
+                }
+            };
+            if (nthreads == 1) work(); else pool.emplace_back(work);
+        }
+        for (auto& th : pool) th.join();
+        return PCQ_OK;
+    };
     int c = 0;
+    int64_t prev_r0 = 0, prev_nr = 0;
     for (int64_t r0 = 0; r0 < n; r0 += rows, ++c) {
         const int b = c & 1;
         const int64_t nr = std::min(rows, n - r0);
@@ -354,11 +389,12 @@ int pcq_eval_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double*
         if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * K * 8)) != PCQ_OK) return rc;
         if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
         if ((rc = pcq_launch_bases(p, p->d_stage[b], nr, s, p->d_out[b], K, st)) != PCQ_OK) return rc;
-        if ((rc = copy_rows(a + r0 * lda, lda, p->d_out[b], K, K, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return rc;
+        PCQ_CUDA(cudaMemcpyAsync(p->h_pin[b], p->d_out[b], (size_t)nr * K * 8, cudaMemcpyDeviceToHost, st));
+        PCQ_CUDA(cudaEventRecord(p->events[b], st));
+        if (c >= 1 && (rc = drain(b ^ 1, prev_r0, prev_nr)) != PCQ_OK) return rc;
+        prev_r0 = r0; prev_nr = nr;
     }
-    PCQ_CUDA(cudaStreamSynchronize(p->streams[0]));
-    PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));
-    return PCQ_OK;
+    return drain((c - 1) & 1, prev_r0, prev_nr);
 }
 
 int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m,

@@ -650,6 +650,7 @@ int launch_gram_fused_w(const GramParams& P, int num_sms, size_t smem_optin, dou
 
 
 
+#if PCQ_BUILD_WS   // experiment, not built by default (slower: profiles/r01_c)
 // ------------------------------------------------------------------------------------------------
 // K3 v4: v2 + one dedicated table-builder warp per scheduler (384 threads).
 //   Measured on v2 (tools/exp): the per-stage table build (dependent FP64 recurrence chains that
@@ -847,6 +848,8 @@ int launch_gram_fused2_w(const GramParams& P, int num_sms, size_t smem_optin, do
     return launch_gram_fused2<W, 4, 16>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
 }
 
+
+#endif  // PCQ_BUILD_WS (K3 v4)
 
 // ------------------------------------------------------------------------------------------------
 // K3 v6: slot tables precomputed per L2-sized chunk and fed to the Gram kernel by TMA.
@@ -1470,6 +1473,7 @@ static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const d
             }
             if (handled || rc != PCQ_OK) return rc;
         }
+#if PCQ_BUILD_WS
         const char* f2env = getenv("PCQ_GRAM_F2");
         if (!v1_only && f2env && atoi(f2env) == 1) {   // experiment, slower than the staggered v2 (profiles/r01_c)
             switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
@@ -1481,6 +1485,7 @@ static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const d
             }
             if (handled || rc != PCQ_OK) return rc;
         }
+#endif
         if (!v1_only) {
             switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
                 case 1: rc = launch_gram_fused_w<1>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;

@@ -47,6 +47,8 @@ struct pcq_plan {
     size_t stage_bytes[2] = {0, 0};
     double* d_out[2] = {nullptr, nullptr};
     size_t out_bytes[2] = {0, 0};
+    double* h_pin[2] = {nullptr, nullptr};   // pinned D2H staging of the host-pointer K1
+    size_t pin_bytes[2] = {0, 0};
     double* d_misc = nullptr;      // coefficients / S matrix for host-pointer calls
     size_t misc_bytes = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};

@@ -14,6 +14,21 @@ from .lreg import lreg
 from .stats import SuffStats
 
 
+def _inverse(mat):
+    """K x K inverse (lreg/anl.py:82).  cuSOLVER through torch.linalg on the device when one is present
+    (a plain library call for the step that is not sample-parallel), numpy otherwise (host-logic tests);
+    singular matrices raise np.linalg.LinAlgError like the reference."""
+    import torch
+    if torch.cuda.is_available():
+        from .. import device as _device
+        t = torch.from_numpy(np.ascontiguousarray(mat)).to(torch.device("cuda", _device.current_device()))
+        inv, info = torch.linalg.inv_ex(t)
+        if int(info) != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        return inv.cpu().numpy()
+    return np.linalg.inv(mat)
+
+
 class anl(lreg):
     def __init__(self, datavar=None, prior_var=None, cov_nugget=0.0, method='full'):
         super().__init__()
@@ -41,7 +56,7 @@ class anl(lreg):
         if self.prior_var is not None:
             ptp += (self.datavar / self.prior_var) * np.eye(nbas)
         ptp += self.cov_nugget * np.eye(nbas)
-        invptp = np.linalg.inv(ptp)          # LinAlgError on singular G, as in the reference
+        invptp = _inverse(ptp)               # LinAlgError on singular G, as in the reference
         self.cf = np.dot(invptp, stats.b(0))
         sigmahatsq = self._sigmahatsq(stats) if self.datavar is None else self.datavar
         self.datavar = sigmahatsq + 0.0
