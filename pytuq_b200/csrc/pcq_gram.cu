@@ -11,18 +11,17 @@
 //   (one CTA per SM).  A CTA therefore works on at most two partial tiles plus complete
 //   tiles in between.  Partial tiles go to a workspace and are summed in CTA order by a
 //   fix-up kernel (deterministic, no atomics); a mirror kernel fills the lower triangle.
-// Per CTA (256 threads, 8 warps as 4 x 2, warp tile 32 x 64, 64 accumulators per thread):
-//   stage it+1: the 1-D recurrences of KT samples go to a shared slot table, then each
-//   thread generates one column of the I or J operand tile for those samples (A is never
-//   written to HBM); stage it: mma.sync.m8n8k4.f64 over the previous stage's tiles.
-//   Operand tiles and slot tables are double buffered: one __syncthreads per stage.
+// Per CTA (256 threads, 8 warps as 4 x 2, warp tile 32 x 64, 64 accumulators per thread): operand
+//   tiles [16 samples][128 columns] are GENERATED in shared memory (A is never written to HBM) as
+//   products of per-sample slot-table entries and contracted with mma.sync.m8n8k4.f64 (DMMA);
+//   generation of stage it+1 is interleaved into the DMMA stream of stage it.
+// Three kernels share this skeleton (dispatch in pcq_launch_gram):
+//   pcq_gram_tma_kernel   (K3, default)  slot tables precomputed per L2-sized sample chunk by
+//                         pcq_tables_kernel and fetched per stage with cp.async.bulk (TMA) + mbarrier
+//   pcq_gram_fused_kernel (K3 fallback, PCQ_GRAM_TMA=0)  tables rebuilt inside the DMMA warps
+//   pcq_gram_kernel       (K4: materialised A; and K3 with > 4 non-zero orders per term)  plain
+//                         generate / barrier / DMMA phases
 #include "pcq_internal.cuh"
-#ifndef PCQ_BUILD_WS
-#define PCQ_BUILD_WS 0
-#endif
-#ifndef PCQ_EXP_GEN
-#define PCQ_EXP_GEN 4   // experiment switch (tools/): 0 none, 1 tables, 2 +gathers, 3 +DMUL, 4 full
-#endif
 #include <cstdlib>
 #include <cstring>
 
@@ -473,16 +472,10 @@ __device__ __forceinline__ void fused_segment(const GramParams& P, const FusedSm
         // Table build = short dependent FP64 chains that queue behind DMMAs on the shared FP64 pipe.
         // The two warps of a scheduler (w and w+4) do it at opposite ends of the stage, so that one
         // of them is always streaming DMMAs (a single warp saturates the pipe).
-#if PCQ_EXP_GEN >= 1
         if (BUILD && early) {
-#if PCQ_EXP_GEN != 5 && PCQ_EXP_GEN != 6
             build_tables(it + 2, xr);      // writes tab[cur] (read by the previous iteration's generator)
-#endif
-#if PCQ_EXP_GEN != 5 && PCQ_EXP_GEN != 7
             load_pairs(it + 3, xr);
-#endif
         }
-#endif
         const double* Tn = sm.tab + (size_t)nxt * NT * TS + rbase;
         double* on = sm.op + (size_t)nxt * 2 * KT * LDT + (size_t)((DIAG ? 0 : half) * KT) * LDT + col +
                      rbase * LDT;
@@ -499,45 +492,25 @@ __device__ __forceinline__ void fused_segment(const GramParams& P, const FusedSm
             for (int j = 0; j < 8; ++j) bf[j] = pb[(size_t)kk * LDT + j * 8];
             // operands of the next stage: rows kk..kk+3 (off-diagonal) or two rows of this half
             double gv[4];
-#if (PCQ_EXP_GEN >= 3 && PCQ_EXP_GEN <= 5)
 #pragma unroll
             for (int q = 0; q < (DIAG ? 2 : 4); ++q) {
                 const int r = DIAG ? (kk + 2 * q) : (kk + q);
                 gv[q] = gen_value(Tn, r);
             }
-#elif PCQ_EXP_GEN == 2
-#pragma unroll
-            for (int q = 0; q < (DIAG ? 2 : 4); ++q) {
-                const int r = DIAG ? (kk + 2 * q) : (kk + q);
-#pragma unroll
-                for (int w = 0; w < W; ++w) { double t = Tn[off[w] + r]; asm volatile("" ::"d"(t)); }
-            }
-#endif
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-#if (PCQ_EXP_GEN == 4 || PCQ_EXP_GEN == 5)
 #pragma unroll
             for (int q = 0; q < (DIAG ? 2 : 4); ++q) {
                 const int r = DIAG ? (kk + 2 * q) : (kk + q);
                 on[(size_t)r * LDT] = gv[q];
             }
-#elif PCQ_EXP_GEN == 3
-#pragma unroll
-            for (int q = 0; q < (DIAG ? 2 : 4); ++q) asm volatile("" ::"d"(gv[q]));
-#endif
         }
-#if PCQ_EXP_GEN >= 1
         if (BUILD && !early) {
-#if PCQ_EXP_GEN != 5 && PCQ_EXP_GEN != 6
             build_tables(it + 2, xr);
-#endif
-#if PCQ_EXP_GEN != 5 && PCQ_EXP_GEN != 7
             load_pairs(it + 3, xr);
-#endif
         }
-#endif
         __syncthreads();
     }
 }
@@ -649,207 +622,6 @@ int launch_gram_fused_w(const GramParams& P, int num_sms, size_t smem_optin, dou
 }
 
 
-
-#if PCQ_BUILD_WS   // experiment, not built by default (slower: profiles/r01_c)
-// ------------------------------------------------------------------------------------------------
-// K3 v4: v2 + one dedicated table-builder warp per scheduler (384 threads).
-//   Measured on v2 (tools/exp): the per-stage table build (dependent FP64 recurrence chains that
-//   queue behind DMMAs on the shared FP64 pipe) costs 10-14 % of the DMMA pipe when it runs inside
-//   the DMMA warps, the x/y prefetch nothing, generation 8 %.  Here warps 8-11 do nothing but
-//   prefetch x/y and build the slot tables two stages ahead; warps 0-7 run the v2 stage body
-//   (DMMA + interleaved operand generation).  Same single __syncthreads per stage for all 12 warps.
-//   setmaxnreg moves registers from the builders (40) to the DMMA warps (232).
-constexpr int F2_THREADS = 384;
-constexpr int F2_BUILDERS = 128;
-
-template <int XPF, int KT>
-__device__ __forceinline__ void builder_segment(const GramParams& P, const FusedSmem& sm, int64_t sbeg,
-                                                int64_t send, const int (&pr)[XPF], const int (&pc)[XPF],
-                                                int btid) {
-    constexpr int TS = KT + 1;
-    const int s = P.sdim;
-    const int NT = P.nslots + P.m + 1;
-    const int ncol = s + P.m;
-    const int nst = (int)((send - sbeg + KT - 1) / KT);
-    auto load_pairs = [&](int st, double (&xr)[XPF]) {
-        const int64_t n0 = sbeg + (int64_t)st * KT;
-#pragma unroll
-        for (int j = 0; j < XPF; ++j) {
-            xr[j] = 0.0;
-            if (pr[j] >= 0 && n0 + pr[j] < send) {
-                const int64_t row = n0 + pr[j];
-                xr[j] = (pc[j] < s) ? P.x[row * P.ldx + pc[j]] : P.y[row * P.ldy + (pc[j] - s)];
-            }
-        }
-    };
-    auto build_one = [&](double* T, int r, int c, double v, bool live) {
-        if (c < s) {
-            if (c == 0) {
-                T[r] = live ? 1.0 : 0.0;
-                T[(size_t)(P.nslots + P.m) * TS + r] = 0.0;
-            }
-            if (P.pmax >= 1) {
-                double pm = 1.0;
-                double pcur = __dmul_rn(v, sm.p1[c]);
-                T[(size_t)(1 + c) * TS + r] = live ? pcur : 0.0;
-                for (int nn = 1; nn < P.pmax; ++nn) {
-                    const double a = sm.rec_a[nn * s + c];
-                    const double b = sm.rec_b[nn * s + c];
-                    const double pn = __dadd_rn(__dmul_rn(__dmul_rn(a, v), pcur), __dmul_rn(b, pm));
-                    T[(size_t)(1 + nn * s + c) * TS + r] = live ? pn : 0.0;
-                    pm = pcur;
-                    pcur = pn;
-                }
-            }
-        } else {
-            T[(size_t)(P.nslots + c - s) * TS + r] = live ? v : 0.0;
-        }
-    };
-    auto build_tables = [&](int st, const double (&xr)[XPF]) {
-        double* T = sm.tab + (size_t)(st & 1) * NT * TS;
-        const int64_t n0 = sbeg + (int64_t)st * KT;
-#pragma unroll
-        for (int j = 0; j < XPF; ++j)
-            if (pr[j] >= 0) build_one(T, pr[j], pc[j], xr[j], n0 + pr[j] < send);
-        for (int idx = btid + XPF * F2_BUILDERS; idx < KT * ncol; idx += F2_BUILDERS) {
-            const int r = idx / ncol, c = idx - r * ncol;
-            const bool live = n0 + r < send;
-            double v = 0.0;
-            if (live) v = (c < s) ? P.x[(n0 + r) * P.ldx + c] : P.y[(n0 + r) * P.ldy + (c - s)];
-            build_one(T, r, c, v, live);
-        }
-    };
-    // barrier sequence identical to fused_segment's
-    __syncthreads();
-    double xr[XPF];
-    load_pairs(0, xr);
-    build_tables(0, xr);
-    load_pairs(1, xr);
-    build_tables(1, xr);
-    load_pairs(2, xr);
-    __syncthreads();
-    __syncthreads();
-    for (int it = 0; it < nst; ++it) {
-        build_tables(it + 2, xr);
-        load_pairs(it + 3, xr);
-        __syncthreads();
-    }
-}
-
-template <int W, int XPF, int KT>
-__global__ void __launch_bounds__(F2_THREADS, 1) pcq_gram_fused2_kernel(GramParams P) {
-    constexpr int TS = KT + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedSmem sm;
-    const int NT = P.nslots + P.m + 1;
-    sm.op = reinterpret_cast<double*>(smem_raw);
-    sm.tab = sm.op + 2 * 2 * KT * LDT;
-    sm.rec_a = sm.tab + (size_t)2 * NT * TS;
-    sm.rec_b = sm.rec_a + (P.pmax + 1) * P.sdim;
-    sm.p1 = sm.rec_b + (P.pmax + 1) * P.sdim;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (P.pmax + 1) * P.sdim; i += F2_THREADS) {
-        sm.rec_a[i] = P.rec_a[i];
-        sm.rec_b[i] = P.rec_b[i];
-    }
-    for (int i = tid; i < P.sdim; i += F2_THREADS) sm.p1[i] = P.p1[i];
-
-    const int64_t G = gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * P.total / G;
-    const int64_t hi = ((int64_t)blockIdx.x + 1) * P.total / G;
-    const int64_t first_tile = (hi > lo) ? lo / P.nblk : -1;
-
-    if (tid >= G_THREADS) {
-        // -------- table builders (warps 8-11) --------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
-        const int btid = tid - G_THREADS;
-        const int ncol = P.sdim + P.m;
-        int pr[XPF], pc[XPF];
-#pragma unroll
-        for (int j = 0; j < XPF; ++j) {
-            const int idx = btid + j * F2_BUILDERS;
-            pr[j] = -1; pc[j] = 0;
-            if (idx < KT * ncol) { pr[j] = idx / ncol; pc[j] = idx - pr[j] * ncol; }
-        }
-        int64_t u = lo;
-        while (u < hi) {
-            const int64_t t = u / P.nblk;
-            const int64_t b0 = u - t * P.nblk;
-            const int64_t seg_end = min(hi, (t + 1) * P.nblk);
-            const int64_t sbeg = b0 * GRAM_SB;
-            const int64_t send = min(P.n, (b0 + (seg_end - u)) * GRAM_SB);
-            builder_segment<XPF, KT>(P, sm, sbeg, send, pr, pc, btid);
-            u = seg_end;
-        }
-    } else {
-        // -------- DMMA + operand generation (warps 0-7) --------
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
-        const int lane = tid & 31, warp = tid >> 5;
-        const int g = lane >> 2, tig = lane & 3, wm = warp & 3, wn = warp >> 2;
-        const int dummy_pr[1] = {-1}, dummy_pc[1] = {0};
-        int64_t u = lo;
-        while (u < hi) {
-            const int64_t t = u / P.nblk;
-            const int64_t b0 = u - t * P.nblk;
-            const int64_t seg_end = min(hi, (t + 1) * P.nblk);
-            const int64_t nb = seg_end - u;
-            const int64_t sbeg = b0 * GRAM_SB;
-            const int64_t send = min(P.n, (b0 + nb) * GRAM_SB);
-            int I, J;
-            tile_decode(t, P.ntile, I, J);
-            double acc[4][8][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-            if (I == J) fused_segment<W, 1, true, KT, false>(P, sm, I, J, sbeg, send, acc, dummy_pr, dummy_pc);
-            else fused_segment<W, 1, false, KT, false>(P, sm, I, J, sbeg, send, acc, dummy_pr, dummy_pc);
-            flush_tile(P, acc, I, J, nb == P.nblk, (t == first_tile) ? 0 : 1, wm, wn, g, tig);
-            u = seg_end;
-        }
-    }
-}
-
-template <int W, int XPF, int KT>
-int launch_gram_fused2(const GramParams& P0, int num_sms, size_t smem_optin, double** ws,
-                       size_t* ws_bytes, cudaStream_t st, bool* handled) {
-    constexpr int TS = KT + 1;
-    GramParams P = P0;
-    const int NT = P.nslots + P.m + 1;
-    const size_t smem = ((size_t)2 * 2 * KT * LDT + (size_t)2 * NT * TS + (size_t)2 * (P.pmax + 1) * P.sdim +
-                         P.sdim) * sizeof(double);
-    *handled = false;
-    if (smem > smem_optin) return PCQ_OK;
-    *handled = true;
-    auto kern = pcq_gram_fused2_kernel<W, XPF, KT>;
-    PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)(P.total < num_sms ? P.total : num_sms);
-    int rc = pcq_ensure_dev(ws, ws_bytes, (size_t)grid * 2 * GT * GT * sizeof(double));
-    if (rc != PCQ_OK) return rc;
-    P.ws = *ws;
-    kern<<<grid, F2_THREADS, smem, st>>>(P);
-    PCQ_LAUNCH_CHECK("pcq_gram_fused2_kernel");
-    const int ntri = P.ntile * (P.ntile + 1) / 2;
-    pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
-    PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
-    const int nb32 = (P.L + 31) / 32;
-    if (P.mirror) {
-        pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
-        PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
-    }
-    return PCQ_OK;
-}
-
-template <int W>
-int launch_gram_fused2_w(const GramParams& P, int num_sms, size_t smem_optin, double** ws,
-                         size_t* ws_bytes, cudaStream_t st, bool* handled) {
-    if (16 * (P.sdim + P.m) <= 3 * F2_BUILDERS)
-        return launch_gram_fused2<W, 3, 16>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
-    return launch_gram_fused2<W, 4, 16>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
-}
-
-
-#endif  // PCQ_BUILD_WS (K3 v4)
 
 // ------------------------------------------------------------------------------------------------
 // K3 v6: slot tables precomputed per L2-sized chunk and fed to the Gram kernel by TMA.
@@ -1117,299 +889,6 @@ int launch_gram_tma(const GramParams& P0, pcq_plan* p, int num_sms, size_t smem_
     return PCQ_OK;
 }
 
-#if PCQ_BUILD_WS
-// ------------------------------------------------------------------------------------------------
-// K3 v3 (experiment, not built by default: slower, see profiles/r01_c): warp-specialised fused kernel (384 threads: 1 producer warpgroup + 2 consumer warpgroups).
-//   The interleaved v2 loses ~25 % of the DMMA pipe to in-order issue stalls of the generator
-//   (LDS -> DMUL -> STS chains in the same warp as the DMMAs): with generation compiled out the
-//   same loop runs at 98 % of the DMMA peak (tools/exp, profiles/r01_c).  Here the 8 consumer warps
-//   run nothing but fragment loads + DMMA; 4 producer warps (one per scheduler) prefetch x/y, run
-//   the recurrences into the slot table and generate the operand tiles two stages ahead.
-//   Hand-off through named barriers (full[2] / empty[2]); the stage counter runs across segment
-//   boundaries, so producers prefill the next tile while consumers flush their accumulators.
-//   Registers are re-partitioned with setmaxnreg (producers 72, consumers 216).
-constexpr int WS_THREADS = 384;
-constexpr int WS_PROD = 128;
-
-__device__ __forceinline__ void named_sync(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_arrive(int id, int count) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3, BAR_PROD = 5 };
-
-template <int W, int XPF, int KT>
-__global__ void __launch_bounds__(WS_THREADS, 1) pcq_gram_ws_kernel(GramParams P) {
-    constexpr int TS = KT + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NT = P.nslots + P.m + 1;
-    double* op = reinterpret_cast<double*>(smem_raw);          // [2][2][KT][LDT]
-    double* tab = op + 2 * 2 * KT * LDT;                        // [2][NT][TS]
-    double* s_rec_a = tab + (size_t)2 * NT * TS;
-    double* s_rec_b = s_rec_a + (P.pmax + 1) * P.sdim;
-    double* s_p1 = s_rec_b + (P.pmax + 1) * P.sdim;
-
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (P.pmax + 1) * P.sdim; i += WS_THREADS) {
-        s_rec_a[i] = P.rec_a[i];
-        s_rec_b[i] = P.rec_b[i];
-    }
-    for (int i = tid; i < P.sdim; i += WS_THREADS) s_p1[i] = P.p1[i];
-    __syncthreads();
-
-    const int64_t G = gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * P.total / G;
-    const int64_t hi = ((int64_t)blockIdx.x + 1) * P.total / G;
-    const int64_t first_tile = (hi > lo) ? lo / P.nblk : -1;
-
-    if (tid >= WS_THREADS - WS_PROD) {
-        // producers are the HIGHEST-numbered warps: the issue arbiter favours high warp ids, and the
-        // producers' DMULs must not starve behind the consumers' DMMAs on the shared FP64 pipe
-        const int ptid = tid - (WS_THREADS - WS_PROD);
-        // ============================== producer warpgroup ==============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
-        const int s = P.sdim;
-        const int ncol = s + P.m;
-        int pr[XPF], pc[XPF];
-#pragma unroll
-        for (int j = 0; j < XPF; ++j) {
-            const int idx = ptid + j * WS_PROD;
-            pr[j] = -1; pc[j] = 0;
-            if (idx < KT * ncol) { pr[j] = idx / ncol; pc[j] = idx - pr[j] * ncol; }
-        }
-        auto build_one = [&](double* T, int r, int c, double v, bool live) {
-            if (c < s) {
-                if (c == 0) {
-                    T[r] = live ? 1.0 : 0.0;
-                    T[(size_t)(P.nslots + P.m) * TS + r] = 0.0;
-                }
-                if (P.pmax >= 1) {
-                    double pm = 1.0;
-                    double pcur = __dmul_rn(v, s_p1[c]);
-                    T[(size_t)(1 + c) * TS + r] = live ? pcur : 0.0;
-                    for (int nn = 1; nn < P.pmax; ++nn) {
-                        const double a = s_rec_a[nn * s + c];
-                        const double b = s_rec_b[nn * s + c];
-                        const double pn = __dadd_rn(__dmul_rn(__dmul_rn(a, v), pcur), __dmul_rn(b, pm));
-                        T[(size_t)(1 + nn * s + c) * TS + r] = live ? pn : 0.0;
-                        pm = pcur;
-                        pcur = pn;
-                    }
-                }
-            } else {
-                T[(size_t)(P.nslots + c - s) * TS + r] = live ? v : 0.0;
-            }
-        };
-        int gst = 0;                     // global stage counter (runs across segments)
-        int64_t u = lo;
-        while (u < hi) {
-            const int64_t t = u / P.nblk;
-            const int64_t b0 = u - t * P.nblk;
-            const int64_t seg_end = min(hi, (t + 1) * P.nblk);
-            const int64_t sbeg = b0 * GRAM_SB;
-            const int64_t send = min(P.n, (b0 + (seg_end - u)) * GRAM_SB);
-            int I, J;
-            tile_decode(t, P.ntile, I, J);
-            const bool diag = (I == J);
-            const int nst = (int)((send - sbeg + KT - 1) / KT);
-            // descriptors of this thread's columns: column ptid of the I tile and of the J tile
-            int offI[W], offJ[W];
-#pragma unroll
-            for (int q = 0; q < W; ++q) { offI[q] = 0; offJ[q] = 0; }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int gc = (h == 0 ? I : J) * GT + ptid;
-                int o[W];
-#pragma unroll
-                for (int q = 0; q < W; ++q) o[q] = 0;
-                if (gc < P.kb) {
-                    const unsigned long long d = P.desc4[gc];
-#pragma unroll
-                    for (int q = 0; q < W; ++q) o[q] = (int)((d >> (16 * q)) & 0xffffull) * TS;
-                } else if (gc < P.kb + P.m) {
-                    o[W - 1] = (P.nslots + gc - P.kb) * TS;
-                } else if (gc > P.kb + P.m) {
-                    o[W - 1] = (P.nslots + P.m) * TS;
-                }
-#pragma unroll
-                for (int q = 0; q < W; ++q) { if (h == 0) offI[q] = o[q]; else offJ[q] = o[q]; }
-            }
-            auto load_pairs = [&](int st, double (&xr)[XPF]) {
-                const int64_t n0 = sbeg + (int64_t)st * KT;
-#pragma unroll
-                for (int j = 0; j < XPF; ++j) {
-                    xr[j] = 0.0;
-                    if (pr[j] >= 0 && n0 + pr[j] < send) {
-                        const int64_t row = n0 + pr[j];
-                        xr[j] = (pc[j] < s) ? P.x[row * P.ldx + pc[j]] : P.y[row * P.ldy + (pc[j] - s)];
-                    }
-                }
-            };
-            double xr[XPF];
-            load_pairs(0, xr);
-            for (int st = 0; st < nst; ++st, ++gst) {
-                const int buf = gst & 1;
-                double* T = tab + (size_t)buf * NT * TS;
-                const int64_t n0 = sbeg + (int64_t)st * KT;
-                // tables of this stage (the table buffer of stage gst-2 is free: every producer has
-                // passed the BAR_PROD of stage gst-1, which follows its generation of stage gst-2)
-#pragma unroll
-                for (int j = 0; j < XPF; ++j)
-                    if (pr[j] >= 0) build_one(T, pr[j], pc[j], xr[j], n0 + pr[j] < send);
-                for (int idx = ptid + XPF * WS_PROD; idx < KT * ncol; idx += WS_PROD) {
-                    const int r = idx / ncol, c = idx - r * ncol;
-                    const bool live = n0 + r < send;
-                    double v = 0.0;
-                    if (live) v = (c < s) ? P.x[(n0 + r) * P.ldx + c] : P.y[(n0 + r) * P.ldy + (c - s)];
-                    build_one(T, r, c, v, live);
-                }
-                load_pairs(st + 1, xr);                       // prefetch the next stage's x / y
-                named_sync(BAR_PROD, WS_PROD);                // tables complete
-                if (gst >= 2) named_sync(BAR_EMPTY0 + buf, WS_THREADS);   // consumers released op[buf]
-                double* oI = op + (size_t)buf * 2 * KT * LDT + ptid;
-                double* oJ = oI + KT * LDT;
-#pragma unroll
-                for (int r = 0; r < KT; ++r) {
-                    double v = T[offI[0] + r];
-#pragma unroll
-                    for (int q = 1; q < W; ++q) v = __dmul_rn(v, T[offI[q] + r]);
-                    oI[(size_t)r * LDT] = v;
-                }
-                if (!diag) {
-#pragma unroll
-                    for (int r = 0; r < KT; ++r) {
-                        double v = T[offJ[0] + r];
-#pragma unroll
-                        for (int q = 1; q < W; ++q) v = __dmul_rn(v, T[offJ[q] + r]);
-                        oJ[(size_t)r * LDT] = v;
-                    }
-                }
-                named_arrive(BAR_FULL0 + buf, WS_THREADS);    // op[buf] is ready
-            }
-            u = seg_end;
-        }
-    } else {
-        // ============================== consumer warpgroups ==============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
-        const int ctid = tid;
-        const int lane = ctid & 31, warp = ctid >> 5;
-        const int g = lane >> 2, tig = lane & 3, wm = warp & 3, wn = warp >> 2;
-        int gst = 0;
-        int64_t u = lo;
-        while (u < hi) {
-            const int64_t t = u / P.nblk;
-            const int64_t b0 = u - t * P.nblk;
-            const int64_t seg_end = min(hi, (t + 1) * P.nblk);
-            const int64_t nb = seg_end - u;
-            const int64_t sbeg = b0 * GRAM_SB;
-            const int64_t send = min(P.n, (b0 + nb) * GRAM_SB);
-            int I, J;
-            tile_decode(t, P.ntile, I, J);
-            const bool diag = (I == J);
-            const int nst = (int)((send - sbeg + KT - 1) / KT);
-            double acc[4][8][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-            for (int st = 0; st < nst; ++st, ++gst) {
-                const int buf = gst & 1;
-                named_sync(BAR_FULL0 + buf, WS_THREADS);      // wait for the producers
-                const double* oa = op + (size_t)buf * 2 * KT * LDT;
-                const double* ob = oa + (diag ? 0 : KT * LDT);
-                const double* pa = oa + (size_t)tig * LDT + wm * 32 + g;
-                const double* pb = ob + (size_t)tig * LDT + wn * 64 + g;
-#pragma unroll
-                for (int kk = 0; kk < KT; kk += 4) {
-                    double af[4], bf[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) af[i] = pa[(size_t)kk * LDT + i * 8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) bf[j] = pb[(size_t)kk * LDT + j * 8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-                }
-                named_arrive(BAR_EMPTY0 + buf, WS_THREADS);   // op[buf] may be overwritten
-            }
-            // flush (producers are already filling the next segment's first stages)
-            const bool complete = (nb == P.nblk);
-            if (complete) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = I * GT + wm * 32 + i * 8 + g;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c = J * GT + wn * 64 + j * 8 + 2 * tig;
-                        if (row < P.L) {
-                            double* dst = P.s_out + (size_t)row * P.L + c;
-                            if (c < P.L) dst[0] = (P.accumulate ? dst[0] : 0.0) + acc[i][j][0];
-                            if (c + 1 < P.L) dst[1] = (P.accumulate ? dst[1] : 0.0) + acc[i][j][1];
-                        }
-                    }
-                }
-            } else {
-                const int slot = (t == first_tile) ? 0 : 1;
-                double* w = P.ws + ((size_t)blockIdx.x * 2 + slot) * GT * GT;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = wm * 32 + i * 8 + g;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c = wn * 64 + j * 8 + 2 * tig;
-                        *reinterpret_cast<double2*>(w + (size_t)row * GT + c) =
-                            make_double2(acc[i][j][0], acc[i][j][1]);
-                    }
-                }
-            }
-            u = seg_end;
-        }
-    }
-}
-
-template <int W, int XPF, int KT>
-int launch_gram_ws(const GramParams& P0, int num_sms, size_t smem_optin, double** ws,
-                   size_t* ws_bytes, cudaStream_t st, bool* handled) {
-    constexpr int TS = KT + 1;
-    GramParams P = P0;
-    const int NT = P.nslots + P.m + 1;
-    const size_t smem = ((size_t)2 * 2 * KT * LDT + (size_t)2 * NT * TS + (size_t)2 * (P.pmax + 1) * P.sdim +
-                         P.sdim) * sizeof(double);
-    *handled = false;
-    if (smem > smem_optin) return PCQ_OK;
-    *handled = true;
-    auto kern = pcq_gram_ws_kernel<W, XPF, KT>;
-    PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)(P.total < num_sms ? P.total : num_sms);
-    int rc = pcq_ensure_dev(ws, ws_bytes, (size_t)grid * 2 * GT * GT * sizeof(double));
-    if (rc != PCQ_OK) return rc;
-    P.ws = *ws;
-    kern<<<grid, WS_THREADS, smem, st>>>(P);
-    PCQ_LAUNCH_CHECK("pcq_gram_ws_kernel");
-    const int ntri = P.ntile * (P.ntile + 1) / 2;
-    pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
-    PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
-    const int nb32 = (P.L + 31) / 32;
-    if (P.mirror) {
-        pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
-        PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
-    }
-    return PCQ_OK;
-}
-
-template <int W>
-int launch_gram_ws_w(const GramParams& P, int num_sms, size_t smem_optin, double** ws,
-                     size_t* ws_bytes, cudaStream_t st, bool* handled) {
-    // values prefetched per producer thread and stage: KT*(s+M)/128, kept in registers up to 4
-    if (16 * (P.sdim + P.m) <= 3 * WS_PROD)
-        return launch_gram_ws<W, 3, 16>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
-    return launch_gram_ws<W, 4, 16>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
-}
-
-#endif  // PCQ_BUILD_WS
-
 __global__ void pcq_fill_kernel(double* p, size_t n, double v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x)
@@ -1449,19 +928,6 @@ static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const d
         bool handled = false;
         int rc = PCQ_OK;
         const int v1_only = getenv("PCQ_GRAM_V1") != nullptr;
-#if PCQ_BUILD_WS
-        const char* wsenv = getenv("PCQ_GRAM_WS");
-        if (!v1_only && wsenv && atoi(wsenv) == 1) {
-            switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
-                case 1: rc = launch_gram_ws_w<1>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 2: rc = launch_gram_ws_w<2>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 3: rc = launch_gram_ws_w<3>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 4: rc = launch_gram_ws_w<4>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                default: break;
-            }
-            if (handled || rc != PCQ_OK) return rc;
-        }
-#endif
         const char* tmaenv = getenv("PCQ_GRAM_TMA");
         if (!v1_only && !(tmaenv && atoi(tmaenv) == 0)) {
             switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
@@ -1473,19 +939,6 @@ static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const d
             }
             if (handled || rc != PCQ_OK) return rc;
         }
-#if PCQ_BUILD_WS
-        const char* f2env = getenv("PCQ_GRAM_F2");
-        if (!v1_only && f2env && atoi(f2env) == 1) {   // experiment, slower than the staggered v2 (profiles/r01_c)
-            switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
-                case 1: rc = launch_gram_fused2_w<1>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 2: rc = launch_gram_fused2_w<2>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 3: rc = launch_gram_fused2_w<3>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 4: rc = launch_gram_fused2_w<4>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                default: break;
-            }
-            if (handled || rc != PCQ_OK) return rc;
-        }
-#endif
         if (!v1_only) {
             switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
                 case 1: rc = launch_gram_fused_w<1>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
