@@ -488,6 +488,11 @@ int launch_evalpc2_cfg(pcq_plan* p, const EvalParams& P, cudaStream_t st, double
 template <int W, bool GERM>
 int launch_evalpc2_w(pcq_plan* p, const EvalParams& P, int mode, cudaStream_t st, double* sums, bool* handled) {
     const bool fast = (mode & 1) != 0;
+    if (fast && !GERM && P.m >= 16) {
+        // many outputs (quadratic forms, KL modes): 16 accumulators per sample amortise the basis
+        // product and the descriptor traffic over 16 fused multiply-adds
+        return launch_evalpc2_cfg<W, 16, true, false>(p, P, st, sums, handled);
+    }
     if (P.m >= 4) {
         return fast ? launch_evalpc2_cfg<W, 4, true, GERM>(p, P, st, sums, handled)
                     : launch_evalpc2_cfg<W, 4, false, GERM>(p, P, st, sums, handled);

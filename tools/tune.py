@@ -65,6 +65,20 @@ for name, fam, d, p, n in shapes:
             setenv(PCQ_K2_CFG=None)
             ms = timeit(lambda: _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n, d, c.data_ptr(), 1, y.data_ptr(), 1, mode, st)))
             print(f"{name} K2 mode{mode} auto: {ms:8.3f} ms", flush=True)
+    if "k2m" in which:
+        for M in (16, 64, 256):
+            cm = torch.randn((M, K), dtype=torch.float64, device="cuda", generator=g)
+            nn = min(n, 200_000)
+            ym = torch.empty((nn, M), dtype=torch.float64, device="cuda")
+            for cfg in (None, 0, 1, 2, 3):
+                setenv(PCQ_K2_CFG=cfg)
+                try:
+                    ms = timeit(lambda: _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), nn, d, cm.data_ptr(), M, ym.data_ptr(), M, 1, st)), reps=3, warm=1)
+                except Exception as ex:
+                    print(f"{name} K2 M={M} cfg{cfg}: failed"); continue
+                print(f"{name} K2 fast M={M} cfg={cfg}: n={nn} {ms:8.3f} ms  {2.0 * nn * K * M / ms / 1e9:6.2f} TFLOP/s (2NKM)", flush=True)
+            setenv(PCQ_K2_CFG=None)
+            del cm, ym
     if "k3chunk" in which and name == "C2":
         S = torch.empty((K + 2, K + 2), dtype=torch.float64, device="cuda")
         for mb in (0, 24, 48, 96):
