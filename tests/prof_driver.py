@@ -1,7 +1,6 @@
 """Small driver for ncu: launches each hot kernel a few times on the C2 shape (HG, d=20, p=3)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 from pytuq_b200 import _native
 from pytuq_b200.rv.pcrv import PCRV

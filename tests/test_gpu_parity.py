@@ -5,7 +5,7 @@ tensor-pipe statistics (BLAS-order sums have no defined order in the reference e
 import numpy as np
 import pytest
 
-from conftest import load_golden, golden_cases, case_mis_cfs, case_types
+from conftest import load_golden, case_mis_cfs, case_types
 from oracle import pc_oracle as orc
 
 pytestmark = pytest.mark.gpu

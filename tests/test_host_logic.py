@@ -11,7 +11,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden, golden_cases, case_mis_cfs, case_types
+from conftest import ROOT, load_golden, case_mis_cfs, case_types
 from oracle import pc_oracle as orc
 
 

@@ -2,9 +2,8 @@
 unmodified PyTUQ (tests/golden/make_golden.py) and the known-answer vectors of SURVEY.md
 Appendix A.  Bit-exact where the arithmetic order is defined, 1e-12 for LAPACK solves."""
 import numpy as np
-import pytest
 
-from conftest import load_golden, golden_cases, case_mis_cfs, case_types
+from conftest import load_golden, case_mis_cfs, case_types
 from oracle import pc_oracle as orc
 
 

@@ -1,6 +1,6 @@
 """Times the hot kernels (CUDA events, device-resident inputs) for the BASELINE shapes and the
 compile-time variants selectable through PCQ_* environment switches."""
-import os, sys, json
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
