@@ -345,6 +345,25 @@ def main():
             fl = n * (4.0 * D * (P - 1) + 3.0 * K)
             kernels[tag] = {"rows": n, "ms": ms, "samples_per_s": n / (ms * 1e-3),
                             "TFLOPs_algorithmic": fl / (ms * 1e-3) / 1e12, "bound": "fp64"}
+        # K2 specialised per multi-index (opt-in, NVRTC): same call, after pcq_plan_specialize
+        t0 = time.perf_counter()
+        rc = lib.pcq_plan_specialize(plan.handle, 3)
+        t_comp = time.perf_counter() - t0
+        if rc == 0:
+            for mode, tag in ((0, "K2s_evalPC_exact_specialised"), (1, "K2s_evalPC_fast_specialised")):
+                ts = []
+                for it in range(5):
+                    e0.record()
+                    _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n, D, c_true.data_ptr(), 1,
+                                                      yy.data_ptr(), 1, mode, stream))
+                    e1.record(); e1.synchronize()
+                    if it >= 2:
+                        ts.append(e0.elapsed_time(e1))
+                ms = float(np.mean(ts))
+                fl = n * (4.0 * D * (P - 1) + 3.0 * K)
+                kernels[tag] = {"rows": n, "ms": ms, "samples_per_s": n / (ms * 1e-3),
+                                "TFLOPs_algorithmic": fl / (ms * 1e-3) / 1e12, "bound": "fp64",
+                                "nvrtc_compile_s": t_comp}
     peak = peaks.get("fp64_dmma_tflops")
     traffic = None
     try:   # DRAM bytes per step of the dominant kernel, from the committed ncu capture of this workload
@@ -364,7 +383,7 @@ def main():
         kernels["K1_evalBases"]["hbm_peak_GBps"] = hb
         kernels["K1_evalBases"]["hbm_peak_source"] = "MEASURED_PEAKS.json" if "hbm_gbs" in mp else "fallback"
     if peaks.get("fp64_dfma_tflops"):
-        for tag in ("K2_evalPC_exact", "K2_evalPC_fast"):
+        for tag in ("K2_evalPC_exact", "K2_evalPC_fast", "K2s_evalPC_exact_specialised", "K2s_evalPC_fast_specialised"):
             if tag in kernels:
                 kernels[tag]["frac_of_fp64_peak"] = kernels[tag]["TFLOPs_algorithmic"] / peaks["fp64_dfma_tflops"]
 

@@ -73,8 +73,16 @@ int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms,
                     const double* p1_scale);
 int pcq_plan_destroy(pcq_plan* plan);
 /* queries: 0 sdim, 1 nterms, 2 pmax, 3 width (max non-zero orders per term),
- *          4 device, 5 downward-closed flag, 6 number of SMs */
+ *          4 device, 5 downward-closed flag, 6 number of SMs, 7 specialised modes (bit 0 exact, bit 1 fast) */
 int64_t pcq_plan_info(const pcq_plan* plan, int what);
+
+/* Opt-in: compiles (NVRTC, at run time) evalPC kernels specialised for this plan's multi-index -- the
+ * term list unrolled into straight-line code with the 1-D tables in registers.  Bit-identical to the
+ * generic kernels in exact mode and 3-4x faster, but costs ~3 ms of compile time per term, so it pays
+ * only for large propagation jobs or many repeated evaluations (MCMC).  modes: bit 0 exact, bit 1 fast.
+ * Once built, pcq_eval_pc(_dev) (up to 8 outputs, no quadratic-form mode) and pcq_propagate_dev use them.
+ * Returns PCQ_ERR_UNSUPPORTED when libnvrtc is not available; the generic kernels stay in use. */
+int pcq_plan_specialize(pcq_plan* plan, int modes);
 
 /* ---- K1: design matrix -----------------------------------------------------
  * A[n,k] = prod_i phi^{(i)}_{mi[k,i]}(x[n,i])          PCRV.evalBases, rv/pcrv.py:413-442

@@ -200,6 +200,10 @@ int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms, const int3
     p->device = device;
     p->sdim = sdim; p->nterms = nterms; p->pmax = pmax; p->nslots = (int)nslots64;
     p->width = width; p->downward_closed = closed;
+    p->h_mi.assign(mi, mi + (size_t)nterms * sdim);
+    p->h_rec_a.assign(rec_a, rec_a + (size_t)(pmax + 1) * sdim);
+    p->h_rec_b.assign(rec_b, rec_b + (size_t)(pmax + 1) * sdim);
+    p->h_p1.assign(p1_scale, p1_scale + sdim);
     int rc = device_props(device, &p->num_sms, &p->smem_optin);
     const size_t nrec = (size_t)(pmax + 1) * sdim;
     if (rc == PCQ_OK) rc = dev_upload(&p->d_rec_a, rec_a, nrec);
@@ -220,6 +224,8 @@ int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms, const int3
 int pcq_plan_destroy(pcq_plan* p) {
     if (!p) return PCQ_OK;
     DeviceGuard guard(p->device);
+    pcq_spec_free(p->spec[0]);
+    pcq_spec_free(p->spec[1]);
     cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
     cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_tabs);
     for (int i = 0; i < 2; ++i) {
@@ -242,8 +248,18 @@ int64_t pcq_plan_info(const pcq_plan* p, int what) {
         case 4: return p->device;
         case 5: return p->downward_closed;
         case 6: return p->num_sms;
+        case 7: return (p->spec[0] ? 1 : 0) | (p->spec[1] ? 2 : 0);
         default: return PCQ_ERR_ARG;
     }
+}
+
+int pcq_plan_specialize(pcq_plan* p, int modes) {
+    if (!p || (modes & ~3)) { pcq_set_error("specialize: bad argument"); return PCQ_ERR_ARG; }
+    DeviceGuard guard(p->device);
+    int rc = PCQ_OK;
+    if ((modes & 1) && (rc = pcq_spec_build(p, 0)) != PCQ_OK) return rc;
+    if ((modes & 2) && (rc = pcq_spec_build(p, 1)) != PCQ_OK) return rc;
+    return PCQ_OK;
 }
 
 // ------------------------------------------------------------------ device-pointer entry points

@@ -568,6 +568,46 @@ int launch_evalpc_any(pcq_plan* p, const EvalParams& P, int mode, cudaStream_t s
     return launch_evalpc_w<0, GERM>(p, P, mode, st, sums);
 }
 
+// per-output power sums of a materialised y chunk (specialised propagation path): per-warp partial rows
+__global__ void __launch_bounds__(256) pcq_moments_kernel(const double* __restrict__ y, int64_t n, int64_t ldy,
+                                                          int m, double* part) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int j = 0; j < m; ++j) {
+        double v1 = 0.0, v2 = 0.0, mn = INFINITY, mx = -INFINITY;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+            const double v = y[i * ldy + j];
+            v1 += v; v2 = fma(v, v, v2); mn = fmin(mn, v); mx = fmax(mx, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) {
+            double* q = part + ((size_t)warp * m + j) * 4;
+            q[0] = v1; q[1] = v2; q[2] = mn; q[3] = mx;
+        }
+    }
+}
+
+// sums <- sums (+) tmp  (first != 0: sums <- tmp)
+__global__ void pcq_moments_combine_kernel(double* sums, const double* tmp, int m, int first) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    if (first) {
+        for (int q = 0; q < 4; ++q) sums[j * 4 + q] = tmp[j * 4 + q];
+    } else {
+        sums[j * 4 + 0] += tmp[j * 4 + 0];
+        sums[j * 4 + 1] += tmp[j * 4 + 1];
+        sums[j * 4 + 2] = fmin(sums[j * 4 + 2], tmp[j * 4 + 2]);
+        sums[j * 4 + 3] = fmax(sums[j * 4 + 3], tmp[j * 4 + 3]);
+    }
+}
+
 void fill_eval_params(pcq_plan* p, EvalParams& P) {
     memset(&P, 0, sizeof(P));
     P.sdim = p->sdim; P.nterms = p->nterms; P.pmax = p->pmax; P.nslots = p->nslots;
@@ -585,6 +625,15 @@ int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, cons
     fill_eval_params(p, P);
     P.x = x; P.cf = cf; P.y = y; P.n = n; P.ldx = ldx; P.ldy = ldy; P.m = m;
     P.sumsq = (mode & 2) ? 1 : 0;
+    const int fast = mode & 1;
+    if (!P.sumsq && p->spec[fast] && m <= 8) {
+        // multi-index-specialised kernels (pcq_plan_specialize): one output per launch sequence
+        for (int j = 0; j < m; ++j) {
+            int rc = pcq_spec_launch(p, fast, x, n, ldx, cf + (size_t)j * p->nterms, y + j, ldy, st);
+            if (rc != PCQ_OK) return rc;
+        }
+        return PCQ_OK;
+    }
     return launch_evalpc_any<false>(p, P, mode, st, nullptr);
 }
 
@@ -606,6 +655,40 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
     if (rc != PCQ_OK) return rc;
     P.cf = cf; P.y = y; P.n = n; P.ldy = ldy; P.m = m;
     P.seed = seed; P.first_index = first; P.germ_kind = dkind;
+    const int fast = mode & 1;
+    if (p->spec[fast] && m <= 8) {
+        // specialised path: germ chunk -> HBM (160 B per sample, far below the evaluation cost) ->
+        // specialised evalPC -> power sums; chunks of 4M samples, sums combined on the device
+        const int64_t chunk = (int64_t)1 << 22;
+        const int s = p->sdim;
+        if ((rc = pcq_ensure_dev(&p->d_stage[0], &p->stage_bytes[0], (size_t)chunk * s * 8)) != PCQ_OK) return rc;
+        if (!y && (rc = pcq_ensure_dev(&p->d_out[0], &p->out_bytes[0], (size_t)chunk * m * 8)) != PCQ_OK) return rc;
+        const int mgrid = p->num_sms * 4;
+        const int nrows = mgrid * 8;
+        if ((rc = pcq_ensure_dev(&p->d_ws, &p->ws_bytes, ((size_t)nrows * m * 4 + (size_t)m * 4) * 8)) != PCQ_OK) return rc;
+        double* part = p->d_ws;
+        double* tmp = p->d_ws + (size_t)nrows * m * 4;
+        bool firstc = true;
+        for (int64_t r0 = 0; r0 < n || firstc; r0 += chunk) {
+            const int64_t nr = (n - r0 < chunk) ? (n - r0 > 0 ? n - r0 : 0) : chunk;
+            double* yc = y ? y + r0 * ldy : p->d_out[0];
+            const int64_t ldc = y ? ldy : m;
+            if (nr > 0) {
+                if ((rc = pcq_launch_germ(p, seed, first + r0, nr, germ_kind, p->d_stage[0], s, st)) != PCQ_OK) return rc;
+                for (int j = 0; j < m; ++j)
+                    if ((rc = pcq_spec_launch(p, fast, p->d_stage[0], nr, s, cf + (size_t)j * p->nterms, yc + j, ldc, st)) != PCQ_OK)
+                        return rc;
+            }
+            pcq_moments_kernel<<<mgrid, 256, 0, st>>>(yc, nr, ldc, m, part);
+            PCQ_LAUNCH_CHECK("pcq_moments_kernel");
+            pcq_prop_reduce_kernel<<<(m + 127) / 128, 128, 0, st>>>(part, nrows, m, tmp);
+            PCQ_LAUNCH_CHECK("pcq_prop_reduce_kernel");
+            pcq_moments_combine_kernel<<<(m + 127) / 128, 128, 0, st>>>(sums, tmp, m, firstc ? 1 : 0);
+            PCQ_LAUNCH_CHECK("pcq_moments_combine_kernel");
+            firstc = false;
+        }
+        return PCQ_OK;
+    }
     return launch_evalpc_any<true>(p, P, mode, st, sums);
 }
 

@@ -8,6 +8,8 @@
 
 #include "pcq.h"
 
+struct pcq_spec;   // NVRTC-specialised evalPC kernels of one plan (pcq_spec.cu)
+
 #define PCQ_MAXW_FAST 4   // terms with <= 4 non-zero orders use the packed 8-byte descriptor
 
 // Slot numbering of the per-sample table of 1-D polynomial values:
@@ -36,6 +38,10 @@ struct pcq_plan {
     uint16_t* d_descw = nullptr;            // K x width (always valid)
     uint8_t* d_flags = nullptr;             // K, bit 0: first W-1 slots differ from the previous term's
 
+    // host copies kept for the (opt-in) multi-index-specialised kernels
+    std::vector<int32_t> h_mi;
+    std::vector<double> h_rec_a, h_rec_b, h_p1;
+    pcq_spec* spec[2] = {nullptr, nullptr};   // [0] exact, [1] fast
     // precomputed slot-table blobs of the current Gram chunk (lazily grown)
     double* d_tabs = nullptr;
     size_t tabs_bytes = 0;
@@ -97,6 +103,11 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
                          double* y, int64_t ldy, int mode, cudaStream_t st);
 int pcq_launch_germ(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
                     const int32_t* germ_kind, double* x, int64_t ldx, cudaStream_t st);
+// multi-index-specialised evalPC (pcq_spec.cu)
+int pcq_spec_build(pcq_plan* p, int fast);
+int pcq_spec_launch(pcq_plan* p, int fast, const double* x, int64_t n, int64_t ldx, const double* cf,
+                    double* y, int64_t ldy, cudaStream_t st);
+void pcq_spec_free(pcq_spec* sp);
 
 // device helpers -----------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -265,6 +265,39 @@ def test_k5_germ_stream_and_propagation():
     np.testing.assert_allclose(fast["mean"], out["mean"], rtol=1e-11, atol=1e-13)
 
 
+def test_k2_specialised_kernels_bitexact():
+    """Opt-in NVRTC-specialised evalPC: bit-identical to the generic kernel (and so to the reference) in
+    exact mode, rounding-level in fast mode, and consistent through propagate."""
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(99)
+    for (types, p, d, n) in [("HG", 3, 6, 3001), (["LU", "HG", "nLU", "nHG"], 4, 4, 777), ("LU", 2, 30, 257)]:
+        mi = orc.get_mi(p, d)                      # (2, 30): 496 terms; (3, 6): 84; all < 512 -> one chunk
+        if d == 6:
+            mi = np.vstack([mi] * 8)[: 600]       # 600 terms (duplicates allowed) -> two chunks
+        K = mi.shape[0]
+        cfs = rng.standard_normal((2, K))
+        tlist = [types] * d if isinstance(types, str) else types
+        x = np.stack([rng.uniform(-1, 1, n) if t.endswith("LU") else rng.standard_normal(n) for t in tlist], axis=1)
+        gen = PCRV(2, d, types, mi=mi, cfs=cfs)
+        y_exact, y_fast = gen.evalPC(x), gen.evalPC(x, exact=False)
+        spec = PCRV(2, d, types, mi=mi.copy(), cfs=cfs)     # a different plan (content key differs by identity? no: same content)
+        if not spec.specialize():
+            pytest.skip("NVRTC not available on this box")
+        from pytuq_b200 import _native
+        assert _native.lib().pcq_plan_info(spec._plan(spec.mindices[0]).handle, 7) == 3
+        ys = spec.evalPC(x)
+        assert np.array_equal(ys, y_exact), (types, p, d)
+        assert np.array_equal(ys, orc.eval_pc(x, [mi, mi], list(cfs), types)), (types, p, d)
+        assert rel_err(spec.evalPC(x, exact=False), y_fast) < 1e-13
+        a = spec.propagate(5000, seed=3, exact=True, return_samples=True)
+        assert np.array_equal(a["samples"].shape, (5000, 2))
+        np.testing.assert_allclose(a["sum"], a["samples"].sum(axis=0), rtol=1e-12)
+        np.testing.assert_allclose(a["sumsq"], (a["samples"] ** 2).sum(axis=0), rtol=1e-12)
+        assert np.array_equal(a["min"], a["samples"].min(axis=0)) and np.array_equal(a["max"], a["samples"].max(axis=0))
+        b = spec.propagate(5000, seed=3, exact=False)
+        np.testing.assert_allclose(b["mean"], a["mean"], rtol=1e-11, atol=1e-13)
+
+
 # ----------------------------------------------------------------------------- fitters and workflows
 def test_fitters_vs_reference(fit_cases):
     from pytuq_b200.rv.pcrv import PCRV
