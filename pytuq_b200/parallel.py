@@ -146,10 +146,10 @@ def propagate(pcrv, nsam, seed=0, exact=False, return_samples=False, first_index
         pcrv._check_orders(mindex)
         groups.setdefault(id(mindex), []).append(j)
     kinds = pcrv._germ_kinds()
-    # multi-index-specialised kernels (NVRTC, ~0.2 ms of compile time per term on a 16-core host) pay off
-    # once the job is a few 1e12 sample-terms; "auto" applies that threshold, True / False force it
-    nterms = max(m.shape[0] for m in pcrv.mindices)
-    if specialize is True or (specialize == "auto" and float(hi - lo) * nterms >= 3.0e12):
+    # multi-index-specialised kernels (NVRTC, ~0.3 ms of compile time per term and mode on the GPU box's
+    # host) save ~6.5e-13 s per sample-term: break-even near 5e8 samples per rank whatever K is; "auto"
+    # applies that threshold, True / False force it
+    if specialize is True or (specialize == "auto" and (hi - lo) >= 500_000_000):
         pcrv.specialize(exact=exact, fast=not exact)
     tdev = torch.device("cuda", dev)
     sums = np.zeros((pcrv.pdim, 4))
