@@ -185,6 +185,11 @@ def main():
     from pytuq_b200.lreg import lsq, PCBasisEvaluator
     from pytuq_b200.lreg.lreg import solve_normal, solve_normal_device
 
+    # stdout must carry exactly one JSON line, but libraries write there too (NCCL's version banner on
+    # communicator creation): route fd 1 to stderr while working and restore it for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -429,6 +434,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
