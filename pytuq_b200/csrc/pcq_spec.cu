@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -25,7 +26,7 @@ namespace {
 constexpr int SPEC_CHUNK = 512;
 constexpr int SPEC_THREADS = 128;
 
-struct SpecChunk { cudaKernel_t kern = nullptr; int k0 = 0, k1 = 0; };
+struct SpecChunk { cudaKernel_t kern = nullptr; void* cfc = nullptr; int k0 = 0, k1 = 0; };
 
 }  // namespace
 
@@ -87,9 +88,11 @@ std::string gen_source(const pcq_plan* p, int k0, int k1, bool fast, const std::
     const int s = p->sdim;
     std::string o;
     o.reserve((size_t)(k1 - k0) * 96 + 4096);
+    // the chunk's coefficients live in the constant bank (copied there in-stream before every launch):
+    // FP64 instructions take them as direct operands, no load instruction per term
+    o += "__constant__ double " + name + "_cf[" + std::to_string(SPEC_CHUNK) + "];\n";
     o += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(SPEC_THREADS) + ") " + name +
-         "(const double* __restrict__ x, long long n, long long ldx, const double* __restrict__ cf, "
-         "double* __restrict__ y, long long ldy) {\n";
+         "(const double* __restrict__ x, long long n, long long ldx, double* __restrict__ y, long long ldy) {\n";
     o += "  const long long nb = (n + " + std::to_string(SPEC_THREADS - 1) + ") / " + std::to_string(SPEC_THREADS) + ";\n";
     o += "  for (long long blk = blockIdx.x; blk < nb; blk += gridDim.x) {\n";
     o += "    const long long i = blk * " + std::to_string(SPEC_THREADS) + " + threadIdx.x;\n";
@@ -113,8 +116,17 @@ std::string gen_source(const pcq_plan* p, int k0, int k1, bool fast, const std::
         }
     }
     o += std::string("    double acc = ") + (k0 == 0 ? "0.0" : "(live ? y[i * ldy] : 0.0)") + ";\n";
+    // A CTA barrier every few terms: it bounds how far ptxas hoists the (table x coefficient) products
+    // ahead of the serial accumulation chain -- without it the first chunk of an exact kernel needs
+    // >255 registers and spills 2.5 KB per thread -- and keeps the warps of a CTA on the same cache lines
+    // of this long straight-line code.
+    int sync_every = 64;
+    if (const char* e = getenv("PCQ_SPEC_SYNC")) sync_every = atoi(e);
+    // (independent partial sums in fast mode were measured SLOWER: 0.50 -> 0.52 (2) -> 0.76 ms (4), the
+    // extra scheduling freedom costs registers; one serial accumulator it is)
     for (int k = k0; k < k1; ++k) {
-        const std::string c = "__ldg(cf + " + std::to_string(k) + ")";
+        if (sync_every > 0 && k > k0 && (k - k0) % sync_every == 0) o += "    __syncthreads();\n";
+        const std::string c = name + "_cf[" + std::to_string(k - k0) + "]";
         if (!fast) {
             // rv/pcrv.py:492-495: prd = cf[k]; prd *= phi_i (i ascending); val += prd  (x1.0 factors dropped: exact)
             std::string e = c;
@@ -214,6 +226,10 @@ int pcq_spec_build(pcq_plan* p, int fast) {
             sp->libs.push_back(lib);
             e = cudaLibraryGetKernel(&c.kern, lib, names[j].c_str());
         }
+        if (e == cudaSuccess) {
+            size_t bytes = 0;
+            e = cudaLibraryGetGlobal(&c.cfc, &bytes, lib, (names[j] + "_cf").c_str());
+        }
         if (e != cudaSuccess) {
             pcq_set_error("specialize: loading chunk %d failed: %s", j, cudaGetErrorString(e));
             pcq_spec_free(sp);
@@ -238,7 +254,8 @@ int pcq_spec_launch(pcq_plan* p, int fast, const double* x, int64_t n, int64_t l
     const int grid = (int)(nblocks < cap ? nblocks : cap);
     long long nn = n, lx = ldx, ly = ldy;
     for (const SpecChunk& c : sp->chunks) {
-        void* args[] = {(void*)&x, (void*)&nn, (void*)&lx, (void*)&cf, (void*)&y, (void*)&ly};
+        PCQ_CUDA(cudaMemcpyAsync(c.cfc, cf + c.k0, (size_t)(c.k1 - c.k0) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        void* args[] = {(void*)&x, (void*)&nn, (void*)&lx, (void*)&y, (void*)&ly};
         PCQ_CUDA(cudaLaunchKernel((const void*)c.kern, dim3(grid), dim3(SPEC_THREADS), args, 0, st));
         g_pcq_launches.fetch_add(1, std::memory_order_relaxed);
     }

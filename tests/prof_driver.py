@@ -19,6 +19,15 @@ x = torch.randn((n, d), dtype=torch.float64, device="cuda", generator=g)
 c = torch.randn(K, dtype=torch.float64, device="cuda", generator=g)
 y = torch.empty((n, 1), dtype=torch.float64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
+if which == "k2s":
+    _native.check(lib.pcq_plan_specialize(plan.handle, 3))
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    for mode in (0, 1):
+        for rep in range(4):
+            e0.record()
+            _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n, d, c.data_ptr(), 1, y.data_ptr(), 1, mode, st))
+            e1.record(); e1.synchronize()
+            print("k2s mode", mode, "rep", rep, "ms", e0.elapsed_time(e1))
 for rep in range(3):
     if which in ("all", "k2"):
         _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n, d, c.data_ptr(), 1, y.data_ptr(), 1, 0, st))
