@@ -298,12 +298,12 @@ int pcq_suffstats_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, cons
     }
     DeviceGuard guard(p->device);
     return pcq_launch_gram(p, p->num_sms, p->smem_optin, x, n, ldx, nullptr, 0, 0, y, ldy, m, s,
-                           accumulate, &p->d_ws, &p->ws_bytes, (cudaStream_t)stream);
+                           accumulate, &p->d_ws, &p->ws_bytes, &p->d_tabs, &p->tabs_bytes, (cudaStream_t)stream);
 }
 
 namespace {
 // K4 has no plan: keep one workspace per device
-struct GramCtx { double* ws = nullptr; size_t ws_bytes = 0; double* stage[2] = {nullptr, nullptr};
+struct GramCtx { double* ws = nullptr; size_t ws_bytes = 0; double* zp = nullptr; size_t zp_bytes = 0; double* stage[2] = {nullptr, nullptr};
                  size_t stage_bytes[2] = {0, 0}; double* s = nullptr; size_t s_bytes = 0;
                  double* ys[2] = {nullptr, nullptr}; size_t ys_bytes[2] = {0, 0}; };
 GramCtx g_gram_ctx[64];
@@ -323,7 +323,7 @@ int pcq_gram_dev(int device, const double* a, int64_t n, int64_t lda, int kcols,
     if (rc != PCQ_OK) return rc;
     GramCtx& c = g_gram_ctx[device];
     return pcq_launch_gram(nullptr, num_sms, smem_optin, nullptr, n, 0, a, lda, kcols, y, ldy, m, s,
-                           accumulate, &c.ws, &c.ws_bytes, (cudaStream_t)stream);
+                           accumulate, &c.ws, &c.ws_bytes, &c.zp, &c.zp_bytes, (cudaStream_t)stream);
 }
 
 int pcq_propagate_dev(pcq_plan* p, uint64_t seed, int64_t first_index, int64_t n,
@@ -465,7 +465,7 @@ int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const do
     cudaStream_t sk = p->streams[0];
     if (n == 0) {
         if ((rc = pcq_launch_gram(p, p->num_sms, p->smem_optin, nullptr, 0, s, nullptr, 0, 0, nullptr,
-                                  std::max(m, 1), m, p->d_misc, 0, &p->d_ws, &p->ws_bytes, sk)) != PCQ_OK)
+                                  std::max(m, 1), m, p->d_misc, 0, &p->d_ws, &p->ws_bytes, &p->d_tabs, &p->tabs_bytes, sk)) != PCQ_OK)
             return rc;
     }
     const int64_t rows = chunk_rows((int64_t)(s + m) * 8, n);
@@ -487,7 +487,7 @@ int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const do
         PCQ_CUDA(cudaEventDestroy(copied));
         if ((rc = pcq_launch_gram(p, p->num_sms, p->smem_optin, p->d_stage[b], nr, s, nullptr, 0, 0,
                                   p->d_out[b], std::max(m, 1), m, p->d_misc, c > 0, &p->d_ws,
-                                  &p->ws_bytes, sk)) != PCQ_OK)
+                                  &p->ws_bytes, &p->d_tabs, &p->tabs_bytes, sk)) != PCQ_OK)
             return rc;
         PCQ_CUDA(cudaEventRecord(p->events[b], sk));
     }

@@ -967,7 +967,16 @@ static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const d
 int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n,
                     int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,
                     int64_t ldy, int m, double* s, int accumulate, double** ws,
-                    size_t* ws_bytes, cudaStream_t st) {
+                    size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st) {
+    {
+        const char* e = getenv("PCQ_GRAM_SYRK");
+        if (n > 0 && !(e && atoi(e) == 0)) {
+            bool handled = false;
+            const int rc = pcq_launch_syrk(p, num_sms, smem_optin, x, n, ldx, a, lda, kcols, y, ldy, m, s, accumulate,
+                                           ws, ws_bytes, zbuf, zbuf_bytes, st, &handled);
+            if (handled || rc != PCQ_OK) return rc;
+        }
+    }
     if (n == 0)
         return launch_gram_once(p, num_sms, smem_optin, x, 0, ldx, a, lda, kcols, y, ldy, m, s, accumulate, 1,
                                 ws, ws_bytes, st);

@@ -97,7 +97,12 @@ int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, cons
 int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n,
                     int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,
                     int64_t ldy, int m, double* s, int accumulate, double** ws,
-                    size_t* ws_bytes, cudaStream_t st);
+                    size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st);
+// pack + SYRK form of the same (pcq_syrk.cu); *handled = false when it does not apply
+int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n, int64_t ldx,
+                    const double* a, int64_t lda, int kcols, const double* y, int64_t ldy, int m, double* s,
+                    int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes,
+                    cudaStream_t st, bool* handled);
 int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
                          const int32_t* germ_kind, const double* cf, int m, double* sums,
                          double* y, int64_t ldy, int mode, cudaStream_t st);

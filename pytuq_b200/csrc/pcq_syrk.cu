@@ -1,0 +1,493 @@
+// K3 / K4, "pack + SYRK" form: S = Z^T Z on the FP64 tensor pipe with NOTHING but DMMA and 128-bit
+// shared-memory loads in the inner loop.
+//
+//   z_n = [ Psi(x_n) (K) | y_n (M) | 1 | 0-padding ],  Lp = 128 * ceil((K + M + 1) / 128) columns
+//
+// The fused generator (pcq_gram.cu) rebuilds every design-matrix element once per output tile that
+// uses it (~L/128 times); its products and table gathers share the FP64 pipe and the issue slots with
+// the DMMAs and cap it at ~80 % of the executed-DMMA peak.  Here the two concerns are separated:
+//
+//   pack   (pcq_pack_bases_kernel / pcq_pack_matrix_kernel, HBM-bound, ~3 % of the time)
+//          writes a chunk of Z ONCE, in the order the tensor-pipe fragments want it:
+//              Zp[sample block b (8 samples)][column c (Lp)][8 samples]         (doubles)
+//          so that a (128 columns x 8 samples) operand chunk is one contiguous 8 KB run, and a lane's
+//          two k-step values of a column are adjacent (one LDS.128, conflict free).  The k index of
+//          mma.m8n8k4 is a summation index, so lane tig may feed samples (2 tig, 2 tig + 1) of a
+//          block in its two k-steps as long as both operands agree.
+//   syrk   (pcq_syrk_kernel)  one persistent CTA per SM: 8 consumer warps (4 x 2, warp tile 32 x 64,
+//          64 accumulators per thread) + 1 producer warp that keeps a 3-stage ring of
+//          (2 operands x 4 blocks x 8 KB) filled with cp.async.bulk (TMA) on mbarriers; consumers
+//          signal "empty" per warp, so there is no CTA-wide barrier anywhere in the main loop.
+//          Work units are (sample part, upper-triangle tile), part-major, dealt round-robin: the
+//          number of parts S is chosen so that ntri * S fills the SMs in whole waves (105 tiles on
+//          148 SMs: S = 7 -> 4.97 waves), and CTAs of a wave sweep the same sample window at the same
+//          time, so the operand chunks are shared through L2 instead of re-read from HBM.
+//   fixup  sums the S partial tiles of every output tile in part order (deterministic, no atomics);
+//          the mirror kernel fills the lower triangle.
+#include "pcq_internal.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+constexpr int ST = 128;            // output tile edge (columns of Z)
+constexpr int SB = 8;              // samples per block (two DMMA k-steps)
+constexpr int KS = 4;              // blocks per pipeline stage (32 samples)
+constexpr int NSTAGE = 3;
+constexpr int CHUNK = ST * SB;     // doubles per operand chunk (8 KB)
+constexpr int CONSUMER_WARPS = 8;
+constexpr int SY_THREADS = CONSUMER_WARPS * 32;
+constexpr int STAGE_SAMPLES = KS * SB;
+
+struct SyrkParams {
+    const double* zp;
+    int Lp, L, ntile, ntri, nsplit;
+    int64_t nstages;       // stages (of STAGE_SAMPLES samples) in this chunk
+    double* s_out;
+    int accumulate;
+    double* ws;            // [ntri][nsplit][ST*ST], used when nsplit > 1
+};
+
+struct PackParams {
+    const double* x; int64_t ldx;
+    const double* a; int64_t lda;
+    const double* y; int64_t ldy;
+    int kb, m, Lp;
+    int64_t n;             // live samples in this chunk
+    int64_t npairs;        // 16-sample groups to write (covers the stage padding)
+    int sdim, pmax, nslots, width;
+    const double* rec_a; const double* rec_b; const double* p1;
+    const unsigned long long* desc4; const uint16_t* descw;
+    double* zp;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void tile_decode(int t, int ntile, int& I, int& J) {
+    int i = 0, rem = t;
+    while (rem >= ntile - i) { rem -= (ntile - i); ++i; }
+    I = i;
+    J = i + rem;
+}
+
+// ------------------------------------------------------------------------------------------ pack
+// K3: basis values generated from x (bit-identical to K1: same recurrence, same product order)
+template <int W>
+__global__ void __launch_bounds__(256) pcq_pack_bases_kernel(PackParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TS = 17;
+    double* T = reinterpret_cast<double*>(smem_raw);     // [nslots + m + 1][17]: 1, phi..., y..., 0
+    const int s = P.sdim, tid = threadIdx.x;
+    const int nrow = P.nslots + P.m + 1;
+    const int zero_slot = P.nslots + P.m;
+    for (int i = tid; i < nrow * TS; i += 256) T[i] = 0.0;
+    for (int64_t pair = blockIdx.x; pair < P.npairs; pair += gridDim.x) {
+        const int64_t n0 = pair * 16;
+        __syncthreads();
+        if (n0 + 16 > P.n)      // ragged tail: dead samples must contribute exact zeros
+            for (int i = tid; i < zero_slot * TS; i += 256) T[i] = 0.0;
+        if (n0 + 16 > P.n) __syncthreads();
+        for (int idx = tid; idx < 16 * s; idx += 256) {
+            const int sm = idx / s, c = idx - sm * s;
+            const int64_t n = n0 + sm;
+            if (n >= P.n) continue;
+            if (c == 0) T[sm] = 1.0;
+            pcq_fill_1d(P.x[n * P.ldx + c], c, s, P.pmax, P.rec_a, P.rec_b, P.p1, T + sm, TS);
+        }
+        for (int idx = tid; idx < 16 * P.m; idx += 256) {
+            const int sm = idx / P.m, c = idx - sm * P.m;
+            const int64_t n = n0 + sm;
+            if (n < P.n) T[(P.nslots + c) * TS + sm] = P.y[n * P.ldy + c];
+        }
+        __syncthreads();
+        double* out = P.zp + (size_t)pair * 2 * P.Lp * SB;
+        for (int col = tid; col < P.Lp; col += 256) {
+            double v[16];
+            if (col < P.kb) {
+                if (W > 0) {
+                    const unsigned long long d = P.desc4[col];
+                    int off[W > 0 ? W : 1];
+#pragma unroll
+                    for (int q = 0; q < W; ++q) off[q] = (int)((d >> (16 * q)) & 0xffffull) * TS;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        double t = T[off[0] + r];
+#pragma unroll
+                        for (int q = 1; q < W; ++q) t = __dmul_rn(t, T[off[q] + r]);
+                        v[r] = t;
+                    }
+                } else {
+                    const uint16_t* dw = P.descw + (size_t)col * P.width;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) v[r] = T[(int)dw[0] * TS + r];
+                    for (int q = 1; q < P.width; ++q) {
+                        const int o = (int)dw[q] * TS;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) v[r] = __dmul_rn(v[r], T[o + r]);
+                    }
+                }
+            } else {
+                const int slot = col < P.kb + P.m ? P.nslots + (col - P.kb) : (col == P.kb + P.m ? 0 : zero_slot);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = T[slot * TS + r];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double2* dst = reinterpret_cast<double2*>(out + ((size_t)h * P.Lp + col) * SB);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) dst[r] = make_double2(v[h * 8 + 2 * r], v[h * 8 + 2 * r + 1]);
+            }
+        }
+    }
+}
+
+// K4: the caller's design matrix (row-major, any lda) transposed into block order through shared memory
+__global__ void __launch_bounds__(256) pcq_pack_matrix_kernel(PackParams P) {
+    __shared__ double tile[16][257];
+    const int tid = threadIdx.x;
+    const int ncg = (P.Lp + 255) / 256;
+    const int64_t total = P.npairs * ncg;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const int64_t pair = w / ncg;
+        const int c0 = (int)(w - pair * ncg) * 256;
+        const int64_t n0 = pair * 16;
+        const int col = c0 + tid;
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < 16; ++r) {
+            const int64_t n = n0 + r;
+            double v = 0.0;
+            if (n < P.n) {
+                if (col < P.kb) v = P.a[n * P.lda + col];
+                else if (col < P.kb + P.m) v = P.y[n * P.ldy + (col - P.kb)];
+                else if (col == P.kb + P.m) v = 1.0;
+            }
+            tile[r][tid] = v;
+        }
+        __syncthreads();
+        if (col < P.Lp) {
+            double* out = P.zp + (size_t)pair * 2 * P.Lp * SB;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double2* dst = reinterpret_cast<double2*>(out + ((size_t)h * P.Lp + col) * SB);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    dst[r] = make_double2(tile[h * 8 + 2 * r][tid], tile[h * 8 + 2 * r + 1][tid]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ syrk
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// producer cursor: the (unit, stage) sequence this CTA walks, one step ahead of the consumers
+struct SyCursor {
+    int u; int I, J; int64_t st, st1; uint32_t pit;
+};
+__device__ __forceinline__ void cursor_open(const SyrkParams& P, SyCursor& c, int units) {
+    while (c.u < units) {
+        const int part = c.u / P.ntri, t = c.u - part * P.ntri;
+        tile_decode(t, P.ntile, c.I, c.J);
+        c.st = (int64_t)part * P.nstages / P.nsplit;
+        c.st1 = (int64_t)(part + 1) * P.nstages / P.nsplit;
+        if (c.st < c.st1) return;
+        c.u += gridDim.x;
+    }
+}
+
+__global__ void __launch_bounds__(SY_THREADS, 1) pcq_syrk_kernel(SyrkParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* ops = reinterpret_cast<double*>(smem_raw);                        // [NSTAGE][2][KS][CHUNK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ops + (size_t)NSTAGE * 2 * KS * CHUNK);
+    uint64_t* empty = full + NSTAGE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int b = 0; b < NSTAGE; ++b) { mbar_init(full + b, 1); mbar_init(empty + b, CONSUMER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int units = P.ntri * P.nsplit;
+    uint32_t it = 0;      // stages consumed so far by this CTA (same sequence in every warp)
+
+    // Warp 0 doubles as the producer (a ninth warp would cost a whole 4-warp register allocation
+    // granule: 168 registers/thread instead of 255).  It refills the ring buffer that stage it-1
+    // used as soon as all eight warps have released it, polling between its own DMMA blocks.
+    SyCursor cur;
+    cur.u = blockIdx.x; cur.pit = 0; cur.I = cur.J = 0; cur.st = cur.st1 = 0;
+    if (warp == 0) cursor_open(P, cur, units);
+    auto try_issue = [&](bool blocking) {
+        if (cur.u >= units || cur.pit >= it + NSTAGE) return;
+        const int b = cur.pit % NSTAGE;
+        const uint32_t ph = (cur.pit / NSTAGE) & 1u;
+        if (blocking) mbar_wait(empty + b, ph ^ 1u);
+        else if (!mbar_try(empty + b, ph ^ 1u)) return;
+        const bool diag = (cur.I == cur.J);
+        if (lane == 0) mbar_expect_tx(full + b, (diag ? 1u : 2u) * KS * CHUNK * 8u);
+        __syncwarp();
+        if (lane < 2 * KS && (lane < KS || !diag)) {
+            const int op = lane / KS, kb = lane % KS;
+            const double* src = P.zp + ((size_t)(cur.st * KS + kb) * P.Lp + (size_t)(op ? cur.J : cur.I) * ST) * SB;
+            tma_bulk_g2s(ops + ((size_t)(b * 2 + op) * KS + kb) * CHUNK, src, CHUNK * 8u, full + b);
+        }
+        ++cur.pit;
+        if (++cur.st >= cur.st1) { cur.u += gridDim.x; cursor_open(P, cur, units); }
+    };
+    if (warp == 0) {
+        try_issue(true);
+        try_issue(true);
+    }
+
+    // -------------------- consumer warps
+    const int g = lane >> 2, tig = lane & 3, wm = warp & 3, wn = warp >> 2;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int part = u / P.ntri, t = u - part * P.ntri;
+        int I, J;
+        tile_decode(t, P.ntile, I, J);
+        const bool diag = (I == J);
+        const int64_t st0 = (int64_t)part * P.nstages / P.nsplit;
+        const int64_t st1 = (int64_t)(part + 1) * P.nstages / P.nsplit;
+        double acc[4][8][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+        for (int64_t st = st0; st < st1; ++st, ++it) {
+            const int b = it % NSTAGE;
+            const uint32_t ph = (it / NSTAGE) & 1u;
+            mbar_wait(full + b, ph);
+            const double* oa = ops + (size_t)(b * 2) * KS * CHUNK;
+            const double* ob = diag ? oa : oa + (size_t)KS * CHUNK;
+            const double* pa = oa + (wm * 32 + g) * SB + 2 * tig;
+            const double* pb = ob + (wn * 64 + g) * SB + 2 * tig;
+#pragma unroll
+            for (int kb = 0; kb < KS; ++kb) {
+                double2 af[4], bf[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double2*>(pa + kb * CHUNK + i * 8 * SB);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bf[j] = *reinterpret_cast<const double2*>(pb + kb * CHUNK + j * 8 * SB);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+                if (warp == 0) try_issue(kb == KS - 1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + b);
+        }
+
+        if (P.nsplit == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = I * ST + wm * 32 + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = J * ST + wn * 64 + j * 8 + 2 * tig;
+                    if (row < P.L) {
+                        double* dst = P.s_out + (size_t)row * P.L + c;
+                        if (c < P.L) dst[0] = (P.accumulate ? dst[0] : 0.0) + acc[i][j][0];
+                        if (c + 1 < P.L) dst[1] = (P.accumulate ? dst[1] : 0.0) + acc[i][j][1];
+                    }
+                }
+            }
+        } else {
+            double* w = P.ws + ((size_t)t * P.nsplit + part) * ST * ST;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = wm * 32 + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = wn * 64 + j * 8 + 2 * tig;
+                    *reinterpret_cast<double2*>(w + (size_t)row * ST + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+            }
+        }
+    }
+}
+
+// sums the nsplit partial tiles of every output tile, in part order; grid (ntri, 8)
+__global__ void __launch_bounds__(256) pcq_syrk_fixup_kernel(SyrkParams P) {
+    const int t = blockIdx.x;
+    int I, J;
+    tile_decode(t, P.ntile, I, J);
+    const double* w = P.ws + (size_t)t * P.nsplit * ST * ST;
+    for (int e = blockIdx.y * 2048 + threadIdx.x; e < (blockIdx.y + 1) * 2048; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        const int row = I * ST + r, cc = J * ST + c;
+        if (row >= P.L || cc >= P.L) continue;
+        double sum = 0.0;
+        for (int q = 0; q < P.nsplit; ++q) sum += w[(size_t)q * ST * ST + e];
+        double* dst = P.s_out + (size_t)row * P.L + cc;
+        *dst = (P.accumulate ? *dst : 0.0) + sum;
+    }
+}
+
+// lower triangle <- upper triangle
+__global__ void __launch_bounds__(256) pcq_syrk_mirror_kernel(double* s, int L) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int row = bi * 32 + r, c = bj * 32 + tx;
+        tile[r][tx] = (row < L && c < L) ? s[(size_t)row * L + c] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int row = bj * 32 + r, c = bi * 32 + tx;
+        if (row < L && c < L && row > c) s[(size_t)row * L + c] = tile[tx][r];
+    }
+}
+
+// number of sample parts: fill the SMs in whole waves (time ~ ceil(ntri * S / G) / S), ties -> fewer parts
+int choose_split(int ntri, int grid, int64_t nstages) {
+    int best = 1;
+    double best_cost = 1e300;
+    const int smax = (int)(nstages < 16 ? nstages : 16);
+    for (int S = 1; S <= smax; ++S) {
+        const int64_t waves = ((int64_t)ntri * S + grid - 1) / grid;
+        // every part is ceil(nstages / S) stages at worst; a small per-unit term for the tile flush
+        const double cost = (double)waves * ((double)((nstages + S - 1) / S) + 0.5);
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = S; }
+    }
+    return best;
+}
+
+}  // namespace
+
+size_t pcq_syrk_smem_bytes() { return (size_t)NSTAGE * 2 * KS * CHUNK * sizeof(double) + 2 * NSTAGE * sizeof(uint64_t); }
+
+// S (+)= Z^T Z over n samples, generated from the plan (a == nullptr) or taken from a materialised A.
+// zbuf: lazily grown device scratch for the packed chunk; ws: workspace for the partial tiles.
+int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n, int64_t ldx,
+                    const double* a, int64_t lda, int kcols, const double* y, int64_t ldy, int m, double* s,
+                    int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes,
+                    cudaStream_t st, bool* handled) {
+    *handled = false;
+    const bool fused = (a == nullptr);
+    const int kb = fused ? p->nterms : kcols;
+    const int L = kb + m + 1;
+    const int ntile = (L + ST - 1) / ST;
+    const int Lp = ntile * ST;
+    const int ntri = ntile * (ntile + 1) / 2;
+    const size_t smem = pcq_syrk_smem_bytes();
+    size_t smem_pack = 0;
+    if (fused) smem_pack = (size_t)(p->nslots + m + 1) * 17 * sizeof(double);
+    if (smem > smem_optin || smem_pack > smem_optin || n <= 0) return PCQ_OK;
+    *handled = true;
+
+    const char* env = getenv("PCQ_SYRK_CHUNK_MB");
+    const int64_t target = (int64_t)(env ? atoi(env) : 2048) << 20;
+    int64_t rows = target / ((int64_t)Lp * 8);
+    rows = (rows / STAGE_SAMPLES) * STAGE_SAMPLES;
+    if (rows < STAGE_SAMPLES) rows = STAGE_SAMPLES;
+    const int64_t npad = (n + STAGE_SAMPLES - 1) / STAGE_SAMPLES * STAGE_SAMPLES;
+    if (rows > npad) rows = npad;
+    int rc = pcq_ensure_dev(zbuf, zbuf_bytes, (size_t)rows * Lp * sizeof(double));
+    if (rc != PCQ_OK) return rc;
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t nr = (n - r0 < rows) ? n - r0 : rows;
+        const int64_t nstages = (nr + STAGE_SAMPLES - 1) / STAGE_SAMPLES;
+        PackParams K;
+        memset(&K, 0, sizeof(K));
+        K.kb = kb; K.m = m; K.Lp = Lp; K.n = nr; K.npairs = nstages * (STAGE_SAMPLES / 16); K.zp = *zbuf;
+        K.y = y ? y + r0 * ldy : nullptr; K.ldy = ldy;
+        if (fused) {
+            K.x = x + r0 * ldx; K.ldx = ldx;
+            K.sdim = p->sdim; K.pmax = p->pmax; K.nslots = p->nslots; K.width = p->width;
+            K.rec_a = p->d_rec_a; K.rec_b = p->d_rec_b; K.p1 = p->d_p1; K.desc4 = p->d_desc4; K.descw = p->d_descw;
+            const int64_t cap = (int64_t)num_sms * 8;
+            const int grid = (int)(K.npairs < cap ? K.npairs : cap);
+            auto launch = [&](auto kern) -> int {
+                PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pack));
+                kern<<<grid, 256, smem_pack, st>>>(K);
+                return PCQ_OK;
+            };
+            switch (p->width <= 4 ? p->width : 0) {
+                case 1: rc = launch(pcq_pack_bases_kernel<1>); break;
+                case 2: rc = launch(pcq_pack_bases_kernel<2>); break;
+                case 3: rc = launch(pcq_pack_bases_kernel<3>); break;
+                case 4: rc = launch(pcq_pack_bases_kernel<4>); break;
+                default: rc = launch(pcq_pack_bases_kernel<0>); break;
+            }
+            if (rc != PCQ_OK) return rc;
+            PCQ_LAUNCH_CHECK("pcq_pack_bases_kernel");
+        } else {
+            K.a = a + r0 * lda; K.lda = lda;
+            const int64_t want = K.npairs * ((Lp + 255) / 256);
+            const int64_t cap = (int64_t)num_sms * 16;
+            pcq_pack_matrix_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(K);
+            PCQ_LAUNCH_CHECK("pcq_pack_matrix_kernel");
+        }
+
+        SyrkParams P;
+        memset(&P, 0, sizeof(P));
+        P.zp = *zbuf; P.Lp = Lp; P.L = L; P.ntile = ntile; P.ntri = ntri; P.nstages = nstages;
+        P.s_out = s; P.accumulate = (accumulate || r0 > 0) ? 1 : 0;
+        const char* senv = getenv("PCQ_SYRK_SPLIT");
+        P.nsplit = senv ? atoi(senv) : choose_split(ntri, num_sms, nstages);
+        if (P.nsplit < 1) P.nsplit = 1;
+        if (P.nsplit > nstages) P.nsplit = (int)nstages;
+        if (P.nsplit > 1) {
+            rc = pcq_ensure_dev(ws, ws_bytes, (size_t)ntri * P.nsplit * ST * ST * sizeof(double));
+            if (rc != PCQ_OK) return rc;
+            P.ws = *ws;
+        }
+        const int units = ntri * P.nsplit;
+        pcq_syrk_kernel<<<units < num_sms ? units : num_sms, SY_THREADS, smem, st>>>(P);
+        PCQ_LAUNCH_CHECK("pcq_syrk_kernel");
+        if (P.nsplit > 1) {
+            pcq_syrk_fixup_kernel<<<dim3(ntri, 8), 256, 0, st>>>(P);
+            PCQ_LAUNCH_CHECK("pcq_syrk_fixup_kernel");
+        }
+    }
+    const int nb32 = (L + 31) / 32;
+    pcq_syrk_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(s, L);
+    PCQ_LAUNCH_CHECK("pcq_syrk_mirror_kernel");
+    return PCQ_OK;
+}
