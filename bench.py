@@ -372,7 +372,7 @@ def main():
     peak = peaks.get("fp64_dmma_tflops")
     traffic = None
     try:   # DRAM bytes per step of the dominant kernel, from the committed ncu capture of this workload
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_g_k3_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_j_k3_traffic.json")))
         if n == N_PER_GPU:
             traffic = tj["dram_bytes_per_step_main_kernel"]
     except Exception:
@@ -417,10 +417,16 @@ def main():
         "breakdown_ms": {"k3_suffstats": k3_mean_ms, "allreduce": float(np.mean(ar_ms)),
                          "solve_kxk": 1e3 * float(np.mean(solve_s))},
         "max_abs_coef_error_vs_truth": err,
-        "roofline": {"bound": "tensor", "kernel": "pcq_gram_tma_kernel (K3: operands generated on chip from TMA-fed slot tables + DMMA SYRK; 13 L2-sized chunk launches per step)",
+        "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; 94.7 % of the step, the rest is "
+                               "pcq_pack_bases_kernel 4.1 %, fix-up/mirror 0.2 %, K x K solve 1 %; profiles/r01_j_k3_traffic.json)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if peak else None, "traffic": traffic,
-                     "traffic_note": "DRAM read+write bytes of the 13 chunk launches of one step (ncu, profiles/r01_g_k3_traffic.json); algorithmic input bytes = %d" % (8 * n * (D + 1)),
+                     "traffic_note": "DRAM read+write bytes of the 9 pcq_syrk_kernel launches of one step (ncu, "
+                                     "profiles/r01_j_k3_traffic.json): the packed design matrix (17.9 GB, written once by the "
+                                     "pack kernel) is read 1.43x; the kernel is tensor-pipe bound (DMMA pipe 97.5 %% active), "
+                                     "DRAM runs at ~0.2 TB/s; algorithmic input bytes = %d" % (8 * n * (D + 1)),
+                     "achieved_note": "algorithmic flops of one step / duration of the whole pcq_suffstats_dev call "
+                                      "(pack + SYRK + fix-up + mirror launches), CUDA events on the launching stream",
                      "algorithmic_flops_per_launch": flops,
                      "peak_source": "FP64 DMMA m8n8k4 register-chain micro-benchmark run live on this GPU "
                                     "(pcq_measure_peak); MEASURED_PEAKS.json has no FP64 figure"},

@@ -1,4 +1,7 @@
-// K3 / K4: sufficient statistics S = sum_n z_n z_n^T on the FP64 tensor pipe (DMMA) for sm_100a.
+// K3 / K4, fused-generator form: S = sum_n z_n z_n^T on the FP64 tensor pipe (DMMA) with the design
+// matrix generated on chip.  Since r01-j the DEFAULT path is pack + SYRK (pcq_syrk.cu, ~15 % faster);
+// this file is what runs with PCQ_GRAM_SYRK=0 -- it needs no scratch buffer for the packed chunk and
+// never writes a design-matrix element to HBM -- and for n == 0.
 //
 //   z_n = [ Psi(x_n) (K) | y_n (M) | 1 ],  L = K + M + 1
 //   S[:K,:K] = A^T A (anl.fita lreg/anl.py:78, bcs_fit lreg/bcs.py:84,95,100)
@@ -12,15 +15,14 @@
 //   tiles in between.  Partial tiles go to a workspace and are summed in CTA order by a
 //   fix-up kernel (deterministic, no atomics); a mirror kernel fills the lower triangle.
 // Per CTA (256 threads, 8 warps as 4 x 2, warp tile 32 x 64, 64 accumulators per thread): operand
-//   tiles [16 samples][128 columns] are GENERATED in shared memory (A is never written to HBM) as
-//   products of per-sample slot-table entries and contracted with mma.sync.m8n8k4.f64 (DMMA);
-//   generation of stage it+1 is interleaved into the DMMA stream of stage it.
-// Three kernels share this skeleton (dispatch in pcq_launch_gram):
-//   pcq_gram_tma_kernel   (K3, default)  slot tables precomputed per L2-sized sample chunk by
-//                         pcq_tables_kernel and fetched per stage with cp.async.bulk (TMA) + mbarrier
-//   pcq_gram_fused_kernel (K3 fallback, PCQ_GRAM_TMA=0)  tables rebuilt inside the DMMA warps
-//   pcq_gram_kernel       (K4: materialised A; and K3 with > 4 non-zero orders per term)  plain
-//                         generate / barrier / DMMA phases
+//   tiles [16 samples][128 columns] are GENERATED in shared memory as products of per-sample
+//   slot-table entries and contracted with mma.sync.m8n8k4.f64 (DMMA); generation of stage it+1 is
+//   interleaved into the DMMA stream of stage it.
+// Two kernels share this skeleton (dispatch in pcq_launch_gram):
+//   pcq_gram_tma_kernel   slot tables precomputed per L2-sized sample chunk by pcq_tables_kernel and
+//                         fetched per stage with cp.async.bulk (TMA) + mbarrier (<= 4 non-zero orders)
+//   pcq_gram_kernel       generic: any width, and a materialised A; plain generate / barrier / DMMA
+//                         phases
 #include "pcq_internal.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -32,7 +34,7 @@ constexpr int KT = 16;           // samples per pipeline stage
 constexpr int LDT = GT + 4;      // padded operand row: conflict-free DMMA fragment loads
 constexpr int G_THREADS = 256;
 constexpr int GRAM_SB = 64;      // samples per scheduling unit (multiple of KT)
-constexpr int XPF = 4;           // x values prefetched per thread per stage
+constexpr int XPF = 4;           // x values prefetched per thread per stage (pcq_gram_kernel)
 
 struct GramParams {
     const double* x; int64_t ldx;
@@ -336,291 +338,6 @@ int launch_gram_t(const GramParams& P0, int num_sms, size_t smem_optin, double**
     }
     return PCQ_OK;
 }
-
-
-// ------------------------------------------------------------------------------------------------
-// K3 v2: software-pipelined fused kernel.
-//   * every column of the augmented row z = [Psi | y | 1 | 0-padding] is a product of W table
-//     slots: y_m, the constant 1 and the zero padding are extra slots of the per-sample table, so
-//     operand generation is branch free;
-//   * the table is laid out [slot][sample] (stride TS = KT+1 doubles, conflict-free for the
-//     builder) so that, with the sample loop unrolled, every shared-memory address of the
-//     generator is register + immediate;
-//   * generation of stage it+1 is written inside the k-loop of the DMMA stage `it` (one basic
-//     block): its LDS/DMUL/STS issue in the slots between DMMAs instead of a separate phase;
-//   * stage it+2's tables are built and stage it+3's x/y values prefetched in the same iteration;
-//     one __syncthreads per stage.
-
-struct FusedSmem {
-    double* op;     // [2][2][KT][LDT]
-    double* tab;    // [2][NT][TS],  NT = nslots + M + 1
-    double* rec_a;  // (pmax+1) x s
-    double* rec_b;
-    double* p1;     // s
-};
-
-template <int W, int XPF, bool DIAG, int KT, bool BUILD>
-__device__ __forceinline__ void fused_segment(const GramParams& P, const FusedSmem& sm, int I, int J,
-                                              int64_t sbeg, int64_t send, double (&acc)[4][8][2],
-                                              const int (&pr)[XPF], const int (&pc)[XPF]) {
-    constexpr int TS = KT + 1;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int g = lane >> 2, tig = lane & 3;
-    const int wm = warp & 3, wn = warp >> 2;
-    const int half = tid >> 7, col = tid & 127;
-    const int s = P.sdim;
-    const int NT = P.nslots + P.m + 1;
-    const int ncol = s + P.m;             // prefetched values per sample: x dims then y columns
-    const int nst = (int)((send - sbeg + KT - 1) / KT);
-
-    // descriptor of this thread's generated column: W table offsets (in doubles)
-    const int gc = ((half == 0 || DIAG) ? I : J) * GT + col;
-    int off[W];
-#pragma unroll
-    for (int q = 0; q < W; ++q) off[q] = 0;
-    if (gc < P.kb) {
-        const unsigned long long d = P.desc4[gc];
-#pragma unroll
-        for (int q = 0; q < W; ++q) off[q] = (int)((d >> (16 * q)) & 0xffffull) * TS;
-    } else if (gc < P.kb + P.m) {
-        off[0] = (P.nslots + gc - P.kb) * TS;
-    } else if (gc > P.kb + P.m) {
-        off[0] = (P.nslots + P.m) * TS;   // the all-zero slot
-    }
-    const int rbase = DIAG ? half : 0;    // diagonal tiles: the two halves split the samples
-    const bool early = warp < 4;
-
-    auto load_pairs = [&](int st, double (&xr)[XPF]) {
-        const int64_t n0 = sbeg + (int64_t)st * KT;
-#pragma unroll
-        for (int j = 0; j < XPF; ++j) {
-            xr[j] = 0.0;
-            if (pr[j] >= 0 && n0 + pr[j] < send) {
-                const int64_t row = n0 + pr[j];
-                xr[j] = (pc[j] < s) ? P.x[row * P.ldx + pc[j]] : P.y[row * P.ldy + (pc[j] - s)];
-            }
-        }
-    };
-    auto build_one = [&](double* T, int r, int c, double v, bool live) {
-        if (c < s) {
-            if (c == 0) {
-                T[r] = live ? 1.0 : 0.0;                              // slot 0: the constant
-                T[(size_t)(P.nslots + P.m) * TS + r] = 0.0;           // zero slot
-            }
-            if (P.pmax >= 1) {
-                double pm = 1.0;
-                double pcur = __dmul_rn(v, sm.p1[c]);
-                T[(size_t)(1 + c) * TS + r] = live ? pcur : 0.0;
-                for (int nn = 1; nn < P.pmax; ++nn) {
-                    const double a = sm.rec_a[nn * s + c];
-                    const double b = sm.rec_b[nn * s + c];
-                    const double pn = __dadd_rn(__dmul_rn(__dmul_rn(a, v), pcur), __dmul_rn(b, pm));
-                    T[(size_t)(1 + nn * s + c) * TS + r] = live ? pn : 0.0;
-                    pm = pcur;
-                    pcur = pn;
-                }
-            }
-        } else {
-            T[(size_t)(P.nslots + c - s) * TS + r] = live ? v : 0.0;
-        }
-    };
-    auto build_tables = [&](int st, const double (&xr)[XPF]) {
-        double* T = sm.tab + (size_t)(st & 1) * NT * TS;
-        const int64_t n0 = sbeg + (int64_t)st * KT;
-#pragma unroll
-        for (int j = 0; j < XPF; ++j) {
-            if (pr[j] >= 0) build_one(T, pr[j], pc[j], xr[j], n0 + pr[j] < send);
-        }
-        // values beyond the prefetch registers (many outputs / many dimensions): direct loads
-        for (int idx = tid + XPF * G_THREADS; idx < KT * ncol; idx += G_THREADS) {
-            const int r = idx / ncol, c = idx - r * ncol;
-            const bool live = n0 + r < send;
-            double v = 0.0;
-            if (live) v = (c < s) ? P.x[(n0 + r) * P.ldx + c] : P.y[(n0 + r) * P.ldy + (c - s)];
-            build_one(T, r, c, v, live);
-        }
-    };
-    auto gen_value = [&](const double* Tn, int r) {
-        double v = Tn[off[0] + r];
-#pragma unroll
-        for (int q = 1; q < W; ++q) v = __dmul_rn(v, Tn[off[q] + r]);
-        return v;
-    };
-
-    __syncthreads();   // previous segment's readers are done with op / tab
-    double xr[XPF];
-    if (BUILD) {
-        load_pairs(0, xr);
-        build_tables(0, xr);
-        load_pairs(1, xr);
-        build_tables(1, xr);
-        load_pairs(2, xr);
-    }
-    __syncthreads();
-    {   // stage 0 operands (not overlapped)
-        const double* T0 = sm.tab + rbase;
-        double* o0 = sm.op + (size_t)((DIAG ? 0 : half) * KT) * LDT + col + rbase * LDT;
-#pragma unroll
-        for (int r = 0; r < KT; r += (DIAG ? 2 : 1)) o0[(size_t)r * LDT] = gen_value(T0, r);
-    }
-    __syncthreads();
-
-    for (int it = 0; it < nst; ++it) {
-        const int cur = it & 1, nxt = cur ^ 1;
-        // Table build = short dependent FP64 chains that queue behind DMMAs on the shared FP64 pipe.
-        // The two warps of a scheduler (w and w+4) do it at opposite ends of the stage, so that one
-        // of them is always streaming DMMAs (a single warp saturates the pipe).
-        if (BUILD && early) {
-            build_tables(it + 2, xr);      // writes tab[cur] (read by the previous iteration's generator)
-            load_pairs(it + 3, xr);
-        }
-        const double* Tn = sm.tab + (size_t)nxt * NT * TS + rbase;
-        double* on = sm.op + (size_t)nxt * 2 * KT * LDT + (size_t)((DIAG ? 0 : half) * KT) * LDT + col +
-                     rbase * LDT;
-        const double* oa = sm.op + (size_t)cur * 2 * KT * LDT;
-        const double* ob = oa + (DIAG ? 0 : KT * LDT);
-        const double* pa = oa + (size_t)tig * LDT + wm * 32 + g;
-        const double* pb = ob + (size_t)tig * LDT + wn * 64 + g;
-#pragma unroll
-        for (int kk = 0; kk < KT; kk += 4) {
-            double af[4], bf[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = pa[(size_t)kk * LDT + i * 8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = pb[(size_t)kk * LDT + j * 8];
-            // operands of the next stage: rows kk..kk+3 (off-diagonal) or two rows of this half
-            double gv[4];
-#pragma unroll
-            for (int q = 0; q < (DIAG ? 2 : 4); ++q) {
-                const int r = DIAG ? (kk + 2 * q) : (kk + q);
-                gv[q] = gen_value(Tn, r);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-#pragma unroll
-            for (int q = 0; q < (DIAG ? 2 : 4); ++q) {
-                const int r = DIAG ? (kk + 2 * q) : (kk + q);
-                on[(size_t)r * LDT] = gv[q];
-            }
-        }
-        if (BUILD && !early) {
-            build_tables(it + 2, xr);
-            load_pairs(it + 3, xr);
-        }
-        __syncthreads();
-    }
-}
-
-template <int W, int XPF, int KT>
-__global__ void __launch_bounds__(G_THREADS, 1) pcq_gram_fused_kernel(GramParams P) {
-    constexpr int TS = KT + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedSmem sm;
-    const int NT = P.nslots + P.m + 1;
-    sm.op = reinterpret_cast<double*>(smem_raw);
-    sm.tab = sm.op + 2 * 2 * KT * LDT;
-    sm.rec_a = sm.tab + (size_t)2 * NT * TS;
-    sm.rec_b = sm.rec_a + (P.pmax + 1) * P.sdim;
-    sm.p1 = sm.rec_b + (P.pmax + 1) * P.sdim;
-
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (P.pmax + 1) * P.sdim; i += G_THREADS) {
-        sm.rec_a[i] = P.rec_a[i];
-        sm.rec_b[i] = P.rec_b[i];
-    }
-    for (int i = tid; i < P.sdim; i += G_THREADS) sm.p1[i] = P.p1[i];
-
-    // (sample, column) pairs this thread builds every stage: fixed for the kernel's lifetime
-    const int ncol = P.sdim + P.m;
-    int pr[XPF], pc[XPF];
-#pragma unroll
-    for (int j = 0; j < XPF; ++j) {
-        const int idx = tid + j * G_THREADS;
-        pr[j] = -1; pc[j] = 0;
-        if (idx < KT * ncol) { pr[j] = idx / ncol; pc[j] = idx - pr[j] * ncol; }
-    }
-
-    const int lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, tig = lane & 3, wm = warp & 3, wn = warp >> 2;
-    const int64_t G = gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * P.total / G;
-    const int64_t hi = ((int64_t)blockIdx.x + 1) * P.total / G;
-    const int64_t first_tile = (hi > lo) ? lo / P.nblk : -1;
-
-    int64_t u = lo;
-    while (u < hi) {
-        const int64_t t = u / P.nblk;
-        const int64_t b0 = u - t * P.nblk;
-        const int64_t seg_end = min(hi, (t + 1) * P.nblk);
-        const int64_t nb = seg_end - u;
-        const int64_t sbeg = b0 * GRAM_SB;
-        const int64_t send = min(P.n, (b0 + nb) * GRAM_SB);
-        int I, J;
-        tile_decode(t, P.ntile, I, J);
-        double acc[4][8][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-        if (I == J) fused_segment<W, XPF, true, KT, true>(P, sm, I, J, sbeg, send, acc, pr, pc);
-        else fused_segment<W, XPF, false, KT, true>(P, sm, I, J, sbeg, send, acc, pr, pc);
-        flush_tile(P, acc, I, J, nb == P.nblk, (t == first_tile) ? 0 : 1, wm, wn, g, tig);
-        u = seg_end;
-    }
-}
-
-template <int W, int XPF, int KT>
-int launch_gram_fused(const GramParams& P0, int num_sms, size_t smem_optin, double** ws,
-                      size_t* ws_bytes, cudaStream_t st, bool* handled) {
-    constexpr int TS = KT + 1;
-    GramParams P = P0;
-    const int NT = P.nslots + P.m + 1;
-    const size_t smem = ((size_t)2 * 2 * KT * LDT + (size_t)2 * NT * TS + (size_t)2 * (P.pmax + 1) * P.sdim +
-                         P.sdim) * sizeof(double);
-    *handled = false;
-    if (smem > smem_optin) return PCQ_OK;     // caller falls back to the v1 kernel
-    *handled = true;
-    auto kern = pcq_gram_fused_kernel<W, XPF, KT>;
-    PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)(P.total < num_sms ? P.total : num_sms);
-    int rc = pcq_ensure_dev(ws, ws_bytes, (size_t)grid * 2 * GT * GT * sizeof(double));
-    if (rc != PCQ_OK) return rc;
-    P.ws = *ws;
-    kern<<<grid, G_THREADS, smem, st>>>(P);
-    PCQ_LAUNCH_CHECK("pcq_gram_fused_kernel");
-    const int ntri = P.ntile * (P.ntile + 1) / 2;
-    pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
-    PCQ_LAUNCH_CHECK("pcq_gram_fixup_kernel");
-    const int nb32 = (P.L + 31) / 32;
-    if (P.mirror) {
-        pcq_gram_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(P.s_out, P.L);
-        PCQ_LAUNCH_CHECK("pcq_gram_mirror_kernel");
-    }
-    return PCQ_OK;
-}
-
-template <int W>
-int launch_gram_fused_w(const GramParams& P, int num_sms, size_t smem_optin, double** ws,
-                        size_t* ws_bytes, cudaStream_t st, bool* handled) {
-    // 16 samples per stage by default; PCQ_GRAM_KT=32 selects the 32-sample variant (no faster: the
-    // barrier is not the limiter, profiles/r01_c)
-    const char* env = getenv("PCQ_GRAM_KT");
-    const int want = env ? atoi(env) : 16;
-    int rc = PCQ_OK;
-    *handled = false;
-    if (want >= 32) {
-        rc = launch_gram_fused<W, 4, 32>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
-        if (*handled || rc != PCQ_OK) return rc;
-    }
-    if (16 * (P.sdim + P.m) <= 2 * G_THREADS)
-        return launch_gram_fused<W, 2, 16>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
-    return launch_gram_fused<W, 4, 16>(P, num_sms, smem_optin, ws, ws_bytes, st, handled);
-}
-
 
 
 // ------------------------------------------------------------------------------------------------
@@ -928,23 +645,12 @@ static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const d
         bool handled = false;
         int rc = PCQ_OK;
         const int v1_only = getenv("PCQ_GRAM_V1") != nullptr;
-        const char* tmaenv = getenv("PCQ_GRAM_TMA");
-        if (!v1_only && !(tmaenv && atoi(tmaenv) == 0)) {
+        if (!v1_only) {
             switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
                 case 1: rc = launch_gram_tma<1>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
                 case 2: rc = launch_gram_tma<2>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
                 case 3: rc = launch_gram_tma<3>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
                 case 4: rc = launch_gram_tma<4>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                default: break;
-            }
-            if (handled || rc != PCQ_OK) return rc;
-        }
-        if (!v1_only) {
-            switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
-                case 1: rc = launch_gram_fused_w<1>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 2: rc = launch_gram_fused_w<2>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 3: rc = launch_gram_fused_w<3>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 4: rc = launch_gram_fused_w<4>(P, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
                 default: break;
             }
             if (handled || rc != PCQ_OK) return rc;
@@ -981,9 +687,7 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
         return launch_gram_once(p, num_sms, smem_optin, x, 0, ldx, a, lda, kcols, y, ldy, m, s, accumulate, 1,
                                 ws, ws_bytes, st);
     const bool fused = (a == nullptr);
-    const char* tmaenv = getenv("PCQ_GRAM_TMA");
-    const bool use_tma = fused && p->width <= PCQ_MAXW_FAST && !(tmaenv && atoi(tmaenv) == 0) &&
-                         getenv("PCQ_GRAM_V1") == nullptr;
+    const bool use_tma = fused && p->width <= PCQ_MAXW_FAST && getenv("PCQ_GRAM_V1") == nullptr;
     const int64_t row_bytes = use_tma ? (int64_t)tb_slots_even(p->nslots, m) * TB_TS * 8 / TB_KT
                                       : 8 * (int64_t)((fused ? p->sdim : kcols) + m);
     const char* env = getenv("PCQ_GRAM_CHUNK_MB");

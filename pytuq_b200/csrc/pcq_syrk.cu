@@ -14,10 +14,10 @@
 //          two k-step values of a column are adjacent (one LDS.128, conflict free).  The k index of
 //          mma.m8n8k4 is a summation index, so lane tig may feed samples (2 tig, 2 tig + 1) of a
 //          block in its two k-steps as long as both operands agree.
-//   syrk   (pcq_syrk_kernel)  one persistent CTA per SM: 8 consumer warps (4 x 2, warp tile 32 x 64,
-//          64 accumulators per thread) + 1 producer warp that keeps a 3-stage ring of
-//          (2 operands x 4 blocks x 8 KB) filled with cp.async.bulk (TMA) on mbarriers; consumers
-//          signal "empty" per warp, so there is no CTA-wide barrier anywhere in the main loop.
+//   syrk   (pcq_syrk_kernel)  one persistent CTA per SM: 8 warps (4 x 2, warp tile 32 x 64, 64
+//          accumulators per thread); warp 0 also keeps a 3-stage ring of (2 operands x 4 blocks x
+//          8 KB) filled with cp.async.bulk (TMA) on "full" mbarriers and every warp releases a stage
+//          on an "empty" mbarrier, so there is no CTA-wide barrier anywhere in the main loop.
 //          Work units are (sample part, upper-triangle tile), part-major, dealt round-robin: the
 //          number of parts S is chosen so that ntri * S fills the SMs in whole waves (105 tiles on
 //          148 SMs: S = 7 -> 4.97 waves), and CTAs of a wave sweep the same sample window at the same
@@ -38,6 +38,7 @@ constexpr int CHUNK = ST * SB;     // doubles per operand chunk (8 KB)
 constexpr int CONSUMER_WARPS = 8;
 constexpr int SY_THREADS = CONSUMER_WARPS * 32;
 constexpr int STAGE_SAMPLES = KS * SB;
+constexpr int PACK_TS = 18;        // slot-table row stride of the pack kernel
 
 struct SyrkParams {
     const double* zp;
@@ -103,8 +104,10 @@ __device__ __forceinline__ void tile_decode(int t, int ntile, int& I, int& J) {
 template <int W>
 __global__ void __launch_bounds__(256) pcq_pack_bases_kernel(PackParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int TS = 17;
-    double* T = reinterpret_cast<double*>(smem_raw);     // [nslots + m + 1][17]: 1, phi..., y..., 0
+    // [nslots + m + 1][18]: 1, phi..., y..., 0.  Row stride 18: sample pairs are 16-byte aligned
+    // (LDS.128) and eight consecutive slots fall into distinct bank groups.
+    constexpr int TS = PACK_TS;
+    double* T = reinterpret_cast<double*>(smem_raw);
     const int s = P.sdim, tid = threadIdx.x;
     const int nrow = P.nslots + P.m + 1;
     const int zero_slot = P.nslots + P.m;
@@ -112,9 +115,10 @@ __global__ void __launch_bounds__(256) pcq_pack_bases_kernel(PackParams P) {
     for (int64_t pair = blockIdx.x; pair < P.npairs; pair += gridDim.x) {
         const int64_t n0 = pair * 16;
         __syncthreads();
-        if (n0 + 16 > P.n)      // ragged tail: dead samples must contribute exact zeros
+        if (n0 + 16 > P.n) {     // ragged tail: dead samples must contribute exact zeros
             for (int i = tid; i < zero_slot * TS; i += 256) T[i] = 0.0;
-        if (n0 + 16 > P.n) __syncthreads();
+            __syncthreads();
+        }
         for (int idx = tid; idx < 16 * s; idx += 256) {
             const int sm = idx / s, c = idx - sm * s;
             const int64_t n = n0 + sm;
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(256) pcq_pack_bases_kernel(PackParams P) {
         __syncthreads();
         double* out = P.zp + (size_t)pair * 2 * P.Lp * SB;
         for (int col = tid; col < P.Lp; col += 256) {
-            double v[16];
+            double2 v[8];
             if (col < P.kb) {
                 if (W > 0) {
                     const unsigned long long d = P.desc4[col];
@@ -138,32 +142,40 @@ __global__ void __launch_bounds__(256) pcq_pack_bases_kernel(PackParams P) {
 #pragma unroll
                     for (int q = 0; q < W; ++q) off[q] = (int)((d >> (16 * q)) & 0xffffull) * TS;
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        double t = T[off[0] + r];
+                    for (int r = 0; r < 8; ++r) {
+                        double2 t = *reinterpret_cast<const double2*>(T + off[0] + 2 * r);
 #pragma unroll
-                        for (int q = 1; q < W; ++q) t = __dmul_rn(t, T[off[q] + r]);
+                        for (int q = 1; q < W; ++q) {
+                            const double2 f = *reinterpret_cast<const double2*>(T + off[q] + 2 * r);
+                            t.x = __dmul_rn(t.x, f.x);
+                            t.y = __dmul_rn(t.y, f.y);
+                        }
                         v[r] = t;
                     }
                 } else {
                     const uint16_t* dw = P.descw + (size_t)col * P.width;
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) v[r] = T[(int)dw[0] * TS + r];
+                    for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const double2*>(T + (int)dw[0] * TS + 2 * r);
                     for (int q = 1; q < P.width; ++q) {
                         const int o = (int)dw[q] * TS;
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) v[r] = __dmul_rn(v[r], T[o + r]);
+                        for (int r = 0; r < 8; ++r) {
+                            const double2 f = *reinterpret_cast<const double2*>(T + o + 2 * r);
+                            v[r].x = __dmul_rn(v[r].x, f.x);
+                            v[r].y = __dmul_rn(v[r].y, f.y);
+                        }
                     }
                 }
             } else {
                 const int slot = col < P.kb + P.m ? P.nslots + (col - P.kb) : (col == P.kb + P.m ? 0 : zero_slot);
 #pragma unroll
-                for (int r = 0; r < 16; ++r) v[r] = T[slot * TS + r];
+                for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const double2*>(T + slot * TS + 2 * r);
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 double2* dst = reinterpret_cast<double2*>(out + ((size_t)h * P.Lp + col) * SB);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) dst[r] = make_double2(v[h * 8 + 2 * r], v[h * 8 + 2 * r + 1]);
+                for (int r = 0; r < 4; ++r) __stcs(dst + r, v[h * 4 + r]);
             }
         }
     }
@@ -415,7 +427,7 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
     const int ntri = ntile * (ntile + 1) / 2;
     const size_t smem = pcq_syrk_smem_bytes();
     size_t smem_pack = 0;
-    if (fused) smem_pack = (size_t)(p->nslots + m + 1) * 17 * sizeof(double);
+    if (fused) smem_pack = (size_t)(p->nslots + m + 1) * PACK_TS * sizeof(double);
     if (smem > smem_optin || smem_pack > smem_optin || n <= 0) return PCQ_OK;
     *handled = true;
 
