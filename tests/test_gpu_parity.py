@@ -231,6 +231,51 @@ def test_k4_gram_of_materialised_matrix():
         assert rel_err(st.S, ref) < 1e-12, (n, K, M)
 
 
+def test_k3_k4_syrk_chunks_splits_and_fused_fallback(monkeypatch):
+    """The pack + SYRK path under forced chunking (accumulation across chunk launches), forced numbers of
+    sample parts (direct flush vs workspace + fix-up), and the fused-generator path (PCQ_GRAM_SYRK=0):
+    all must agree with the oracle."""
+    import torch
+    from pytuq_b200 import _native
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(77)
+    d, p, n, M = 6, 3, 9001, 2            # K = 84 -> one tile; n is not a multiple of 8/16/32
+    mi = orc.get_mi(p, d)
+    x = rng.standard_normal((n, d))
+    Y = rng.standard_normal((n, M))
+    pc = PCRV(1, d, "HG", mi=mi)
+    ref = orc.suffstats(orc.eval_bases(x, mi, "HG"), Y)
+    d2, n2 = 12, 2111                      # K = 455 -> 4 tiles (10 upper-triangle tiles)
+    mi2 = orc.get_mi(3, d2)
+    x2 = rng.uniform(-1, 1, (n2, d2))
+    y2 = rng.standard_normal(n2)
+    pc2 = PCRV(1, d2, "LU", mi=mi2)
+    ref2 = orc.suffstats(orc.eval_bases(x2, mi2, "LU"), y2)
+    for env in ({}, {"PCQ_SYRK_CHUNK_MB": "1"}, {"PCQ_SYRK_SPLIT": "1"}, {"PCQ_SYRK_SPLIT": "5"},
+                {"PCQ_SYRK_CHUNK_MB": "1", "PCQ_SYRK_SPLIT": "3"}, {"PCQ_GRAM_SYRK": "0"},
+                {"PCQ_GRAM_SYRK": "0", "PCQ_GRAM_V1": "1"}):
+        for k in ("PCQ_SYRK_CHUNK_MB", "PCQ_SYRK_SPLIT", "PCQ_GRAM_SYRK", "PCQ_GRAM_V1"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        st = pc.suffStats(x, Y, 0)
+        assert rel_err(st.S, ref) < 1e-12, env
+        assert np.array_equal(st.S, st.S.T), env
+        st2 = pc2.suffStats(x2, y2, 0)
+        assert rel_err(st2.S, ref2) < 1e-12, env
+        # K4 from a device matrix with an odd leading dimension and an offset y column
+        A = rng.standard_normal((700, 131))
+        buf = torch.zeros((700, 137), dtype=torch.float64, device="cuda")
+        buf[:, :131] = torch.from_numpy(A).cuda()
+        yb = torch.from_numpy(rng.standard_normal((700, 3))).cuda()
+        L = 131 + 1 + 1
+        sd = torch.full((L, L), np.nan, dtype=torch.float64, device="cuda")
+        _native.check(_native.lib().pcq_gram_dev(0, buf.data_ptr(), 700, 137, 131, yb[:, 1:].data_ptr(), 3, 1,
+                                                 sd.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert rel_err(sd.cpu().numpy(), orc.suffstats(A, yb[:, 1].cpu().numpy())) < 1e-12, env
+
+
 # ----------------------------------------------------------------------------- K5
 def test_k5_germ_stream_and_propagation():
     import torch
