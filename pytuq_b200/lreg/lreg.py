@@ -32,12 +32,17 @@ class PCBasisEvaluator:
         return pars[0].evalBases(x, self.jdim)
 
 
-def _scaled_pivots_ok(diagG, diagL):
-    # cond of the equilibrated G well below 1e12: pivots L_ii / sqrt(G_ii) stay away from 0
-    return bool((diagL.abs() / diagG.sqrt()).min() > 1.0e-6)
+def _scaled_pivots_ok(diagG, diagL, tol=1.0e-6):
+    # cond of the equilibrated G well below 1/tol^2: pivots L_ii / sqrt(G_ii) stay away from 0
+    return bool((diagL.abs() / diagG.sqrt()).min() > tol)
 
 
-def solve_normal_device(G_t, B_t):
+def _current_device():
+    from .. import device as _device
+    return _device.current_device()
+
+
+def solve_normal_device(G_t, B_t, pivot_tol=1.0e-6):
     """Cholesky solve of G C = B on the GPU (torch tensors, float64).  The K x K factorisation is not
     sample-parallel; it is a plain library call (cuSOLVER potrf/potrs through
     torch.linalg), kept on the device so that only K coefficients travel back to the host.
@@ -47,7 +52,7 @@ def solve_normal_device(G_t, B_t):
     if not bool(torch.all(diag > 0.0)):
         return None
     L, info = torch.linalg.cholesky_ex(G_t)
-    if int(info) != 0 or not _scaled_pivots_ok(diag, torch.diagonal(L)):
+    if int(info) != 0 or not _scaled_pivots_ok(diag, torch.diagonal(L), pivot_tol):
         return None
     C = torch.cholesky_solve(B_t if B_t.ndim == 2 else B_t[:, None], L)
     if not bool(torch.all(torch.isfinite(C))):
@@ -212,22 +217,82 @@ class lreg(fitbase):
 
 class lsq(lreg):
     """Least squares.  The reference solves min ||A c - y|| with an SVD of the N x K matrix
-    (scipy gelsd, lreg/lreg.py:328-339); here the sample axis is reduced on the GPU and the
-    K x K normal equations are solved, which agrees to ~1e-14 for the well-conditioned
-    bases of the PC path (cond(G) ~ 10..100)."""
+    (scipy gelsd, cond=1e-13, lreg/lreg.py:328-339).  Here the sample axis is reduced on the GPU:
 
-    def __init__(self):
+    * well-conditioned systems (every PC basis sampled from its own measure: cond(G) ~ 10..100) go through
+      the sufficient statistics (K3/K4) and a Cholesky solve of the K x K normal equations, which agrees
+      with the SVD solution to ~1e-14;
+    * when N < 4 K, or the scaled Cholesky pivots say cond(G) is beyond ~1e6, the fit switches to the QR
+      statistic (``tsqr``): same singular values as A and the same truncated minimum-norm solution as the
+      reference, for square, underdetermined, nearly collinear and rank-deficient systems.
+
+    ``solver`` ('auto' | 'gram' | 'qr') is an extension of the reference's argument-free constructor."""
+
+    def __init__(self, solver='auto'):
         super().__init__()
+        assert solver in ('auto', 'gram', 'qr')
+        self.solver = solver
+        self.rank = None
 
-    def _fit_stats(self, stats):
-        K = stats.K
-        cf = None
-        sysdev = stats.dev_system()
-        if sysdev is not None:             # statistics still on the device: solve there, bring back K doubles
-            C = solve_normal_device(sysdev[0], sysdev[1][:, 0])
-            if C is not None:
-                cf = C.cpu().numpy()
-        self.cf = cf if cf is not None else solve_normal(stats.G, stats.b(0))
+    def _finish(self, cf):
+        K = cf.shape[0]
+        self.cf = cf
         self.cf_cov = np.zeros((K, K))
         self.fitted = True
         self.used = np.arange(K)
+
+    def _try_gram(self, stats, strict):
+        """Cholesky of the normal equations on the device; False when G is not comfortably positive
+        definite (strict: pivot test at 1e-3, i.e. cond(G) ~ 1e6, so that the answer matches the SVD
+        solution to ~1e-10)."""
+        sysdev = stats.dev_system()
+        if sysdev is None:
+            import torch
+            if not torch.cuda.is_available():
+                return False
+            dev = torch.device("cuda", _current_device())
+            sysdev = (torch.from_numpy(np.ascontiguousarray(stats.G)).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(stats.B())).to(dev))
+        C = solve_normal_device(sysdev[0], sysdev[1][:, 0], 1.0e-3 if strict else 1.0e-6)
+        if C is None:
+            return False
+        self._finish(C.cpu().numpy())
+        self.rank = stats.K
+        return True
+
+    def _fit_r(self, R, K):
+        from . import tsqr
+        C, _, rank = tsqr.lstsq_from_r(R, K)
+        self._finish(np.ascontiguousarray(C[:, 0]))
+        self.rank = rank
+
+    def _fit_stats(self, stats):
+        if not self._try_gram(stats, strict=False):
+            self._finish(solve_normal(stats.G, stats.b(0)))
+
+    def fit(self, x, y):
+        assert(self.basisEvaluatorSet)
+        if not isinstance(self.basisEval, PCBasisEvaluator):
+            return self.fita(self.basisEval(x, self.basisEvalPars), y)
+        from . import tsqr
+        pc, jdim = self.basisEvalPars[0], self.basisEval.jdim
+        K = pc.mindices[jdim].shape[0]
+        N = np.shape(x)[0]
+        if self.solver != 'qr' and (self.solver == 'gram' or N >= 4 * K):
+            stats = SuffStats.from_pc(pc, x, y, jdim)
+            if self._try_gram(stats, strict=self.solver == 'auto'):
+                return
+            if self.solver == 'gram':
+                return self._fit_stats(stats)
+        self._fit_r(tsqr.r_factor_pc(pc, x, y, jdim), K)
+
+    def fita(self, Amat, y):
+        from . import tsqr
+        N, K = np.shape(Amat)
+        if self.solver != 'qr' and (self.solver == 'gram' or N >= 4 * K):
+            stats = SuffStats.from_matrix(Amat, y)
+            if self._try_gram(stats, strict=self.solver == 'auto'):
+                return
+            if self.solver == 'gram':
+                return self._fit_stats(stats)
+        self._fit_r(tsqr.r_factor_matrix(Amat, y), K)

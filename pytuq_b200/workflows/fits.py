@@ -36,16 +36,25 @@ def pc_fit(x, y, order=3, pctype='LU', method='anl', **kwargs):
     pcrv = PCRV(nout, ndim, pctype, mi=mindex)
 
     # one pass over the samples for all outputs
-    stats = SuffStats.from_pc(pcrv, x, y, 0)
-
-    # lsq: all outputs share G -> one batched Cholesky solve on the device for the K x M block
-    batched = None
-    if method == 'lsq' and stats.dev_system() is not None:
+    K = mindex.shape[0]
+    batched, stats = None, None
+    if method == 'lsq':
+        # all outputs share the design matrix -> one batched solve on the device for the K x M block:
+        # Cholesky of the shared Gram when the system is tall and well conditioned, else the QR statistic
+        # (same switch as lsq.fit)
         from ..lreg.lreg import solve_normal_device
-        G_t, B_t = stats.dev_system()
-        C = solve_normal_device(G_t, B_t)
-        if C is not None:
-            batched = C.cpu().numpy()
+        from ..lreg import tsqr
+        if nsam >= 4 * K:
+            stats = SuffStats.from_pc(pcrv, x, y, 0)
+            if stats.dev_system() is not None:
+                G_t, B_t = stats.dev_system()
+                C = solve_normal_device(G_t, B_t, 1.0e-3)
+                if C is not None:
+                    batched = C.cpu().numpy()
+        if batched is None:
+            batched = tsqr.lstsq_from_r(tsqr.r_factor_pc(pcrv, x, y, 0), K)[0]
+    else:
+        stats = SuffStats.from_pc(pcrv, x, y, 0)
 
     mindices_list, cfs_list, lregs = [], [], []
     for iout in range(nout):

@@ -42,8 +42,39 @@ def germ(rng, fam, shape):
     return rng.uniform(-1, 1, shape) if fam in ("LU", "nLU") else rng.standard_normal(shape)
 
 
+def illcond(R):
+    """lsq on ill-conditioned / square / underdetermined / rank-deficient systems: the cases where the
+    reference's SVD least squares (scipy gelsd, cond=1e-13, lreg/lreg.py:335) and a normal-equation solve
+    part ways.  Written to lsq_illcond.npz."""
+    PCRV, get_mi = R["PCRV"], R["get_mi"]
+    out = {}
+
+    def case(name, pctype, mi, x, y):
+        pc = PCRV(1, x.shape[1], pctype, mi=mi)
+        A = pc.evalBases(x, 0)
+        l = R["lsq"](); l.fita(A, y)
+        sv = np.linalg.svd(A, compute_uv=False)
+        out[f"{name}__x"] = x; out[f"{name}__y"] = y; out[f"{name}__mi"] = mi
+        out[f"{name}__type"] = np.array(pctype); out[f"{name}__lsq_cf"] = l.cf; out[f"{name}__sv"] = sv
+        print(f"  {name}: N={x.shape[0]} K={mi.shape[0]} cond={sv[0] / max(sv[-1], 1e-300):.3g}")
+
+    rng = np.random.default_rng(41)
+    f = lambda x: np.cos(1.0 + x @ (1.0 / (1.0 + np.arange(x.shape[1])) ** 2)) + 0.1 * x[:, 0] ** 3
+    mi = get_mi(4, 4)                                    # K = 70
+    x = rng.uniform(-1, 1, (70, 4));  case("square_lu_d4p4", "LU", mi, x, f(x))
+    x = rng.uniform(-1, 1, (40, 4));  case("under_lu_d4p4", "LU", mi, x, f(x))
+    mi = get_mi(5, 3)                                    # K = 56, narrow germ: nearly collinear columns
+    x = 0.05 * rng.standard_normal((300, 3));  case("collinear_hg_d3p5", "HG", mi, x, f(x))
+    mi = np.vstack([get_mi(2, 3), get_mi(2, 3)[3:5]])    # two duplicated columns: rank deficient
+    x = rng.uniform(-1, 1, (200, 3));  case("rankdef_lu_d3p2", "LU", mi, x, f(x) + 1e-3 * rng.standard_normal(200))
+    np.savez_compressed(os.path.join(HERE, "lsq_illcond.npz"), **out)
+    print(f"lsq_illcond.npz  {os.path.getsize(os.path.join(HERE, 'lsq_illcond.npz')) / 1024:.1f} KiB")
+
+
 def main():
     R = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "illcond":
+        return illcond(R)
     PCRV, PC1d, get_mi = R["PCRV"], R["PC1d"], R["get_mi"]
     out = {}
 
@@ -195,6 +226,7 @@ def main():
     for f in ("pc1d", "mindex", "pcrv_cases", "fits", "workflow"):
         p = os.path.join(HERE, f + ".npz")
         print(f"{f}.npz  {os.path.getsize(p) / 1024:.1f} KiB")
+    illcond(R)
 
 
 if __name__ == "__main__":

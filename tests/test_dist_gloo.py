@@ -52,6 +52,15 @@ def _worker(rank, world, port, out):
         gathered = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)
         assert all(torch.equal(g, gathered[0]) for g in gathered)
+        # QR statistic (8(f2)): R factors of the row shards combine to the R factor of the whole matrix
+        from pytuq_b200.lreg import tsqr
+        Z = torch.from_numpy(np.hstack([A, Y[:, :1]]))
+        R = tsqr.allgather_r(torch.linalg.qr(Z[lo:hi], mode="r").R)
+        Rf = torch.linalg.qr(Z, mode="r").R
+        np.testing.assert_allclose((R.T @ R).numpy(), (Rf.T @ Rf).numpy(), rtol=1e-12, atol=1e-10)
+        cq, sv, rank_ = tsqr.lstsq_from_r(R, mi.shape[0])
+        np.testing.assert_allclose(cq[:, 0], ref, rtol=1e-10, atol=1e-12)
+        assert rank_ == mi.shape[0]
         out.put((rank, "ok"))
     except Exception as e:   # pragma: no cover
         out.put((rank, repr(e)))

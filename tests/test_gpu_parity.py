@@ -396,6 +396,65 @@ def test_fitters_vs_reference(fit_cases):
         assert l.predict(c["xt"])[1] is None
 
 
+def test_lsq_qr_route_on_illconditioned_systems():
+    """8(f2): where the normal equations cannot follow the reference's SVD least squares, lsq switches to the
+    QR statistic.  Golden coefficients come from the unmodified reference (tests/golden/lsq_illcond.npz)."""
+    from conftest import load_golden, golden_cases
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import lsq, PCBasisEvaluator
+    for name, c in golden_cases(load_golden("lsq_illcond")).items():
+        fam, mi, x, y = str(c["type"]), c["mi"], c["x"], c["y"]
+        pc = PCRV(1, x.shape[1], fam, mi=mi)
+        A = pc.evalBases(x, 0)
+        ref = c["lsq_cf"]
+        for route in ("fit", "fita"):
+            f = lsq()
+            if route == "fit":
+                f.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+                f.fit(x, y)
+            else:
+                f.fita(A, y)
+            scale = np.abs(y).max()
+            # same fitted values as the reference (the minimum-norm solution is what makes them unique)
+            assert np.max(np.abs(A @ f.cf - A @ ref)) < 1e-7 * scale, (name, route)
+            if name == "collinear_hg_d3p5":      # cond(A) = 2.5e8: forward error of any stable solver ~ cond * eps
+                assert rel_err(f.cf, ref) < 1e-4, (name, route)
+            else:
+                assert rel_err(f.cf, ref) < 1e-8, (name, route, rel_err(f.cf, ref))
+            expect_rank = {"rankdef_lu_d3p2": 10, "under_lu_d4p4": 40}.get(name, mi.shape[0])
+            assert f.rank == expect_rank, (name, route, f.rank)
+            assert f.cf_cov.shape == (mi.shape[0],) * 2 and not f.cf_cov.any()
+    # chunked R accumulation equals the one-shot factorisation (forced tiny chunks), M = 2
+    from pytuq_b200.lreg import tsqr
+    rng = np.random.default_rng(3)
+    mi = orc.get_mi(3, 4)
+    x = rng.uniform(-1, 1, (1500, 4))
+    Y = rng.standard_normal((1500, 2))
+    pc = PCRV(1, 4, "LU", mi=mi)
+    R1 = tsqr.r_factor_pc(pc, x, Y, 0).cpu().numpy()
+    R2 = tsqr.r_factor_pc(pc, x, Y, 0, chunk_bytes=8 * 37 * 100).cpu().numpy()
+    assert rel_err(R2.T @ R2, R1.T @ R1) < 1e-12
+    Z = np.hstack([orc.eval_bases(x, mi, "LU"), Y])
+    assert rel_err(R1.T @ R1, Z.T @ Z) < 1e-12
+    C, sv, rank = tsqr.lstsq_from_r(tsqr.r_factor_pc(pc, x, Y, 0), mi.shape[0])
+    assert rank == 35 and rel_err(C, np.linalg.lstsq(Z[:, :35], Y, rcond=None)[0]) < 1e-11
+    # a well-conditioned tall problem still takes the Gram route and agrees with the QR route
+    g, q = lsq(), lsq(solver="qr")
+    for f in (g, q):
+        f.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+        f.fit(x, Y[:, 0])
+    assert rel_err(g.cf, q.cf) < 1e-12
+    # pc_fit(lsq) with fewer than 4 K samples: one batched QR solve for all outputs
+    import io, contextlib
+    from pytuq_b200.workflows.fits import pc_fit
+    xs, Ys = x[:90], np.stack([np.sin(x[:90, 0]) + x[:90, 1] * x[:90, 2], np.exp(0.3 * x[:90, 3])], axis=1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        pcf, regs = pc_fit(xs, Ys, order=3, pctype="LU", method="lsq")
+    As = orc.eval_bases(xs, mi, "LU")
+    for j in range(2):
+        assert rel_err(regs[j].cf, orc.lsq_fit(As, Ys[:, j])) < 1e-9
+
+
 def test_pc_fit_workflow_vs_reference():
     import contextlib, io
     from pytuq_b200.workflows.fits import pc_fit

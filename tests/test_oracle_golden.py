@@ -114,6 +114,22 @@ def test_fitters_match_reference(fit_cases):
             np.testing.assert_allclose(Sig, c[f"{tag}_cov"], rtol=1e-10, atol=1e-20)
 
 
+def test_lsq_on_illconditioned_systems_matches_reference():
+    """Square, underdetermined, nearly collinear and rank-deficient systems (lsq_illcond.npz, generated from the
+    unmodified reference): the oracle's gelsd restatement reproduces the reference's coefficients."""
+    from conftest import load_golden, golden_cases
+    cases = golden_cases(load_golden("lsq_illcond"))
+    assert set(cases) == {"square_lu_d4p4", "under_lu_d4p4", "collinear_hg_d3p5", "rankdef_lu_d3p2"}
+    for name, c in cases.items():
+        A = orc.eval_bases(c["x"], c["mi"], str(c["type"]))
+        np.testing.assert_allclose(np.linalg.svd(A, compute_uv=False), c["sv"], rtol=1e-9, atol=1e-12 * c["sv"][0])
+        cf = orc.lsq_fit(A, c["y"])
+        # two runs of the same LAPACK driver on bit-identical A: equal up to threading effects
+        np.testing.assert_allclose(A @ cf, A @ c["lsq_cf"], rtol=0, atol=1e-9 * np.abs(c["y"]).max(), err_msg=name)
+        if name != "collinear_hg_d3p5":
+            np.testing.assert_allclose(cf, c["lsq_cf"], rtol=1e-8, atol=1e-10, err_msg=name)
+
+
 def test_philox_known_answer():
     # Random123 known-answer test: counter = key = 0 and the all-ones / pi vectors
     out = orc.philox4x32_10((0, 0, 0, 0), (0, 0))
