@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <set>
 #include <thread>
@@ -227,7 +228,7 @@ int pcq_plan_destroy(pcq_plan* p) {
     pcq_spec_free(p->spec[0]);
     pcq_spec_free(p->spec[1]);
     cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
-    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_tabs);
+    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc);
     for (int i = 0; i < 2; ++i) {
         cudaFree(p->d_stage[i]); cudaFree(p->d_out[i]);
         if (p->h_pin[i]) cudaFreeHost(p->h_pin[i]);
@@ -284,6 +285,30 @@ int pcq_eval_pc_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const 
     return pcq_launch_evalpc(p, x, n, ldx, cf, m, y, ldy, mode, (cudaStream_t)stream);
 }
 
+namespace {
+// The packed chunk of the pack + SYRK path can be 2 GB: it is ONE lazily grown buffer per device, shared by
+// all plans and by K4, not a per-plan allocation.  A lease serialises the enqueueing host threads and orders
+// the streams that use the buffer one after the other with an event.
+struct DevScratch {
+    std::mutex mu;
+    double* zp = nullptr; size_t zp_bytes = 0;
+    cudaEvent_t last = nullptr; cudaStream_t last_stream = nullptr; bool used = false;
+};
+DevScratch g_scratch[64];
+struct ScratchLease {
+    DevScratch& d; cudaStream_t st;
+    ScratchLease(int device, cudaStream_t stream) : d(g_scratch[device & 63]), st(stream) {
+        d.mu.lock();
+        if (d.used && d.last_stream != st) cudaStreamWaitEvent(st, d.last, 0);
+    }
+    ~ScratchLease() {
+        if (!d.last) cudaEventCreateWithFlags(&d.last, cudaEventDisableTiming);
+        if (d.last) { cudaEventRecord(d.last, st); d.last_stream = st; d.used = true; }
+        d.mu.unlock();
+    }
+};
+}  // namespace
+
 int64_t pcq_suffstats_dim(const pcq_plan* p, int m) {
     if (!p || m < 0) return PCQ_ERR_ARG;
     return (int64_t)p->nterms + m + 1;
@@ -297,13 +322,14 @@ int pcq_suffstats_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, cons
         return PCQ_ERR_ARG;
     }
     DeviceGuard guard(p->device);
+    ScratchLease lease(p->device, (cudaStream_t)stream);
     return pcq_launch_gram(p, p->num_sms, p->smem_optin, x, n, ldx, nullptr, 0, 0, y, ldy, m, s,
-                           accumulate, &p->d_ws, &p->ws_bytes, &p->d_tabs, &p->tabs_bytes, (cudaStream_t)stream);
+                           accumulate, &p->d_ws, &p->ws_bytes, &lease.d.zp, &lease.d.zp_bytes, (cudaStream_t)stream);
 }
 
 namespace {
 // K4 has no plan: keep one workspace per device
-struct GramCtx { double* ws = nullptr; size_t ws_bytes = 0; double* zp = nullptr; size_t zp_bytes = 0; double* stage[2] = {nullptr, nullptr};
+struct GramCtx { double* ws = nullptr; size_t ws_bytes = 0; double* stage[2] = {nullptr, nullptr};
                  size_t stage_bytes[2] = {0, 0}; double* s = nullptr; size_t s_bytes = 0;
                  double* ys[2] = {nullptr, nullptr}; size_t ys_bytes[2] = {0, 0}; };
 GramCtx g_gram_ctx[64];
@@ -322,8 +348,9 @@ int pcq_gram_dev(int device, const double* a, int64_t n, int64_t lda, int kcols,
     int rc = device_props(device, &num_sms, &smem_optin);
     if (rc != PCQ_OK) return rc;
     GramCtx& c = g_gram_ctx[device];
+    ScratchLease lease(device, (cudaStream_t)stream);     // also guards the per-device K4 workspace
     return pcq_launch_gram(nullptr, num_sms, smem_optin, nullptr, n, 0, a, lda, kcols, y, ldy, m, s,
-                           accumulate, &c.ws, &c.ws_bytes, &c.zp, &c.zp_bytes, (cudaStream_t)stream);
+                           accumulate, &c.ws, &c.ws_bytes, &lease.d.zp, &lease.d.zp_bytes, (cudaStream_t)stream);
 }
 
 int pcq_propagate_dev(pcq_plan* p, uint64_t seed, int64_t first_index, int64_t n,
@@ -463,9 +490,10 @@ int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const do
     // copies go on stream 1 / 0 alternately, all Gram launches are ordered on stream 0 through
     // events (they accumulate into the same S)
     cudaStream_t sk = p->streams[0];
+    ScratchLease lease(p->device, sk);
     if (n == 0) {
         if ((rc = pcq_launch_gram(p, p->num_sms, p->smem_optin, nullptr, 0, s, nullptr, 0, 0, nullptr,
-                                  std::max(m, 1), m, p->d_misc, 0, &p->d_ws, &p->ws_bytes, &p->d_tabs, &p->tabs_bytes, sk)) != PCQ_OK)
+                                  std::max(m, 1), m, p->d_misc, 0, &p->d_ws, &p->ws_bytes, &lease.d.zp, &lease.d.zp_bytes, sk)) != PCQ_OK)
             return rc;
     }
     const int64_t rows = chunk_rows((int64_t)(s + m) * 8, n);
@@ -487,7 +515,7 @@ int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const do
         PCQ_CUDA(cudaEventDestroy(copied));
         if ((rc = pcq_launch_gram(p, p->num_sms, p->smem_optin, p->d_stage[b], nr, s, nullptr, 0, 0,
                                   p->d_out[b], std::max(m, 1), m, p->d_misc, c > 0, &p->d_ws,
-                                  &p->ws_bytes, &p->d_tabs, &p->tabs_bytes, sk)) != PCQ_OK)
+                                  &p->ws_bytes, &lease.d.zp, &lease.d.zp_bytes, sk)) != PCQ_OK)
             return rc;
         PCQ_CUDA(cudaEventRecord(p->events[b], sk));
     }

@@ -569,8 +569,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) pcq_gram_tma_kernel(GramParams P
 }
 
 template <int W>
-int launch_gram_tma(const GramParams& P0, pcq_plan* p, int num_sms, size_t smem_optin, double** ws,
-                    size_t* ws_bytes, cudaStream_t st, bool* handled) {
+int launch_gram_tma(const GramParams& P0, int num_sms, size_t smem_optin, double** ws,
+                    size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st, bool* handled) {
     GramParams P = P0;
     const int NTe = tb_slots_even(P.nslots, P.m);
     const size_t blob = (size_t)NTe * TB_TS;
@@ -580,12 +580,12 @@ int launch_gram_tma(const GramParams& P0, pcq_plan* p, int num_sms, size_t smem_
     if (smem > smem_optin || smem_tab > smem_optin) return PCQ_OK;
     *handled = true;
     const int64_t nblocks16 = (P.n + TB_KT - 1) / TB_KT;
-    int rc = pcq_ensure_dev(&p->d_tabs, &p->tabs_bytes, (size_t)nblocks16 * blob * sizeof(double));
+    int rc = pcq_ensure_dev(zbuf, zbuf_bytes, (size_t)nblocks16 * blob * sizeof(double));
     if (rc != PCQ_OK) return rc;
     PCQ_CUDA(cudaFuncSetAttribute(pcq_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab));
     const int64_t want = (nblocks16 + 7) / 8;
     const int tgrid = (int)(want < (int64_t)num_sms * 2 ? want : (int64_t)num_sms * 2);
-    pcq_tables_kernel<<<tgrid, 256, smem_tab, st>>>(P, p->d_tabs, nblocks16);
+    pcq_tables_kernel<<<tgrid, 256, smem_tab, st>>>(P, *zbuf, nblocks16);
     PCQ_LAUNCH_CHECK("pcq_tables_kernel");
     auto kern = pcq_gram_tma_kernel<W>;
     PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -593,7 +593,7 @@ int launch_gram_tma(const GramParams& P0, pcq_plan* p, int num_sms, size_t smem_
     rc = pcq_ensure_dev(ws, ws_bytes, (size_t)grid * 2 * GT * GT * sizeof(double));
     if (rc != PCQ_OK) return rc;
     P.ws = *ws;
-    kern<<<grid, G_THREADS, smem, st>>>(P, p->d_tabs);
+    kern<<<grid, G_THREADS, smem, st>>>(P, *zbuf);
     PCQ_LAUNCH_CHECK("pcq_gram_tma_kernel");
     const int ntri = P.ntile * (P.ntile + 1) / 2;
     pcq_gram_fixup_kernel<<<dim3(ntri, 4), 256, 0, st>>>(P, grid);
@@ -617,7 +617,7 @@ __global__ void pcq_fill_kernel(double* p, size_t n, double v) {
 static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n,
                             int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,
                             int64_t ldy, int m, double* s, int accumulate, int mirror, double** ws,
-                            size_t* ws_bytes, cudaStream_t st) {
+                            size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st) {
     GramParams P;
     memset(&P, 0, sizeof(P));
     P.mirror = mirror;
@@ -647,10 +647,10 @@ static int launch_gram_once(pcq_plan* p, int num_sms, size_t smem_optin, const d
         const int v1_only = getenv("PCQ_GRAM_V1") != nullptr;
         if (!v1_only) {
             switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {
-                case 1: rc = launch_gram_tma<1>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 2: rc = launch_gram_tma<2>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 3: rc = launch_gram_tma<3>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
-                case 4: rc = launch_gram_tma<4>(P, p, num_sms, smem_optin, ws, ws_bytes, st, &handled); break;
+                case 1: rc = launch_gram_tma<1>(P, num_sms, smem_optin, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled); break;
+                case 2: rc = launch_gram_tma<2>(P, num_sms, smem_optin, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled); break;
+                case 3: rc = launch_gram_tma<3>(P, num_sms, smem_optin, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled); break;
+                case 4: rc = launch_gram_tma<4>(P, num_sms, smem_optin, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled); break;
                 default: break;
             }
             if (handled || rc != PCQ_OK) return rc;
@@ -685,7 +685,7 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
     }
     if (n == 0)
         return launch_gram_once(p, num_sms, smem_optin, x, 0, ldx, a, lda, kcols, y, ldy, m, s, accumulate, 1,
-                                ws, ws_bytes, st);
+                                ws, ws_bytes, zbuf, zbuf_bytes, st);
     const bool fused = (a == nullptr);
     const bool use_tma = fused && p->width <= PCQ_MAXW_FAST && getenv("PCQ_GRAM_V1") == nullptr;
     const int64_t row_bytes = use_tma ? (int64_t)tb_slots_even(p->nslots, m) * TB_TS * 8 / TB_KT
@@ -700,7 +700,7 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
         const int last = (r0 + nr >= n);
         int rc = launch_gram_once(p, num_sms, smem_optin, fused ? x + r0 * ldx : nullptr, nr, ldx,
                                   fused ? nullptr : a + r0 * lda, lda, kcols, y ? y + r0 * ldy : nullptr, ldy, m,
-                                  s, accumulate || r0 > 0, last, ws, ws_bytes, st);
+                                  s, accumulate || r0 > 0, last, ws, ws_bytes, zbuf, zbuf_bytes, st);
         if (rc != PCQ_OK) return rc;
     }
     return PCQ_OK;

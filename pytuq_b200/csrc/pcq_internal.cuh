@@ -42,9 +42,6 @@ struct pcq_plan {
     std::vector<int32_t> h_mi;
     std::vector<double> h_rec_a, h_rec_b, h_p1;
     pcq_spec* spec[2] = {nullptr, nullptr};   // [0] exact, [1] fast
-    // precomputed slot-table blobs of the current Gram chunk (lazily grown)
-    double* d_tabs = nullptr;
-    size_t tabs_bytes = 0;
     // Gram workspace (lazily grown)
     double* d_ws = nullptr;
     size_t ws_bytes = 0;

@@ -94,6 +94,29 @@ def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None):
     return plan
 
 
+# A plan that keeps being evaluated (MCMC likelihoods, repeated surrogate sweeps) is worth compiling for:
+# once the generic evalPC kernel has processed this many sample-terms through one plan, the plan's
+# multi-index-specialised kernels are built (NVRTC, ~1 s per 2000 terms) and used from then on -- 3-4x
+# faster and bit-identical in exact mode.  The threshold is ~4 s of generic-kernel time, so the compile can
+# at worst double the cost of a job that stops right after it.  PCQ_AUTO_SPECIALIZE=0 disables, any other
+# number replaces the threshold.
+_AUTO_SPECIALIZE = float(os.environ.get("PCQ_AUTO_SPECIALIZE", "4e12"))
+_AUTO_SPECIALIZE_MAX_TERMS = 40000
+
+
+def note_evalpc_work(plan, nsam, nterms, nout, mode):
+    if _AUTO_SPECIALIZE <= 0 or nterms > _AUTO_SPECIALIZE_MAX_TERMS or nout > 8:
+        return
+    bit = 2 if (mode & 1) else 1
+    if getattr(plan, "_spec_tried", 0) & bit:
+        return
+    work = getattr(plan, "_evalpc_work", 0.0) + float(nsam) * nterms * nout
+    plan._evalpc_work = work
+    if work >= _AUTO_SPECIALIZE:
+        plan._spec_tried = getattr(plan, "_spec_tried", 0) | bit
+        _native.lib().pcq_plan_specialize(plan.handle, bit)     # failure (no NVRTC): generic kernels stay
+
+
 def clear_plans():
     with _lock:
         _plans.clear()

@@ -308,6 +308,7 @@ class PCRV(MRV):
         for outs in groups.values():
             mindex = self.mindices[outs[0]]
             plan = self._plan(mindex)
+            _device.note_evalpc_work(plan, nsam, mindex.shape[0], len(outs), mode)
             runs = [list(g) for _, g in itertools.groupby(outs, key=lambda j, c=itertools.count(): j - next(c))]
             for run in runs:     # consecutive outputs -> adjacent columns of y
                 cf = np.ascontiguousarray(np.stack([self.coefs[j] for j in run]), dtype=np.float64)

@@ -344,6 +344,29 @@ def test_k2_specialised_kernels_bitexact():
 
 
 # ----------------------------------------------------------------------------- fitters and workflows
+def test_k2_hot_plan_is_specialised_automatically(monkeypatch):
+    """A plan that keeps being evaluated gets its specialised kernels built once the accumulated work passes
+    the threshold; results stay bit-identical across the switch."""
+    from pytuq_b200 import device as _device
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(12)
+    mi = orc.get_mi(3, 7)[:97]            # a plan no other test uses
+    pc = PCRV(1, 7, "LU", mi=mi, cfs=[rng.standard_normal(97)])
+    x = rng.uniform(-1, 1, (3000, 7))
+    monkeypatch.setattr(_device, "_AUTO_SPECIALIZE", 2.5 * 3000 * 97)
+    plan = pc._plan(pc.mindices[0])
+    y1 = pc.evalPC(x)
+    assert plan.info(7) == 0
+    y2 = pc.evalPC(x)
+    assert plan.info(7) == 0
+    y3 = pc.evalPC(x)                     # third call crosses the threshold: built, then used
+    if plan.info(7) == 0:
+        pytest.skip("NVRTC not available on this box")
+    assert plan.info(7) == 1
+    assert np.array_equal(y1, y2) and np.array_equal(y1, y3)
+    assert np.array_equal(y1, orc.eval_pc(x, [mi], [pc.coefs[0]], "LU"))
+
+
 def test_fitters_vs_reference(fit_cases):
     from pytuq_b200.rv.pcrv import PCRV
     from pytuq_b200.lreg import lsq, anl, bcs, PCBasisEvaluator
