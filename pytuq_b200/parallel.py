@@ -100,10 +100,19 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
         if N == 0:
             _native.check(lib.pcq_suffstats_dev(plan.handle, None, 0, s, None, max(M, 1), M, S_t.data_ptr(), 0,
                                                 main.cuda_stream), "pcq_suffstats_dev")
+        # chunk schedule: the first host memcpy + H2D cannot overlap anything, so the pipeline ramps up
+        # (1/8, 1/4, 1/2 of a stage) before it settles on full stages
+        bounds, r0 = [], 0
+        for frac in (8, 4, 2):
+            if N - r0 > rows:
+                bounds.append((r0, max(rows // frac, 4096)))
+                r0 += bounds[-1][1]
+        while r0 < N:
+            bounds.append((r0, min(rows, N - r0)))
+            r0 += bounds[-1][1]
         c = 0
-        for r0 in range(0, N, rows):
+        for r0, nr in bounds:
             b = c & 1
-            nr = min(rows, N - r0)
             if c >= 2:
                 consumed[b].synchronize()          # staging buffer b free again (host and device side)
             hx = pin[b][:nr * s].view(nr, s)
