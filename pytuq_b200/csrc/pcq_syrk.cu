@@ -132,51 +132,51 @@ __global__ void __launch_bounds__(256) pcq_pack_bases_kernel(PackParams P) {
             if (n < P.n) T[(P.nslots + c) * TS + sm] = P.y[n * P.ldy + c];
         }
         __syncthreads();
+        // four lanes per column (lane & 3 = sample pair): a warp store instruction covers 8 columns x 64 B
+        // = 512 contiguous bytes of the packed chunk
         double* out = P.zp + (size_t)pair * 2 * P.Lp * SB;
-        for (int col = tid; col < P.Lp; col += 256) {
-            double2 v[8];
+        const int q2 = 2 * (tid & 3);
+        for (int col = tid >> 2; col < P.Lp; col += 64) {
+            double2 v[2];
             if (col < P.kb) {
                 if (W > 0) {
                     const unsigned long long d = P.desc4[col];
                     int off[W > 0 ? W : 1];
 #pragma unroll
-                    for (int q = 0; q < W; ++q) off[q] = (int)((d >> (16 * q)) & 0xffffull) * TS;
+                    for (int q = 0; q < W; ++q) off[q] = (int)((d >> (16 * q)) & 0xffffull) * TS + q2;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        double2 t = *reinterpret_cast<const double2*>(T + off[0] + 2 * r);
+                    for (int h = 0; h < 2; ++h) {
+                        double2 t = *reinterpret_cast<const double2*>(T + off[0] + 8 * h);
 #pragma unroll
                         for (int q = 1; q < W; ++q) {
-                            const double2 f = *reinterpret_cast<const double2*>(T + off[q] + 2 * r);
+                            const double2 f = *reinterpret_cast<const double2*>(T + off[q] + 8 * h);
                             t.x = __dmul_rn(t.x, f.x);
                             t.y = __dmul_rn(t.y, f.y);
                         }
-                        v[r] = t;
+                        v[h] = t;
                     }
                 } else {
                     const uint16_t* dw = P.descw + (size_t)col * P.width;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const double2*>(T + (int)dw[0] * TS + 2 * r);
+                    for (int h = 0; h < 2; ++h) v[h] = *reinterpret_cast<const double2*>(T + (int)dw[0] * TS + q2 + 8 * h);
                     for (int q = 1; q < P.width; ++q) {
-                        const int o = (int)dw[q] * TS;
+                        const int o = (int)dw[q] * TS + q2;
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            const double2 f = *reinterpret_cast<const double2*>(T + o + 2 * r);
-                            v[r].x = __dmul_rn(v[r].x, f.x);
-                            v[r].y = __dmul_rn(v[r].y, f.y);
+                        for (int h = 0; h < 2; ++h) {
+                            const double2 f = *reinterpret_cast<const double2*>(T + o + 8 * h);
+                            v[h].x = __dmul_rn(v[h].x, f.x);
+                            v[h].y = __dmul_rn(v[h].y, f.y);
                         }
                     }
                 }
             } else {
                 const int slot = col < P.kb + P.m ? P.nslots + (col - P.kb) : (col == P.kb + P.m ? 0 : zero_slot);
 #pragma unroll
-                for (int r = 0; r < 8; ++r) v[r] = *reinterpret_cast<const double2*>(T + slot * TS + 2 * r);
+                for (int h = 0; h < 2; ++h) v[h] = *reinterpret_cast<const double2*>(T + slot * TS + q2 + 8 * h);
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                double2* dst = reinterpret_cast<double2*>(out + ((size_t)h * P.Lp + col) * SB);
-#pragma unroll
-                for (int r = 0; r < 4; ++r) __stcs(dst + r, v[h * 4 + r]);
-            }
+            for (int h = 0; h < 2; ++h)
+                __stcs(reinterpret_cast<double2*>(out + ((size_t)h * P.Lp + col) * SB + q2), v[h]);
         }
     }
 }
