@@ -98,11 +98,22 @@ for name, fam, d, p, n in shapes:
     if "k3" in which:
         S = torch.empty((K + 2, K + 2), dtype=torch.float64, device="cuda")
         n3 = min(n, 400_000 if K < 3000 else 60_000)
-        for tag, env in (("ws", dict(PCQ_GRAM_WS=None, PCQ_GRAM_KT=None)), ("v2 KT=16", dict(PCQ_GRAM_WS=0, PCQ_GRAM_KT=16))):
+        for tag, env in (("pack+syrk", dict(PCQ_GRAM_SYRK=None)), ("fused generator", dict(PCQ_GRAM_SYRK=0))):
             setenv(**env)
             ms = timeit(lambda: _native.check(lib.pcq_suffstats_dev(plan.handle, x.data_ptr(), n3, d, y.data_ptr(), 1, 1, S.data_ptr(), 0, st)), reps=3, warm=1)
             fl = float(n3) * K * (K + 1) + 2.0 * n3 * K + 2.0 * n3
             print(f"{name} K3 {tag}: n={n3} {ms:8.3f} ms  {fl / ms / 1e9:6.2f} TFLOP/s(alg)", flush=True)
-        setenv(PCQ_GRAM_WS=None)
-        setenv(PCQ_GRAM_KT=None)
+        setenv(PCQ_GRAM_SYRK=None)
         del S
+    if "k4" in which:
+        n4 = min(n, int(4e9 // (8 * K)))
+        A = torch.empty((n4, K), dtype=torch.float64, device="cuda")
+        _native.check(lib.pcq_eval_bases_dev(plan.handle, x.data_ptr(), n4, d, A.data_ptr(), K, st))
+        S = torch.empty((K + 2, K + 2), dtype=torch.float64, device="cuda")
+        for tag, env in (("pack+syrk", dict(PCQ_GRAM_SYRK=None)), ("v1 generic", dict(PCQ_GRAM_SYRK=0))):
+            setenv(**env)
+            ms = timeit(lambda: _native.check(lib.pcq_gram_dev(0, A.data_ptr(), n4, K, K, y.data_ptr(), 1, 1, S.data_ptr(), 0, st)), reps=3, warm=1)
+            fl = float(n4) * K * (K + 1) + 2.0 * n4 * K + 2.0 * n4
+            print(f"{name} K4 {tag}: n={n4} {ms:8.3f} ms  {fl / ms / 1e9:6.2f} TFLOP/s(alg)", flush=True)
+        setenv(PCQ_GRAM_SYRK=None)
+        del S, A
