@@ -417,8 +417,8 @@ def main():
         "breakdown_ms": {"k3_suffstats": k3_mean_ms, "allreduce": float(np.mean(ar_ms)),
                          "solve_kxk": 1e3 * float(np.mean(solve_s))},
         "max_abs_coef_error_vs_truth": err,
-        "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; 94.7 % of the step, the rest is "
-                               "pcq_pack_bases_kernel 4.1 %, fix-up/mirror 0.2 %, K x K solve 1 %; profiles/r01_j_k3_traffic.json)",
+        "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; 96.3 % of the step, the rest is "
+                               "pcq_pack_bases_kernel 2.6 %, fix-up/mirror 0.2 %, K x K solve 1 %; profiles/r01_j_k3_traffic.json)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if peak else None, "traffic": traffic,
                      "traffic_note": "DRAM read+write bytes of the 9 pcq_syrk_kernel launches of one step (ncu, "
