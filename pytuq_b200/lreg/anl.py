@@ -42,7 +42,7 @@ class anl(lreg):
 
     def _sigmahatsq(self, stats):
         # lreg/anl.py:57-66 with y.(y - A cf) written on the statistics
-        bp = (stats.yty(0) - float(stats.b(0) @ self.cf)) / 2.
+        bp = stats.y_dot_residual(self.cf, 0) / 2.
         ap = (stats.n - stats.K) / 2.
         return max(bp / (ap - 1.), 0.0)
 

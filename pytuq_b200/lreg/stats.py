@@ -22,7 +22,12 @@ class SuffStats:
     made lazily (once, shared by all per-output views) for the fitters that work on K x K slices with
     numpy (anl, bcs).  ``select(j)`` is a zero-copy view exposing one output."""
 
-    def __init__(self, S, nbasis, nout, S_dev=None, cols=None, parent=None):
+    # when the identity-based residual falls below this fraction of y^T y its leading digits have
+    # cancelled; the exact residual pass (if the data are still reachable) takes over
+    RESIDUAL_REFINE = 1.0e-8
+
+    def __init__(self, S, nbasis, nout, S_dev=None, cols=None, parent=None, residual=None):
+        self._residual = residual     # callable (cf (K,), output column) -> (sum r^2, sum y r), or None
         self._S = S
         self.S_dev = S_dev
         self.K = int(nbasis)
@@ -78,11 +83,25 @@ class SuffStats:
             used = np.arange(self.K)
         Gu = self.G[np.ix_(used, used)]
         bu = self.b(j)[used]
-        return self.yty(j) - 2.0 * float(cf @ bu) + float(cf @ (Gu @ cf))
+        val = self.yty(j) - 2.0 * float(cf @ bu) + float(cf @ (Gu @ cf))
+        if self._residual is not None and val <= self.RESIDUAL_REFINE * self.yty(j):
+            full = np.zeros(self.K)
+            full[np.asarray(used)] = cf
+            val = self._residual(full, self.cols[j])[0]
+        return val
+
+    def y_dot_residual(self, cf, j=0):
+        """y . (y - A cf) for a full-length cf (lreg/anl.py:61): y^T y - cf^T b on the statistics, or the exact
+        pass over the data when that difference has cancelled."""
+        val = self.yty(j) - float(self.b(j) @ cf)
+        if self._residual is not None and abs(val) <= self.RESIDUAL_REFINE * self.yty(j):
+            val = self._residual(np.asarray(cf, dtype=np.float64), self.cols[j])[1]
+        return val
 
     def select(self, j):
         """Statistics of output j alone (a view: the shared G is neither copied nor re-downloaded)."""
-        return SuffStats(self._S, self.K, self._Mall, S_dev=self.S_dev, cols=[self.cols[j]], parent=self)
+        return SuffStats(self._S, self.K, self._Mall, S_dev=self.S_dev, cols=[self.cols[j]], parent=self,
+                         residual=self._residual)
 
     def dev_system(self):
         """(G, B) as device tensors for the exposed outputs, or None when the statistics are host-only."""
@@ -99,8 +118,11 @@ class SuffStats:
     @classmethod
     def from_pc(cls, pcrv, x, y=None, jdim=0):
         """Fused path (K3): statistics of the jdim-th PC basis at germ points x, no A."""
-        from ..parallel import suffstats_pc
-        return suffstats_pc(pcrv, x, y, jdim)
+        from ..parallel import suffstats_pc, residual_sums_pc
+        st = suffstats_pc(pcrv, x, y, jdim)
+        if y is not None:
+            st._residual = lambda cf, col: residual_sums_pc(pcrv, x, y, col, jdim, cf)
+        return st
 
     @classmethod
     def from_matrix(cls, Amat, y=None):
@@ -120,4 +142,8 @@ class SuffStats:
         st = _native.lib().pcq_gram(_device.current_device(), _native.ptr(A), N, K, K,
                                     _native.ptr(Y), max(M, 1), M, _native.ptr(S))
         _native.check(st, "pcq_gram")
-        return cls(S, K, M)
+        out = cls(S, K, M)
+        if M:
+            from ..parallel import residual_sums_matrix
+            out._residual = lambda cf, col: residual_sums_matrix(A, Y, col, cf)
+        return out

@@ -138,7 +138,65 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
             else:
                 S_t = torch.from_numpy(allreduce_stats(S_t.cpu().numpy())).to(tdev)
         main.synchronize()
+    pcrv._distributed_stats = bool(distributed)
     return SuffStats(None, K, M, S_dev=S_t)
+
+
+_RESID_ROWS = 1 << 20
+
+
+def residual_sums_pc(pcrv, x, y, col, jdim, cf):
+    """(sum_n r_n^2, sum_n y_n r_n) with r = y[:, col] - Psi(x) cf, evaluated over the data: the surrogate
+    through K2 (fast mode, no A), the two sums reduced on the device.  This is the residual pass of
+    bcs_fit (lreg/bcs.py:229) and anl (lreg/anl.py:61) for fits whose residual is so small that the
+    statistics identity  y^T y - 2 cf^T b + cf^T G cf  has cancelled (noise-free training data)."""
+    import torch
+    _device.require_device()
+    dev = _device.current_device()
+    tdev = torch.device("cuda", dev)
+    mindex = pcrv.mindices[jdim]
+    plan = pcrv._plan(mindex, dev=dev)
+    lib = _native.lib()
+    xin = np.ascontiguousarray(x, dtype=np.float64)
+    N, s = xin.shape
+    Y = np.asarray(y, dtype=np.float64).reshape(N, -1)
+    sums = torch.zeros(2, dtype=torch.float64, device=tdev)
+    with torch.cuda.device(tdev):
+        stream = torch.cuda.current_stream().cuda_stream
+        cf_t = torch.from_numpy(np.ascontiguousarray(cf, dtype=np.float64)).to(tdev)
+        for r0 in range(0, N, _RESID_ROWS):
+            r1 = min(N, r0 + _RESID_ROWS)
+            xd = torch.from_numpy(xin[r0:r1]).to(tdev)
+            yd = torch.from_numpy(np.ascontiguousarray(Y[r0:r1, col])).to(tdev)
+            yh = torch.empty(r1 - r0, dtype=torch.float64, device=tdev)
+            _native.check(lib.pcq_eval_pc_dev(plan.handle, xd.data_ptr(), r1 - r0, s, cf_t.data_ptr(), 1,
+                                              yh.data_ptr(), 1, 1, stream), "pcq_eval_pc_dev")
+            r = yd - yh
+            sums += torch.stack([torch.dot(r, r), torch.dot(yd, r)])
+        if dist_info()[1] > 1 and getattr(pcrv, "_distributed_stats", False):
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    out = sums.cpu().numpy()
+    return float(out[0]), float(out[1])
+
+
+def residual_sums_matrix(A, Y, col, cf):
+    """Same two sums for a caller-supplied design matrix (host numpy), chunks contracted on the device."""
+    import torch
+    _device.require_device()
+    tdev = torch.device("cuda", _device.current_device())
+    N, K = A.shape
+    rows = max(1, (256 << 20) // (8 * K))
+    sums = torch.zeros(2, dtype=torch.float64, device=tdev)
+    cf_t = torch.from_numpy(np.ascontiguousarray(cf, dtype=np.float64)).to(tdev)
+    for r0 in range(0, N, rows):
+        r1 = min(N, r0 + rows)
+        Ad = torch.from_numpy(np.ascontiguousarray(A[r0:r1])).to(tdev)
+        yd = torch.from_numpy(np.ascontiguousarray(Y[r0:r1, col])).to(tdev)
+        r = yd - Ad @ cf_t
+        sums += torch.stack([torch.dot(r, r), torch.dot(yd, r)])
+    out = sums.cpu().numpy()
+    return float(out[0]), float(out[1])
 
 
 def propagate(pcrv, nsam, seed=0, exact=False, return_samples=False, first_index=0, specialize="auto"):

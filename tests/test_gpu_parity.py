@@ -478,6 +478,55 @@ def test_lsq_qr_route_on_illconditioned_systems():
         assert rel_err(regs[j].cf, orc.lsq_fit(As, Ys[:, j])) < 1e-9
 
 
+def test_small_residuals_take_the_exact_residual_pass():
+    """Noise far below the data scale: the statistics identity for the residual sum of squares cancels
+    (relative size 1e-18 of y^T y at noise 1e-9), so bcs's re-estimated sigma2 (lreg/bcs.py:229) must come
+    from the residual pass over the data (K2) -- compared with the reference algorithm on a materialised A.
+    anl's estimate uses y.(y - A cf) (lreg/anl.py:61), which at such noise levels is dominated by the rounding
+    of the K x K solve in the reference itself; there only the order of magnitude is comparable."""
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import anl, bcs, PCBasisEvaluator
+    from pytuq_b200.lreg.stats import SuffStats
+    rng = np.random.default_rng(17)
+    d, p, n = 4, 3, 4000
+    mi = orc.get_mi(p, d)
+    K = mi.shape[0]
+    x = rng.uniform(-1, 1, (n, d))
+    A = orc.eval_bases(x, mi, "LU")
+    c = np.zeros(K); c[[0, 2, 7, 19]] = [1.0, -0.5, 0.25, 0.8]
+    pc = PCRV(1, d, "LU", mi=mi)
+    for noise in (1e-6, 1e-9):
+        y = A @ c + noise * rng.standard_normal(n)
+        w_ref, _, used_ref, s2_ref, _ = orc.bcs_fit(A, y, eta=1e-8)
+        s2_ref = float(np.ravel(s2_ref)[0])
+        assert s2_ref < 1e-9          # far below RESIDUAL_REFINE * y^T y / N: the identity alone would cancel
+        for route in ("fit", "fita"):
+            b = bcs(eta=1e-8)
+            if route == "fit":
+                b.setBasisEvaluator(PCBasisEvaluator(0), (pc,)); b.fit(x, y)
+            else:
+                b.fita(A, y)
+            assert np.array_equal(np.sort(b.used), np.sort(used_ref)), (noise, route)
+            s2 = float(np.ravel(b.datavar)[0])
+            assert abs(s2 - s2_ref) < 1e-4 * s2_ref, (noise, route, s2, s2_ref)
+        # the residual accessor itself, against a direct evaluation
+        st = SuffStats.from_pc(pc, x, y, 0)
+        r = y - A[:, used_ref] @ w_ref
+        assert abs(st.rss(w_ref, used_ref, 0) - r @ r) < 1e-6 * (r @ r)
+        a = anl(); a.setBasisEvaluator(PCBasisEvaluator(0), (pc,)); a.fit(x, y)
+        cf_ref, _, dv_ref = orc.anl_fit(A, y)
+        assert rel_err(a.cf, cf_ref) < 1e-9
+        assert a.datavar >= 0.0 and a.datavar < 30 * noise ** 2 + 1e-13
+    # the identity is kept whenever it is accurate: no residual pass for ordinary noise levels
+    y = A @ c + 1e-2 * rng.standard_normal(n)
+    st = SuffStats.from_pc(pc, x, y, 0)
+    calls = []
+    inner = st._residual
+    st._residual = lambda cf, col: (calls.append(1), inner(cf, col))[1]
+    a = anl(); a._fit_stats(st)
+    assert not calls and abs(a.datavar - orc.anl_fit(A, y)[2]) < 1e-9 * a.datavar
+
+
 def test_pc_fit_workflow_vs_reference():
     import contextlib, io
     from pytuq_b200.workflows.fits import pc_fit
