@@ -122,8 +122,11 @@ int pcq_eval_pc(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
  *     S[:K,K:K+M]   = A^T Y      lreg/anl.py:83 ; lreg/bcs.py:83
  *     S[K:K+M,K:K+M]= Y^T Y      lreg/anl.py:57 ; lreg/bcs.py:229
  *     S[:K,L-1]     = A^T 1,  S[K:K+M,L-1] = sum_n y_n,  S[L-1,L-1] = N
- * A is generated tile by tile on chip from x and never written to HBM; the
- * contraction runs on the FP64 tensor pipe (DMMA).
+ * The contraction runs on the FP64 tensor pipe (DMMA).  The design matrix is never
+ * materialised as a whole: sample chunks of the augmented rows are generated on the
+ * device into a fragment-ordered scratch buffer (<= 2 GB per device, PCQ_SYRK_CHUNK_MB)
+ * and contracted by a TMA-fed SYRK kernel; with PCQ_GRAM_SYRK=0 they are generated tile
+ * by tile in shared memory instead and nothing of A touches HBM.
  *   accumulate != 0 adds to the existing contents of s_out (for streaming and
  *   for sample-sharded partial sums), otherwise s_out is overwritten.
  *   y may be NULL when m == 0.
@@ -135,6 +138,16 @@ int pcq_suffstats_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ld
                       double* s_dev, int accumulate, void* stream);
 int pcq_suffstats(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
                   const double* y_host, int64_t ldy, int m, double* s_host);
+
+/* Residual pass of one output: with r_n = y_n - sum_k cf[k] Psi_k(x_n) (surrogate through K2, fast mode),
+ *   sums_dev[0] (+)= sum_n r_n^2      bcs_fit's final noise estimate, lreg/bcs.py:229
+ *   sums_dev[1] (+)= sum_n y_n r_n    anl._compute_sigmahatsq, lreg/anl.py:61
+ * Needed when the fit is so close that  y^T y - 2 cf^T b + cf^T G cf  on the statistics has cancelled
+ * (noise-free training data).  cf has K entries (zeros for unused terms); y is one column with stride ldy.
+ * Partial sums are combined in a fixed order (deterministic). */
+int pcq_residual_ss_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,
+                        const double* y_dev, int64_t ldy, const double* cf_dev,
+                        double* sums_dev, int accumulate, void* stream);
 
 /* ---- K4: sufficient statistics from a materialised design matrix ---------------
  * Same S as above but z_n = [ A[n,:] | y_n | 1 ] with A given (lreg.fita(Amat, y),

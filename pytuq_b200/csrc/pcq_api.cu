@@ -309,6 +309,16 @@ struct ScratchLease {
 };
 }  // namespace
 
+int pcq_residual_ss_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
+                        const double* cf, double* sums, int accumulate, void* stream) {
+    if (!p || n < 0 || !cf || !sums || (n > 0 && (!x || !y)) || ldx < p->sdim || ldy < 1) {
+        pcq_set_error("residual_ss: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    return pcq_launch_residual(p, x, n, ldx, y, ldy, cf, sums, accumulate, (cudaStream_t)stream);
+}
+
 int64_t pcq_suffstats_dim(const pcq_plan* p, int m) {
     if (!p || m < 0) return PCQ_ERR_ARG;
     return (int64_t)p->nterms + m + 1;

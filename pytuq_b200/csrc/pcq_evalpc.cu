@@ -9,6 +9,7 @@
 //   mode 0 (exact): prd = cf[k]; prd *= phi (dims ascending); val += prd   -- bit-identical
 //   mode 1 (fast) : psi = prod phi; acc[m] = fma(cf[m][k], psi, acc[m])
 #include "pcq_internal.cuh"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -608,6 +609,36 @@ __global__ void pcq_moments_combine_kernel(double* sums, const double* tmp, int 
     }
 }
 
+// residual sums of one output: per-warp partials of (sum r^2, sum y r), r = y - yhat
+__global__ void __launch_bounds__(256) pcq_resid_kernel(const double* __restrict__ y, int64_t ldy,
+                                                        const double* __restrict__ yhat, int64_t n, double* part) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double rr = 0.0, yr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double yv = y[i * ldy];
+        const double r = yv - yhat[i];
+        rr = fma(r, r, rr);
+        yr = fma(yv, r, yr);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rr += __shfl_xor_sync(0xffffffffu, rr, o);
+        yr += __shfl_xor_sync(0xffffffffu, yr, o);
+    }
+    if (lane == 0) { part[2 * warp] = rr; part[2 * warp + 1] = yr; }
+}
+
+// fixed-order sum of the per-warp partials; sums (+)= result
+__global__ void __launch_bounds__(64) pcq_resid_reduce_kernel(const double* part, int nwarps, double* sums, int accumulate) {
+    const int q = threadIdx.x;
+    if (q >= 2) return;
+    double acc = 0.0;
+    for (int w = 0; w < nwarps; ++w) acc += part[2 * w + q];
+    sums[q] = (accumulate ? sums[q] : 0.0) + acc;
+}
+
 void fill_eval_params(pcq_plan* p, EvalParams& P) {
     memset(&P, 0, sizeof(P));
     P.sdim = p->sdim; P.nterms = p->nterms; P.pmax = p->pmax; P.nslots = p->nslots;
@@ -690,6 +721,30 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
         return PCQ_OK;
     }
     return launch_evalpc_any<true>(p, P, mode, st, sums);
+}
+
+int pcq_launch_residual(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
+                        const double* cf, double* sums, int accumulate, cudaStream_t st) {
+    const int64_t chunk = 1 << 22;
+    const int grid = p->num_sms * 4;
+    const int nwarps = grid * 8;
+    int rc;
+    if ((rc = pcq_ensure_dev(&p->d_out[0], &p->out_bytes[0], (size_t)std::min<int64_t>(chunk, std::max<int64_t>(n, 1)) * 8)) != PCQ_OK) return rc;
+    if ((rc = pcq_ensure_dev(&p->d_ws, &p->ws_bytes, (size_t)nwarps * 2 * 8)) != PCQ_OK) return rc;
+    if (n == 0) {
+        pcq_resid_reduce_kernel<<<1, 64, 0, st>>>(p->d_ws, 0, sums, accumulate);
+        PCQ_LAUNCH_CHECK("pcq_resid_reduce_kernel");
+        return PCQ_OK;
+    }
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t nr = std::min(chunk, n - r0);
+        if ((rc = pcq_launch_evalpc(p, x + r0 * ldx, nr, ldx, cf, 1, p->d_out[0], 1, 1, st)) != PCQ_OK) return rc;
+        pcq_resid_kernel<<<grid, 256, 0, st>>>(y + r0 * ldy, ldy, p->d_out[0], nr, p->d_ws);
+        PCQ_LAUNCH_CHECK("pcq_resid_kernel");
+        pcq_resid_reduce_kernel<<<1, 64, 0, st>>>(p->d_ws, nwarps, sums, (accumulate || r0 > 0) ? 1 : 0);
+        PCQ_LAUNCH_CHECK("pcq_resid_reduce_kernel");
+    }
+    return PCQ_OK;
 }
 
 int pcq_launch_germ(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,

@@ -103,6 +103,8 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
 int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
                          const int32_t* germ_kind, const double* cf, int m, double* sums,
                          double* y, int64_t ldy, int mode, cudaStream_t st);
+int pcq_launch_residual(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
+                        const double* cf, double* sums, int accumulate, cudaStream_t st);
 int pcq_launch_germ(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
                     const int32_t* germ_kind, double* x, int64_t ldx, cudaStream_t st);
 // multi-index-specialised evalPC (pcq_spec.cu)

@@ -168,11 +168,9 @@ def residual_sums_pc(pcrv, x, y, col, jdim, cf):
             r1 = min(N, r0 + _RESID_ROWS)
             xd = torch.from_numpy(xin[r0:r1]).to(tdev)
             yd = torch.from_numpy(np.ascontiguousarray(Y[r0:r1, col])).to(tdev)
-            yh = torch.empty(r1 - r0, dtype=torch.float64, device=tdev)
-            _native.check(lib.pcq_eval_pc_dev(plan.handle, xd.data_ptr(), r1 - r0, s, cf_t.data_ptr(), 1,
-                                              yh.data_ptr(), 1, 1, stream), "pcq_eval_pc_dev")
-            r = yd - yh
-            sums += torch.stack([torch.dot(r, r), torch.dot(yd, r)])
+            _native.check(lib.pcq_residual_ss_dev(plan.handle, xd.data_ptr(), r1 - r0, s, yd.data_ptr(), 1,
+                                                  cf_t.data_ptr(), sums.data_ptr(), 1, stream),
+                          "pcq_residual_ss_dev")
         if dist_info()[1] > 1 and getattr(pcrv, "_distributed_stats", False):
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM)
