@@ -71,10 +71,51 @@ def illcond(R):
     print(f"lsq_illcond.npz  {os.path.getsize(os.path.join(HERE, 'lsq_illcond.npz')) / 1024:.1f} KiB")
 
 
+def klsurr(R):
+    """KLE and the PC branch of KLSurr (linred/kle.py, linred/klsurr.py:61-136,247-306).  klsurr.py itself cannot
+    be imported without QUiNN (hard sys.exit at import), so its PC branch is replayed here line by line with the
+    reference's own KLE, pc_fit, micf_join and PCRV.  Written to klsurr.npz; only quantities that do not depend
+    on the (arbitrary) signs of the eigenvectors are compared by the tests."""
+    import io, contextlib
+    from pytuq.linred.kle import KLE
+    from pytuq.utils.mindex import micf_join
+    PCRV = R["PCRV"]
+    rng = np.random.default_rng(51)
+    N, d, nt = 300, 3, 25
+    x = rng.uniform(-1, 1, (N, d))
+    t = np.linspace(0, 1, nt)
+    y = (np.sin(x[:, :1] + 2 * t[None, :]) + x[:, 1:2] * t[None, :] ** 2 + 0.5 * x[:, 2:3] * np.cos(5 * t[None, :])
+         + 0.3 * x[:, :1] * x[:, 1:2] * np.sin(3 * t[None, :]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        kl = KLE(); kl.build(y.T, plot=False)
+        neig = kl.get_neig(0.99)
+        xitrain = kl.xi[:, :neig]
+        pcrv, _ = R["pc_fit"](x, xitrain, order=3, pctype='LU', method='bcs', eta=1.e-8)
+        ytrain_kl = kl.eval(neig=neig)
+        xi_pred = pcrv.function(x)
+        ytrain_klsurr = kl.eval(xi=xi_pred, neig=neig)
+        xt = rng.uniform(-1, 1, (17, d))
+        ytest = kl.eval(xi=pcrv.function(xt), neig=neig)
+        mindex_all, cfs_all = micf_join(pcrv.mindices, pcrv.coefs)
+        pe = PCRV(neig, d, pcrv.pctypes, mi=mindex_all, cfs=cfs_all)
+        cfs_glob = np.dot(np.dot(cfs_all.T, np.diag(np.sqrt(kl.eigval[:neig]))), kl.modes[:, :neig].T)
+        cfs_glob[0, :] += kl.mean
+        pp = PCRV(nt, d, pcrv.pctypes, mi=mindex_all, cfs=cfs_glob.T)
+        out = dict(x=x, y=y, xt=xt, eigval=kl.eigval, mean=kl.mean, neig=np.array(neig), abs_xi=np.abs(xitrain),
+                   relvar=kl.compute_relvar()[:, :neig], ytrain_kl=ytrain_kl, ytrain_klsurr=ytrain_klsurr,
+                   ytest=ytest, sens_eig_main=pe.computeSens(), sens_eig_total=pe.computeTotSens(),
+                   sens_main=pp.computeSens(), sens_total=pp.computeTotSens(), mindex_all=mindex_all,
+                   abs_cfs_all=np.abs(cfs_all))
+    np.savez_compressed(os.path.join(HERE, "klsurr.npz"), **out)
+    print(f"klsurr.npz  neig={neig} K_union={mindex_all.shape[0]}  {os.path.getsize(os.path.join(HERE, 'klsurr.npz')) / 1024:.1f} KiB")
+
+
 def main():
     R = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "illcond":
         return illcond(R)
+    if len(sys.argv) > 1 and sys.argv[1] == "klsurr":
+        return klsurr(R)
     PCRV, PC1d, get_mi = R["PCRV"], R["PC1d"], R["get_mi"]
     out = {}
 
@@ -227,6 +268,7 @@ def main():
         p = os.path.join(HERE, f + ".npz")
         print(f"{f}.npz  {os.path.getsize(p) / 1024:.1f} KiB")
     illcond(R)
+    klsurr(R)
 
 
 if __name__ == "__main__":

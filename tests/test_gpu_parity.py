@@ -527,6 +527,46 @@ def test_small_residuals_take_the_exact_residual_pass():
     assert not calls and abs(a.datavar - orc.anl_fit(A, y)[2]) < 1e-9 * a.datavar
 
 
+def test_kle_and_klsurr_vs_reference():
+    """8(f3): KL expansion + PC surrogate of a field output (BASELINE config 5 shape) against vectors generated
+    with the reference's KLE / pc_fit / PCRV (tests/golden/klsurr.npz).  Eigenvector signs are arbitrary, so
+    only sign-invariant quantities are compared."""
+    import io, contextlib
+    from conftest import load_golden
+    from pytuq_b200.linred.kle import KLE
+    from pytuq_b200.linred.klsurr import KLSurr
+    g = load_golden("klsurr")
+    x, y = g["x"], g["y"]
+    kl = KLE()
+    kl.build(y.T, plot=False)
+    big = g["eigval"] > 1e-12 * g["eigval"][0]
+    assert rel_err(kl.eigval[big], g["eigval"][big]) < 1e-9
+    assert rel_err(kl.mean, g["mean"]) < 1e-13
+    neig = int(g["neig"])
+    assert rel_err(np.abs(kl.xi[:, :neig]), g["abs_xi"]) < 1e-8
+    assert rel_err(kl.compute_relvar()[:, :neig], g["relvar"]) < 1e-9
+    assert rel_err(kl.eval(neig=neig), g["ytrain_kl"]) < 1e-10
+    assert rel_err(kl.eval(xi=kl.project(y.T), neig=neig), g["ytrain_kl"]) < 1e-10
+    ks = KLSurr()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ks.build(x, y, pc_order=3, bcs_eta=1.e-8)
+        sens = ks.compute_sens_pc(totmain='main')
+        sens_eig = ks.sens_eig
+        sens_tot = ks.compute_sens_pc(totmain='total')
+    assert ks.neig == neig and ks.built
+    assert rel_err(ks.ytrain_kl, g["ytrain_kl"]) < 1e-10
+    assert rel_err(ks.ytrain_klsurr, g["ytrain_klsurr"]) < 1e-8
+    assert rel_err(ks.eval(g["xt"]), g["ytest"]) < 1e-8
+    assert rel_err(ks.function(g["xt"]), g["ytest"].T) < 1e-8
+    from pytuq_b200.utils.mindex import micf_join
+    mi_all, cf_all = micf_join(ks.smodel.mindices, ks.smodel.coefs)
+    assert np.array_equal(mi_all, g["mindex_all"])
+    assert rel_err(np.abs(cf_all), g["abs_cfs_all"]) < 1e-8
+    assert rel_err(sens_eig, g["sens_eig_main"]) < 1e-8
+    assert rel_err(sens, g["sens_main"]) < 1e-8
+    assert rel_err(sens_tot, g["sens_total"]) < 1e-8
+
+
 def test_pc_fit_workflow_vs_reference():
     import contextlib, io
     from pytuq_b200.workflows.fits import pc_fit
