@@ -15,7 +15,7 @@ for what in $1; do
       timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1 ;;
     k1|k2|k3)
-      case $what in k1) PAT=pcq_bases_kernel;; k2) PAT=pcq_evalpc_kernel;; k3) PAT="pcq_gram.*kernel";; esac
+      case $what in k1) PAT=pcq_bases_kernel;; k2) PAT=pcq_evalpc_kernel;; k3) PAT="pcq_syrk_kernel|pcq_pack";; esac
       CMD="python tests/prof_driver.py $what 200000"
       timeout 300 $CMD > gpurun_out/plain_$what.log 2>&1 &&
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:$PAT -s 2 -c 2 -f -o gpurun_out/prof_$what $CMD > gpurun_out/ncu_$what.log 2>&1

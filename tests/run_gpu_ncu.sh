@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 what=$1; n=${2:-200000}
-case $what in k1) PAT=pcq_bases;; k2) PAT=pcq_evalpc;; k3) PAT="pcq_gram_(ws|fused|kernel)";; esac
+case $what in k1) PAT=pcq_bases;; k2) PAT=pcq_evalpc;; k3) PAT="pcq_syrk_kernel|pcq_pack";; esac
 PAT=${3:-$PAT}
 CMD="python tests/prof_driver.py $what $n"
 timeout 300 $CMD > gpurun_out/plain_$what.log 2>&1 &&
