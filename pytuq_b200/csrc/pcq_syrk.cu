@@ -438,6 +438,11 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
     if (rows < STAGE_SAMPLES) rows = STAGE_SAMPLES;
     const int64_t npad = (n + STAGE_SAMPLES - 1) / STAGE_SAMPLES * STAGE_SAMPLES;
     if (rows > npad) rows = npad;
+    {   // equal chunks instead of full ones plus a small remainder (the remainder launch quantises badly)
+        const int64_t nchunks = (n + rows - 1) / rows;
+        const int64_t even = ((n + nchunks - 1) / nchunks + STAGE_SAMPLES - 1) / STAGE_SAMPLES * STAGE_SAMPLES;
+        if (even < rows) rows = even;
+    }
     int rc = pcq_ensure_dev(zbuf, zbuf_bytes, (size_t)rows * Lp * sizeof(double));
     if (rc != PCQ_OK) return rc;
     PCQ_CUDA(cudaFuncSetAttribute(pcq_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
