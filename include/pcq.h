@@ -139,6 +139,15 @@ int pcq_suffstats_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ld
 int pcq_suffstats(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
                   const double* y_host, int64_t ldy, int m, double* s_host);
 
+/* ---- K6: quadratic forms on the tensor pipe ---------------------------------------
+ * v[n] = Psi(x_n)^T C Psi(x_n)  for a symmetric K x K matrix C (row-major, leading dimension ldc; only its
+ * upper triangle is read).  With C = cf_cov this is the pushed-forward variance of lreg.predict /
+ * compute_stdev (lreg/lreg.py:112-143, 164-198) for a full coefficient covariance: N K^2 flops on DMMA
+ * (triangular GEMM + row-wise product), the design matrix only ever exists as a packed chunk in scratch.
+ * v has stride ldv. */
+int pcq_quadform_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,
+                     const double* c_dev, int64_t ldc, double* v_dev, int64_t ldv, void* stream);
+
 /* Residual pass of one output: with r_n = y_n - sum_k cf[k] Psi_k(x_n) (surrogate through K2, fast mode),
  *   sums_dev[0] (+)= sum_n r_n^2      bcs_fit's final noise estimate, lreg/bcs.py:229
  *   sums_dev[1] (+)= sum_n y_n r_n    anl._compute_sigmahatsq, lreg/anl.py:61

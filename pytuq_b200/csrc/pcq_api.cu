@@ -228,7 +228,7 @@ int pcq_plan_destroy(pcq_plan* p) {
     pcq_spec_free(p->spec[0]);
     pcq_spec_free(p->spec[1]);
     cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
-    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc);
+    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_q);
     for (int i = 0; i < 2; ++i) {
         cudaFree(p->d_stage[i]); cudaFree(p->d_out[i]);
         if (p->h_pin[i]) cudaFreeHost(p->h_pin[i]);
@@ -308,6 +308,18 @@ struct ScratchLease {
     }
 };
 }  // namespace
+
+int pcq_quadform_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* c, int64_t ldc,
+                     double* v, int64_t ldv, void* stream) {
+    if (!p || n < 0 || !c || (n > 0 && (!x || !v)) || ldx < p->sdim || ldc < p->nterms || ldv < 1) {
+        pcq_set_error("quadform: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    ScratchLease lease(p->device, (cudaStream_t)stream);
+    return pcq_launch_qform(p, x, n, ldx, c, ldc, v, ldv, &p->d_q, &p->q_bytes, &p->d_ws, &p->ws_bytes,
+                            &lease.d.zp, &lease.d.zp_bytes, (cudaStream_t)stream);
+}
 
 int pcq_residual_ss_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
                         const double* cf, double* sums, int accumulate, void* stream) {

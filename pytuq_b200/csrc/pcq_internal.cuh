@@ -45,6 +45,9 @@ struct pcq_plan {
     // Gram workspace (lazily grown)
     double* d_ws = nullptr;
     size_t ws_bytes = 0;
+    // packed upper-triangular operand of the quadratic-form kernel (lazily grown)
+    double* d_q = nullptr;
+    size_t q_bytes = 0;
     // staging for the host-pointer entry points (lazily grown)
     double* d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes[2] = {0, 0};
@@ -103,6 +106,9 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
 int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
                          const int32_t* germ_kind, const double* cf, int m, double* sums,
                          double* y, int64_t ldy, int mode, cudaStream_t st);
+int pcq_launch_qform(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* c, int64_t ldc, double* v,
+                     int64_t ldv, double** bq, size_t* bq_bytes, double** ws, size_t* ws_bytes, double** zbuf,
+                     size_t* zbuf_bytes, cudaStream_t st);
 int pcq_launch_residual(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
                         const double* cf, double* sums, int accumulate, cudaStream_t st);
 int pcq_launch_germ(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,

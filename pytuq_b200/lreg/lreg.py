@@ -147,8 +147,9 @@ class lreg(fitbase):
 
     def predict(self, x, msc=0, pp=False):
         r"""Mean (and variance) of the fit at x (lreg/lreg.py:80-94).  With a PC basis evaluator and
-        msc in (0, 1) nothing of size N x K is formed: the mean is an evalPC (K2) and the variance
-        || Psi(x_n) F ||^2, cf_cov = F F^T, is K2's quadratic-form mode."""
+        msc in (0, 1) nothing of size N x K is formed: the mean is an evalPC (K2) and the variance is the
+        quadratic form psi^T cf_cov psi -- on the tensor pipe (K6) for dense covariances with enough work,
+        else as || Psi(x_n) F ||^2, cf_cov = F F^T, through K2's quadratic-form mode."""
         assert(self.basisEvaluatorSet)
         if isinstance(self.basisEval, PCBasisEvaluator) and msc in (0, 1):
             assert(self.fitted)
@@ -157,10 +158,14 @@ class lreg(fitbase):
                 ypred = pcrv.evalLinearForms(x, self.cf[None, :], jdim)[:, 0]
                 if msc == 0:
                     return ypred, None, None
-                F = self._cov_factor()
-                if F is None:
+                K = self.cf.shape[0]
+                if self.cf_cov is None or not np.any(self.cf_cov):
                     ypred_var = np.zeros(ypred.shape[0])
+                elif K >= 96 and float(ypred.shape[0]) * K * K >= 2.0e8:
+                    # dense covariance, enough work: psi^T C psi as a triangular GEMM on the tensor pipe (K6)
+                    ypred_var = np.maximum(pcrv.evalQuadForm(x, self.cf_cov, jdim), 0.0)
                 else:
+                    F = self._cov_factor()
                     ypred_var = pcrv.evalLinearForms(x, np.ascontiguousarray(F.T), jdim, sumsq=True)
                 ypred_var += int(pp) * self.datavar
                 return ypred, ypred_var, None

@@ -336,6 +336,38 @@ class PCRV(MRV):
                       "pcq_eval_pc")
         return out[:, 0] if sumsq else out
 
+    def evalQuadForm(self, x, Cmat, jdim=0):
+        r"""v[n] = Psi(x_n)^T C Psi(x_n) on the jdim-th basis for a symmetric (K, K) matrix C (its upper triangle
+        is what is read): K6, a triangular GEMM on the FP64 tensor pipe over packed design-matrix chunks --
+        N K^2 flops, the pushed-forward variance of a fit with full coefficient covariance C.  Rounding can
+        leave tiny negative values for a semi-definite C; callers that take square roots clip at zero."""
+        import torch
+        mindex = self.mindices[jdim]
+        K = mindex.shape[0]
+        assert(self.sdim == x.shape[1] and Cmat.shape == (K, K))
+        self._check_orders(mindex)
+        xin = self._as_input(x)
+        nsam = xin.shape[0]
+        out = np.zeros(nsam)
+        if nsam == 0:
+            return out
+        dev = _device.current_device()
+        tdev = torch.device("cuda", dev)
+        plan = self._plan(mindex, dev=dev)
+        lib = _native.lib()
+        with torch.cuda.device(tdev):
+            stream = torch.cuda.current_stream().cuda_stream
+            c_t = torch.from_numpy(np.ascontiguousarray(Cmat, dtype=np.float64)).to(tdev)
+            rows = 1 << 20
+            for r0 in range(0, nsam, rows):
+                r1 = min(nsam, r0 + rows)
+                xd = torch.from_numpy(xin[r0:r1]).to(tdev)
+                vd = torch.empty(r1 - r0, dtype=torch.float64, device=tdev)
+                _native.check(lib.pcq_quadform_dev(plan.handle, xd.data_ptr(), r1 - r0, self.sdim, c_t.data_ptr(), K,
+                                                   vd.data_ptr(), 1, stream), "pcq_quadform_dev")
+                out[r0:r1] = vd.cpu().numpy()
+        return out
+
     def specialize(self, exact=True, fast=True):
         r"""Opt-in: compile (NVRTC) evalPC kernels specialised for the current multi-indices -- term list
         unrolled, 1-D tables in registers.  Bit-identical in exact mode and 3-4x faster, at ~3 ms of compile

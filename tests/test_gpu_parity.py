@@ -277,6 +277,47 @@ def test_k3_k4_syrk_chunks_splits_and_fused_fallback(monkeypatch):
         assert rel_err(sd.cpu().numpy(), orc.suffstats(A, yb[:, 1].cpu().numpy())) < 1e-12, env
 
 
+# ----------------------------------------------------------------------------- K6
+def test_k6_quadratic_forms_on_the_tensor_pipe():
+    """v_n = psi_n^T C psi_n (pcq_quadform_dev) against the design-matrix formula, over shapes that exercise
+    the padding of terms (K not a multiple of 128) and samples (N not a multiple of 128 / 16), generic
+    descriptor widths, several column tiles, chunking, and lreg.predict's use of it."""
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import anl, PCBasisEvaluator
+    rng = np.random.default_rng(66)
+    for fam, p, d, n in [("LU", 3, 6, 1000), ("HG", 3, 12, 777), ("LU", 2, 3, 5), ("LU", 4, 7, 2049)]:
+        mi = orc.get_mi(p, d)
+        K = mi.shape[0]
+        x = rng.uniform(-1, 1, (n, d)) if fam == "LU" else rng.standard_normal((n, d))
+        B = rng.standard_normal((K, K))
+        Cm = B @ B.T / K
+        pc = PCRV(1, d, fam, mi=mi)
+        A = orc.eval_bases(x, mi, fam)
+        ref = np.einsum("ni,ij,nj->n", A, Cm, A)
+        v = pc.evalQuadForm(x, Cm, 0)
+        assert np.max(np.abs(v - ref)) < 1e-12 * np.max(np.abs(ref)), (fam, p, d, n)
+    mi = rng.integers(0, 3, size=(150, 6))                     # generic width (up to 6 non-zero orders)
+    x = rng.uniform(-1, 1, (300, 6))
+    Cm = np.diag(rng.uniform(0.5, 2.0, 150))
+    pc = PCRV(1, 6, "LU", mi=mi)
+    A = orc.eval_bases(x, mi, "LU")
+    assert rel_err(pc.evalQuadForm(x, Cm, 0), np.einsum("ni,ij,nj->n", A, Cm, A)) < 1e-12
+    # through lreg.predict (anl, full covariance): same mean / variance as predicta on the materialised matrix
+    d, p, n = 8, 3, 9000
+    mi = orc.get_mi(p, d)
+    x = rng.uniform(-1, 1, (n, d))
+    pc = PCRV(1, d, "LU", mi=mi)
+    A = orc.eval_bases(x, mi, "LU")
+    y = A @ (rng.standard_normal(mi.shape[0]) / (1 + mi.sum(1))) + 0.05 * rng.standard_normal(n)
+    a = anl()
+    a.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+    a.fit(x, y)
+    assert float(n) * mi.shape[0] ** 2 >= 2.0e8            # takes the K6 route
+    m1, v1, _ = a.predict(x, msc=1)
+    m2, v2, _ = a.predicta(A, msc=1)
+    assert rel_err(m1, m2) < 1e-12 and rel_err(v1, v2) < 1e-9
+
+
 # ----------------------------------------------------------------------------- K5
 def test_k5_germ_stream_and_propagation():
     import torch

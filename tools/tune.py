@@ -117,3 +117,15 @@ for name, fam, d, p, n in shapes:
             print(f"{name} K4 {tag}: n={n4} {ms:8.3f} ms  {fl / ms / 1e9:6.2f} TFLOP/s(alg)", flush=True)
         setenv(PCQ_GRAM_SYRK=None)
         del S, A
+    if "k6" in which:
+        n6 = min(n, 400_000 if K < 3000 else 60_000)
+        Cm = torch.randn((K, K), dtype=torch.float64, device="cuda", generator=g)
+        Cm = Cm @ Cm.T / K
+        v = torch.empty(n6, dtype=torch.float64, device="cuda")
+        ms = timeit(lambda: _native.check(lib.pcq_quadform_dev(plan.handle, x.data_ptr(), n6, d, Cm.data_ptr(), K, v.data_ptr(), 1, st)), reps=3, warm=1)
+        print(f"{name} K6 quadform: n={n6} {ms:8.3f} ms  {float(n6) * K * K / ms / 1e9:6.2f} TFLOP/s (N K^2)", flush=True)
+        F = torch.linalg.cholesky(Cm + 1e-9 * torch.eye(K, dtype=torch.float64, device="cuda")).T.contiguous()
+        n6b = min(n6, 100_000)
+        ms = timeit(lambda: _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n6b, d, F.data_ptr(), K, v.data_ptr(), 1, 3, st)), reps=2, warm=1)
+        print(f"{name} K2 quadratic-form mode (factor, {K} outputs): n={n6b} {ms:8.3f} ms  -> {ms * n6 / n6b:8.3f} ms at n={n6}", flush=True)
+        del Cm, F, v
