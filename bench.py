@@ -369,6 +369,22 @@ def main():
                 kernels[tag] = {"rows": n, "ms": ms, "samples_per_s": n / (ms * 1e-3),
                                 "TFLOPs_algorithmic": fl / (ms * 1e-3) / 1e12, "bound": "fp64",
                                 "nvrtc_compile_s": t_comp}
+        # K6: predictive variance psi^T C psi as a triangular GEMM on the tensor pipe (N K^2 flops)
+        n6 = min(n, 400_000)
+        Cm = torch.randn((K, K), dtype=torch.float64, device=dev)
+        Cm = Cm @ Cm.T / K
+        v6 = torch.empty(n6, dtype=torch.float64, device=dev)
+        ts = []
+        for it in range(4):
+            e0.record()
+            _native.check(lib.pcq_quadform_dev(plan.handle, x.data_ptr(), n6, D, Cm.data_ptr(), K, v6.data_ptr(), 1, stream))
+            e1.record(); e1.synchronize()
+            if it >= 1:
+                ts.append(e0.elapsed_time(e1))
+        ms = float(np.mean(ts))
+        kernels["K6_quadform_variance"] = {"rows": n6, "ms": ms, "samples_per_s": n6 / (ms * 1e-3),
+                                           "TFLOPs_algorithmic": float(n6) * K * K / (ms * 1e-3) / 1e12, "bound": "tensor"}
+        del Cm, v6
     peak = peaks.get("fp64_dmma_tflops")
     traffic = None
     try:   # DRAM bytes per step of the dominant kernel, from the committed ncu capture of this workload
