@@ -12,6 +12,8 @@
 #include "pcq_internal.cuh"
 
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +50,7 @@ struct Nvrtc {
     int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
     int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
     int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    int (*Version)(int*, int*) = nullptr;
     bool ok = false;
 };
 
@@ -70,6 +73,7 @@ Nvrtc& nvrtc() {
         PCQ_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
         PCQ_SYM(GetProgramLog, "nvrtcGetProgramLog");
         PCQ_SYM(DestroyProgram, "nvrtcDestroyProgram");
+        PCQ_SYM(Version, "nvrtcVersion");
 #undef PCQ_SYM
         N.ok = N.CreateProgram && N.CompileProgram && N.GetCUBINSize && N.GetCUBIN && N.GetProgramLogSize &&
                N.GetProgramLog && N.DestroyProgram;
@@ -151,8 +155,68 @@ std::string gen_source(const pcq_plan* p, int k0, int k1, bool fast, const std::
     return o;
 }
 
+// ---- cubin cache on disk -------------------------------------------------------------------
+// The generated source is a pure function of (multi-index chunk, recurrence constants, mode), so its cubin can
+// be reused across processes: $PCQ_SPEC_CACHE_DIR (default $HOME/.cache/pcq_k2s; empty string disables) holds
+// one file per chunk, named by a 128-bit FNV-1a hash of the source and the NVRTC version.  Writes go through a
+// temporary file + rename, so concurrent ranks never read a partial cubin.
+std::string cache_dir() {
+    const char* e = getenv("PCQ_SPEC_CACHE_DIR");
+    if (e) return std::string(e);
+    const char* home = getenv("HOME");
+    return home ? std::string(home) + "/.cache/pcq_k2s" : std::string();
+}
+
+std::string cache_key(const std::string& src) {
+    unsigned long long h1 = 1469598103934665603ull, h2 = 1099511628211ull * 7919ull;
+    int major = 0, minor = 0;
+    if (nvrtc().Version) nvrtc().Version(&major, &minor);
+    const std::string salted = src + "|sm_100a|nvrtc" + std::to_string(major) + "." + std::to_string(minor);
+    for (unsigned char ch : salted) {
+        h1 = (h1 ^ ch) * 1099511628211ull;
+        h2 = (h2 ^ (ch + 0x9eu)) * 0x100000001b3ull + 0x632be59bd9b4e019ull;
+    }
+    char buf[40];
+    snprintf(buf, sizeof(buf), "%016llx%016llx", h1, h2);
+    return buf;
+}
+
+bool cache_load(const std::string& key, std::vector<char>& cubin) {
+    const std::string dir = cache_dir();
+    if (dir.empty()) return false;
+    FILE* f = fopen((dir + "/" + key + ".cubin").c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    bool ok = sz > 0;
+    if (ok) {
+        cubin.resize((size_t)sz);
+        ok = fread(cubin.data(), 1, (size_t)sz, f) == (size_t)sz;
+    }
+    fclose(f);
+    return ok;
+}
+
+void cache_store(const std::string& key, const std::vector<char>& cubin) {
+    const std::string dir = cache_dir();
+    if (dir.empty()) return;
+    std::string partial;
+    for (size_t i = 1; i <= dir.size(); ++i)          // mkdir -p
+        if (i == dir.size() || dir[i] == '/') { partial = dir.substr(0, i); mkdir(partial.c_str(), 0755); }
+    const std::string tmp = dir + "/" + key + "." + std::to_string((long)getpid()) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    fclose(f);
+    if (ok) rename(tmp.c_str(), (dir + "/" + key + ".cubin").c_str());
+    else remove(tmp.c_str());
+}
+
 int compile_chunk(const std::string& src, const std::string& name, std::vector<char>& cubin, std::string& err) {
     Nvrtc& N = nvrtc();
+    const std::string key = cache_key(src);
+    if (cache_load(key, cubin)) return PCQ_OK;
     nvrtcProgram prog = nullptr;
     if (N.CreateProgram(&prog, src.c_str(), (name + ".cu").c_str(), 0, nullptr, nullptr) != 0) {
         err = "nvrtcCreateProgram failed";
@@ -174,6 +238,7 @@ int compile_chunk(const std::string& src, const std::string& name, std::vector<c
     cubin.resize(cs);
     N.GetCUBIN(prog, cubin.data());
     N.DestroyProgram(&prog);
+    cache_store(key, cubin);
     return PCQ_OK;
 }
 

@@ -386,6 +386,34 @@ def test_k2_specialised_kernels_bitexact():
 
 
 # ----------------------------------------------------------------------------- fitters and workflows
+def test_k2_specialised_cubins_are_cached_on_disk(monkeypatch, tmp_path):
+    """Second build of the same plan (new process in real life; here: plan cache cleared) loads the cubins from
+    PCQ_SPEC_CACHE_DIR instead of compiling, and evaluates to the same bits."""
+    import time
+    from pytuq_b200 import device as _device
+    from pytuq_b200.rv.pcrv import PCRV
+    monkeypatch.setenv("PCQ_SPEC_CACHE_DIR", str(tmp_path / "k2s"))
+    rng = np.random.default_rng(13)
+    mi = orc.get_mi(3, 9)[:211]
+    cf = rng.standard_normal(211)
+    x = rng.standard_normal((500, 9))
+    times, ys = [], []
+    for rep in range(2):
+        _device.clear_plans()
+        pc = PCRV(1, 9, "HG", mi=mi, cfs=[cf])
+        t0 = time.perf_counter()
+        if not pc.specialize(exact=True, fast=False):
+            pytest.skip("NVRTC not available on this box")
+        times.append(time.perf_counter() - t0)
+        ys.append(pc.evalPC(x))
+        if rep == 0:
+            files = sorted(p.name for p in (tmp_path / "k2s").iterdir())
+            assert len(files) == 1 and files[0].endswith(".cubin")
+    assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], orc.eval_pc(x, [mi], [cf], "HG"))
+    assert times[1] < 0.5 * times[0], times
+    _device.clear_plans()
+
+
 def test_k2_hot_plan_is_specialised_automatically(monkeypatch):
     """A plan that keeps being evaluated gets its specialised kernels built once the accumulated work passes
     the threshold; results stay bit-identical across the switch."""
