@@ -97,10 +97,11 @@ def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None):
 # A plan that keeps being evaluated (MCMC likelihoods, repeated surrogate sweeps) is worth compiling for:
 # once the generic evalPC kernel has processed this many sample-terms through one plan, the plan's
 # multi-index-specialised kernels are built (NVRTC, ~1 s per 2000 terms) and used from then on -- 3-4x
-# faster and bit-identical in exact mode.  The threshold is ~4 s of generic-kernel time, so the compile can
+# faster and bit-identical in exact mode.  The threshold is ~1.5 s of generic-kernel time (about the compile
+# time itself: the ski-rental break-even; cubins are cached on disk afterwards), so the compile can
 # at worst double the cost of a job that stops right after it.  PCQ_AUTO_SPECIALIZE=0 disables, any other
 # number replaces the threshold.
-_AUTO_SPECIALIZE = float(os.environ.get("PCQ_AUTO_SPECIALIZE", "4e12"))
+_AUTO_SPECIALIZE = float(os.environ.get("PCQ_AUTO_SPECIALIZE", "1.5e12"))
 _AUTO_SPECIALIZE_MAX_TERMS = 40000
 
 
