@@ -32,7 +32,8 @@ namespace {
 
 struct SyrkParams {
     const double* zp;
-    int Lp, L, ntile, ntri, nsplit;
+    int Lp, L, ntile, ntri, nsplit;   // ntri: tiles of THIS launch (all, off-diagonal only, or diagonal only)
+    int kind;                         // 0 all upper-triangle tiles, 1 off-diagonal tiles, 2 diagonal tiles
     int64_t nstages;       // stages (of STAGE_SAMPLES samples) in this chunk
     double* s_out;
     int accumulate;
@@ -179,6 +180,27 @@ __global__ void __launch_bounds__(256) pcq_pack_matrix_kernel(PackParams P) {
 }
 
 // ------------------------------------------------------------------------------------------ syrk
+__device__ __forceinline__ void tile_of(int kind, int t, int ntile, int& I, int& J) {
+    if (kind == 2) { I = J = t; return; }
+    if (kind == 0) { tile_decode(t, ntile, I, J); return; }
+    int i = 0, rem = t;                       // off-diagonal: row i holds ntile - 1 - i tiles
+    while (rem >= ntile - 1 - i) { rem -= ntile - 1 - i; ++i; }
+    I = i;
+    J = i + 1 + rem;
+}
+
+// Diagonal tiles only need their upper triangle.  In 32 x 32 sub-blocks that is 10 of 16; they are dealt to the
+// eight warps so that the four schedulers (warp % 4) carry 3, 3, 2, 2 of them -- the DMMA pipe is per scheduler
+// and one warp saturates it -- which makes a diagonal unit cost 3/4 of a full tile instead of 1.
+__device__ __forceinline__ void diag_blocks(int warp, int& nh, int (&hr)[2], int (&hc)[2]) {
+    // first block of warp 0..7: (0,0) (1,1) (2,2) (3,3) (0,2) (0,3) (1,3) (2,3); warps 0, 1 also take (0,1), (1,2)
+    hr[0] = warp < 4 ? warp : (warp < 6 ? 0 : warp - 5);
+    hc[0] = warp < 4 ? warp : (warp == 4 ? 2 : 3);
+    nh = warp < 2 ? 2 : 1;
+    hr[1] = warp < 2 ? warp : 0;
+    hc[1] = warp < 2 ? warp + 1 : 0;          // warp 0: (0,1), warp 1: (1,2)
+}
+
 // producer cursor: the (unit, stage) sequence this CTA walks, one step ahead of the consumers
 struct SyCursor {
     int u; int I, J; int64_t st, st1; uint32_t pit;
@@ -186,7 +208,7 @@ struct SyCursor {
 __device__ __forceinline__ void cursor_open(const SyrkParams& P, SyCursor& c, int units) {
     while (c.u < units) {
         const int part = c.u / P.ntri, t = c.u - part * P.ntri;
-        tile_decode(t, P.ntile, c.I, c.J);
+        tile_of(P.kind, t, P.ntile, c.I, c.J);
         c.st = (int64_t)part * P.nstages / P.nsplit;
         c.st1 = (int64_t)(part + 1) * P.nstages / P.nsplit;
         if (c.st < c.st1) return;
@@ -194,7 +216,7 @@ __device__ __forceinline__ void cursor_open(const SyrkParams& P, SyCursor& c, in
     }
 }
 
-template <int ST>
+template <int ST, bool DIAGH>      // DIAGH: diagonal tiles computed as balanced 32 x 32 sub-blocks (P.kind == 2, ST == 128)
 __global__ void __launch_bounds__(SY_THREADS, 1) pcq_syrk_kernel(SyrkParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int CHUNK = ST * SB;        // doubles per operand chunk (8 KB at ST = 128)
@@ -242,13 +264,16 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_syrk_kernel(SyrkParams P) {
 
     // -------------------- consumer warps
     const int g = lane >> 2, tig = lane & 3, wm = warp & 3, wn = warp >> 2;
+    int nh = 0, hr[2] = {0, 0}, hc[2] = {0, 0};
+    if (DIAGH) diag_blocks(warp, nh, hr, hc);
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int part = u / P.ntri, t = u - part * P.ntri;
         int I, J;
-        tile_decode(t, P.ntile, I, J);
+        tile_of(P.kind, t, P.ntile, I, J);
         const bool diag = (I == J);
         const int64_t st0 = (int64_t)part * P.nstages / P.nsplit;
         const int64_t st1 = (int64_t)(part + 1) * P.nstages / P.nsplit;
+        // DIAGH: acc[h*2 + i/2 ...] is viewed as two 32 x 32 blocks: acc[i][4 h + j], h = block, i, j < 4
         double acc[FM][FN][2];
 #pragma unroll
         for (int i = 0; i < FM; ++i)
@@ -260,53 +285,84 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_syrk_kernel(SyrkParams P) {
             const uint32_t ph = (it / NSTAGE) & 1u;
             mbar_wait(full + b, ph);
             const double* oa = ops + (size_t)(b * 2) * KS * CHUNK;
-            const double* ob = diag ? oa : oa + (size_t)KS * CHUNK;
-            const double* pa = oa + (wm * (FM * 8) + g) * SB + 2 * tig;
-            const double* pb = ob + (wn * (FN * 8) + g) * SB + 2 * tig;
+            if (DIAGH) {
+                const double* q = oa + g * SB + 2 * tig;
 #pragma unroll
-            for (int kb = 0; kb < KS; ++kb) {
-                double2 af[FM], bf[FN];
+                for (int kb = 0; kb < KS; ++kb) {
 #pragma unroll
-                for (int i = 0; i < FM; ++i) af[i] = *reinterpret_cast<const double2*>(pa + kb * CHUNK + i * 8 * SB);
+                    for (int h = 0; h < 2; ++h) {
+                        if (h < nh) {
+                            double2 af[4], bf[4];
 #pragma unroll
-                for (int j = 0; j < FN; ++j) bf[j] = *reinterpret_cast<const double2*>(pb + kb * CHUNK + j * 8 * SB);
+                            for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double2*>(q + kb * CHUNK + (hr[h] * 32 + i * 8) * SB);
 #pragma unroll
-                for (int i = 0; i < FM; ++i)
+                            for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double2*>(q + kb * CHUNK + (hc[h] * 32 + j * 8) * SB);
 #pragma unroll
-                    for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+                            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int i = 0; i < FM; ++i)
+                                for (int j = 0; j < 4; ++j) dmma(acc[i][4 * h + j][0], acc[i][4 * h + j][1], af[i].x, bf[j].x);
 #pragma unroll
-                    for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
-                if (warp == 0) try_issue(kb == KS - 1);
+                            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) dmma(acc[i][4 * h + j][0], acc[i][4 * h + j][1], af[i].y, bf[j].y);
+                        }
+                    }
+                    if (warp == 0) try_issue(kb == KS - 1);
+                }
+            } else {
+                const double* ob = diag ? oa : oa + (size_t)KS * CHUNK;
+                const double* pa = oa + (wm * (FM * 8) + g) * SB + 2 * tig;
+                const double* pb = ob + (wn * (FN * 8) + g) * SB + 2 * tig;
+#pragma unroll
+                for (int kb = 0; kb < KS; ++kb) {
+                    double2 af[FM], bf[FN];
+#pragma unroll
+                    for (int i = 0; i < FM; ++i) af[i] = *reinterpret_cast<const double2*>(pa + kb * CHUNK + i * 8 * SB);
+#pragma unroll
+                    for (int j = 0; j < FN; ++j) bf[j] = *reinterpret_cast<const double2*>(pb + kb * CHUNK + j * 8 * SB);
+#pragma unroll
+                    for (int i = 0; i < FM; ++i)
+#pragma unroll
+                        for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+                    for (int i = 0; i < FM; ++i)
+#pragma unroll
+                        for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+                    if (warp == 0) try_issue(kb == KS - 1);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + b);
         }
 
-        if (P.nsplit == 1) {
+        // tile-local (row, column) of accumulator (i, j): the regular 4 x 2 warp grid, or this warp's sub-blocks
+        auto rc_of = [&](int i, int j, int& row, int& c) {
+            if (DIAGH) {
+                const int h = j >> 2;
+                row = hr[h] * 32 + i * 8 + g;
+                c = hc[h] * 32 + (j & 3) * 8 + 2 * tig;
+            } else {
+                row = wm * (FM * 8) + i * 8 + g;
+                c = wn * (FN * 8) + j * 8 + 2 * tig;
+            }
+        };
+        double* w = P.nsplit == 1 ? nullptr : P.ws + ((size_t)t * P.nsplit + part) * ST * ST;
 #pragma unroll
-            for (int i = 0; i < FM; ++i) {
-                const int row = I * ST + wm * (FM * 8) + i * 8 + g;
+        for (int i = 0; i < FM; ++i) {
 #pragma unroll
-                for (int j = 0; j < FN; ++j) {
-                    const int c = J * ST + wn * (FN * 8) + j * 8 + 2 * tig;
+            for (int j = 0; j < FN; ++j) {
+                if (DIAGH && (j >> 2) >= nh) continue;
+                int rl, cl;
+                rc_of(i, j, rl, cl);
+                if (w) {
+                    *reinterpret_cast<double2*>(w + (size_t)rl * ST + cl) = make_double2(acc[i][j][0], acc[i][j][1]);
+                } else {
+                    const int row = I * ST + rl, c = J * ST + cl;
                     if (row < P.L) {
                         double* dst = P.s_out + (size_t)row * P.L + c;
                         if (c < P.L) dst[0] = (P.accumulate ? dst[0] : 0.0) + acc[i][j][0];
                         if (c + 1 < P.L) dst[1] = (P.accumulate ? dst[1] : 0.0) + acc[i][j][1];
                     }
-                }
-            }
-        } else {
-            double* w = P.ws + ((size_t)t * P.nsplit + part) * ST * ST;
-#pragma unroll
-            for (int i = 0; i < FM; ++i) {
-                const int row = wm * (FM * 8) + i * 8 + g;
-#pragma unroll
-                for (int j = 0; j < FN; ++j) {
-                    const int c = wn * (FN * 8) + j * 8 + 2 * tig;
-                    *reinterpret_cast<double2*>(w + (size_t)row * ST + c) = make_double2(acc[i][j][0], acc[i][j][1]);
                 }
             }
         }
@@ -318,13 +374,13 @@ template <int ST>
 __global__ void __launch_bounds__(256) pcq_syrk_fixup_kernel(SyrkParams P) {
     const int t = blockIdx.x;
     int I, J;
-    tile_decode(t, P.ntile, I, J);
+    tile_of(P.kind, t, P.ntile, I, J);
     const double* w = P.ws + (size_t)t * P.nsplit * ST * ST;
     constexpr int PER = ST * ST / 8;      // elements per blockIdx.y slice
     for (int e = blockIdx.y * PER + threadIdx.x; e < (blockIdx.y + 1) * PER; e += 256) {
         const int r = e / ST, c = e - r * ST;
         const int row = I * ST + r, cc = J * ST + c;
-        if (row >= P.L || cc >= P.L) continue;
+        if (row >= P.L || cc >= P.L || row > cc) continue;      // the mirror kernel fills the lower triangle
         double sum = 0.0;
         for (int q = 0; q < P.nsplit; ++q) sum += w[(size_t)q * ST * ST + e];
         double* dst = P.s_out + (size_t)row * P.L + cc;
@@ -353,7 +409,7 @@ __global__ void __launch_bounds__(256) pcq_syrk_mirror_kernel(double* s, int L) 
 int choose_split(int ntri, int grid, int64_t nstages) {
     int best = 1;
     double best_cost = 1e300;
-    const int smax = (int)(nstages < 16 ? nstages : 16);
+    const int smax = (int)(nstages < 32 ? nstages : 32);
     for (int S = 1; S <= smax; ++S) {
         const int64_t waves = ((int64_t)ntri * S + grid - 1) / grid;
         // every part is ceil(nstages / S) stages at worst; a small per-unit term for the tile flush
@@ -407,8 +463,9 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
     }
     int rc = pcq_ensure_dev(zbuf, zbuf_bytes, (size_t)rows * Lp * sizeof(double));
     if (rc != PCQ_OK) return rc;
-    PCQ_CUDA(cudaFuncSetAttribute(pcq_syrk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem_bytes(128)));
-    PCQ_CUDA(cudaFuncSetAttribute(pcq_syrk_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem_bytes(96)));
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_syrk_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem_bytes(128)));
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_syrk_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem_bytes(128)));
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_syrk_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem_bytes(96)));
 
     for (int64_t r0 = 0; r0 < n; r0 += rows) {
         const int64_t nr = (n - r0 < rows) ? n - r0 : rows;
@@ -445,28 +502,57 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
             PCQ_LAUNCH_CHECK("pcq_pack_matrix_kernel");
         }
 
-        SyrkParams P;
-        memset(&P, 0, sizeof(P));
-        P.zp = *zbuf; P.Lp = Lp; P.L = L; P.ntile = ntile; P.ntri = ntri; P.nstages = nstages;
-        P.s_out = s; P.accumulate = (accumulate || r0 > 0) ? 1 : 0;
-        const char* senv = getenv("PCQ_SYRK_SPLIT");
-        P.nsplit = senv ? atoi(senv) : choose_split(ntri, num_sms, nstages);
-        if (P.nsplit < 1) P.nsplit = 1;
-        if (P.nsplit > nstages) P.nsplit = (int)nstages;
-        if (P.nsplit > 1) {
-            rc = pcq_ensure_dev(ws, ws_bytes, (size_t)ntri * P.nsplit * ST * ST * sizeof(double));
-            if (rc != PCQ_OK) return rc;
-            P.ws = *ws;
+        // One launch over all upper-triangle tiles, or -- 128-wide tiles, more than one tile -- two: the
+        // off-diagonal tiles, then the diagonal tiles as balanced sub-blocks (3/4 of the cost each).  Each
+        // launch gets its own number of sample parts, so both fill the SMs in whole waves
+        // (K = 1771: 91 tiles x 13 parts = 7.99 waves, 14 diagonal tiles x 21 parts = 1.99 waves).
+        const char* denv = getenv("PCQ_SYRK_DIAG");
+        const bool split_diag = ST == 128 && !(denv && atoi(denv) == 0);
+        struct Pass { int kind, ntiles; bool diagh; };
+        Pass passes[2];
+        int npass = 0;
+        if (split_diag) {
+            if (ntri - ntile > 0) passes[npass++] = {1, ntri - ntile, false};
+            passes[npass++] = {2, ntile, true};
+        } else {
+            passes[npass++] = {0, ntri, false};
         }
-        const int units = ntri * P.nsplit;
-        const int sgrid = units < num_sms ? units : num_sms;
-        if (ST == 128) pcq_syrk_kernel<128><<<sgrid, SY_THREADS, smem, st>>>(P);
-        else pcq_syrk_kernel<96><<<sgrid, SY_THREADS, smem, st>>>(P);
-        PCQ_LAUNCH_CHECK("pcq_syrk_kernel");
-        if (P.nsplit > 1) {
-            if (ST == 128) pcq_syrk_fixup_kernel<128><<<dim3(ntri, 8), 256, 0, st>>>(P);
-            else pcq_syrk_fixup_kernel<96><<<dim3(ntri, 8), 256, 0, st>>>(P);
-            PCQ_LAUNCH_CHECK("pcq_syrk_fixup_kernel");
+        const char* senv = getenv("PCQ_SYRK_SPLIT");
+        int nsplit[2] = {1, 1};
+        size_t ws_need = 0;
+        for (int q = 0; q < npass; ++q) {
+            int S = senv ? atoi(senv) : choose_split(passes[q].ntiles, num_sms, nstages);
+            if (S < 1) S = 1;
+            if (S > nstages) S = (int)nstages;
+            nsplit[q] = S;
+            if (S > 1) ws_need += (size_t)passes[q].ntiles * S * ST * ST * sizeof(double);
+        }
+        if (ws_need) {
+            rc = pcq_ensure_dev(ws, ws_bytes, ws_need);
+            if (rc != PCQ_OK) return rc;
+        }
+        size_t ws_off = 0;
+        for (int q = 0; q < npass; ++q) {
+            SyrkParams P;
+            memset(&P, 0, sizeof(P));
+            P.zp = *zbuf; P.Lp = Lp; P.L = L; P.ntile = ntile; P.ntri = passes[q].ntiles; P.kind = passes[q].kind;
+            P.nstages = nstages; P.nsplit = nsplit[q];
+            P.s_out = s; P.accumulate = (accumulate || r0 > 0) ? 1 : 0;
+            if (P.nsplit > 1) {
+                P.ws = *ws + ws_off;
+                ws_off += (size_t)P.ntri * P.nsplit * ST * ST;
+            }
+            const int units = P.ntri * P.nsplit;
+            const int sgrid = units < num_sms ? units : num_sms;
+            if (passes[q].diagh) pcq_syrk_kernel<128, true><<<sgrid, SY_THREADS, smem, st>>>(P);
+            else if (ST == 128) pcq_syrk_kernel<128, false><<<sgrid, SY_THREADS, smem, st>>>(P);
+            else pcq_syrk_kernel<96, false><<<sgrid, SY_THREADS, smem, st>>>(P);
+            PCQ_LAUNCH_CHECK("pcq_syrk_kernel");
+            if (P.nsplit > 1) {
+                if (ST == 128) pcq_syrk_fixup_kernel<128><<<dim3(P.ntri, 8), 256, 0, st>>>(P);
+                else pcq_syrk_fixup_kernel<96><<<dim3(P.ntri, 8), 256, 0, st>>>(P);
+                PCQ_LAUNCH_CHECK("pcq_syrk_fixup_kernel");
+            }
         }
     }
     const int nb32 = (L + 31) / 32;
