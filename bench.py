@@ -433,14 +433,16 @@ def main():
         "breakdown_ms": {"k3_suffstats": k3_mean_ms, "allreduce": float(np.mean(ar_ms)),
                          "solve_kxk": 1e3 * float(np.mean(solve_s))},
         "max_abs_coef_error_vs_truth": err,
-        "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; 96.3 % of the step, the rest is "
-                               "pcq_pack_bases_kernel 2.6 %, fix-up/mirror 0.2 %, K x K solve 1 %; profiles/r01_j_k3_traffic.json)",
+        "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; per chunk one launch over the "
+                               "off-diagonal tiles, 85.1 % of the step, and one over the diagonal tiles, 10.8 %; the rest is "
+                               "pcq_pack_bases_kernel 2.6 %, fix-up/mirror 0.5 %, K x K solve 1 %; profiles/r01_j_k3_traffic.json)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if peak else None, "traffic": traffic,
-                     "traffic_note": "DRAM read+write bytes of the 9 pcq_syrk_kernel launches of one step (ncu, "
+                     "traffic_note": "DRAM read+write bytes of the 18 pcq_syrk_kernel launches of one step (ncu, "
                                      "profiles/r01_j_k3_traffic.json): the packed design matrix (17.9 GB, written once by the "
-                                     "pack kernel) is read 1.43x; the kernel is tensor-pipe bound (DMMA pipe 97.5 %% active), "
-                                     "DRAM runs at ~0.2 TB/s; algorithmic input bytes = %d" % (8 * n * (D + 1)),
+                                     "pack kernel) is read 1.4x by the off-diagonal pass and once by the diagonal pass; the "
+                                     "kernels are tensor-pipe bound (DMMA pipe 96.6 %% active in the off-diagonal pass), DRAM "
+                                     "runs at ~0.35 TB/s; algorithmic input bytes = %d" % (8 * n * (D + 1)),
                      "achieved_note": "algorithmic flops of one step / duration of the whole pcq_suffstats_dev call "
                                       "(pack + SYRK + fix-up + mirror launches), CUDA events on the launching stream",
                      "algorithmic_flops_per_launch": flops,
