@@ -45,12 +45,43 @@ def test_no_cpu_fallback_without_device():
         pc.evalPC(np.zeros((3, 2)))
     with pytest.raises(_native.PcqError):
         pc.suffStats(np.zeros((3, 2)), np.zeros(3))
+    with pytest.raises(_native.PcqError):
+        pc.evalQuadForm(np.zeros((3, 2)), np.eye(6), 0)
+    from pytuq_b200.lreg import lsq, tsqr
+    with pytest.raises(_native.PcqError):
+        lsq().fita(np.ones((5, 2)), np.ones(5))
+    with pytest.raises(_native.PcqError):
+        tsqr.r_factor_pc(pc, np.zeros((3, 2)), np.zeros(3))
+    from pytuq_b200.linred.kle import KLE
+    with pytest.raises(_native.PcqError):
+        KLE().build(np.ones((4, 9)), plot=False)
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """Argument errors are reported through the status code + pcq_last_error(), on any box."""
+    from pytuq_b200 import _native
+    lib = _native.lib()
+    buf = np.zeros(4)
+    for call in (lambda: lib.pcq_eval_bases_dev(None, _native.ptr(buf), 1, 2, _native.ptr(buf), 2, None),
+                 lambda: lib.pcq_eval_pc_dev(None, _native.ptr(buf), 1, 2, _native.ptr(buf), 1, _native.ptr(buf), 1, 0, None),
+                 lambda: lib.pcq_suffstats_dev(None, _native.ptr(buf), 1, 2, _native.ptr(buf), 1, 1, _native.ptr(buf), 0, None),
+                 lambda: lib.pcq_quadform_dev(None, _native.ptr(buf), 1, 2, _native.ptr(buf), 2, _native.ptr(buf), 1, None),
+                 lambda: lib.pcq_residual_ss_dev(None, _native.ptr(buf), 1, 2, _native.ptr(buf), 1, _native.ptr(buf),
+                                                 _native.ptr(buf), 0, None),
+                 lambda: lib.pcq_gram_dev(0, _native.ptr(buf), 2, 1, 2, None, 1, 0, _native.ptr(buf), 0, None),   # lda < kcols
+                 lambda: lib.pcq_plan_specialize(None, 1)):
+        rc = call()
+        assert rc < 0
+    assert lib.pcq_gram_dev(0, _native.ptr(buf), 2, 1, 2, None, 1, 0, _native.ptr(buf), 0, None) == -1
+    assert b"bad argument" in lib.pcq_last_error()
+    assert lib.pcq_suffstats_dim(None, 1) < 0 and lib.pcq_plan_info(None, 0) < 0
 
 
 def test_product_does_not_import_oracle():
     import subprocess, sys
     code = ("import sys; sys.path.insert(0, %r); import pytuq_b200, pytuq_b200.rv.pcrv, pytuq_b200.lreg, "
-            "pytuq_b200.workflows, pytuq_b200.surrogates.pce, pytuq_b200.gsa.gsa, pytuq_b200.parallel; "
+            "pytuq_b200.workflows, pytuq_b200.surrogates.pce, pytuq_b200.gsa.gsa, pytuq_b200.parallel, "
+            "pytuq_b200.lreg.tsqr, pytuq_b200.linred.kle, pytuq_b200.linred.klsurr; "
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)" % ROOT)
     subprocess.run([sys.executable, "-c", code], check=True)
     for dirpath, _, files in os.walk(os.path.join(ROOT, "pytuq_b200")):
