@@ -12,8 +12,8 @@
 namespace {
 
 // The output tile edge ST is a template parameter of the SYRK kernels: 128 (warp tile 32 x 64), or 96 (warp
-// tile 24 x 48) where 128 would pad L by much more (K = 1326: 1408 vs 1344 columns, 10 % fewer executed
-// flops, 27.7 -> 28.6 TFLOP/s).
+// tile 24 x 48) where 128 would execute clearly more flops.  Since the diagonal tiles have their own
+// sub-block pass (128 only) that is rare: L just below a multiple of 96 and small.
 constexpr int SB = 8;              // contraction values per block (two DMMA k-steps)
 constexpr int KS = 4;              // blocks per pipeline stage
 constexpr int NSTAGE = 3;

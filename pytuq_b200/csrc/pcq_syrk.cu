@@ -189,16 +189,19 @@ __device__ __forceinline__ void tile_of(int kind, int t, int ntile, int& I, int&
     J = i + 1 + rem;
 }
 
-// Diagonal tiles only need their upper triangle.  In 32 x 32 sub-blocks that is 10 of 16; they are dealt to the
-// eight warps so that the four schedulers (warp % 4) carry 3, 3, 2, 2 of them -- the DMMA pipe is per scheduler
-// and one warp saturates it -- which makes a diagonal unit cost 3/4 of a full tile instead of 1.
-__device__ __forceinline__ void diag_blocks(int warp, int& nh, int (&hr)[2], int (&hc)[2]) {
-    // first block of warp 0..7: (0,0) (1,1) (2,2) (3,3) (0,2) (0,3) (1,3) (2,3); warps 0, 1 also take (0,1), (1,2)
-    hr[0] = warp < 4 ? warp : (warp < 6 ? 0 : warp - 5);
-    hc[0] = warp < 4 ? warp : (warp == 4 ? 2 : 3);
-    nh = warp < 2 ? 2 : 1;
-    hr[1] = warp < 2 ? warp : 0;
-    hc[1] = warp < 2 ? warp + 1 : 0;          // warp 0: (0,1), warp 1: (1,2)
+// Diagonal tiles only need their upper triangle: 10 of the 16 32 x 32 sub-blocks.  The sub-blocks of ALL diagonal
+// tiles are laid out in one list (tile-major) and cut into units of eight, one sub-block per warp, so that every
+// scheduler (two warps) carries exactly two of them: a diagonal unit costs half a full tile and 1.25 units cover a
+// tile.  Eight consecutive list entries touch at most two tiles, which arrive in the two operand slots of a stage.
+__device__ __forceinline__ void diag_subblock(int h, int& hr, int& hc) {
+    // h: 0..9 -> (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3)
+    hr = h < 4 ? 0 : (h < 7 ? 1 : (h < 9 ? 2 : 3));
+    hc = h < 4 ? h : (h < 7 ? h - 3 : (h < 9 ? h - 5 : 3));
+}
+__device__ __forceinline__ void diag_unit_tiles(int t, int ntile, int& I, int& J) {
+    I = (t * 8) / 10;
+    J = (t * 8 + 7) / 10;
+    if (J > ntile - 1) J = ntile - 1;
 }
 
 // producer cursor: the (unit, stage) sequence this CTA walks, one step ahead of the consumers
@@ -208,7 +211,8 @@ struct SyCursor {
 __device__ __forceinline__ void cursor_open(const SyrkParams& P, SyCursor& c, int units) {
     while (c.u < units) {
         const int part = c.u / P.ntri, t = c.u - part * P.ntri;
-        tile_of(P.kind, t, P.ntile, c.I, c.J);
+        if (P.kind == 2) diag_unit_tiles(t, P.ntile, c.I, c.J);
+        else tile_of(P.kind, t, P.ntile, c.I, c.J);
         c.st = (int64_t)part * P.nstages / P.nsplit;
         c.st1 = (int64_t)(part + 1) * P.nstages / P.nsplit;
         if (c.st < c.st1) return;
@@ -264,17 +268,26 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_syrk_kernel(SyrkParams P) {
 
     // -------------------- consumer warps
     const int g = lane >> 2, tig = lane & 3, wm = warp & 3, wn = warp >> 2;
-    int nh = 0, hr[2] = {0, 0}, hc[2] = {0, 0};
-    if (DIAGH) diag_blocks(warp, nh, hr, hc);
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int part = u / P.ntri, t = u - part * P.ntri;
         int I, J;
-        tile_of(P.kind, t, P.ntile, I, J);
+        // DIAGH: this warp's sub-block (hr, hc) of diagonal tile mytile, operand slot `which`; idle past the list end
+        int mytile = 0, hr = 0, hc = 0, which = 0;
+        bool active = true;
+        if (DIAGH) {
+            diag_unit_tiles(t, P.ntile, I, J);
+            const int e = t * 8 + warp;
+            active = e < 10 * P.ntile;
+            mytile = active ? e / 10 : I;
+            diag_subblock(active ? e - mytile * 10 : 0, hr, hc);
+            which = (mytile != I) ? 1 : 0;
+        } else {
+            tile_of(P.kind, t, P.ntile, I, J);
+        }
         const bool diag = (I == J);
         const int64_t st0 = (int64_t)part * P.nstages / P.nsplit;
         const int64_t st1 = (int64_t)(part + 1) * P.nstages / P.nsplit;
-        // DIAGH: acc[h*2 + i/2 ...] is viewed as two 32 x 32 blocks: acc[i][4 h + j], h = block, i, j < 4
-        double acc[FM][FN][2];
+        double acc[FM][FN][2];            // DIAGH uses acc[i][j], i, j < 4 (one 32 x 32 sub-block)
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -286,26 +299,23 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_syrk_kernel(SyrkParams P) {
             mbar_wait(full + b, ph);
             const double* oa = ops + (size_t)(b * 2) * KS * CHUNK;
             if (DIAGH) {
-                const double* q = oa + g * SB + 2 * tig;
+                const double* q = oa + (which ? (size_t)KS * CHUNK : 0) + g * SB + 2 * tig;
 #pragma unroll
                 for (int kb = 0; kb < KS; ++kb) {
+                    if (active) {
+                        double2 af[4], bf[4];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h < nh) {
-                            double2 af[4], bf[4];
+                        for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double2*>(q + kb * CHUNK + (hr * 32 + i * 8) * SB);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double2*>(q + kb * CHUNK + (hr[h] * 32 + i * 8) * SB);
+                        for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double2*>(q + kb * CHUNK + (hc * 32 + j * 8) * SB);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double2*>(q + kb * CHUNK + (hc[h] * 32 + j * 8) * SB);
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
+                            for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) dmma(acc[i][4 * h + j][0], acc[i][4 * h + j][1], af[i].x, bf[j].x);
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) dmma(acc[i][4 * h + j][0], acc[i][4 * h + j][1], af[i].y, bf[j].y);
-                        }
+                            for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
                     }
                     if (warp == 0) try_issue(kb == KS - 1);
                 }
@@ -335,33 +345,36 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_syrk_kernel(SyrkParams P) {
             if (lane == 0) mbar_arrive(empty + b);
         }
 
-        // tile-local (row, column) of accumulator (i, j): the regular 4 x 2 warp grid, or this warp's sub-blocks
+        // tile-local (row, column) of accumulator (i, j): the regular 4 x 2 warp grid, or this warp's sub-block
         auto rc_of = [&](int i, int j, int& row, int& c) {
             if (DIAGH) {
-                const int h = j >> 2;
-                row = hr[h] * 32 + i * 8 + g;
-                c = hc[h] * 32 + (j & 3) * 8 + 2 * tig;
+                row = hr * 32 + i * 8 + g;
+                c = hc * 32 + j * 8 + 2 * tig;
             } else {
                 row = wm * (FM * 8) + i * 8 + g;
                 c = wn * (FN * 8) + j * 8 + 2 * tig;
             }
         };
-        double* w = P.nsplit == 1 ? nullptr : P.ws + ((size_t)t * P.nsplit + part) * ST * ST;
+        const int ti = DIAGH ? mytile : I, tj = DIAGH ? mytile : J;     // output tile this warp writes
+        const int tslot = DIAGH ? mytile : t;                            // its workspace slot
+        double* w = P.nsplit == 1 ? nullptr : P.ws + ((size_t)tslot * P.nsplit + part) * ST * ST;
+        if (!DIAGH || active) {
 #pragma unroll
-        for (int i = 0; i < FM; ++i) {
+            for (int i = 0; i < FM; ++i) {
 #pragma unroll
-            for (int j = 0; j < FN; ++j) {
-                if (DIAGH && (j >> 2) >= nh) continue;
-                int rl, cl;
-                rc_of(i, j, rl, cl);
-                if (w) {
-                    *reinterpret_cast<double2*>(w + (size_t)rl * ST + cl) = make_double2(acc[i][j][0], acc[i][j][1]);
-                } else {
-                    const int row = I * ST + rl, c = J * ST + cl;
-                    if (row < P.L) {
-                        double* dst = P.s_out + (size_t)row * P.L + c;
-                        if (c < P.L) dst[0] = (P.accumulate ? dst[0] : 0.0) + acc[i][j][0];
-                        if (c + 1 < P.L) dst[1] = (P.accumulate ? dst[1] : 0.0) + acc[i][j][1];
+                for (int j = 0; j < FN; ++j) {
+                    if (DIAGH && j >= 4) continue;
+                    int rl, cl;
+                    rc_of(i, j, rl, cl);
+                    if (w) {
+                        *reinterpret_cast<double2*>(w + (size_t)rl * ST + cl) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    } else {
+                        const int row = ti * ST + rl, c = tj * ST + cl;
+                        if (row < P.L) {
+                            double* dst = P.s_out + (size_t)row * P.L + c;
+                            if (c < P.L) dst[0] = (P.accumulate ? dst[0] : 0.0) + acc[i][j][0];
+                            if (c + 1 < P.L) dst[1] = (P.accumulate ? dst[1] : 0.0) + acc[i][j][1];
+                        }
                     }
                 }
             }
@@ -436,8 +449,11 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
     // than 128 (36 instead of 64 independent DMMAs between fragment loads); PCQ_SYRK_TILE forces it
     int ST = 128;
     {
-        auto executed = [&](int t) { const double nt = (L + t - 1) / t; return nt * (nt + 1) / 2 * t * t; };
-        if (executed(96) * 1.07 < executed(128)) ST = 96;
+        // cost in flops: 128-wide tiles with the diagonal tiles at 5/8 (sub-block pass), 96-wide tiles in full
+        const double n128 = (L + 127) / 128, n96 = (L + 95) / 96;
+        const double cost128 = (n128 * (n128 - 1) / 2 + 0.625 * n128) * 128.0 * 128.0;
+        const double cost96 = n96 * (n96 + 1) / 2 * 96.0 * 96.0;
+        if (cost96 * 1.07 < cost128) ST = 96;
         if (const char* e = getenv("PCQ_SYRK_TILE")) { const int v = atoi(e); if (v == 96 || v == 128) ST = v; }
     }
     const int ntile = (L + ST - 1) / ST;
@@ -508,14 +524,14 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
         // (K = 1771: 91 tiles x 13 parts = 7.99 waves, 14 diagonal tiles x 21 parts = 1.99 waves).
         const char* denv = getenv("PCQ_SYRK_DIAG");
         const bool split_diag = ST == 128 && !(denv && atoi(denv) == 0);
-        struct Pass { int kind, ntiles; bool diagh; };
+        struct Pass { int kind, ntiles; bool diagh; int wstiles; };     // ntiles: scheduling units per part
         Pass passes[2];
         int npass = 0;
         if (split_diag) {
-            if (ntri - ntile > 0) passes[npass++] = {1, ntri - ntile, false};
-            passes[npass++] = {2, ntile, true};
+            if (ntri - ntile > 0) passes[npass++] = {1, ntri - ntile, false, ntri - ntile};
+            passes[npass++] = {2, (10 * ntile + 7) / 8, true, ntile};
         } else {
-            passes[npass++] = {0, ntri, false};
+            passes[npass++] = {0, ntri, false, ntri};
         }
         const char* senv = getenv("PCQ_SYRK_SPLIT");
         int nsplit[2] = {1, 1};
@@ -525,7 +541,7 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
             if (S < 1) S = 1;
             if (S > nstages) S = (int)nstages;
             nsplit[q] = S;
-            if (S > 1) ws_need += (size_t)passes[q].ntiles * S * ST * ST * sizeof(double);
+            if (S > 1) ws_need += (size_t)passes[q].wstiles * S * ST * ST * sizeof(double);
         }
         if (ws_need) {
             rc = pcq_ensure_dev(ws, ws_bytes, ws_need);
@@ -540,7 +556,7 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
             P.s_out = s; P.accumulate = (accumulate || r0 > 0) ? 1 : 0;
             if (P.nsplit > 1) {
                 P.ws = *ws + ws_off;
-                ws_off += (size_t)P.ntri * P.nsplit * ST * ST;
+                ws_off += (size_t)passes[q].wstiles * P.nsplit * ST * ST;
             }
             const int units = P.ntri * P.nsplit;
             const int sgrid = units < num_sms ? units : num_sms;
@@ -549,8 +565,8 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
             else pcq_syrk_kernel<96, false><<<sgrid, SY_THREADS, smem, st>>>(P);
             PCQ_LAUNCH_CHECK("pcq_syrk_kernel");
             if (P.nsplit > 1) {
-                if (ST == 128) pcq_syrk_fixup_kernel<128><<<dim3(P.ntri, 8), 256, 0, st>>>(P);
-                else pcq_syrk_fixup_kernel<96><<<dim3(P.ntri, 8), 256, 0, st>>>(P);
+                if (ST == 128) pcq_syrk_fixup_kernel<128><<<dim3(passes[q].wstiles, 8), 256, 0, st>>>(P);
+                else pcq_syrk_fixup_kernel<96><<<dim3(passes[q].wstiles, 8), 256, 0, st>>>(P);
                 PCQ_LAUNCH_CHECK("pcq_syrk_fixup_kernel");
             }
         }
