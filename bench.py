@@ -434,8 +434,9 @@ def main():
                          "solve_kxk": 1e3 * float(np.mean(solve_s))},
         "max_abs_coef_error_vs_truth": err,
         "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; per chunk one launch over the "
-                               "off-diagonal tiles, 85.1 % of the step, and one over the diagonal tiles, 10.8 %; the rest is "
-                               "pcq_pack_bases_kernel 2.6 %, fix-up/mirror 0.5 %, K x K solve 1 %; profiles/r01_j_k3_traffic.json)",
+                               "off-diagonal tiles, 86.3 % of the step, and one over the upper-triangle sub-blocks of the diagonal tiles, "
+                               "9.6 %; the rest is pcq_pack_bases_kernel 2.6 %, fix-up/mirror 0.4 %, K x K solve 1 %; "
+                               "profiles/r01_j_k3_traffic.json)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if peak else None, "traffic": traffic,
                      "traffic_note": "DRAM read+write bytes of the 18 pcq_syrk_kernel launches of one step (ncu, "
