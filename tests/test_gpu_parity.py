@@ -252,10 +252,11 @@ def test_k3_k4_syrk_chunks_splits_and_fused_fallback(monkeypatch):
     pc2 = PCRV(1, d2, "LU", mi=mi2)
     ref2 = orc.suffstats(orc.eval_bases(x2, mi2, "LU"), y2)
     for env in ({}, {"PCQ_SYRK_CHUNK_MB": "1"}, {"PCQ_SYRK_SPLIT": "1"}, {"PCQ_SYRK_SPLIT": "5"},
-                {"PCQ_SYRK_CHUNK_MB": "1", "PCQ_SYRK_SPLIT": "3"}, {"PCQ_SYRK_TILE": "96"},
+                {"PCQ_SYRK_CHUNK_MB": "1", "PCQ_SYRK_SPLIT": "3"}, {"PCQ_SYRK_TILE": "96"}, {"PCQ_SYRK_DIAG": "0"},
+                {"PCQ_SYRK_DIAG": "0", "PCQ_SYRK_SPLIT": "2"},
                 {"PCQ_SYRK_TILE": "96", "PCQ_SYRK_SPLIT": "4", "PCQ_SYRK_CHUNK_MB": "1"}, {"PCQ_GRAM_SYRK": "0"},
                 {"PCQ_GRAM_SYRK": "0", "PCQ_GRAM_V1": "1"}):
-        for k in ("PCQ_SYRK_CHUNK_MB", "PCQ_SYRK_SPLIT", "PCQ_SYRK_TILE", "PCQ_GRAM_SYRK", "PCQ_GRAM_V1"):
+        for k in ("PCQ_SYRK_CHUNK_MB", "PCQ_SYRK_SPLIT", "PCQ_SYRK_TILE", "PCQ_SYRK_DIAG", "PCQ_GRAM_SYRK", "PCQ_GRAM_V1"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
