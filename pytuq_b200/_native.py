@@ -10,7 +10,12 @@ c_int32_p = C.POINTER(C.c_int32)
 
 
 class PcqError(RuntimeError):
-    """Raised when a libpcq entry point returns a negative status."""
+    """Raised when a libpcq entry point returns a negative status (kept in ``status``; None when the library or
+    the device itself is missing)."""
+
+    def __init__(self, message, status=None):
+        super().__init__(message)
+        self.status = status
 
 
 # name -> (restype, argtypes); must stay in step with include/pcq.h (tests check this)
@@ -79,7 +84,7 @@ def lib():
 def check(status, what=""):
     if status < 0:
         msg = lib().pcq_last_error()
-        raise PcqError(f"{what or 'libpcq'} failed with status {status}: {msg.decode() if msg else ''}")
+        raise PcqError(f"{what or 'libpcq'} failed with status {status}: {msg.decode() if msg else ''}", status)
     return status
 
 

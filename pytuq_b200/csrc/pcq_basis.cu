@@ -9,6 +9,8 @@
 //     FP64 bound.  Thread per sample, slot table [slot][lane] in shared memory (conflict
 //     free), descriptors and coefficients are warp-uniform loads.
 #include "pcq_internal.cuh"
+#include <algorithm>
+#include <cstring>
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
@@ -215,7 +217,94 @@ int launch_bases2_w(pcq_plan* p, const BasesParams& P, cudaStream_t st, bool* ha
     return PCQ_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Large germ dimension (slot table of a few samples does not fit shared memory, e.g. d = 1000):
+// the per-sample tables go to a global scratch laid out [slot][sample of the chunk] -- warps that walk
+// samples read it coalesced, as they do the shared [slot][lane] tables -- and generic kernels gather
+// from it through L1/L2.  Same recurrence, same product order: results are bit-identical to the
+// shared-memory kernels.  This is the capacity route, not a tuned one.
+__global__ void __launch_bounds__(256) pcq_gtab_kernel(BasesParams P, double* tab, int64_t nc) {
+    const int s = P.sdim;
+    const int64_t total = P.n * s;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx % P.n;            // sample fastest: coalesced table writes
+        const int c = (int)(idx / P.n);
+        if (c == 0) tab[i] = 1.0;
+        pcq_fill_1d(P.x[i * P.ldx + c], c, s, P.pmax, P.rec_a, P.rec_b, P.p1, tab + i, (int)nc);
+    }
+}
+
+// A[i][k] = prod_q tab[slot_q(k)][i]: a 32 x 32 (sample x term) tile per iteration, transposed through
+// shared memory so that table reads run along samples and the stores along terms
+__global__ void __launch_bounds__(256) pcq_bases_g_kernel(BasesParams P, const double* __restrict__ tab, int64_t nc) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t nbi = (P.n + 31) / 32;
+    const int nbk = (P.nterms + 31) / 32;
+    for (int64_t blk = blockIdx.x; blk < nbi * nbk; blk += gridDim.x) {
+        const int64_t i0 = (blk / nbk) * 32;
+        const int k0 = (int)(blk % nbk) * 32;
+        __syncthreads();
+        for (int kk = ty; kk < 32; kk += 8) {
+            const int k = k0 + kk;
+            const int64_t i = i0 + tx;
+            double v = 0.0;
+            if (k < P.nterms && i < P.n) {
+                const uint16_t* dw = P.descw + (size_t)k * P.width;
+                v = tab[(size_t)dw[0] * nc + i];
+                for (int q = 1; q < P.width; ++q) v = __dmul_rn(v, tab[(size_t)dw[q] * nc + i]);
+            }
+            tile[kk][tx] = v;
+        }
+        __syncthreads();
+        for (int ii = ty; ii < 32; ii += 8) {
+            const int64_t i = i0 + ii;
+            const int k = k0 + tx;
+            if (i < P.n && k < P.nterms) P.a[i * P.lda + k] = tile[tx][ii];
+        }
+    }
+}
+
 }  // namespace
+
+bool pcq_table_fits_smem(const pcq_plan* p) {
+    // the tightest consumer is evalPC's [slot][lane] table with 32 threads per CTA
+    return (size_t)p->nslots * sizeof(double) * 32 <= p->smem_optin &&
+           (size_t)K1_ROWS * p->nslots * sizeof(double) <= p->smem_optin;
+}
+
+// slot tables of n samples in global scratch, [slot][nc]; returns the table through *tab
+int pcq_launch_gtab(pcq_plan* p, const double* x, int64_t n, int64_t ldx, int64_t nc, double** tab, cudaStream_t st) {
+    int rc = pcq_ensure_dev(&p->d_gtab, &p->gtab_bytes, (size_t)p->nslots * nc * sizeof(double));
+    if (rc != PCQ_OK) return rc;
+    BasesParams P;
+    memset(&P, 0, sizeof(P));
+    P.x = x; P.n = n; P.ldx = ldx; P.sdim = p->sdim; P.pmax = p->pmax; P.nslots = p->nslots;
+    P.rec_a = p->d_rec_a; P.rec_b = p->d_rec_b; P.p1 = p->d_p1;
+    const int64_t want = (n * p->sdim + 255) / 256, cap = (int64_t)p->num_sms * 8;
+    pcq_gtab_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, p->d_gtab, nc);
+    PCQ_LAUNCH_CHECK("pcq_gtab_kernel");
+    *tab = p->d_gtab;
+    return PCQ_OK;
+}
+
+static int launch_bases_bigdim(pcq_plan* p, const BasesParams& P0, cudaStream_t st) {
+    const int64_t nc = PCQ_GTAB_ROWS;
+    for (int64_t r0 = 0; r0 < P0.n; r0 += nc) {
+        BasesParams P = P0;
+        P.n = std::min<int64_t>(nc, P0.n - r0);
+        P.x = P0.x + r0 * P0.ldx;
+        P.a = P0.a + r0 * P0.lda;
+        double* tab = nullptr;
+        int rc = pcq_launch_gtab(p, P.x, P.n, P.ldx, nc, &tab, st);
+        if (rc != PCQ_OK) return rc;
+        const int64_t want = ((P.n + 31) / 32) * ((P.nterms + 31) / 32), cap = (int64_t)p->num_sms * 8;
+        pcq_bases_g_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, tab, nc);
+        PCQ_LAUNCH_CHECK("pcq_bases_g_kernel");
+    }
+    return PCQ_OK;
+}
 
 int pcq_launch_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double* a,
                      int64_t lda, cudaStream_t st) {
@@ -226,6 +315,7 @@ int pcq_launch_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, doubl
     P.width = p->width;
     P.rec_a = p->d_rec_a; P.rec_b = p->d_rec_b; P.p1 = p->d_p1;
     P.desc4 = p->d_desc4; P.descw = p->d_descw;
+    if (!pcq_table_fits_smem(p)) return launch_bases_bigdim(p, P, st);
     bool handled = false;
     int rc = PCQ_OK;
     switch (p->width <= PCQ_MAXW_FAST ? p->width : 0) {

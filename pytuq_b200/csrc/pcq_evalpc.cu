@@ -639,6 +639,29 @@ __global__ void __launch_bounds__(64) pcq_resid_reduce_kernel(const double* part
     sums[q] = (accumulate ? sums[q] : 0.0) + acc;
 }
 
+// Large germ dimension: evalPC from slot tables in global memory ([slot][nc], pcq_launch_gtab).  One thread per
+// sample, terms in k order, coefficient first, factors in descriptor order -- the reference's rounding sequence,
+// used for both modes (the fast mode may differ from it by rounding only, it need not).
+__global__ void __launch_bounds__(128) pcq_evalpc_g_kernel(EvalParams P, const double* __restrict__ tab, int64_t nc) {
+    const int K = P.nterms, W = P.width;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.n; i += (int64_t)gridDim.x * blockDim.x) {
+        double vsq = 0.0;
+        for (int m = 0; m < P.m; ++m) {
+            const double* cf = P.cf + (size_t)m * K;
+            double acc = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const uint16_t* dw = P.descw + (size_t)k * W;
+                double prd = __ldg(cf + k);
+                for (int q = 0; q < W; ++q) prd = __dmul_rn(prd, tab[(size_t)__ldg(dw + q) * nc + i]);
+                acc = __dadd_rn(acc, prd);
+            }
+            if (P.sumsq) vsq = fma(acc, acc, vsq);
+            else P.y[i * P.ldy + m] = acc;
+        }
+        if (P.sumsq) P.y[i * P.ldy] = vsq;
+    }
+}
+
 void fill_eval_params(pcq_plan* p, EvalParams& P) {
     memset(&P, 0, sizeof(P));
     P.sdim = p->sdim; P.nterms = p->nterms; P.pmax = p->pmax; P.nslots = p->nslots;
@@ -657,6 +680,21 @@ int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, cons
     P.x = x; P.cf = cf; P.y = y; P.n = n; P.ldx = ldx; P.ldy = ldy; P.m = m;
     P.sumsq = (mode & 2) ? 1 : 0;
     const int fast = mode & 1;
+    if (!pcq_table_fits_smem(p)) {
+        const int64_t nc = PCQ_GTAB_ROWS;
+        for (int64_t r0 = 0; r0 < n; r0 += nc) {
+            EvalParams Q = P;
+            Q.n = std::min<int64_t>(nc, n - r0);
+            Q.x = x + r0 * ldx;
+            Q.y = y + r0 * ldy;
+            double* tab = nullptr;
+            int rc = pcq_launch_gtab(p, Q.x, Q.n, ldx, nc, &tab, st);
+            if (rc != PCQ_OK) return rc;
+            pcq_evalpc_g_kernel<<<(int)((Q.n + 127) / 128), 128, 0, st>>>(Q, tab, nc);
+            PCQ_LAUNCH_CHECK("pcq_evalpc_g_kernel");
+        }
+        return PCQ_OK;
+    }
     if (!P.sumsq && p->spec[fast] && m <= 8) {
         // multi-index-specialised kernels (pcq_plan_specialize): one output per launch sequence
         for (int j = 0; j < m; ++j) {
@@ -687,10 +725,12 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
     P.cf = cf; P.y = y; P.n = n; P.ldy = ldy; P.m = m;
     P.seed = seed; P.first_index = first; P.germ_kind = dkind;
     const int fast = mode & 1;
-    if (p->spec[fast] && m <= 8) {
-        // specialised path: germ chunk -> HBM (160 B per sample, far below the evaluation cost) ->
-        // specialised evalPC -> power sums; chunks of 4M samples, sums combined on the device
-        const int64_t chunk = (int64_t)1 << 22;
+    const bool bigdim = !pcq_table_fits_smem(p);
+    if ((p->spec[fast] && m <= 8) || bigdim) {
+        // materialised-germ path: germ chunk -> HBM (160 B per sample, far below the evaluation cost) ->
+        // specialised evalPC (or, for a germ too wide for shared-memory tables, the global-table evalPC) ->
+        // power sums; chunks of 4M samples (64k for wide germs), sums combined on the device
+        const int64_t chunk = bigdim ? ((int64_t)1 << 16) : ((int64_t)1 << 22);
         const int s = p->sdim;
         if ((rc = pcq_ensure_dev(&p->d_stage[0], &p->stage_bytes[0], (size_t)chunk * s * 8)) != PCQ_OK) return rc;
         if (!y && (rc = pcq_ensure_dev(&p->d_out[0], &p->out_bytes[0], (size_t)chunk * m * 8)) != PCQ_OK) return rc;
@@ -706,9 +746,13 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
             const int64_t ldc = y ? ldy : m;
             if (nr > 0) {
                 if ((rc = pcq_launch_germ(p, seed, first + r0, nr, germ_kind, p->d_stage[0], s, st)) != PCQ_OK) return rc;
-                for (int j = 0; j < m; ++j)
-                    if ((rc = pcq_spec_launch(p, fast, p->d_stage[0], nr, s, cf + (size_t)j * p->nterms, yc + j, ldc, st)) != PCQ_OK)
-                        return rc;
+                if (bigdim) {
+                    if ((rc = pcq_launch_evalpc(p, p->d_stage[0], nr, s, cf, m, yc, ldc, mode & 1, st)) != PCQ_OK) return rc;
+                } else {
+                    for (int j = 0; j < m; ++j)
+                        if ((rc = pcq_spec_launch(p, fast, p->d_stage[0], nr, s, cf + (size_t)j * p->nterms, yc + j, ldc, st)) != PCQ_OK)
+                            return rc;
+                }
             }
             pcq_moments_kernel<<<mgrid, 256, 0, st>>>(yc, nr, ldc, m, part);
             PCQ_LAUNCH_CHECK("pcq_moments_kernel");

@@ -24,6 +24,7 @@
 //   pcq_gram_kernel       generic: any width, and a materialised A; plain generate / barrier / DMMA
 //                         phases
 #include "pcq_internal.cuh"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -674,6 +675,24 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
                     int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,
                     int64_t ldy, int m, double* s, int accumulate, double** ws,
                     size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st) {
+    if (n > 0 && a == nullptr && !pcq_table_fits_smem(p)) {
+        // germ too wide for shared-memory slot tables: design-matrix chunks through the global-table K1
+        // (pcq_launch_bases takes that route by itself), then the materialised-matrix path on each chunk
+        const int64_t rows = std::max<int64_t>(32, std::min<int64_t>(n, ((int64_t)1 << 29) / ((int64_t)p->nterms * 8)));
+        int rc = pcq_ensure_dev(&p->d_achunk, &p->achunk_bytes, (size_t)rows * p->nterms * sizeof(double));
+        if (rc != PCQ_OK) return rc;
+        for (int64_t r0 = 0; r0 < n; r0 += rows) {
+            const int64_t nr = std::min(rows, n - r0);
+            if ((rc = pcq_launch_bases(p, x + r0 * ldx, nr, ldx, p->d_achunk, p->nterms, st)) != PCQ_OK) return rc;
+            bool handled = false;
+            rc = pcq_launch_syrk(p, num_sms, smem_optin, nullptr, nr, 0, p->d_achunk, p->nterms, p->nterms,
+                                 y ? y + r0 * ldy : nullptr, ldy, m, s, accumulate || r0 > 0, ws, ws_bytes, zbuf,
+                                 zbuf_bytes, st, &handled);
+            if (rc != PCQ_OK) return rc;
+            if (!handled) { pcq_set_error("suffstats: SYRK pipeline unavailable for the wide-germ route"); return PCQ_ERR_UNSUPPORTED; }
+        }
+        return PCQ_OK;
+    }
     {
         const char* e = getenv("PCQ_GRAM_SYRK");
         if (n > 0 && !(e && atoi(e) == 0)) {

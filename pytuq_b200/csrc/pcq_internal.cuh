@@ -45,6 +45,11 @@ struct pcq_plan {
     // Gram workspace (lazily grown)
     double* d_ws = nullptr;
     size_t ws_bytes = 0;
+    // large germ dimension: slot tables of a sample chunk in global memory, and a design-matrix chunk
+    double* d_gtab = nullptr;
+    size_t gtab_bytes = 0;
+    double* d_achunk = nullptr;
+    size_t achunk_bytes = 0;
     // packed upper-triangular operand of the quadratic-form kernel (lazily grown)
     double* d_q = nullptr;
     size_t q_bytes = 0;
@@ -91,6 +96,10 @@ int pcq_ensure_dev(double** buf, size_t* have, size_t bytes);
 // kernel launchers (defined in the kernel translation units) -----------------------
 int pcq_launch_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double* a,
                      int64_t lda, cudaStream_t st);
+// large germ dimension (slot tables in global memory, pcq_basis.cu)
+constexpr int64_t PCQ_GTAB_ROWS = 4096;
+bool pcq_table_fits_smem(const pcq_plan* p);
+int pcq_launch_gtab(pcq_plan* p, const double* x, int64_t n, int64_t ldx, int64_t nc, double** tab, cudaStream_t st);
 int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf,
                       int m, double* y, int64_t ldy, int mode, cudaStream_t st);
 // generator == plan (fused, p != nullptr) or materialised A (a != nullptr)

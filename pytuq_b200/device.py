@@ -106,8 +106,8 @@ _AUTO_SPECIALIZE_MAX_TERMS = 40000
 
 
 def note_evalpc_work(plan, nsam, nterms, nout, mode):
-    if _AUTO_SPECIALIZE <= 0 or nterms > _AUTO_SPECIALIZE_MAX_TERMS or nout > 8:
-        return
+    if _AUTO_SPECIALIZE <= 0 or nterms > _AUTO_SPECIALIZE_MAX_TERMS or nout > 8 or plan.sdim * max(plan.pmax, 1) > 256:
+        return      # (wide germs: the unrolled kernels would keep the whole 1-D table in registers)
     bit = 2 if (mode & 1) else 1
     if getattr(plan, "_spec_tried", 0) & bit:
         return

@@ -18,6 +18,7 @@ from scipy.linalg.lapack import dpotrf, dpotrs
 
 from ..fit.fit import fitbase
 from .stats import SuffStats
+from .. import _native
 
 
 class PCBasisEvaluator:
@@ -161,12 +162,18 @@ class lreg(fitbase):
                 K = self.cf.shape[0]
                 if self.cf_cov is None or not np.any(self.cf_cov):
                     ypred_var = np.zeros(ypred.shape[0])
-                elif K >= 96 and float(ypred.shape[0]) * K * K >= 2.0e8:
-                    # dense covariance, enough work: psi^T C psi as a triangular GEMM on the tensor pipe (K6)
-                    ypred_var = np.maximum(pcrv.evalQuadForm(x, self.cf_cov, jdim), 0.0)
                 else:
-                    F = self._cov_factor()
-                    ypred_var = pcrv.evalLinearForms(x, np.ascontiguousarray(F.T), jdim, sumsq=True)
+                    ypred_var = None
+                    if K >= 96 and float(ypred.shape[0]) * K * K >= 2.0e8:
+                        # dense covariance, enough work: psi^T C psi as a triangular GEMM on the tensor pipe (K6)
+                        try:
+                            ypred_var = np.maximum(pcrv.evalQuadForm(x, self.cf_cov, jdim), 0.0)
+                        except _native.PcqError as e:
+                            if e.status != -5:         # PCQ_ERR_UNSUPPORTED (germ too wide for K6's pack kernel)
+                                raise
+                    if ypred_var is None:
+                        F = self._cov_factor()
+                        ypred_var = pcrv.evalLinearForms(x, np.ascontiguousarray(F.T), jdim, sumsq=True)
                 ypred_var += int(pp) * self.datavar
                 return ypred, ypred_var, None
         Amat = self.basisEval(x, self.basisEvalPars)

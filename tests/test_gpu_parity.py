@@ -220,6 +220,50 @@ def test_k3_large_orders_and_dims_fall_back_cleanly():
     assert rel_err(pc.evalPC(x)[:, 0], A @ cf) < 1e-12
 
 
+def test_wide_germ_takes_the_global_table_route():
+    """Germ dimensions whose slot tables do not fit shared memory (d = 1000 and up): tables in global memory,
+    same arithmetic -- evalBases / evalPC stay bit-identical, statistics, fits and propagation work."""
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import lsq, anl, PCBasisEvaluator
+    rng = np.random.default_rng(91)
+    for fam, d, p, n, kmax in [("LU", 1000, 1, 700, None), ("HG", 1200, 2, 333, 1500), ("LU", 3000, 1, 150, 2000)]:
+        mi = orc.get_mi(p, d)
+        if kmax:
+            keep = np.sort(rng.choice(mi.shape[0] - 1, kmax - 1, replace=False)) + 1
+            mi = np.vstack([mi[:1], mi[keep]])
+        K = mi.shape[0]
+        x = rng.uniform(-1, 1, (n, d)) if fam == "LU" else rng.standard_normal((n, d))
+        cf = rng.standard_normal(K) / np.sqrt(K)
+        pc = PCRV(1, d, fam, mi=mi, cfs=[cf])
+        A = pc.evalBases(x, 0)
+        Aref = orc.eval_bases(x[:40], mi, fam, np.full(d, p))
+        assert np.array_equal(A[:40], Aref), (fam, d, p)
+        y = pc.evalPC(x)
+        assert np.array_equal(y[:40], orc.eval_pc(x[:40], [mi], [cf], fam, np.full(d, p))), (fam, d, p)
+        Y = (A @ cf + 0.01 * rng.standard_normal(n))
+        st = pc.suffStats(x, Y, 0)
+        assert rel_err(st.S, orc.suffstats(A, Y)) < 1e-12, (fam, d, p)
+        v = pc.evalLinearForms(x, np.stack([cf, 2 * cf]), 0, sumsq=True)
+        assert rel_err(v, 5 * (A @ cf) ** 2) < 1e-12
+    # an overdetermined fit through lreg (statistics route) and a propagation, d = 1000
+    d, n = 1000, 5000
+    mi = orc.get_mi(1, d)
+    x = rng.uniform(-1, 1, (n, d))
+    ctrue = rng.standard_normal(d + 1)
+    pc = PCRV(1, d, "LU", mi=mi)
+    yv = orc.eval_bases(x, mi, "LU", np.full(d, 1)) @ ctrue
+    f = lsq()
+    f.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+    f.fit(x, yv)
+    assert rel_err(f.cf, ctrue) < 1e-9
+    m1, v1, _ = f.predict(x[:50], msc=1)
+    assert rel_err(m1, yv[:50]) < 1e-9 and not v1.any()
+    pc.setCfs([ctrue])
+    res = pc.propagate(200000, seed=3)
+    assert abs(res["mean"][0] - ctrue[0]) < 5 * np.sqrt(pc.computeVar()[0] / 200000)
+    assert abs(res["var"][0] / pc.computeVar()[0] - 1) < 0.05
+
+
 def test_k4_gram_of_materialised_matrix():
     from pytuq_b200.lreg.stats import SuffStats
     rng = np.random.default_rng(8)
