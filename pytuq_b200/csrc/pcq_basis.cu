@@ -133,7 +133,7 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 }
 
 template <int W>
-__global__ void __launch_bounds__(K1_THREADS) pcq_bases2_kernel(BasesParams P, int vec_ok) {
+__global__ void __launch_bounds__(K1_THREADS) pcq_bases2_kernel(BasesParams P, int base_odd) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);     // [nslots][K1_TS]
     const int tid = threadIdx.x;
@@ -183,13 +183,19 @@ __global__ void __launch_bounds__(K1_THREADS) pcq_bases2_kernel(BasesParams P, i
                         b = __dmul_rn(b, lds_f64(o1[q] + r * 8));
                     }
                     double* dst = out + (size_t)r * P.lda;
-                    // n0 is a multiple of 16 and k is even: the pair is 16-byte aligned unless the
-                    // leading dimension is odd and the row is odd
-                    if (vec_ok && v1 && !(lda_odd && (r & 1))) {
-                        __stcs(reinterpret_cast<double2*>(dst), make_double2(a, b));
+                    // n0 is a multiple of 16 and k is even: element k of this row is 16-byte aligned unless
+                    // exactly one of (base pointer, odd leading dimension on an odd row) shifts it by 8 bytes
+                    const bool shifted = (base_odd != 0) != (lda_odd && (r & 1));
+                    if (!shifted) {
+                        if (v1) __stcs(reinterpret_cast<double2*>(dst), make_double2(a, b));
+                        else if (v0) __stcs(dst, a);
                     } else {
-                        if (v0) __stcs(dst, a);
-                        if (v1) __stcs(dst + 1, b);
+                        // aligned pairs are (k+1, k+2): own second value + the next lane's first; the chunk's
+                        // first value and the last lane's second value go out as 8-byte stores
+                        const double an = __shfl_down_sync(0xffffffffu, a, 1);
+                        if (lane == 0 && v0) __stcs(dst, a);
+                        if (lane < 31 && k + 2 < K) __stcs(reinterpret_cast<double2*>(dst + 1), make_double2(b, an));
+                        else if (v1) __stcs(dst + 1, b);
                     }
                 }
             }
@@ -211,8 +217,8 @@ int launch_bases2_w(pcq_plan* p, const BasesParams& P, cudaStream_t st, bool* ha
     const int64_t nblocks = (P.n + K1_ROWS - 1) / K1_ROWS;
     const int64_t cap = (int64_t)p->num_sms * occ;
     const int grid = (int)(nblocks < cap ? nblocks : cap);
-    const int vec_ok = (reinterpret_cast<uintptr_t>(P.a) & 15) == 0;
-    kern<<<grid, K1_THREADS, smem, st>>>(P, vec_ok);
+    const int base_odd = (int)((reinterpret_cast<uintptr_t>(P.a) >> 3) & 1);
+    kern<<<grid, K1_THREADS, smem, st>>>(P, base_odd);
     PCQ_LAUNCH_CHECK("pcq_bases2_kernel");
     return PCQ_OK;
 }

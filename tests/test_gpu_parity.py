@@ -93,7 +93,7 @@ def test_k1_device_pointers_with_leading_dimensions():
     from pytuq_b200 import _native
     from pytuq_b200.rv.pcrv import PCRV
     rng = np.random.default_rng(5)
-    for (p, d) in [(3, 5), (2, 6), (4, 3)]:
+    for (p, d) in [(3, 5), (2, 6), (4, 3), (3, 9)]:
         mi = orc.get_mi(p, d)
         K = mi.shape[0]
         pc = PCRV(1, d, "HG", mi=mi)
@@ -109,6 +109,19 @@ def test_k1_device_pointers_with_leading_dimensions():
         got = ad.cpu().numpy()
         assert np.array_equal(got[:, :K], orc.eval_bases(xh[:, :d].copy(), mi, "HG"))
         assert np.all(got[:, K:] == -7.0)
+        # output shifted by one double (8-byte aligned only), even and odd leading dimensions, K > 64 so that
+        # the shifted 16-byte stores cross lanes and chunk boundaries; canaries all around
+        for extra in (0, 1):
+            lda2 = K + 4 + extra
+            flat = torch.full((n * lda2 + 3,), -7.0, dtype=torch.float64, device="cuda")
+            base = flat[1:]
+            _native.check(_native.lib().pcq_eval_bases_dev(plan.handle, xd.data_ptr(), n, ldx, base.data_ptr(), lda2,
+                                                           torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            fh = flat.cpu().numpy()
+            got2 = fh[1:1 + n * lda2].reshape(n, lda2)
+            assert np.array_equal(got2[:, :K], got[:, :K]), (p, d, extra)
+            assert np.all(got2[:, K:] == -7.0) and fh[0] == -7.0 and np.all(fh[1 + n * lda2:] == -7.0)
 
 
 # ----------------------------------------------------------------------------- K2
