@@ -39,5 +39,11 @@ for rep in range(3):
     if which in ("all", "k3"):
         S = torch.empty((K + 2, K + 2), dtype=torch.float64, device="cuda")
         _native.check(lib.pcq_suffstats_dev(plan.handle, x.data_ptr(), n, d, y.data_ptr(), 1, 1, S.data_ptr(), 0, st))
+if which == "k6":
+    Cm = torch.randn((K, K), dtype=torch.float64, device="cuda", generator=g)
+    Cm = Cm @ Cm.T / K
+    v = torch.empty(n, dtype=torch.float64, device="cuda")
+    for rep in range(2):
+        _native.check(lib.pcq_quadform_dev(plan.handle, x.data_ptr(), n, d, Cm.data_ptr(), K, v.data_ptr(), 1, st))
 torch.cuda.synchronize()
 print("ok", which, n, K)
