@@ -31,7 +31,7 @@ struct QfPackParams {
     double* zq;
 };
 
-// design-matrix chunk in term-block order: thread = (sample of a 16-sample group, block of 8 terms)
+// design-matrix chunk in term-block order: 16-sample groups, four lanes per (sample, block of 8 terms)
 template <int W>
 __global__ void __launch_bounds__(256) pcq_qf_pack_rows_kernel(QfPackParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -55,30 +55,30 @@ __global__ void __launch_bounds__(256) pcq_qf_pack_rows_kernel(QfPackParams P) {
             pcq_fill_1d(P.x[n * P.ldx + c], c, s, P.pmax, P.rec_a, P.rec_b, P.p1, T + sm, TS);
         }
         __syncthreads();
-        for (int idx = tid; idx < 16 * KB; idx += 256) {
-            const int sm = idx & 15, ib = idx >> 4;
-            double v[8];
+        // four lanes per (sample, term block), a term pair each: one warp store instruction covers eight
+        // samples x 64 B = 512 contiguous bytes
+        for (int idx = tid; idx < 64 * KB; idx += 256) {
+            const int q = idx & 3, sm = (idx >> 2) & 15, ib = idx >> 6;
+            double v[2];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const int term = ib * 8 + t;
+            for (int t = 0; t < 2; ++t) {
+                const int term = ib * 8 + 2 * q + t;
                 double val = 0.0;
                 if (term < P.K) {
                     if (W > 0) {
                         const unsigned long long d = P.desc4[term];
                         val = T[(int)(d & 0xffffull) * TS + sm];
 #pragma unroll
-                        for (int q = 1; q < W; ++q) val = __dmul_rn(val, T[(int)((d >> (16 * q)) & 0xffffull) * TS + sm]);
+                        for (int w = 1; w < W; ++w) val = __dmul_rn(val, T[(int)((d >> (16 * w)) & 0xffffull) * TS + sm]);
                     } else {
                         const uint16_t* dw = P.descw + (size_t)term * P.width;
                         val = T[(int)dw[0] * TS + sm];
-                        for (int q = 1; q < P.width; ++q) val = __dmul_rn(val, T[(int)dw[q] * TS + sm]);
+                        for (int w = 1; w < P.width; ++w) val = __dmul_rn(val, T[(int)dw[w] * TS + sm]);
                     }
                 }
                 v[t] = val;
             }
-            double2* dst = reinterpret_cast<double2*>(P.zq + ((size_t)ib * P.Nc + n0 + sm) * 8);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) __stcs(dst + r, make_double2(v[2 * r], v[2 * r + 1]));
+            __stcs(reinterpret_cast<double2*>(P.zq + ((size_t)ib * P.Nc + n0 + sm) * 8 + 2 * q), make_double2(v[0], v[1]));
         }
     }
 }
