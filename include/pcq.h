@@ -73,7 +73,8 @@ int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms,
                     const double* p1_scale);
 int pcq_plan_destroy(pcq_plan* plan);
 /* queries: 0 sdim, 1 nterms, 2 pmax, 3 width (max non-zero orders per term),
- *          4 device, 5 downward-closed flag, 6 number of SMs, 7 specialised modes (bit 0 exact, bit 1 fast) */
+ *          4 device, 5 downward-closed flag, 6 number of SMs, 7 specialised modes (bit 0 exact, bit 1 fast),
+ *          8 modes being built in the background */
 int64_t pcq_plan_info(const pcq_plan* plan, int what);
 
 /* Opt-in: compiles (NVRTC, at run time) evalPC kernels specialised for this plan's multi-index -- the
@@ -83,6 +84,10 @@ int64_t pcq_plan_info(const pcq_plan* plan, int what);
  * Once built, pcq_eval_pc(_dev) (up to 8 outputs, no quadratic-form mode) and pcq_propagate_dev use them.
  * Returns PCQ_ERR_UNSUPPORTED when libnvrtc is not available; the generic kernels stay in use. */
 int pcq_plan_specialize(pcq_plan* plan, int modes);
+/* Same build on a background host thread: returns at once, evaluations keep using the generic kernels until the
+ * specialised ones are installed (pcq_plan_info(plan, 7) reports the installed modes, 8 the modes under way).
+ * A failed build (no NVRTC) leaves the generic kernels in use.  pcq_plan_destroy waits for the thread. */
+int pcq_plan_specialize_async(pcq_plan* plan, int modes);
 
 /* ---- K1: design matrix -----------------------------------------------------
  * A[n,k] = prod_i phi^{(i)}_{mi[k,i]}(x[n,i])          PCRV.evalBases, rv/pcrv.py:413-442

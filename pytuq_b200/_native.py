@@ -28,6 +28,7 @@ SIGNATURES = {
     "pcq_plan_destroy": (C.c_int, [C.c_void_p]),
     "pcq_plan_info": (C.c_int64, [C.c_void_p, C.c_int]),
     "pcq_plan_specialize": (C.c_int, [C.c_void_p, C.c_int]),
+    "pcq_plan_specialize_async": (C.c_int, [C.c_void_p, C.c_int]),
     "pcq_eval_bases_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                      C.c_int64, C.c_void_p]),
     "pcq_eval_bases": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),

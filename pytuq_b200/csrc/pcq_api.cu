@@ -225,8 +225,9 @@ int pcq_plan_create(pcq_plan** out, int device, int sdim, int nterms, const int3
 int pcq_plan_destroy(pcq_plan* p) {
     if (!p) return PCQ_OK;
     DeviceGuard guard(p->device);
-    pcq_spec_free(p->spec[0]);
-    pcq_spec_free(p->spec[1]);
+    if (p->spec_thread.joinable()) p->spec_thread.join();
+    pcq_spec_free(p->spec[0].load());
+    pcq_spec_free(p->spec[1].load());
     cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
     cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_q); cudaFree(p->d_gtab); cudaFree(p->d_achunk);
     for (int i = 0; i < 2; ++i) {
@@ -249,13 +250,31 @@ int64_t pcq_plan_info(const pcq_plan* p, int what) {
         case 4: return p->device;
         case 5: return p->downward_closed;
         case 6: return p->num_sms;
-        case 7: return (p->spec[0] ? 1 : 0) | (p->spec[1] ? 2 : 0);
+        case 7: return (p->spec[0].load(std::memory_order_acquire) ? 1 : 0) | (p->spec[1].load(std::memory_order_acquire) ? 2 : 0);
+        case 8: return p->spec_building.load(std::memory_order_acquire);
         default: return PCQ_ERR_ARG;
     }
 }
 
+int pcq_plan_specialize_async(pcq_plan* p, int modes) {
+    if (!p || (modes & ~3)) { pcq_set_error("specialize_async: bad argument"); return PCQ_ERR_ARG; }
+    if (p->spec[0].load(std::memory_order_acquire)) modes &= ~1;
+    if (p->spec[1].load(std::memory_order_acquire)) modes &= ~2;
+    if (modes == 0 || p->spec_building.load(std::memory_order_acquire)) return PCQ_OK;   // built or under way
+    if (p->spec_thread.joinable()) p->spec_thread.join();
+    p->spec_building.store(modes, std::memory_order_release);
+    p->spec_thread = std::thread([p, modes] {
+        cudaSetDevice(p->device);
+        if (modes & 1) pcq_spec_build(p, 0);      // failure (no NVRTC): the generic kernels simply stay in use
+        if (modes & 2) pcq_spec_build(p, 1);
+        p->spec_building.store(0, std::memory_order_release);
+    });
+    return PCQ_OK;
+}
+
 int pcq_plan_specialize(pcq_plan* p, int modes) {
     if (!p || (modes & ~3)) { pcq_set_error("specialize: bad argument"); return PCQ_ERR_ARG; }
+    if (p->spec_thread.joinable()) p->spec_thread.join();      // a background build finishes first
     DeviceGuard guard(p->device);
     int rc = PCQ_OK;
     if ((modes & 1) && (rc = pcq_spec_build(p, 0)) != PCQ_OK) return rc;

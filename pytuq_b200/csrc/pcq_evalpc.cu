@@ -695,7 +695,7 @@ int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, cons
         }
         return PCQ_OK;
     }
-    if (!P.sumsq && p->spec[fast] && m <= 8) {
+    if (!P.sumsq && p->spec[fast].load(std::memory_order_acquire) && m <= 8) {
         // multi-index-specialised kernels (pcq_plan_specialize): one output per launch sequence
         for (int j = 0; j < m; ++j) {
             int rc = pcq_spec_launch(p, fast, x, n, ldx, cf + (size_t)j * p->nterms, y + j, ldy, st);
@@ -726,7 +726,7 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
     P.seed = seed; P.first_index = first; P.germ_kind = dkind;
     const int fast = mode & 1;
     const bool bigdim = !pcq_table_fits_smem(p);
-    if ((p->spec[fast] && m <= 8) || bigdim) {
+    if ((p->spec[fast].load(std::memory_order_acquire) && m <= 8) || bigdim) {
         // materialised-germ path: germ chunk -> HBM (160 B per sample, far below the evaluation cost) ->
         // specialised evalPC (or, for a germ too wide for shared-memory tables, the global-table evalPC) ->
         // power sums; chunks of 4M samples (64k for wide germs), sums combined on the device

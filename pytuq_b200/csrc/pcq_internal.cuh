@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -41,7 +42,11 @@ struct pcq_plan {
     // host copies kept for the (opt-in) multi-index-specialised kernels
     std::vector<int32_t> h_mi;
     std::vector<double> h_rec_a, h_rec_b, h_p1;
-    pcq_spec* spec[2] = {nullptr, nullptr};   // [0] exact, [1] fast
+    // [0] exact, [1] fast; published with release stores (a background build may install them while
+    // another host thread is launching kernels through this plan)
+    std::atomic<pcq_spec*> spec[2]{};
+    std::thread spec_thread;                  // background build started by pcq_plan_specialize_async
+    std::atomic<int> spec_building{0};        // modes being built in the background (bit 0 exact, bit 1 fast)
     // Gram workspace (lazily grown)
     double* d_ws = nullptr;
     size_t ws_bytes = 0;

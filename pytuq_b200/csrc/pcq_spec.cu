@@ -251,7 +251,7 @@ void pcq_spec_free(pcq_spec* sp) {
 }
 
 int pcq_spec_build(pcq_plan* p, int fast) {
-    if (p->spec[fast]) return PCQ_OK;
+    if (p->spec[fast].load(std::memory_order_acquire)) return PCQ_OK;
     if (!nvrtc().ok) {
         pcq_set_error("specialize: libnvrtc.so.12 not found (the generic kernels stay in use)");
         return PCQ_ERR_UNSUPPORTED;
@@ -304,14 +304,14 @@ int pcq_spec_build(pcq_plan* p, int fast) {
         c.k1 = std::min(K, c.k0 + SPEC_CHUNK);
         sp->chunks.push_back(c);
     }
-    p->spec[fast] = sp;
+    p->spec[fast].store(sp, std::memory_order_release);
     return PCQ_OK;
 }
 
 // y[n*ldy] = sum_k cf[k] Psi_k(x_n) for ONE output; chunks accumulate through y in term order
 int pcq_spec_launch(pcq_plan* p, int fast, const double* x, int64_t n, int64_t ldx, const double* cf, double* y,
                     int64_t ldy, cudaStream_t st) {
-    pcq_spec* sp = p->spec[fast];
+    pcq_spec* sp = p->spec[fast].load(std::memory_order_acquire);
     if (!sp) return PCQ_ERR_ARG;
     if (n == 0) return PCQ_OK;
     const int64_t nblocks = (n + SPEC_THREADS - 1) / SPEC_THREADS;

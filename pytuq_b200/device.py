@@ -94,14 +94,13 @@ def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None):
     return plan
 
 
-# A plan that keeps being evaluated (MCMC likelihoods, repeated surrogate sweeps) is worth compiling for:
-# once the generic evalPC kernel has processed this many sample-terms through one plan, the plan's
-# multi-index-specialised kernels are built (NVRTC, ~1 s per 2000 terms) and used from then on -- 3-4x
-# faster and bit-identical in exact mode.  The threshold is ~1.5 s of generic-kernel time (about the compile
-# time itself: the ski-rental break-even; cubins are cached on disk afterwards), so the compile can
-# at worst double the cost of a job that stops right after it.  PCQ_AUTO_SPECIALIZE=0 disables, any other
-# number replaces the threshold.
-_AUTO_SPECIALIZE = float(os.environ.get("PCQ_AUTO_SPECIALIZE", "1.5e12"))
+# A plan that keeps being evaluated (MCMC likelihoods, repeated surrogate sweeps) is worth compiling for: once the
+# generic evalPC kernel has processed this many sample-terms through one plan (~20 ms of kernel time), its
+# multi-index-specialised kernels are built on a BACKGROUND host thread (NVRTC, ~1 s per 2000 terms; cubins are
+# cached on disk) and installed when ready -- evaluations never wait for the compiler, they just get 3-4x faster,
+# bit-identically in exact mode, from some call on.  PCQ_AUTO_SPECIALIZE=0 disables, any other number replaces
+# the threshold.
+_AUTO_SPECIALIZE = float(os.environ.get("PCQ_AUTO_SPECIALIZE", "2e10"))
 _AUTO_SPECIALIZE_MAX_TERMS = 40000
 
 
@@ -115,7 +114,7 @@ def note_evalpc_work(plan, nsam, nterms, nout, mode):
     plan._evalpc_work = work
     if work >= _AUTO_SPECIALIZE:
         plan._spec_tried = getattr(plan, "_spec_tried", 0) | bit
-        _native.lib().pcq_plan_specialize(plan.handle, bit)     # failure (no NVRTC): generic kernels stay
+        _native.lib().pcq_plan_specialize_async(plan.handle, bit)
 
 
 def clear_plans():
