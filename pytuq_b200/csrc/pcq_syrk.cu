@@ -18,10 +18,14 @@
 //          accumulators per thread); warp 0 also keeps a 3-stage ring of (2 operands x 4 blocks x
 //          8 KB) filled with cp.async.bulk (TMA) on "full" mbarriers and every warp releases a stage
 //          on an "empty" mbarrier, so there is no CTA-wide barrier anywhere in the main loop.
-//          Work units are (sample part, upper-triangle tile), part-major, dealt round-robin: the
-//          number of parts S is chosen so that ntri * S fills the SMs in whole waves (105 tiles on
-//          148 SMs: S = 7 -> 4.97 waves), and CTAs of a wave sweep the same sample window at the same
-//          time, so the operand chunks are shared through L2 instead of re-read from HBM.
+//          Per chunk it runs twice: over the off-diagonal tiles (full 128 x 128 units) and over the
+//          diagonal tiles, whose upper-triangle 32 x 32 sub-blocks form one list cut into units of
+//          eight (one per warp, two per scheduler: half the cost of a full tile, 1.25 units per tile).
+//          Work units are (sample part, tile or sub-block group), part-major, dealt round-robin: the
+//          number of parts S is chosen per pass so that units * S fills the SMs in whole waves
+//          (K = 1771: 91 tiles x 13 parts = 7.99 waves; 18 groups x 8 parts = 0.97), and CTAs of a
+//          wave sweep the same sample window at the same time, so the operand chunks are shared
+//          through L2 instead of re-read from HBM.
 //   fixup  sums the S partial tiles of every output tile in part order (deterministic, no atomics);
 //          the mirror kernel fills the lower triangle.
 #include "pcq_mma.cuh"
