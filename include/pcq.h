@@ -188,6 +188,11 @@ int pcq_propagate_dev(pcq_plan* plan, uint64_t seed, int64_t first_index, int64_
                       const int32_t* germ_kind_host, const double* cf_dev, int m,
                       double* sums_dev, double* y_dev, int64_t ldy, int mode,
                       void* stream);
+/* host-pointer form: cf (M x K) and sums (M x 4) in host memory, no per-sample output; returns when the sums
+ * are in host memory */
+int pcq_propagate(pcq_plan* plan, uint64_t seed, int64_t first_index, int64_t n,
+                  const int32_t* germ_kind_host, const double* cf_host, int m,
+                  double* sums_host, int mode);
 /* the germ alone (same stream as above), x_dev N x s */
 int pcq_sample_germ_dev(pcq_plan* plan, uint64_t seed, int64_t first_index, int64_t n,
                         const int32_t* germ_kind_host, double* x_dev, int64_t ldx,

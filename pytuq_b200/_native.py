@@ -49,6 +49,8 @@ SIGNATURES = {
                                C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "pcq_gram": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                            C.c_int, C.c_void_p]),
+    "pcq_propagate": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_int]),
     "pcq_propagate_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                     C.c_void_p]),

@@ -515,6 +515,28 @@ int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const doub
     return PCQ_OK;
 }
 
+int pcq_propagate(pcq_plan* p, uint64_t seed, int64_t first_index, int64_t n, const int32_t* germ_kind,
+                  const double* cf, int m, double* sums, int mode) {
+    if (!p || n < 0 || m <= 0 || !germ_kind || !cf || !sums) {
+        pcq_set_error("propagate: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    int rc = ensure_streams(p);
+    if (rc != PCQ_OK) return rc;
+    const int K = p->nterms;
+    // coefficients and the 4 m sums share the plan's small scratch buffer
+    if ((rc = pcq_ensure_dev(&p->d_misc, &p->misc_bytes, ((size_t)m * K + (size_t)m * 4) * 8)) != PCQ_OK) return rc;
+    cudaStream_t st = p->streams[0];
+    double* d_sums = p->d_misc + (size_t)m * K;
+    PCQ_CUDA(cudaMemcpyAsync(p->d_misc, cf, (size_t)m * K * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = pcq_launch_propagate(p, seed, first_index, n, germ_kind, p->d_misc, m, d_sums, nullptr, m, mode, st)) != PCQ_OK)
+        return rc;
+    PCQ_CUDA(cudaMemcpyAsync(sums, d_sums, (size_t)m * 4 * 8, cudaMemcpyDeviceToHost, st));
+    PCQ_CUDA(cudaStreamSynchronize(st));
+    return PCQ_OK;
+}
+
 int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
                   int m, double* s_host) {
     if (!p || n < 0 || m < 0 || !s_host || (n > 0 && !x) || (n > 0 && m > 0 && !y) ||

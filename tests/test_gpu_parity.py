@@ -410,6 +410,24 @@ def test_k5_germ_stream_and_propagation():
     np.testing.assert_allclose(fast["mean"], out["mean"], rtol=1e-11, atol=1e-13)
 
 
+def test_k5_host_pointer_propagate_matches_device_form():
+    """pcq_propagate (host coefficients in, host sums out) draws the same Philox stream as pcq_propagate_dev."""
+    from pytuq_b200 import _native
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(4)
+    mi = orc.get_mi(3, 5)
+    cfs = rng.standard_normal((2, mi.shape[0]))
+    pc = PCRV(2, 5, "HG", mi=mi, cfs=[cfs[0], cfs[1]])
+    ref = pc.propagate(70001, seed=11)
+    kinds = np.ones(5, dtype=np.int32)
+    sums = np.zeros((2, 4))
+    plan = pc._plan(mi)
+    _native.check(_native.lib().pcq_propagate(plan.handle, 11, 0, 70001, _native.ptr(kinds),
+                                              _native.ptr(np.ascontiguousarray(cfs)), 2, _native.ptr(sums), 1))
+    assert np.allclose(sums[:, 0] / 70001, ref["mean"], rtol=1e-13, atol=0)
+    assert np.array_equal(sums[:, 2], ref["min"]) and np.array_equal(sums[:, 3], ref["max"])
+
+
 def test_k2_specialised_kernels_bitexact():
     """Opt-in NVRTC-specialised evalPC: bit-identical to the generic kernel (and so to the reference) in
     exact mode, rounding-level in fast mode, and consistent through propagate."""
