@@ -426,7 +426,9 @@ __global__ void __launch_bounds__(256) pcq_syrk_mirror_kernel(double* s, int L) 
 int choose_split(int ntri, int grid, int64_t nstages) {
     int best = 1;
     double best_cost = 1e300;
-    const int smax = (int)(nstages < 32 ? nstages : 32);
+    int smax = (int)(nstages < 32 ? nstages : 32);
+    const int mem_cap = 8192 / (ntri > 0 ? ntri : 1);       // partial tiles of one pass stay below ~1 GB of workspace
+    if (smax > mem_cap) smax = mem_cap < 1 ? 1 : mem_cap;
     for (int S = 1; S <= smax; ++S) {
         const int64_t waves = ((int64_t)ntri * S + grid - 1) / grid;
         // every part is ceil(nstages / S) stages at worst; a small per-unit term for the tile flush
