@@ -152,6 +152,8 @@ int pcq_suffstats(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
  * v has stride ldv. */
 int pcq_quadform_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,
                      const double* c_dev, int64_t ldc, double* v_dev, int64_t ldv, void* stream);
+int pcq_quadform(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
+                 const double* c_host, int64_t ldc, double* v_host, int64_t ldv);
 
 /* Residual pass of one output: with r_n = y_n - sum_k cf[k] Psi_k(x_n) (surrogate through K2, fast mode),
  *   sums_dev[0] (+)= sum_n r_n^2      bcs_fit's final noise estimate, lreg/bcs.py:229
@@ -162,6 +164,9 @@ int pcq_quadform_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx
 int pcq_residual_ss_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,
                         const double* y_dev, int64_t ldy, const double* cf_dev,
                         double* sums_dev, int accumulate, void* stream);
+/* host-pointer form: sums_host[0..1] are overwritten */
+int pcq_residual_ss(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
+                    const double* y_host, int64_t ldy, const double* cf_host, double* sums_host);
 
 /* ---- K4: sufficient statistics from a materialised design matrix ---------------
  * Same S as above but z_n = [ A[n,:] | y_n | 1 ] with A given (lreg.fita(Amat, y),

@@ -39,6 +39,10 @@ SIGNATURES = {
     "pcq_suffstats_dim": (C.c_int64, [C.c_void_p, C.c_int]),
     "pcq_quadform_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_int64, C.c_void_p]),
+    "pcq_quadform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                               C.c_void_p, C.c_int64]),
+    "pcq_residual_ss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_void_p]),
     "pcq_residual_ss_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pcq_suffstats_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

@@ -515,6 +515,64 @@ int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const doub
     return PCQ_OK;
 }
 
+int pcq_quadform(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* c, int64_t ldc,
+                 double* v, int64_t ldv) {
+    if (!p || n < 0 || !c || (n > 0 && (!x || !v)) || ldx < p->sdim || ldc < p->nterms || ldv < 1) {
+        pcq_set_error("quadform: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    if (n == 0) return PCQ_OK;
+    DeviceGuard guard(p->device);
+    int rc = ensure_streams(p);
+    if (rc != PCQ_OK) return rc;
+    const int K = p->nterms, s = p->sdim;
+    cudaStream_t st = p->streams[0];
+    // C goes to the plan's small scratch, x / v through the staging buffers, chunk by chunk
+    if ((rc = pcq_ensure_dev(&p->d_misc, &p->misc_bytes, (size_t)K * K * 8)) != PCQ_OK) return rc;
+    if ((rc = copy_rows(p->d_misc, K, c, ldc, K, K, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
+    const int64_t rows = chunk_rows((int64_t)(s + 1) * 8, n);
+    if ((rc = pcq_ensure_dev(&p->d_stage[0], &p->stage_bytes[0], (size_t)rows * s * 8)) != PCQ_OK) return rc;
+    if ((rc = pcq_ensure_dev(&p->d_out[0], &p->out_bytes[0], (size_t)rows * 8)) != PCQ_OK) return rc;
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t nr = std::min(rows, n - r0);
+        if ((rc = copy_rows(p->d_stage[0], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
+        if ((rc = pcq_quadform_dev(p, p->d_stage[0], nr, s, p->d_misc, K, p->d_out[0], 1, st)) != PCQ_OK) return rc;
+        if ((rc = copy_rows(v + r0 * ldv, ldv, p->d_out[0], 1, 1, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return rc;
+    }
+    PCQ_CUDA(cudaStreamSynchronize(st));
+    return PCQ_OK;
+}
+
+int pcq_residual_ss(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
+                    const double* cf, double* sums) {
+    if (!p || n < 0 || !cf || !sums || (n > 0 && (!x || !y)) || ldx < p->sdim || ldy < 1) {
+        pcq_set_error("residual_ss: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    DeviceGuard guard(p->device);
+    int rc = ensure_streams(p);
+    if (rc != PCQ_OK) return rc;
+    const int K = p->nterms, s = p->sdim;
+    cudaStream_t st = p->streams[0];
+    if ((rc = pcq_ensure_dev(&p->d_misc, &p->misc_bytes, (size_t)(K + 2) * 8)) != PCQ_OK) return rc;
+    double* d_sums = p->d_misc + K;
+    PCQ_CUDA(cudaMemcpyAsync(p->d_misc, cf, (size_t)K * 8, cudaMemcpyHostToDevice, st));
+    const int64_t rows = chunk_rows((int64_t)(s + 1) * 8, n);
+    if ((rc = pcq_ensure_dev(&p->d_stage[0], &p->stage_bytes[0], (size_t)rows * s * 8)) != PCQ_OK) return rc;
+    if ((rc = pcq_ensure_dev(&p->d_stage[1], &p->stage_bytes[1], (size_t)rows * 8)) != PCQ_OK) return rc;
+    if (n == 0 && (rc = pcq_launch_residual(p, nullptr, 0, s, nullptr, 1, p->d_misc, d_sums, 0, st)) != PCQ_OK) return rc;
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t nr = std::min(rows, n - r0);
+        if ((rc = copy_rows(p->d_stage[0], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
+        if ((rc = copy_rows(p->d_stage[1], 1, y + r0 * ldy, ldy, 1, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
+        if ((rc = pcq_launch_residual(p, p->d_stage[0], nr, s, p->d_stage[1], 1, p->d_misc, d_sums, r0 > 0, st)) != PCQ_OK)
+            return rc;
+    }
+    PCQ_CUDA(cudaMemcpyAsync(sums, d_sums, 2 * 8, cudaMemcpyDeviceToHost, st));
+    PCQ_CUDA(cudaStreamSynchronize(st));
+    return PCQ_OK;
+}
+
 int pcq_propagate(pcq_plan* p, uint64_t seed, int64_t first_index, int64_t n, const int32_t* germ_kind,
                   const double* cf, int m, double* sums, int mode) {
     if (!p || n < 0 || m <= 0 || !germ_kind || !cf || !sums) {

@@ -142,40 +142,25 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
     return SuffStats(None, K, M, S_dev=S_t)
 
 
-_RESID_ROWS = 1 << 20
-
-
 def residual_sums_pc(pcrv, x, y, col, jdim, cf):
     """(sum_n r_n^2, sum_n y_n r_n) with r = y[:, col] - Psi(x) cf, evaluated over the data: the surrogate
-    through K2 (fast mode, no A), the two sums reduced on the device.  This is the residual pass of
-    bcs_fit (lreg/bcs.py:229) and anl (lreg/anl.py:61) for fits whose residual is so small that the
+    through K2 (fast mode, no A), the two sums reduced on the device (pcq_residual_ss).  This is the residual
+    pass of bcs_fit (lreg/bcs.py:229) and anl (lreg/anl.py:61) for fits whose residual is so small that the
     statistics identity  y^T y - 2 cf^T b + cf^T G cf  has cancelled (noise-free training data)."""
-    import torch
     _device.require_device()
-    dev = _device.current_device()
-    tdev = torch.device("cuda", dev)
     mindex = pcrv.mindices[jdim]
-    plan = pcrv._plan(mindex, dev=dev)
-    lib = _native.lib()
+    plan = pcrv._plan(mindex, dev=_device.current_device())
     xin = np.ascontiguousarray(x, dtype=np.float64)
     N, s = xin.shape
     Y = np.asarray(y, dtype=np.float64).reshape(N, -1)
-    sums = torch.zeros(2, dtype=torch.float64, device=tdev)
-    with torch.cuda.device(tdev):
-        stream = torch.cuda.current_stream().cuda_stream
-        cf_t = torch.from_numpy(np.ascontiguousarray(cf, dtype=np.float64)).to(tdev)
-        for r0 in range(0, N, _RESID_ROWS):
-            r1 = min(N, r0 + _RESID_ROWS)
-            xd = torch.from_numpy(xin[r0:r1]).to(tdev)
-            yd = torch.from_numpy(np.ascontiguousarray(Y[r0:r1, col])).to(tdev)
-            _native.check(lib.pcq_residual_ss_dev(plan.handle, xd.data_ptr(), r1 - r0, s, yd.data_ptr(), 1,
-                                                  cf_t.data_ptr(), sums.data_ptr(), 1, stream),
-                          "pcq_residual_ss_dev")
-        if dist_info()[1] > 1 and getattr(pcrv, "_distributed_stats", False):
-            import torch.distributed as dist
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    out = sums.cpu().numpy()
-    return float(out[0]), float(out[1])
+    ycol = np.ascontiguousarray(Y[:, col])
+    sums = np.zeros(2)
+    _native.check(_native.lib().pcq_residual_ss(plan.handle, _native.ptr(xin), N, s, _native.ptr(ycol), 1,
+                                                _native.ptr(np.ascontiguousarray(cf, dtype=np.float64)),
+                                                _native.ptr(sums)), "pcq_residual_ss")
+    if dist_info()[1] > 1 and getattr(pcrv, "_distributed_stats", False):
+        sums = allreduce_stats(sums)
+    return float(sums[0]), float(sums[1])
 
 
 def residual_sums_matrix(A, Y, col, cf):

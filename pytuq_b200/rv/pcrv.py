@@ -341,7 +341,6 @@ class PCRV(MRV):
         is what is read): K6, a triangular GEMM on the FP64 tensor pipe over packed design-matrix chunks --
         N K^2 flops, the pushed-forward variance of a fit with full coefficient covariance C.  Rounding can
         leave tiny negative values for a semi-definite C; callers that take square roots clip at zero."""
-        import torch
         mindex = self.mindices[jdim]
         K = mindex.shape[0]
         assert(self.sdim == x.shape[1] and Cmat.shape == (K, K))
@@ -349,23 +348,10 @@ class PCRV(MRV):
         xin = self._as_input(x)
         nsam = xin.shape[0]
         out = np.zeros(nsam)
-        if nsam == 0:
-            return out
-        dev = _device.current_device()
-        tdev = torch.device("cuda", dev)
-        plan = self._plan(mindex, dev=dev)
-        lib = _native.lib()
-        with torch.cuda.device(tdev):
-            stream = torch.cuda.current_stream().cuda_stream
-            c_t = torch.from_numpy(np.ascontiguousarray(Cmat, dtype=np.float64)).to(tdev)
-            rows = 1 << 20
-            for r0 in range(0, nsam, rows):
-                r1 = min(nsam, r0 + rows)
-                xd = torch.from_numpy(xin[r0:r1]).to(tdev)
-                vd = torch.empty(r1 - r0, dtype=torch.float64, device=tdev)
-                _native.check(lib.pcq_quadform_dev(plan.handle, xd.data_ptr(), r1 - r0, self.sdim, c_t.data_ptr(), K,
-                                                   vd.data_ptr(), 1, stream), "pcq_quadform_dev")
-                out[r0:r1] = vd.cpu().numpy()
+        if nsam:
+            cm = np.ascontiguousarray(Cmat, dtype=np.float64)
+            _native.check(_native.lib().pcq_quadform(self._plan(mindex).handle, _native.ptr(xin), nsam, self.sdim,
+                                                     _native.ptr(cm), K, _native.ptr(out), 1), "pcq_quadform")
         return out
 
     def specialize(self, exact=True, fast=True):
