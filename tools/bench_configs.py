@@ -83,6 +83,19 @@ def c2():
          evalPC_s=t_eval, fit_s=t_fit, basis_evals_per_s=n * K / t_fit,
          max_abs_coef_err=float(np.max(np.abs(f.cf - c_true))))
 
+    # Bayesian fit with full coefficient covariance + prediction with pushed-forward variance on all points
+    # (lreg.predict msc=1: the second N K^2 pass of the reference workflow; K6 here)
+    def fit_anl():
+        a = anl()
+        a.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+        a.fit(x, y)
+        return a
+    t_anl, a = timed(fit_anl)
+    t_pred, (mean, var, _) = timed(lambda: a.predict(x, msc=1), reps=2)
+    emit(config="C2", desc="anl (full covariance) fit + predict with variance on the 1e6 training points",
+         anl_fit_s=t_anl, predict_mean_var_s=t_pred, rms_resid=float(np.sqrt(np.mean((mean - y) ** 2))),
+         mean_pred_std=float(np.mean(np.sqrt(var))))
+
 
 def c3():
     rng = np.random.default_rng(3)
