@@ -33,11 +33,6 @@ class PCBasisEvaluator:
         return pars[0].evalBases(x, self.jdim)
 
 
-def _scaled_pivots_ok(diagG, diagL, tol=1.0e-6):
-    # cond of the equilibrated G well below 1/tol^2: pivots L_ii / sqrt(G_ii) stay away from 0
-    return bool((diagL.abs() / diagG.sqrt()).min() > tol)
-
-
 def _current_device():
     from .. import device as _device
     return _device.current_device()
@@ -47,16 +42,18 @@ def solve_normal_device(G_t, B_t, pivot_tol=1.0e-6):
     """Cholesky solve of G C = B on the GPU (torch tensors, float64).  The K x K factorisation is not
     sample-parallel; it is a plain library call (cuSOLVER potrf/potrs through
     torch.linalg), kept on the device so that only K coefficients travel back to the host.
-    Returns None when G is not numerically positive definite (callers then take the eigen path)."""
+    Returns None when G is not numerically positive definite (callers then take the QR / eigen path).
+    One host synchronisation decides acceptance: factorisation status, positive diagonal and the scaled
+    pivots L_ii / sqrt(G_ii) (cond of the equilibrated G well below 1 / tol^2) are combined on the device."""
     import torch
     diag = torch.diagonal(G_t)
-    if not bool(torch.all(diag > 0.0)):
-        return None
     L, info = torch.linalg.cholesky_ex(G_t)
-    if int(info) != 0 or not _scaled_pivots_ok(diag, torch.diagonal(L), pivot_tol):
+    ratio = torch.diagonal(L).abs() / diag.clamp_min(0.0).sqrt()          # NaN / inf where diag <= 0
+    ok = (info == 0) & (diag.min() > 0.0) & (torch.nan_to_num(ratio, nan=0.0).min() > pivot_tol)
+    if not bool(ok):
         return None
     C = torch.cholesky_solve(B_t if B_t.ndim == 2 else B_t[:, None], L)
-    if not bool(torch.all(torch.isfinite(C))):
+    if not bool(torch.isfinite(C.sum())):
         return None
     return C if B_t.ndim == 2 else C[:, 0]
 
