@@ -293,6 +293,11 @@ int pcq_eval_bases_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, dou
     return pcq_launch_bases(p, x, n, ldx, a, lda, (cudaStream_t)stream);
 }
 
+// fast mode with many outputs goes to the tensor pipe (packed design-matrix chunk x coefficient matrix),
+// everything else to the K2 kernels
+static int evalpc_any(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m, double* y,
+                      int64_t ldy, int mode, cudaStream_t st);
+
 int pcq_eval_pc_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m,
                     double* y, int64_t ldy, int mode, void* stream) {
     if (!p || n < 0 || m < 0 || (n > 0 && m > 0 && (!x || !cf || !y)) || ldx < p->sdim ||
@@ -301,7 +306,7 @@ int pcq_eval_pc_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const 
         return PCQ_ERR_ARG;
     }
     DeviceGuard guard(p->device);
-    return pcq_launch_evalpc(p, x, n, ldx, cf, m, y, ldy, mode, (cudaStream_t)stream);
+    return evalpc_any(p, x, n, ldx, cf, m, y, ldy, mode, (cudaStream_t)stream);
 }
 
 namespace {
@@ -327,6 +332,15 @@ struct ScratchLease {
     }
 };
 }  // namespace
+
+static int evalpc_any(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m, double* y,
+                      int64_t ldy, int mode, cudaStream_t st) {
+    if (mode == 1 && n >= 1024 && pcq_linforms_applicable(p, m)) {
+        ScratchLease lease(p->device, st);
+        return pcq_launch_linforms(p, x, n, ldx, cf, m, y, ldy, &p->d_q, &p->q_bytes, &lease.d.zp, &lease.d.zp_bytes, st);
+    }
+    return pcq_launch_evalpc(p, x, n, ldx, cf, m, y, ldy, mode, st);
+}
 
 int pcq_quadform_dev(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* c, int64_t ldc,
                      double* v, int64_t ldv, void* stream) {
@@ -506,7 +520,7 @@ int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const doub
         if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
         if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * mo * 8)) != PCQ_OK) return rc;
         if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
-        if ((rc = pcq_launch_evalpc(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], mo, mode, st)) != PCQ_OK)
+        if ((rc = evalpc_any(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], mo, mode, st)) != PCQ_OK)
             return rc;
         if ((rc = copy_rows(y + r0 * ldy, ldy, p->d_out[b], mo, mo, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return rc;
     }

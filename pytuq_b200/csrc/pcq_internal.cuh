@@ -123,6 +123,9 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
 int pcq_launch_qform(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* c, int64_t ldc, double* v,
                      int64_t ldv, double** bq, size_t* bq_bytes, double** ws, size_t* ws_bytes, double** zbuf,
                      size_t* zbuf_bytes, cudaStream_t st);
+bool pcq_linforms_applicable(const pcq_plan* p, int m);
+int pcq_launch_linforms(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m, double* y,
+                        int64_t ldy, double** bq, size_t* bq_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st);
 int pcq_launch_residual(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,
                         const double* cf, double* sums, int accumulate, cudaStream_t st);
 int pcq_launch_germ(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,

@@ -16,11 +16,12 @@ namespace {
 // tile; a second kernel adds the partials of a sample in tile order (deterministic).
 struct QformParams {
     const double* zq;      // [Kp/8][Nc][8]
-    const double* bq;      // [Kp/8][Kp][8]
+    const double* bq;      // [Kp/8][ldb][8]: U (quadratic form, ldb = Kp) or the coefficient vectors (ldb = Mp)
     int64_t Nc;            // samples in this chunk, padded to 128
-    int Kp, nJ;            // padded number of terms, column tiles
+    int Kp, nJ, ldb;       // padded number of terms, column tiles of the B operand, its row count
     int64_t units;         // (Nc / 128) * nJ
-    double* part;          // [nJ][Nc]
+    double* part;          // quadratic form: [nJ][Nc]
+    double* y; int64_t ldy; int64_t n; int m;     // linear forms: Y (n x m), leading dimension ldy
 };
 
 struct QfPackParams {
@@ -98,6 +99,23 @@ __global__ void __launch_bounds__(256) pcq_qf_pack_c_kernel(const double* __rest
     }
 }
 
+// Bq[ib][m][t] = cf[m][ib * 8 + t]  (zero outside M x K)
+__global__ void __launch_bounds__(256) pcq_lf_pack_cf_kernel(const double* __restrict__ cf, int K, int M, int Kp, int Mp,
+                                                             double* __restrict__ bq) {
+    const int64_t total = (int64_t)Kp * Mp;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(e & 7);
+        const int64_t r = e >> 3;
+        const int m = (int)(r % Mp), ib = (int)(r / Mp);
+        const int i = ib * 8 + t;
+        bq[e] = (m < M && i < K) ? cf[(size_t)m * K + i] : 0.0;
+    }
+}
+
+// LF = false: quadratic forms (triangular U, row-wise product epilogue).
+// LF = true:  linear forms Y = Psi C^T for many coefficient vectors (evalPC fast mode with M >= 64 outputs): same
+//             pipeline, every unit contracts all Kp terms and the epilogue stores the 128 x 128 tile of Y.
+template <bool LF>
 __global__ void __launch_bounds__(SY_THREADS, 1) pcq_qform_kernel(QformParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ST = 128, CHUNK = ST * SB, FM = 4, FN = 8;
@@ -119,7 +137,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_qform_kernel(QformParams P)
     auto open_unit = [&]() {
         if (pu < P.units) {
             pmt = (int)(pu / P.nJ); pJ = (int)(pu - (int64_t)pmt * P.nJ);
-            pst = 0; pst1 = (pJ + 1) * (ST / (KS * SB));
+            pst = 0; pst1 = LF ? P.Kp / (KS * SB) : (pJ + 1) * (ST / (KS * SB));
         }
     };
     if (warp == 0) open_unit();
@@ -134,7 +152,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_qform_kernel(QformParams P)
         if (lane < 2 * KS) {
             const int op = lane / KS, kb = lane % KS;
             const size_t ib = (size_t)pst * KS + kb;
-            const double* src = op ? P.bq + (ib * P.Kp + (size_t)pJ * ST) * SB
+            const double* src = op ? P.bq + (ib * P.ldb + (size_t)pJ * ST) * SB
                                    : P.zq + (ib * P.Nc + (size_t)pmt * ST) * SB;
             tma_bulk_g2s(ops + ((size_t)(b * 2 + op) * KS + kb) * CHUNK, src, CHUNK * 8u, full + b);
         }
@@ -149,7 +167,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_qform_kernel(QformParams P)
     const int g = lane >> 2, tig = lane & 3, wm = warp & 3, wn = warp >> 2;
     for (int64_t u = blockIdx.x; u < P.units; u += gridDim.x) {
         const int mt = (int)(u / P.nJ), J = (int)(u - (int64_t)mt * P.nJ);
-        const int nst = (J + 1) * (ST / (KS * SB));
+        const int nst = LF ? P.Kp / (KS * SB) : (J + 1) * (ST / (KS * SB));
         double acc[FM][FN][2];
 #pragma unroll
         for (int i = 0; i < FM; ++i)
@@ -182,6 +200,21 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_qform_kernel(QformParams P)
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + b);
+        }
+        if (LF) {
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const int64_t row = (int64_t)mt * ST + wm * 32 + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < FN; ++j) {
+                    const int col = J * ST + wn * 64 + j * 8 + 2 * tig;
+                    if (row < P.n) {
+                        if (col < P.m) P.y[row * P.ldy + col] = acc[i][j][0];
+                        if (col + 1 < P.m) P.y[row * P.ldy + col + 1] = acc[i][j][1];
+                    }
+                }
+            }
+            continue;
         }
         // epilogue: rowsum_s = sum_j acc[s][j] * Psi[s][j] over this tile's 128 columns
         double rs[FM];
@@ -249,7 +282,7 @@ int pcq_launch_qform(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const
     if (rows > npad) rows = npad;
     if ((rc = pcq_ensure_dev(zbuf, zbuf_bytes, (size_t)rows * Kp * sizeof(double))) != PCQ_OK) return rc;
     if ((rc = pcq_ensure_dev(ws, ws_bytes, (size_t)nJ * rows * sizeof(double))) != PCQ_OK) return rc;
-    PCQ_CUDA(cudaFuncSetAttribute(pcq_qform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_qform_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int64_t r0 = 0; r0 < n; r0 += rows) {
         const int64_t nr = (n - r0 < rows) ? n - r0 : rows;
@@ -279,13 +312,76 @@ int pcq_launch_qform(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const
 
         QformParams Q;
         memset(&Q, 0, sizeof(Q));
-        Q.zq = *zbuf; Q.bq = *bq; Q.Nc = Nc; Q.Kp = Kp; Q.nJ = nJ; Q.units = (Nc / 128) * nJ; Q.part = *ws;
+        Q.zq = *zbuf; Q.bq = *bq; Q.Nc = Nc; Q.Kp = Kp; Q.nJ = nJ; Q.ldb = Kp; Q.units = (Nc / 128) * nJ; Q.part = *ws;
         const int grid = (int)(Q.units < p->num_sms ? Q.units : p->num_sms);
-        pcq_qform_kernel<<<grid, SY_THREADS, smem, st>>>(Q);
+        pcq_qform_kernel<false><<<grid, SY_THREADS, smem, st>>>(Q);
         PCQ_LAUNCH_CHECK("pcq_qform_kernel");
         const int64_t want = (nr + 255) / 256;
         pcq_qf_reduce_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(*ws, Nc, nJ, nr, v + r0 * ldv, ldv);
         PCQ_LAUNCH_CHECK("pcq_qf_reduce_kernel");
+    }
+    return PCQ_OK;
+}
+
+// Y[i][j] = sum_k cf[j][k] Psi_k(x_i)  for m coefficient vectors at once (evalPC fast mode, many outputs): the
+// design-matrix chunk is packed once and contracted with all vectors on the tensor pipe.
+bool pcq_linforms_applicable(const pcq_plan* p, int m) {
+    return m >= 64 && syrk_smem_bytes(128) <= p->smem_optin &&
+           (size_t)(p->nslots + 1) * PACK_TS * sizeof(double) <= p->smem_optin && pcq_table_fits_smem(p);
+}
+
+int pcq_launch_linforms(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m, double* y,
+                        int64_t ldy, double** bq, size_t* bq_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st) {
+    if (n == 0 || m == 0) return PCQ_OK;
+    const int K = p->nterms;
+    const int Kp = (K + 127) / 128 * 128, Mp = (m + 127) / 128 * 128;
+    const int nJ = Mp / 128;
+    const size_t smem = syrk_smem_bytes(128);
+    const size_t smem_pack = (size_t)(p->nslots + 1) * PACK_TS * sizeof(double);
+    int rc = pcq_ensure_dev(bq, bq_bytes, (size_t)Kp * Mp * sizeof(double));
+    if (rc != PCQ_OK) return rc;
+    pcq_lf_pack_cf_kernel<<<p->num_sms * 4, 256, 0, st>>>(cf, K, m, Kp, Mp, *bq);
+    PCQ_LAUNCH_CHECK("pcq_lf_pack_cf_kernel");
+    const char* env = getenv("PCQ_SYRK_CHUNK_MB");
+    const int64_t target = (int64_t)(env ? atoi(env) : 2048) << 20;
+    int64_t rows = (target / ((int64_t)Kp * 8)) / 128 * 128;
+    if (rows < 128) rows = 128;
+    const int64_t npad = (n + 127) / 128 * 128;
+    if (rows > npad) rows = npad;
+    if ((rc = pcq_ensure_dev(zbuf, zbuf_bytes, (size_t)rows * Kp * sizeof(double))) != PCQ_OK) return rc;
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_qform_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t nr = (n - r0 < rows) ? n - r0 : rows;
+        const int64_t Nc = (nr + 127) / 128 * 128;
+        QfPackParams K1;
+        memset(&K1, 0, sizeof(K1));
+        K1.x = x + r0 * ldx; K1.ldx = ldx; K1.n = nr; K1.Nc = Nc; K1.npairs = Nc / 16;
+        K1.K = K; K1.Kp = Kp; K1.sdim = p->sdim; K1.pmax = p->pmax; K1.nslots = p->nslots; K1.width = p->width;
+        K1.rec_a = p->d_rec_a; K1.rec_b = p->d_rec_b; K1.p1 = p->d_p1; K1.desc4 = p->d_desc4; K1.descw = p->d_descw;
+        K1.zq = *zbuf;
+        const int64_t cap = (int64_t)p->num_sms * 8;
+        const int pgrid = (int)(K1.npairs < cap ? K1.npairs : cap);
+        auto launch = [&](auto kern) -> int {
+            PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pack));
+            kern<<<pgrid, 256, smem_pack, st>>>(K1);
+            return PCQ_OK;
+        };
+        switch (p->width <= 4 ? p->width : 0) {
+            case 1: rc = launch(pcq_qf_pack_rows_kernel<1>); break;
+            case 2: rc = launch(pcq_qf_pack_rows_kernel<2>); break;
+            case 3: rc = launch(pcq_qf_pack_rows_kernel<3>); break;
+            case 4: rc = launch(pcq_qf_pack_rows_kernel<4>); break;
+            default: rc = launch(pcq_qf_pack_rows_kernel<0>); break;
+        }
+        if (rc != PCQ_OK) return rc;
+        PCQ_LAUNCH_CHECK("pcq_qf_pack_rows_kernel");
+        QformParams Q;
+        memset(&Q, 0, sizeof(Q));
+        Q.zq = *zbuf; Q.bq = *bq; Q.Nc = Nc; Q.Kp = Kp; Q.nJ = nJ; Q.ldb = Mp; Q.units = (Nc / 128) * nJ;
+        Q.y = y + r0 * ldy; Q.ldy = ldy; Q.n = nr; Q.m = m;
+        const int grid = (int)(Q.units < p->num_sms ? Q.units : p->num_sms);
+        pcq_qform_kernel<true><<<grid, SY_THREADS, smem, st>>>(Q);
+        PCQ_LAUNCH_CHECK("pcq_qform_kernel");
     }
     return PCQ_OK;
 }

@@ -335,6 +335,37 @@ def test_k3_k4_syrk_chunks_splits_and_fused_fallback(monkeypatch):
         assert rel_err(sd.cpu().numpy(), orc.suffstats(A, yb[:, 1].cpu().numpy())) < 1e-12, env
 
 
+def test_k2_fast_mode_many_outputs_on_the_tensor_pipe():
+    """evalPC fast mode with >= 64 outputs runs as a packed GEMM on DMMA (pcq_qform_kernel<true>): same values as
+    the design-matrix product to rounding, ragged N / K / M, both entry points."""
+    import torch
+    from pytuq_b200 import _native
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(8)
+    for fam, p, d, n, M in [("LU", 3, 6, 3000, 64), ("HG", 3, 9, 2047, 130), ("LU", 4, 5, 1500, 257)]:
+        mi = orc.get_mi(p, d)
+        K = mi.shape[0]
+        x = rng.uniform(-1, 1, (n, d)) if fam == "LU" else rng.standard_normal((n, d))
+        cf = rng.standard_normal((M, K))
+        pc = PCRV(1, d, fam, mi=mi)
+        A = orc.eval_bases(x, mi, fam)
+        ref = A @ cf.T
+        got = pc.evalLinearForms(x, cf, 0, exact=False)
+        assert got.shape == (n, M) and rel_err(got, ref) < 1e-12, (fam, p, d, n, M)
+        # device entry point with a leading dimension and canary columns
+        plan = pc._plan(mi)
+        xd = torch.from_numpy(x).cuda(); cd = torch.from_numpy(cf).cuda()
+        yd = torch.full((n, M + 3), -7.0, dtype=torch.float64, device="cuda")
+        _native.check(_native.lib().pcq_eval_pc_dev(plan.handle, xd.data_ptr(), n, d, cd.data_ptr(), M, yd.data_ptr(),
+                                                    M + 3, 1, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        yh = yd.cpu().numpy()
+        assert rel_err(yh[:, :M], ref) < 1e-12 and np.all(yh[:, M:] == -7.0)
+        # exact mode is untouched by the route: still bit-identical
+        assert np.array_equal(pc.evalLinearForms(x[:50], cf[:3], 0, exact=True),
+                              orc.eval_pc(x[:50], [mi] * 3, list(cf[:3]), fam))
+
+
 # ----------------------------------------------------------------------------- K6
 def test_k6_quadratic_forms_on_the_tensor_pipe():
     """v_n = psi_n^T C psi_n (pcq_quadform_dev) against the design-matrix formula, over shapes that exercise

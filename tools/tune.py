@@ -129,3 +129,11 @@ for name, fam, d, p, n in shapes:
         ms = timeit(lambda: _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), n6b, d, F.data_ptr(), K, v.data_ptr(), 1, 3, st)), reps=2, warm=1)
         print(f"{name} K2 quadratic-form mode (factor, {K} outputs): n={n6b} {ms:8.3f} ms  -> {ms * n6 / n6b:8.3f} ms at n={n6}", flush=True)
         del Cm, F, v
+    if "k2lf" in which:
+        for M in (64, 256):
+            cm = torch.randn((M, K), dtype=torch.float64, device="cuda", generator=g)
+            nn = min(n, 200_000)
+            ym = torch.empty((nn, M), dtype=torch.float64, device="cuda")
+            ms = timeit(lambda: _native.check(lib.pcq_eval_pc_dev(plan.handle, x.data_ptr(), nn, d, cm.data_ptr(), M, ym.data_ptr(), M, 1, st)), reps=3, warm=1)
+            print(f"{name} evalPC fast M={M} (tensor pipe): n={nn} {ms:8.3f} ms  {2.0 * nn * K * M / ms / 1e9:6.2f} TFLOP/s (2NKM)", flush=True)
+            del cm, ym
