@@ -118,5 +118,23 @@ def note_evalpc_work(plan, nsam, nterms, nout, mode):
 
 
 def clear_plans():
+    """Drops the cached plans; a native handle is destroyed when the last reference to its Plan goes (which also
+    waits for a background specialisation build that may still be running)."""
     with _lock:
         _plans.clear()
+
+
+def _close_all_at_exit():
+    # destroy the cached plans (joining background builds) before the interpreter tears the CUDA runtime down
+    with _lock:
+        plans = list(_plans.values())
+        _plans.clear()
+    for plan in plans:
+        try:
+            plan.close()
+        except Exception:
+            pass
+
+
+import atexit  # noqa: E402
+atexit.register(_close_all_at_exit)
