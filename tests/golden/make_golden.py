@@ -110,6 +110,59 @@ def klsurr(R):
     print(f"klsurr.npz  neig={neig} K_union={mindex_all.shape[0]}  {os.path.getsize(os.path.join(HERE, 'klsurr.npz')) / 1024:.1f} KiB")
 
 
+def uqpc_model(p):
+    """The 'online_example' stand-in model of the replay below: two observables of three parameters."""
+    return np.stack([np.exp(0.3 * p[:, 0]) + p[:, 1] * p[:, 2], np.sin(p[:, 0]) + 0.1 * p[:, 2] ** 2 + p[:, 1]], axis=1)
+
+
+def uqpc(R):
+    """apps/uqpc/uq_pc.py:120-345 (parameter-domain input, regime online_example, sampling 'rand') replayed step by
+    step with the reference's own objects.  The sample files are written with np.savetxt exactly as the app does
+    and committed as fixtures (tests/golden/uqpc/*.txt); everything computed from them goes to uqpc.npz."""
+    import io, contextlib
+    d = os.path.join(HERE, "uqpc")
+    os.makedirs(d, exist_ok=True)
+    f = lambda name: os.path.join(d, name)                                  # noqa: E731
+    np.savetxt(f("pdomain.txt"), np.array([[-1.0, 2.0], [0.5, 1.5], [-3.0, -1.0]]))
+    pdom = np.loadtxt(f("pdomain.txt")).reshape(-1, 2)                      # uq_pc.py:139
+    pcf_all = np.vstack((0.5 * (pdom[:, 1] + pdom[:, 0]), np.diag(0.5 * (pdom[:, 1] - pdom[:, 0]))))
+    in_pcdim, npar = pdom.shape[0], pcf_all.shape[1]
+    pc = R["PCRV"](in_pcdim, in_pcdim, "LU", mi=R["get_mi"](1, in_pcdim), cfs=pcf_all.T)   # uq_pc.py:191-192
+    germ_train = pc.sampleGerm(240, seed=7)                                 # uq_pc.py:206-207
+    np.savetxt(f("qtrain.txt"), germ_train)
+    np.savetxt(f("ptrain.txt"), pc.evalPC(germ_train))                      # uq_pc.py:217-218
+    germ_test = pc.sampleGerm(50, seed=7)                                   # uq_pc.py:224-229
+    np.savetxt(f("qtest.txt"), germ_test)
+    np.savetxt(f("ptest.txt"), pc.evalPC(germ_test))
+    ptrain = np.loadtxt(f("ptrain.txt")).reshape(-1, npar)                  # uq_pc.py:234-240
+    germ_train = np.loadtxt(f("qtrain.txt")).reshape(-1, in_pcdim)
+    ptest = np.loadtxt(f("ptest.txt")).reshape(-1, npar)
+    germ_test = np.loadtxt(f("qtest.txt")).reshape(-1, in_pcdim)
+    ytrain, ytest = uqpc_model(ptrain), uqpc_model(ptest)                   # uq_pc.py:252-258
+    np.savetxt(f("ytrain.txt"), ytrain)
+    np.savetxt(f("ytest.txt"), ytest)
+    out = {}
+    for method in ("lsq", "anl", "bcs"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            opc, lregs = R["pc_fit"](germ_train, ytrain, order=3, pctype="LU", method=method, eta=1e-6)
+        out[f"{method}__ytrain_pc"] = opc.function(germ_train)              # uq_pc.py:306-308
+        out[f"{method}__ytest_pc"] = opc.function(germ_test)
+        vtr, vte = np.empty(ytrain.shape), np.empty(ytest.shape)
+        for iout, lreg in enumerate(lregs):                                 # uq_pc.py:311-314
+            vtr[:, iout] = lreg.predicta(opc.evalBases(germ_train, iout), msc=1)[1]
+            vte[:, iout] = lreg.predicta(opc.evalBases(germ_test, iout), msc=1)[1]
+            out[f"{method}__mi{iout}"] = opc.mindices[iout]
+            out[f"{method}__cf{iout}"] = opc.coefs[iout]
+        out[f"{method}__ytrain_pc_var"], out[f"{method}__ytest_pc_var"] = vtr, vte
+        out[f"{method}__relerr_train"] = np.linalg.norm(ytrain - out[f"{method}__ytrain_pc"], axis=0) / np.linalg.norm(ytrain, axis=0)
+        out[f"{method}__relerr_test"] = np.linalg.norm(ytest - out[f"{method}__ytest_pc"], axis=0) / np.linalg.norm(ytest, axis=0)
+        out[f"{method}__main"] = opc.computeSens()                          # uq_pc.py:332-334
+        out[f"{method}__total"] = opc.computeTotSens()
+        out[f"{method}__joint"] = opc.computeJointSens()
+    np.savez_compressed(os.path.join(HERE, "uqpc.npz"), **out)
+    print(f"uqpc.npz  {os.path.getsize(os.path.join(HERE, 'uqpc.npz')) / 1024:.1f} KiB  (+ uqpc/*.txt)")
+
+
 def main():
     R = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "illcond":
@@ -269,6 +322,7 @@ def main():
         print(f"{f}.npz  {os.path.getsize(p) / 1024:.1f} KiB")
     illcond(R)
     klsurr(R)
+    uqpc(R)
 
 
 if __name__ == "__main__":

@@ -962,3 +962,69 @@ def test_full_size_c2_properties():
     # oracle spot check on rows from the far end of the array
     idx = [0, 1, m - 1]
     assert np.array_equal(A[idx].cpu().numpy(), orc.eval_bases(x[idx].cpu().numpy(), mi, "HG"))
+
+
+def uqpc_model(p):
+    # the stand-in model of the replay; same expression as tests/golden/make_golden.py:uqpc_model
+    return np.stack([np.exp(0.3 * p[:, 0]) + p[:, 1] * p[:, 2], np.sin(p[:, 0]) + 0.1 * p[:, 2] ** 2 + p[:, 1]], axis=1)
+
+
+def test_uqpc_app_replay_through_sample_files(tmp_path):
+    """apps/uqpc/uq_pc.py:120-345 (parameter-domain input, regime online_example) replayed with this package and its
+    sample-file I/O against the same replay done with the reference (tests/golden/make_golden.py:uqpc): the files
+    the app writes are reproduced byte for byte (evalPC is bit-identical), fits / predictions / variances /
+    Sobol indices to the north-star tolerances."""
+    import contextlib, io as _io, os
+    from conftest import GOLDEN
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.utils import io
+    from pytuq_b200.utils.mindex import get_mi
+    from pytuq_b200.workflows.fits import pc_fit
+    gold = os.path.join(GOLDEN, "uqpc")
+    g = load_golden("uqpc")
+    pdom = io.loadtxt(os.path.join(gold, "pdomain.txt")).reshape(-1, 2)
+    pcf_all = np.vstack((0.5 * (pdom[:, 1] + pdom[:, 0]), np.diag(0.5 * (pdom[:, 1] - pdom[:, 0]))))
+    in_pcdim, npar = pdom.shape[0], pcf_all.shape[1]
+    pc = PCRV(in_pcdim, in_pcdim, "LU", mi=get_mi(1, in_pcdim), cfs=pcf_all.T)
+
+    def same_file(name):
+        return open(tmp_path / name, "rb").read() == open(os.path.join(gold, name), "rb").read()
+
+    for q, p, n in (("qtrain.txt", "ptrain.txt", 240), ("qtest.txt", "ptest.txt", 50)):
+        germ = pc.sampleGerm(n, seed=7)
+        io.savetxt(str(tmp_path / q), germ)
+        io.savetxt(str(tmp_path / p), pc.evalPC(germ))
+        assert same_file(q) and same_file(p), (q, p)
+    ptrain = io.loadtxt(str(tmp_path / "ptrain.txt")).reshape(-1, npar)
+    germ_train = io.loadtxt(str(tmp_path / "qtrain.txt")).reshape(-1, in_pcdim)
+    ptest = io.loadtxt(str(tmp_path / "ptest.txt")).reshape(-1, npar)
+    germ_test = io.loadtxt(str(tmp_path / "qtest.txt")).reshape(-1, in_pcdim)
+    # model outputs: read from the files as the app's offline regime does (uq_pc.py:262-265) -- exp / sin of the
+    # host's numpy may differ in the last bit from box to box, so the model itself is only checked to 1e-14
+    ytrain = io.loadtxt(os.path.join(gold, "ytrain.txt")).reshape(ptrain.shape[0], -1)
+    ytest = io.loadtxt(os.path.join(gold, "ytest.txt")).reshape(ptest.shape[0], -1)
+    np.testing.assert_allclose(uqpc_model(ptrain), ytrain, rtol=1e-14, atol=1e-15)
+    np.testing.assert_allclose(uqpc_model(ptest), ytest, rtol=1e-14, atol=1e-15)
+    io.savetxt(str(tmp_path / "ytrain.txt"), ytrain)
+    assert same_file("ytrain.txt")
+
+    for method in ("lsq", "anl", "bcs"):
+        with contextlib.redirect_stdout(_io.StringIO()):
+            opc, lregs = pc_fit(germ_train, ytrain, order=3, pctype="LU", method=method, eta=1e-6)
+        ytrain_pc, ytest_pc = opc.function(germ_train), opc.function(germ_test)
+        vtr, vte = np.empty(ytrain.shape), np.empty(ytest.shape)
+        for iout, lreg in enumerate(lregs):
+            assert np.array_equal(opc.mindices[iout], g[f"{method}__mi{iout}"]), (method, iout)
+            np.testing.assert_allclose(opc.coefs[iout], g[f"{method}__cf{iout}"], rtol=1e-10, atol=1e-12)
+            vtr[:, iout] = lreg.predicta(opc.evalBases(germ_train, iout), msc=1)[1]
+            vte[:, iout] = lreg.predicta(opc.evalBases(germ_test, iout), msc=1)[1]
+        np.testing.assert_allclose(ytrain_pc, g[f"{method}__ytrain_pc"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(ytest_pc, g[f"{method}__ytest_pc"], rtol=1e-10, atol=1e-12)
+        vscale = max(np.max(g[f"{method}__ytrain_pc_var"]), 1e-300)
+        np.testing.assert_allclose(vtr, g[f"{method}__ytrain_pc_var"], rtol=1e-7, atol=1e-9 * vscale)
+        np.testing.assert_allclose(vte, g[f"{method}__ytest_pc_var"], rtol=1e-7, atol=1e-9 * vscale)
+        relerr = np.linalg.norm(ytrain - ytrain_pc, axis=0) / np.linalg.norm(ytrain, axis=0)
+        np.testing.assert_allclose(relerr, g[f"{method}__relerr_train"], rtol=1e-7)
+        np.testing.assert_allclose(opc.computeSens(), g[f"{method}__main"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(opc.computeTotSens(), g[f"{method}__total"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(opc.computeJointSens(), g[f"{method}__joint"], rtol=1e-10, atol=1e-13)

@@ -190,3 +190,22 @@ def test_round_trip_of_arbitrary_doubles(values):
         assert open(f_np, "rb").read() == open(f_us, "rb").read()
         assert _same_bits(io.loadtxt(f_us, ndmin=1), X)
         assert _same_bits(np.loadtxt(f_us, ndmin=1), X)
+
+
+def test_germ_sample_files_of_the_uqpc_app_are_reproduced_byte_for_byte(tmp_path):
+    """apps/uqpc/uq_pc.py:206-207,224-226: seeded germ samples written with savetxt.  The germ stream is the host's
+    numpy stream (no GPU), so this part of the app's file exchange is checked here; the parameter files, which go
+    through evalPC, are checked on the GPU (tests/test_gpu_parity.py::test_uqpc_app_replay_through_sample_files)."""
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.utils.mindex import get_mi
+    gold = os.path.join(ROOT, "tests", "golden", "uqpc")
+    pdom = io.loadtxt(os.path.join(gold, "pdomain.txt")).reshape(-1, 2)
+    assert np.array_equal(pdom, np.loadtxt(os.path.join(gold, "pdomain.txt")).reshape(-1, 2))
+    pcf_all = np.vstack((0.5 * (pdom[:, 1] + pdom[:, 0]), np.diag(0.5 * (pdom[:, 1] - pdom[:, 0]))))
+    pc = PCRV(3, 3, "LU", mi=get_mi(1, 3), cfs=pcf_all.T)
+    for name, n in (("qtrain.txt", 240), ("qtest.txt", 50)):
+        io.savetxt(str(tmp_path / name), pc.sampleGerm(n, seed=7))
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(gold, name), "rb").read()
+    for name in ("ptrain.txt", "ytrain.txt", "qtrain.txt"):
+        want = np.loadtxt(os.path.join(gold, name))
+        assert np.array_equal(io.loadtxt(os.path.join(gold, name)), want)
