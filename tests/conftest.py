@@ -44,3 +44,15 @@ def case_mis_cfs(case):
 
 def case_types(case):
     return [str(t) for t in case["types"]]
+
+
+def c1_inputs(n=100_000, d=10):
+    """BASELINE.json configs[0] / SURVEY 8(d) C1 synthetic inputs, as tests/golden/make_golden.py:c1_inputs:
+    x uniform on [-1,1]^10 (seed 1), Genz oscillatory target (func/genz.py:32-54, shift 0.25, weights 1/(1+i)^2 on
+    (x+1)/2) + 1e-2 N(0,1)."""
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, (n, d))
+    w = 1.0 / (1 + np.arange(d)) ** 2
+    noise = 1e-2 * rng.standard_normal(n)
+    y = np.cos(2 * np.pi * 0.25 + ((x + 1) / 2) @ w) + noise
+    return x, y

@@ -163,6 +163,50 @@ def uqpc(R):
     print(f"uqpc.npz  {os.path.getsize(os.path.join(HERE, 'uqpc.npz')) / 1024:.1f} KiB  (+ uqpc/*.txt)")
 
 
+def c1_inputs(n=100_000, d=10):
+    """BASELINE.json configs[0] / SURVEY 8(d) C1 synthetic inputs (seed = config number)."""
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, (n, d))
+    w = 1.0 / (1 + np.arange(d)) ** 2
+    noise = 1e-2 * rng.standard_normal(n)
+    return x, w, noise
+
+
+def c1_full(R):
+    """BASELINE.json configs[0] at FULL size with the unmodified reference: Legendre PCE, total order 4, d=10
+    (K=1001), lsq and anl fits of the Genz oscillatory function (func/genz.py:32-54, shift 0.25, weights
+    1/(1+i)^2 on (x+1)/2) + 1e-2 noise on 1e5 uniform samples.  Stores the fitted coefficients, Sobol indices
+    and three design-matrix rows; the inputs are regenerated from the seed by the test."""
+    import time
+    from pytuq.func.genz import GenzOscillatory
+    x, w, noise = c1_inputs()
+    n, d = x.shape
+    genz = GenzOscillatory(shift=0.25, weights=w)
+    y = genz((x + 1) / 2)[:, 0] + noise
+    y_formula = np.cos(2 * np.pi * 0.25 + ((x + 1) / 2) @ w) + noise
+    assert np.max(np.abs(y - y_formula)) < 1e-14
+    mi = R["get_mi"](4, d)
+    pc = R["PCRV"](1, d, "LU", mi=mi)
+    t0 = time.perf_counter()
+    A = pc.evalBases(x, 0)
+    t1 = time.perf_counter()
+    f_lsq = R["lsq"]()
+    f_lsq.fita(A, y)
+    t2 = time.perf_counter()
+    f_anl = R["anl"]()
+    f_anl.fita(A, y)
+    t3 = time.perf_counter()
+    pc.setCfs([f_lsq.cf])
+    out = dict(y_head=y[:16], y_sum=np.array(y.sum()), rows=np.array([0, 1, n - 1]), A_rows=A[[0, 1, n - 1]],
+               cf_lsq=f_lsq.cf, cf_anl=f_anl.cf, anl_datavar=np.array(f_anl.datavar),
+               anl_cov_diag=np.diag(f_anl.cf_cov).copy(), mean=pc.computeMean(), var=pc.computeVar(),
+               main=pc.computeSens(), total=pc.computeTotSens(),
+               ref_seconds=np.array([t1 - t0, t2 - t1, t3 - t2]), ref_cores=np.array(os.cpu_count()))
+    np.savez_compressed(os.path.join(HERE, "c1_full.npz"), **out)
+    print(f"c1_full.npz  {os.path.getsize(os.path.join(HERE, 'c1_full.npz')) / 1024:.1f} KiB; reference: evalBases "
+          f"{t1 - t0:.2f} s, lsq.fita {t2 - t1:.2f} s, anl.fita {t3 - t2:.2f} s on {os.cpu_count()} cores")
+
+
 def main():
     R = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "illcond":
@@ -323,6 +367,7 @@ def main():
     illcond(R)
     klsurr(R)
     uqpc(R)
+    c1_full(R)
 
 
 if __name__ == "__main__":

@@ -1028,3 +1028,41 @@ def test_uqpc_app_replay_through_sample_files(tmp_path):
         np.testing.assert_allclose(opc.computeSens(), g[f"{method}__main"], rtol=1e-10, atol=1e-13)
         np.testing.assert_allclose(opc.computeTotSens(), g[f"{method}__total"], rtol=1e-10, atol=1e-13)
         np.testing.assert_allclose(opc.computeJointSens(), g[f"{method}__joint"], rtol=1e-10, atol=1e-13)
+
+
+def test_full_size_baseline_config_1_vs_reference():
+    """BASELINE.json configs[0] at FULL size — Legendre PCE of total order 4 in d=10 (K=1001), lsq and anl fits of
+    the Genz oscillatory function on 1e5 uniform samples — against the unmodified reference run on the same inputs
+    (tests/golden/c1_full.npz, make_golden.py:c1_full).  Bars of the north star: basis values bit-identical,
+    coefficients and Sobol indices within 1e-10."""
+    from conftest import c1_inputs
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import lsq, anl, PCBasisEvaluator
+    g = load_golden("c1_full")
+    x, y = c1_inputs()
+    np.testing.assert_allclose(y[:16], g["y_head"], rtol=0, atol=1e-14)
+    mi = orc.get_mi(4, 10)
+    pc = PCRV(1, 10, "LU", mi=mi)
+    A = pc.evalBases(x, 0)
+    assert A.shape == (100_000, 1001) and np.array_equal(A[g["rows"]], g["A_rows"])
+    scale = np.max(np.abs(g["cf_lsq"]))
+    fits = {}
+    for name, make in (("lsq", lsq), ("anl", anl)):
+        fused = make()
+        fused.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+        fused.fit(x, y)                       # K3: statistics without a design matrix
+        given = make()
+        given.fita(A, y)                      # K4: statistics of the caller's matrix
+        for f in (fused, given):
+            np.testing.assert_allclose(f.cf, g[f"cf_{name}"], rtol=0, atol=1e-10 * scale)
+            assert np.array_equal(f.used, np.arange(1001))
+        fits[name] = fused
+    np.testing.assert_allclose(fits["anl"].datavar, g["anl_datavar"], rtol=1e-9)
+    np.testing.assert_allclose(np.diag(fits["anl"].cf_cov), g["anl_cov_diag"], rtol=1e-8)
+    pc.setCfs([fits["lsq"].cf])
+    np.testing.assert_allclose(pc.computeMean(), g["mean"], rtol=1e-10)
+    np.testing.assert_allclose(pc.computeVar(), g["var"], rtol=1e-10)
+    np.testing.assert_allclose(pc.computeSens(), g["main"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(pc.computeTotSens(), g["total"], rtol=1e-10, atol=1e-13)
+    # surrogate evaluation equals the design matrix times the coefficients (sequential vs BLAS order)
+    np.testing.assert_allclose(pc.evalPC(x[:4096])[:, 0], A[:4096] @ fits["lsq"].cf, rtol=1e-12, atol=1e-13)

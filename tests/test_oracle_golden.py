@@ -143,3 +143,25 @@ def test_philox_known_answer():
     assert abs(x[:, 0].mean()) < 0.02 and abs(x[:, 0].var() - 1 / 3) < 0.01
     assert abs(x[:, 1].mean()) < 0.03 and abs(x[:, 1].var() - 1) < 0.04
     assert abs(np.corrcoef(x[:, 1], x[:, 2])[0, 1]) < 0.03
+
+
+def test_oracle_at_full_size_baseline_config_1():
+    """BASELINE.json configs[0] at FULL size (LU, order 4, d=10, K=1001, lsq + anl fit of the Genz oscillatory
+    function on 1e5 samples): the oracle against the unmodified reference (tests/golden/c1_full.npz)."""
+    from conftest import c1_inputs
+    g = load_golden("c1_full")
+    x, y = c1_inputs()
+    np.testing.assert_allclose(y[:16], g["y_head"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(y.sum(), g["y_sum"], rtol=1e-13)
+    mi = orc.get_mi(4, 10)
+    A = orc.eval_bases(x, mi, "LU")
+    assert A.shape == (100_000, 1001)
+    assert np.array_equal(A[g["rows"]], g["A_rows"])
+    scale = np.max(np.abs(g["cf_lsq"]))
+    np.testing.assert_allclose(orc.lsq_fit(A, y), g["cf_lsq"], rtol=0, atol=1e-12 * scale)
+    cf, cov, sig = orc.anl_fit(A, y)
+    np.testing.assert_allclose(cf, g["cf_anl"], rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(sig, g["anl_datavar"], rtol=1e-12)
+    np.testing.assert_allclose(np.diag(cov), g["anl_cov_diag"], rtol=1e-11)
+    np.testing.assert_allclose(orc.sobol_main(mi, g["cf_lsq"], "LU"), g["main"][0], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(orc.sobol_total(mi, g["cf_lsq"], "LU"), g["total"][0], rtol=1e-12, atol=1e-15)
