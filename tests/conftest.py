@@ -56,3 +56,13 @@ def c1_inputs(n=100_000, d=10):
     noise = 1e-2 * rng.standard_normal(n)
     y = np.cos(2 * np.pi * 0.25 + ((x + 1) / 2) @ w) + noise
     return x, y
+
+
+def golden_generator():
+    """tests/golden/make_golden.py as a module (loaded by path; importing it does not import the reference): the
+    tests regenerate the synthetic inputs of the larger goldens with the very functions that made them."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pcq_make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -207,6 +207,88 @@ def c1_full(R):
           f"{t1 - t0:.2f} s, lsq.fita {t2 - t1:.2f} s, anl.fita {t3 - t2:.2f} s on {os.cpu_count()} cores")
 
 
+def shape_inputs(config):
+    """Reduced-N synthetic inputs at the shapes of BASELINE.json configs 3, 4, 5; only elementwise
+    numpy arithmetic, so the test regenerates them bit for bit from the seeds.  Needs get_mi from the caller."""
+    rng = np.random.default_rng(config)
+    if config == 3:      # BCS: LU d=50 p=2 (K=1326), 40-sparse truth, 1 % noise
+        n, d, p, fam = 20_000, 50, 2, "LU"
+        x = rng.uniform(-1, 1, (n, d))
+        idx = np.sort(rng.choice(1326, 40, replace=False))
+        val = rng.standard_normal(40)
+        noise = rng.standard_normal(n)
+        return dict(n=n, d=d, p=p, fam=fam, x=x, idx=idx, val=val, noise=noise)
+    if config == 4:      # forward propagation surrogate: HG d=20 p=4 (K=10626)
+        n, d, p, fam = 2048, 20, 4, "HG"
+        cf = rng.standard_normal(10626) / np.arange(1, 10627)
+        x = rng.standard_normal((n, d))
+        return dict(n=n, d=d, p=p, fam=fam, x=x, cf=cf)
+    if config == 5:      # KL+PC multi-output: LU d=30 p=3 (K=5456), M outputs sharing one design matrix
+        n, d, p, fam, m = 25_000, 30, 3, "LU", 4
+        x = rng.uniform(-1, 1, (n, d))
+        y = np.stack([np.exp(0.2 * (j + 1) * x[:, j]) * (1.0 + 0.5 * x[:, j + 1] * x[:, j + 2]) / (1 + j)
+                      for j in range(m)], axis=1) + 1e-3 * rng.standard_normal((n, m))
+        return dict(n=n, d=d, p=p, fam=fam, x=x, y=y)
+    raise ValueError(config)
+
+
+def sparse_target(A, idx, val, noise):
+    """y = sum_j val_j A[:, idx_j] + 1 % noise, accumulated term by term (no BLAS: reproducible anywhere)."""
+    y = np.zeros(A.shape[0])
+    for j, v in zip(idx, val):
+        y = y + v * A[:, j]
+    return y + 0.01 * np.std(y) * noise
+
+
+def config_shapes(R):
+    """BASELINE.json configs 3, 4, 5 at their own (d, p, K) with the sample count reduced to what the reference
+    finishes in about a minute here: BCS (C3), evalPC + moments + Sobol of the big surrogate (C4), multi-output
+    pc_fit with anl (C5)."""
+    import io, contextlib, time
+    rows = np.array([0, 1, 777])
+    # --- C3
+    c = shape_inputs(3)
+    mi = R["get_mi"](c["p"], c["d"])
+    pc = R["PCRV"](1, c["d"], c["fam"], mi=mi)
+    t0 = time.perf_counter()
+    A = pc.evalBases(c["x"], 0)
+    y = sparse_target(A, c["idx"], c["val"], c["noise"])
+    fit = R["bcs"](eta=1e-8)
+    t1 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        fit.fita(A, y)
+    t2 = time.perf_counter()
+    out = dict(rows=rows, A_rows=A[rows], y_head=y[:16], used=np.asarray(fit.used), cf=fit.cf,
+               datavar=np.asarray(fit.datavar, dtype=float).reshape(-1), cov_diag=np.diag(fit.cf_cov).copy(),
+               ref_seconds=np.array([t1 - t0, t2 - t1]))
+    np.savez_compressed(os.path.join(HERE, "c3_shape.npz"), **out)
+    print(f"c3_shape.npz  {os.path.getsize(os.path.join(HERE, 'c3_shape.npz')) / 1024:.1f} KiB; {len(fit.used)} terms kept "
+          f"({len(set(fit.used) & set(c['idx']))} of the 40 true ones); bcs {t2 - t1:.1f} s")
+    # --- C4
+    c = shape_inputs(4)
+    mi = R["get_mi"](c["p"], c["d"])
+    pc = R["PCRV"](1, c["d"], c["fam"], mi=mi, cfs=c["cf"])
+    t0 = time.perf_counter()
+    yv = pc.evalPC(c["x"])
+    t1 = time.perf_counter()
+    out = dict(y=yv, mean=pc.computeMean(), var=pc.computeVar(), main=pc.computeSens(), total=pc.computeTotSens(),
+               ref_seconds=np.array([t1 - t0]))
+    np.savez_compressed(os.path.join(HERE, "c4_shape.npz"), **out)
+    print(f"c4_shape.npz  {os.path.getsize(os.path.join(HERE, 'c4_shape.npz')) / 1024:.1f} KiB; evalPC of {c['n']} rows {t1 - t0:.1f} s")
+    # --- C5
+    c = shape_inputs(5)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        pc, lregs = R["pc_fit"](c["x"], c["y"], order=c["p"], pctype=c["fam"], method="anl")
+    t1 = time.perf_counter()
+    out = dict(cf=np.stack(pc.coefs, axis=1), datavar=np.array([float(l.datavar) for l in lregs]),
+               cov_diag=np.stack([np.diag(l.cf_cov) for l in lregs], axis=1),
+               main=pc.computeSens(), total=pc.computeTotSens(), eval=pc.function(c["x"][:64]),
+               ref_seconds=np.array([t1 - t0]))
+    np.savez_compressed(os.path.join(HERE, "c5_shape.npz"), **out)
+    print(f"c5_shape.npz  {os.path.getsize(os.path.join(HERE, 'c5_shape.npz')) / 1024:.1f} KiB; pc_fit(anl, {c['y'].shape[1]} outputs) {t1 - t0:.1f} s")
+
+
 def main():
     R = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "illcond":
@@ -368,6 +450,7 @@ def main():
     klsurr(R)
     uqpc(R)
     c1_full(R)
+    config_shapes(R)
 
 
 if __name__ == "__main__":

@@ -1066,3 +1066,65 @@ def test_full_size_baseline_config_1_vs_reference():
     np.testing.assert_allclose(pc.computeTotSens(), g["total"], rtol=1e-10, atol=1e-13)
     # surrogate evaluation equals the design matrix times the coefficients (sequential vs BLAS order)
     np.testing.assert_allclose(pc.evalPC(x[:4096])[:, 0], A[:4096] @ fits["lsq"].cf, rtol=1e-12, atol=1e-13)
+
+
+def test_shapes_of_baseline_configs_3_4_5_vs_reference():
+    """The CUDA path at the (d, p, K) of BASELINE.json configs 3, 4, 5 (sample counts reduced to what the unmodified
+    reference finishes in about a minute) against that reference (tests/golden/c{3,4,5}_shape.npz,
+    make_golden.py:config_shapes).  Basis values and exact-mode evalPC bit-identical; coefficients, moments and
+    Sobol indices within 1e-10; BCS keeps the identical term set."""
+    import contextlib, io as _io
+    from conftest import golden_generator
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import bcs, PCBasisEvaluator
+    from pytuq_b200.workflows.fits import pc_fit
+    gen = golden_generator()
+
+    # --- C3: BCS sparse regression, LU d=50 p=2 (K=1326), 40-sparse truth
+    g, c = load_golden("c3_shape"), gen.shape_inputs(3)
+    mi = orc.get_mi(c["p"], c["d"])
+    pc = PCRV(1, c["d"], c["fam"], mi=mi)
+    A = pc.evalBases(c["x"], 0)
+    assert np.array_equal(A[g["rows"]], g["A_rows"])
+    y = gen.sparse_target(A, c["idx"], c["val"], c["noise"])
+    assert np.array_equal(y[:16], g["y_head"])
+    fused = bcs(eta=1e-8)
+    fused.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+    given = bcs(eta=1e-8)
+    with contextlib.redirect_stdout(_io.StringIO()):
+        fused.fit(c["x"], y)                  # K3, Gram-form iteration
+        given.fita(A, y)                      # K4
+    for f in (fused, given):
+        assert np.array_equal(f.used, g["used"]) and set(f.used) == set(c["idx"])
+        np.testing.assert_allclose(f.cf, g["cf"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(np.reshape(f.datavar, -1), g["datavar"], rtol=1e-7)
+        np.testing.assert_allclose(np.diag(f.cf_cov), g["cov_diag"], rtol=1e-7)
+
+    # --- C4: the d=20 p=4 surrogate (K=10626): evalPC, moments, Sobol indices
+    g, c = load_golden("c4_shape"), gen.shape_inputs(4)
+    mi = orc.get_mi(c["p"], c["d"])
+    pc = PCRV(1, c["d"], c["fam"], mi=mi, cfs=c["cf"])
+    assert np.array_equal(pc.evalPC(c["x"]), g["y"])
+    np.testing.assert_allclose(pc.evalPC(c["x"], exact=False), g["y"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(pc.computeMean(), g["mean"], rtol=1e-14)
+    np.testing.assert_allclose(pc.computeVar(), g["var"], rtol=1e-10)
+    np.testing.assert_allclose(pc.computeSens(), g["main"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(pc.computeTotSens(), g["total"], rtol=1e-10, atol=1e-14)
+    # forward propagation with the device germ reproduces the closed-form moments statistically
+    mom = pc.propagate(2_000_000, seed=4)
+    sd = np.sqrt(g["var"][0])
+    assert abs(mom["mean"][0] - g["mean"][0]) < 6 * sd / np.sqrt(2e6)
+    assert abs(mom["var"][0] / g["var"][0] - 1.0) < 0.05
+
+    # --- C5: multi-output fit sharing one design matrix, LU d=30 p=3 (K=5456), anl
+    g, c = load_golden("c5_shape"), gen.shape_inputs(5)
+    with contextlib.redirect_stdout(_io.StringIO()):
+        opc, lregs = pc_fit(c["x"], c["y"], order=c["p"], pctype=c["fam"], method="anl")
+    cf = np.stack(opc.coefs, axis=1)
+    assert cf.shape == (5456, 4)
+    np.testing.assert_allclose(cf, g["cf"], rtol=0, atol=1e-10 * np.max(np.abs(g["cf"])))
+    np.testing.assert_allclose([float(l.datavar) for l in lregs], g["datavar"], rtol=1e-7)
+    np.testing.assert_allclose(np.stack([np.diag(l.cf_cov) for l in lregs], axis=1), g["cov_diag"], rtol=1e-7)
+    np.testing.assert_allclose(opc.computeSens(), g["main"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(opc.computeTotSens(), g["total"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(opc.function(c["x"][:64]), g["eval"], rtol=1e-10, atol=1e-12)

@@ -165,3 +165,39 @@ def test_oracle_at_full_size_baseline_config_1():
     np.testing.assert_allclose(np.diag(cov), g["anl_cov_diag"], rtol=1e-11)
     np.testing.assert_allclose(orc.sobol_main(mi, g["cf_lsq"], "LU"), g["main"][0], rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(orc.sobol_total(mi, g["cf_lsq"], "LU"), g["total"][0], rtol=1e-12, atol=1e-15)
+
+
+def test_oracle_at_the_shapes_of_baseline_configs_3_4_5():
+    """Oracle vs the unmodified reference at the (d, p, K) of BASELINE.json configs 3, 4, 5 with reduced sample
+    counts (tests/golden/c{3,4,5}_shape.npz, make_golden.py:config_shapes).  C5's 25000 x 5456 design matrix is
+    checked on its statistics-free parts only here (rows + Sobol); its fit is the GPU test's job."""
+    from conftest import golden_generator
+    gen = golden_generator()
+    # C3: BCS, LU d=50 p=2
+    g, c = load_golden("c3_shape"), gen.shape_inputs(3)
+    mi = orc.get_mi(c["p"], c["d"])
+    A = orc.eval_bases(c["x"], mi, c["fam"])
+    assert np.array_equal(A[g["rows"]], g["A_rows"])
+    y = gen.sparse_target(A, c["idx"], c["val"], c["noise"])
+    assert np.array_equal(y[:16], g["y_head"])
+    weights, errbars, used, sigma2, Sig = orc.bcs_fit(A, y, eta=1e-8)
+    assert np.array_equal(used, g["used"]) and set(used) == set(c["idx"])
+    np.testing.assert_allclose(weights, g["cf"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(np.reshape(sigma2, -1), g["datavar"], rtol=1e-10)
+    # C4: evalPC of the d=20 p=4 surrogate (K=10626), moments and Sobol indices
+    g, c = load_golden("c4_shape"), gen.shape_inputs(4)
+    mi = orc.get_mi(c["p"], c["d"])
+    assert mi.shape == (10626, 20)
+    assert np.array_equal(orc.eval_pc(c["x"][:256], [mi], [c["cf"]], c["fam"]), g["y"][:256])
+    np.testing.assert_allclose(orc.pc_mean(mi, c["cf"]), g["mean"][0], rtol=1e-14)
+    np.testing.assert_allclose(orc.pc_var(mi, c["cf"], c["fam"]), g["var"][0], rtol=1e-12)
+    np.testing.assert_allclose(orc.sobol_main(mi, c["cf"], c["fam"]), g["main"][0], rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(orc.sobol_total(mi, c["cf"], c["fam"]), g["total"][0], rtol=1e-11, atol=1e-15)
+    # C5: Sobol indices of the fitted multi-output surrogate from its coefficients
+    g, c = load_golden("c5_shape"), gen.shape_inputs(5)
+    mi = orc.get_mi(c["p"], c["d"])
+    assert g["cf"].shape == (5456, 4)
+    for j in range(4):
+        np.testing.assert_allclose(orc.sobol_main(mi, g["cf"][:, j], c["fam"]), g["main"][j], rtol=1e-11, atol=1e-15)
+        np.testing.assert_allclose(orc.sobol_total(mi, g["cf"][:, j], c["fam"]), g["total"][j], rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(orc.eval_pc(c["x"][:64], [mi] * 4, list(g["cf"].T), c["fam"]), g["eval"], rtol=1e-13, atol=1e-14)
