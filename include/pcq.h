@@ -203,6 +203,25 @@ int pcq_sample_germ_dev(pcq_plan* plan, uint64_t seed, int64_t first_index, int6
                         const int32_t* germ_kind_host, double* x_dev, int64_t ldx,
                         void* stream);
 
+/* ---- sample files straight into HBM ---------------------------------------------
+ * PyTUQ's applications read their samples with np.loadtxt (apps/uqpc/uq_pc.py:232-265) and hand the
+ * matrices to pc_fit.  These three calls put the TEXT of such a file into device memory and convert it
+ * there (csrc/pcq_text.cu), so the fit's inputs are born in HBM: no host parse, no upload of the binary
+ * matrix.  Values are bit-identical to np.loadtxt's (the conversion is the one of pcq_io.h; the few
+ * tokens it cannot decide on the device — ties, subnormals, > 19 digits — are converted by the host's
+ * strtod and patched in).  Plain decimal tables only (what np.savetxt writes: numbers separated by
+ * blanks, one row per line, blank lines allowed): '#' comments, inf/nan or other delimiters return
+ * PCQ_ERR_UNSUPPORTED and belong to the host reader pcqio_open (pcq_io.h); ragged rows and
+ * unconvertible tokens return PCQ_ERR_ARG.
+ *   pcq_text_open       maps the file, copies its bytes to `device`, counts *rows x *cols there;
+ *   pcq_text_parse_dev  converts into out_dev (rows x cols, leading dimension ld >= cols) on `stream`
+ *                       and returns once the result is complete (it synchronises the stream);
+ *   pcq_text_close      frees the device text and unmaps the file. */
+typedef struct pcq_text pcq_text;
+int pcq_text_open(int device, const char* path, pcq_text** out, int64_t* rows, int64_t* cols);
+int pcq_text_parse_dev(pcq_text* text, double* out_dev, int64_t ld, void* stream);
+int pcq_text_close(pcq_text* text);
+
 /* ---- roofline denominators (micro-benchmarks) ---------------------
  * kind 0: FP64 DFMA register-resident chain   -> TFLOP/s
  * kind 1: FP64 DMMA (mma.sync m8n8k4 f64) chain -> TFLOP/s

@@ -60,6 +60,9 @@ SIGNATURES = {
                                     C.c_void_p]),
     "pcq_sample_germ_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p]),
+    "pcq_text_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pcq_text_parse_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pcq_text_close": (C.c_int, [C.c_void_p]),
     "pcq_measure_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
     "pcq_launch_count": (C.c_int64, []),
 }

@@ -2,6 +2,7 @@
 // See include/pcq_io.h for the contract and the reference call sites (apps/uqpc/uq_pc.py:202-271).
 #include "pcq_io.h"
 #include "pcq_io_pow10.h"
+#include "pcq_decimal.h"
 
 #include <atomic>
 #include <cerrno>
@@ -55,18 +56,6 @@ locale_t c_locale() {
 
 // ---------------------------------------------------------------------------------------- writing
 
-struct U192 {
-    uint64_t r2, r1, r0;
-};
-
-// m * (hi:lo), all 192 bits
-inline U192 mul_64x128(uint64_t m, uint64_t hi, uint64_t lo) {
-    const unsigned __int128 a = (unsigned __int128)m * lo;
-    const unsigned __int128 b = (unsigned __int128)m * hi;
-    const unsigned __int128 mid = (a >> 64) + (uint64_t)b;
-    return U192{(uint64_t)(b >> 64) + (uint64_t)(mid >> 64), (uint64_t)mid, (uint64_t)a};
-}
-
 std::atomic<int64_t> g_slow_formats{0}, g_slow_parses{0};   // conversions that took the libc route
 
 // '%.18e' % v the way libc prints it in the C locale (correctly rounded, exponent of at least two digits),
@@ -109,7 +98,7 @@ inline int format_value(char* dst, double v) {
             return format_value_libc(dst, v);
         }
         const pcqio_pow10& P = PCQIO_POW10[s10 - PCQIO_Q_MIN];
-        const U192 r = mul_64x128(m, P.hi, P.lo);
+        const pcq_u192 r = pcq_mul_64x128(m, P.hi, P.lo);
         const int sh = -(e2 + P.e);             // v * 10^s10 = r / 2^sh
         if (sh >= 129 && sh <= 191) {
             const int t = sh - 128;
@@ -293,91 +282,10 @@ bool parse_decimal_libc(const char* t, size_t n, double* out, locale_t loc) {
     return true;
 }
 
-// [+-]digits[.digits][e[+-]digits] with at most 19 significant digits -> w * 10^q -> one 64 x 128-bit product
-// with the truncated table entry.  The 53-bit result is certain unless the bits behind it are within the
-// product's error (< 2^66 of 2^139) of the half-way point; then, and for subnormal / overflowing results,
-// longer inputs or malformed tokens, it returns false and the libc route decides (or rejects the token).
-inline bool parse_decimal_fast(const char* t, size_t n, double* out) {
-    const char* p = t;
-    const char* end = t + n;
-    bool neg = false;
-    if (p < end && (*p == '+' || *p == '-')) neg = *p++ == '-';
-    uint64_t w = 0;
-    int nd = 0, ndig_total = 0;
-    int64_t q = 0;
-    while (p < end && *p >= '0' && *p <= '9') {
-        if (w || *p != '0') {
-            if (nd == 19) return false;
-            w = w * 10 + (uint64_t)(*p - '0');
-            ++nd;
-        }
-        ++p;
-        ++ndig_total;
-    }
-    if (p < end && *p == '.') {
-        ++p;
-        while (p < end && *p >= '0' && *p <= '9') {
-            if (w || *p != '0') {
-                if (nd == 19) return false;
-                w = w * 10 + (uint64_t)(*p - '0');
-                ++nd;
-            }
-            --q;
-            ++p;
-            ++ndig_total;
-        }
-    }
-    if (!ndig_total) return false;
-    if (p < end && (*p == 'e' || *p == 'E')) {
-        ++p;
-        bool eneg = false;
-        if (p < end && (*p == '+' || *p == '-')) eneg = *p++ == '-';
-        if (p >= end) return false;
-        int64_t ex = 0;
-        int ne = 0;
-        while (p < end && *p >= '0' && *p <= '9') {
-            if (++ne > 6) return false;
-            ex = ex * 10 + (*p - '0');
-            ++p;
-        }
-        q += eneg ? -ex : ex;
-    }
-    if (p != end) return false;
-    if (w == 0) {
-        *out = neg ? -0.0 : 0.0;
-        return true;
-    }
-    if (q < PCQIO_Q_MIN || q > PCQIO_Q_MAX) return false;
-    const int lz = __builtin_clzll(w);
-    const pcqio_pow10& P = PCQIO_POW10[q - PCQIO_Q_MIN];
-    U192 r = mul_64x128(w << lz, P.hi, P.lo);
-    int e = P.e - lz;                           // value = r * 2^e, up to the table's truncation
-    if (!(r.r2 >> 63)) {
-        r.r2 = (r.r2 << 1) | (r.r1 >> 63);
-        r.r1 = (r.r1 << 1) | (r.r0 >> 63);
-        r.r0 <<= 1;
-        --e;
-    }
-    uint64_t m53 = r.r2 >> 11;
-    const uint64_t low = r.r2 & 0x7ff;
-    if (low == 0x3ff && r.r1 >= ~0ull - 8) return false;
-    if (low == 0x400 && r.r1 <= 8) return false;
-    if (low >= 0x400) ++m53;
-    int be = e + 139 + 52 + 1023;               // biased exponent of m53 * 2^(e+139)
-    if (m53 >> 53) {
-        m53 >>= 1;
-        ++be;
-    }
-    if (be < 1 || be > 2046) return false;
-    const uint64_t bits = ((uint64_t)neg << 63) | ((uint64_t)be << 52) | (m53 & ((1ull << 52) - 1));
-    memcpy(out, &bits, 8);
-    return true;
-}
-
 // One token -> double with the acceptance rules of numpy's float converter (PyOS_string_to_double:
 // decimal literals, [+-]inf, [+-]infinity, [+-]nan, any case; no hex, no underscores).
 bool parse_token(const char* t, size_t n, double* out, locale_t loc) {
-    if (parse_decimal_fast(t, n, out)) return true;
+    if (pcq_parse_decimal_fast(t, n, out, PCQIO_POW10)) return true;
     bool numeric = true;
     for (size_t i = 0; i < n; ++i) {
         const char c = t[i];

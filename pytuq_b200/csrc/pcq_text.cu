@@ -1,0 +1,427 @@
+// pcq_text.cu — sample files straight into HBM: the text of a numeric table (what numpy.savetxt writes) is copied
+// to the device as bytes and converted there, so a fit that reads its samples from files never parses on the host
+// and never uploads the binary matrix (reference call sites apps/uqpc/uq_pc.py:232-265).
+//
+//   scan kernel   one thread per 32 bytes: token starts and first-tokens-of-a-line are counted per CTA, any byte
+//                 that is not part of a plain decimal table raises a flag (the host reader of pcq_io.h takes such
+//                 files: comments, inf/nan, other delimiters);
+//   host          exclusive scan of the per-CTA token counts (a few MB), rows x cols from the totals;
+//   parse kernel  same partition; a CTA-wide exclusive scan numbers the tokens, each token start converts its token
+//                 with pcq_parse_decimal_fast (pcq_decimal.h — the very function the host library uses) and stores
+//                 out[token / cols][token % cols]; the first token of every line must have index = 0 (mod cols),
+//                 which together with tokens = rows * cols proves the table is rectangular;
+//   fix-up        the few tokens whose rounding one 64 x 128-bit product cannot decide (ties, subnormals, > 19
+//                 digits) are listed by the kernel, converted by libc's strtod on the host and scattered back.
+//
+// Both kernels are byte streams over the file: algorithmic traffic = file bytes read once per kernel + 8 bytes
+// written per value; the roof is HBM bandwidth (in practice the host -> device copy of the text dominates).
+#define PCQIO_POW10_NO_HOST_TABLE
+#include "pcq_internal.cuh"
+#include "pcq_decimal.h"
+
+#include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <new>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <locale.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace {
+
+__device__ const pcqio_pow10 d_pow10[] = PCQIO_POW10_INIT;
+
+constexpr int TEXT_SPAN = 32;          // bytes per thread
+constexpr int TEXT_THREADS = 256;
+constexpr int TEXT_CTA_BYTES = TEXT_SPAN * TEXT_THREADS;
+constexpr int FIX_CAP = 1 << 20;       // tokens the device may hand to the host per file
+
+struct FixItem {
+    long long token;    // index of the value in the table (row-major)
+    long long offset;   // byte offset of its text
+};
+
+__device__ __forceinline__ bool text_is_space(unsigned char c) {
+    return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f';
+}
+__device__ __forceinline__ bool text_is_eol(unsigned char c) { return c == '\n' || c == '\r'; }
+__device__ __forceinline__ bool text_is_numeric(unsigned char c) {
+    return (c >= '0' && c <= '9') || c == '.' || c == '-' || c == '+' || c == 'e' || c == 'E';
+}
+
+// Is the token that starts at byte i the first one of its line?  (Only blanks between it and the previous line end.)
+__device__ __forceinline__ bool text_first_in_line(const unsigned char* __restrict__ text, long long i) {
+    long long j = i - 1;
+    while (j >= 0 && !text_is_eol(text[j]) && text_is_space(text[j])) --j;
+    return j < 0 || text_is_eol(text[j]);
+}
+
+// The 32 bytes of this thread -> bit masks of token starts; `bad` is set when a byte cannot belong to a decimal table.
+// The buffer is padded with '\n' to a multiple of the CTA size, so no bounds are needed.
+__device__ __forceinline__ unsigned text_token_starts(const unsigned char* __restrict__ text, long long b0, bool* bad) {
+    const uint4* v = reinterpret_cast<const uint4*>(text + b0);
+    const uint4 w0 = v[0], w1 = v[1];
+    const unsigned words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    unsigned char prev = b0 > 0 ? text[b0 - 1] : (unsigned char)'\n';
+    unsigned mask = 0;
+    bool any_bad = false;
+#pragma unroll
+    for (int k = 0; k < TEXT_SPAN; ++k) {
+        const unsigned char c = (unsigned char)(words[k >> 2] >> (8 * (k & 3)));
+        const bool sp = text_is_space(c);
+        any_bad |= !sp && !text_is_numeric(c);
+        if (!sp && text_is_space(prev)) mask |= 1u << k;
+        prev = c;
+    }
+    *bad = any_bad;
+    return mask;
+}
+
+__global__ void __launch_bounds__(TEXT_THREADS)
+pcq_text_scan_kernel(const unsigned char* __restrict__ text, unsigned* __restrict__ cta_tokens,
+                     unsigned* __restrict__ cta_rows, int* __restrict__ flags) {
+    const long long b0 = ((long long)blockIdx.x * TEXT_THREADS + threadIdx.x) * TEXT_SPAN;
+    bool bad;
+    unsigned mask = text_token_starts(text, b0, &bad);
+    unsigned ntok = __popc(mask), nrow = 0;
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        nrow += text_first_in_line(text, b0 + k) ? 1u : 0u;
+    }
+    if (bad) atomicOr(&flags[0], 1);
+    __shared__ unsigned s_tok[TEXT_THREADS / 32], s_row[TEXT_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ntok += __shfl_xor_sync(0xffffffffu, ntok, o);
+        nrow += __shfl_xor_sync(0xffffffffu, nrow, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_tok[threadIdx.x >> 5] = ntok;
+        s_row[threadIdx.x >> 5] = nrow;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0, r = 0;
+#pragma unroll
+        for (int w = 0; w < TEXT_THREADS / 32; ++w) {
+            t += s_tok[w];
+            r += s_row[w];
+        }
+        cta_tokens[blockIdx.x] = t;
+        cta_rows[blockIdx.x] = r;
+    }
+}
+
+__global__ void __launch_bounds__(TEXT_THREADS)
+pcq_text_parse_kernel(const unsigned char* __restrict__ text, const long long* __restrict__ cta_base, long long cols,
+                      double* __restrict__ out, long long ld, FixItem* __restrict__ fix, int* __restrict__ fix_count,
+                      int* __restrict__ flags) {
+    const long long b0 = ((long long)blockIdx.x * TEXT_THREADS + threadIdx.x) * TEXT_SPAN;
+    bool bad;
+    unsigned mask = text_token_starts(text, b0, &bad);
+    // exclusive scan of the per-thread token counts over the CTA
+    const unsigned ntok = __popc(mask);
+    unsigned incl = ntok;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    __shared__ unsigned s_warp[TEXT_THREADS / 32];
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned before = incl - ntok;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    long long token = cta_base[blockIdx.x] + before;
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const long long i = b0 + k;
+        if (text_first_in_line(text, i) && token % cols != 0) atomicOr(&flags[1], 1);
+        size_t n = 1;
+        while (!text_is_space(text[i + n])) ++n;           // the '\n' padding behind the file ends the last token
+        double v;
+        if (pcq_parse_decimal_fast(reinterpret_cast<const char*>(text) + i, n, &v, d_pow10)) {
+            out[(token / cols) * ld + token % cols] = v;
+        } else {
+            const int slot = atomicAdd(fix_count, 1);
+            if (slot < FIX_CAP) fix[slot] = FixItem{token, i};
+        }
+        ++token;
+    }
+}
+
+__global__ void pcq_text_scatter_kernel(double* __restrict__ out, const long long* __restrict__ index,
+                                        const double* __restrict__ value, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[index[j]] = value[j];
+}
+
+struct DevGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr size_t TEXT_STAGE_BYTES = (size_t)32 << 20;
+
+// memcpy by a few host threads (one thread moves ~8 GB/s out of the page cache, the link takes ~50)
+void text_parallel_copy(char* dst, const char* src, size_t n) {
+    const int nthr = (int)std::min<size_t>(6, std::max<size_t>(1, std::thread::hardware_concurrency() / 2));
+    const size_t part = ((n + nthr - 1) / nthr + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (int i = 1; i < nthr; ++i) {
+        const size_t lo = std::min(n, part * i), hi = std::min(n, part * (i + 1));
+        if (hi > lo) pool.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(n, part));
+    for (auto& th : pool) th.join();
+}
+
+locale_t text_c_locale() {
+    static locale_t loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+    return loc;
+}
+
+}  // namespace
+
+struct pcq_text {
+    int device = 0;
+    const char* map = nullptr;      // the file, mapped on the host (kept for the fix-ups)
+    size_t nbytes = 0;
+    unsigned char* d_text = nullptr;
+    size_t padded = 0;
+    long long* d_base = nullptr;    // exclusive scan of the per-CTA token counts
+    long long nctas = 0;
+    long long rows = 0, cols = 0;
+};
+
+extern "C" {
+
+int pcq_text_close(pcq_text* t) {
+    if (!t) return PCQ_OK;
+    DevGuard guard(t->device);
+    if (t->d_text) cudaFree(t->d_text);
+    if (t->d_base) cudaFree(t->d_base);
+    if (t->map) munmap((void*)t->map, t->nbytes);
+    delete t;
+    return PCQ_OK;
+}
+
+int pcq_text_open(int device, const char* path, pcq_text** out, int64_t* rows, int64_t* cols) {
+    if (!path || !out || !rows || !cols || device < 0) {
+        pcq_set_error("text_open: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    *out = nullptr;
+    DevGuard guard(device);
+    if (!guard.ok) { pcq_set_error("text_open: cudaSetDevice(%d) failed", device); return PCQ_ERR_NODEV; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { pcq_set_error("text_open: cannot open %s: %s", path, strerror(errno)); return PCQ_ERR_ARG; }
+    struct stat st;
+    if (fstat(fd, &st) < 0) { close(fd); pcq_set_error("text_open: cannot stat %s", path); return PCQ_ERR_ARG; }
+    pcq_text* t = new (std::nothrow) pcq_text;
+    if (!t) { close(fd); pcq_set_error("text_open: out of memory"); return PCQ_ERR_ALLOC; }
+    t->device = device;
+    t->nbytes = (size_t)st.st_size;
+    if (t->nbytes) {
+        void* m = mmap(nullptr, t->nbytes, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) {
+            close(fd);
+            delete t;
+            pcq_set_error("text_open: cannot map %s: %s", path, strerror(errno));
+            return PCQ_ERR_ARG;
+        }
+        t->map = (const char*)m;
+    }
+    close(fd);
+    *rows = *cols = 0;
+    if (!t->nbytes) { *out = t; return PCQ_OK; }
+
+    int rc = PCQ_OK;
+    unsigned *d_tok = nullptr, *d_row = nullptr;
+    int* d_flags = nullptr;
+    std::vector<unsigned> h_tok, h_row;
+    std::vector<long long> h_base;
+    int h_flags[2] = {0, 0};
+    long long total = 0, nrows = 0, ncols = 0;
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t sent[2] = {nullptr, nullptr};
+    t->nctas = (long long)((t->nbytes + TEXT_CTA_BYTES - 1) / TEXT_CTA_BYTES);
+    t->padded = (size_t)t->nctas * TEXT_CTA_BYTES + TEXT_CTA_BYTES;     // one CTA of '\n' behind the file
+#define TEXT_TRY(call)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess) {                                                                           \
+            pcq_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);     \
+            rc = _e == cudaErrorMemoryAllocation ? PCQ_ERR_ALLOC : PCQ_ERR_CUDA;                           \
+            goto done;                                                                                     \
+        }                                                                                                  \
+    } while (0)
+    TEXT_TRY(cudaMalloc(&t->d_text, t->padded));
+    TEXT_TRY(cudaMemsetAsync(t->d_text + (t->nbytes / 256) * 256, '\n', t->padded - (t->nbytes / 256) * 256, 0));
+    // the text goes over in 32 MB pieces: host threads copy piece i+1 from the page cache into one pinned buffer
+    // while the DMA engine sends piece i from the other (small files: one plain copy)
+    if (t->nbytes <= TEXT_STAGE_BYTES) {
+        TEXT_TRY(cudaMemcpyAsync(t->d_text, t->map, t->nbytes, cudaMemcpyHostToDevice, 0));
+    } else {
+        for (int b = 0; b < 2; ++b) {
+            TEXT_TRY(cudaHostAlloc(&pin[b], TEXT_STAGE_BYTES, cudaHostAllocDefault));
+            TEXT_TRY(cudaEventCreateWithFlags(&sent[b], cudaEventDisableTiming));
+        }
+        int piece = 0;
+        for (size_t off = 0; off < t->nbytes; off += TEXT_STAGE_BYTES, ++piece) {
+            const int b = piece & 1;
+            const size_t nb = std::min(TEXT_STAGE_BYTES, t->nbytes - off);
+            if (piece >= 2) TEXT_TRY(cudaEventSynchronize(sent[b]));
+            text_parallel_copy((char*)pin[b], t->map + off, nb);
+            TEXT_TRY(cudaMemcpyAsync(t->d_text + off, pin[b], nb, cudaMemcpyHostToDevice, 0));
+            TEXT_TRY(cudaEventRecord(sent[b], 0));
+        }
+    }
+    TEXT_TRY(cudaMalloc(&d_tok, (size_t)t->nctas * sizeof(unsigned)));
+    TEXT_TRY(cudaMalloc(&d_row, (size_t)t->nctas * sizeof(unsigned)));
+    TEXT_TRY(cudaMalloc(&d_flags, 2 * sizeof(int)));
+    TEXT_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), 0));
+    pcq_text_scan_kernel<<<(unsigned)t->nctas, TEXT_THREADS>>>(t->d_text, d_tok, d_row, d_flags);
+    TEXT_TRY(cudaGetLastError());
+    g_pcq_launches.fetch_add(1, std::memory_order_relaxed);
+    h_tok.resize((size_t)t->nctas);
+    h_row.resize((size_t)t->nctas);
+    TEXT_TRY(cudaMemcpy(h_tok.data(), d_tok, (size_t)t->nctas * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    TEXT_TRY(cudaMemcpy(h_row.data(), d_row, (size_t)t->nctas * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    TEXT_TRY(cudaMemcpy(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost));
+    if (h_flags[0]) {
+        pcq_set_error("text_open: %s is not a plain decimal table (comments, inf/nan or another delimiter): "
+                      "use the host reader (pcqio_open)", path);
+        rc = PCQ_ERR_UNSUPPORTED;
+        goto done;
+    }
+    h_base.resize((size_t)t->nctas);
+    for (long long b = 0; b < t->nctas; ++b) {
+        h_base[(size_t)b] = total;
+        total += h_tok[(size_t)b];
+        nrows += h_row[(size_t)b];
+    }
+    if (nrows > 0) {
+        ncols = total / nrows;
+        if (ncols * nrows != total) {
+            pcq_set_error("text_open: %s: %lld values in %lld rows: the rows do not all have the same number of "
+                          "columns", path, total, nrows);
+            rc = PCQ_ERR_ARG;
+            goto done;
+        }
+    }
+    TEXT_TRY(cudaMalloc(&t->d_base, (size_t)t->nctas * sizeof(long long)));
+    TEXT_TRY(cudaMemcpy(t->d_base, h_base.data(), (size_t)t->nctas * sizeof(long long), cudaMemcpyHostToDevice));
+    t->rows = nrows;
+    t->cols = ncols;
+done:
+    if (pin[0] || pin[1]) cudaStreamSynchronize(0);      // nothing may still read the staging buffers
+    for (int b = 0; b < 2; ++b) {
+        if (sent[b]) cudaEventDestroy(sent[b]);
+        if (pin[b]) cudaFreeHost(pin[b]);
+    }
+    if (d_tok) cudaFree(d_tok);
+    if (d_row) cudaFree(d_row);
+    if (d_flags) cudaFree(d_flags);
+    if (rc != PCQ_OK) {
+        pcq_text_close(t);
+        return rc;
+    }
+    *rows = t->rows;
+    *cols = t->cols;
+    *out = t;
+    return PCQ_OK;
+}
+
+int pcq_text_parse_dev(pcq_text* t, double* out_dev, int64_t ld, void* stream) {
+    if (!t) { pcq_set_error("text_parse: null handle"); return PCQ_ERR_ARG; }
+    if (t->rows == 0) return PCQ_OK;
+    if (!out_dev || ld < t->cols) { pcq_set_error("text_parse: bad output buffer"); return PCQ_ERR_ARG; }
+    DevGuard guard(t->device);
+    if (!guard.ok) { pcq_set_error("text_parse: cudaSetDevice(%d) failed", t->device); return PCQ_ERR_NODEV; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = PCQ_OK;
+    FixItem* d_fix = nullptr;
+    int* d_ctl = nullptr;       // [0] fix count, [1..2] flags
+    long long* d_index = nullptr;
+    double* d_value = nullptr;
+    int h_ctl[3] = {0, 0, 0};
+    std::vector<FixItem> h_fix;
+    std::vector<long long> h_index;
+    std::vector<double> h_value;
+    TEXT_TRY(cudaMalloc(&d_fix, (size_t)FIX_CAP * sizeof(FixItem)));
+    TEXT_TRY(cudaMalloc(&d_ctl, sizeof h_ctl));
+    TEXT_TRY(cudaMemsetAsync(d_ctl, 0, sizeof h_ctl, s));
+    pcq_text_parse_kernel<<<(unsigned)t->nctas, TEXT_THREADS, 0, s>>>(t->d_text, t->d_base, t->cols, out_dev, ld, d_fix,
+                                                                      d_ctl, d_ctl + 1);
+    TEXT_TRY(cudaGetLastError());
+    g_pcq_launches.fetch_add(1, std::memory_order_relaxed);
+    TEXT_TRY(cudaMemcpyAsync(h_ctl, d_ctl, sizeof h_ctl, cudaMemcpyDeviceToHost, s));
+    TEXT_TRY(cudaStreamSynchronize(s));
+    if (h_ctl[2]) {
+        pcq_set_error("text_parse: the rows do not all have the same number of columns (%lld expected)", t->cols);
+        rc = PCQ_ERR_ARG;
+        goto done;
+    }
+    if (h_ctl[0] > FIX_CAP) {
+        pcq_set_error("text_parse: more than %d values need the host's conversion: use the host reader (pcqio_open)",
+                      FIX_CAP);
+        rc = PCQ_ERR_UNSUPPORTED;
+        goto done;
+    }
+    if (h_ctl[0] > 0) {
+        const int nfix = h_ctl[0];
+        h_fix.resize((size_t)nfix);
+        TEXT_TRY(cudaMemcpy(h_fix.data(), d_fix, (size_t)nfix * sizeof(FixItem), cudaMemcpyDeviceToHost));
+        h_index.resize((size_t)nfix);
+        h_value.resize((size_t)nfix);
+        for (int j = 0; j < nfix; ++j) {
+            const char* p = t->map + h_fix[(size_t)j].offset;
+            const char* end = t->map + t->nbytes;
+            size_t n = 0;
+            while (p + n < end && !isspace((unsigned char)p[n])) ++n;
+            std::string tok(p, n);
+            char* stop = nullptr;
+            const double v = strtod_l(tok.c_str(), &stop, text_c_locale());
+            if (stop != tok.c_str() + n || n == 0) {
+                pcq_set_error("could not convert string '%.60s' to float64 (value %lld of the table)", tok.c_str(),
+                              h_fix[(size_t)j].token);
+                rc = PCQ_ERR_ARG;
+                goto done;
+            }
+            h_index[(size_t)j] = (h_fix[(size_t)j].token / t->cols) * ld + h_fix[(size_t)j].token % t->cols;
+            h_value[(size_t)j] = v;
+        }
+        TEXT_TRY(cudaMalloc(&d_index, (size_t)nfix * sizeof(long long)));
+        TEXT_TRY(cudaMalloc(&d_value, (size_t)nfix * sizeof(double)));
+        TEXT_TRY(cudaMemcpyAsync(d_index, h_index.data(), (size_t)nfix * sizeof(long long), cudaMemcpyHostToDevice, s));
+        TEXT_TRY(cudaMemcpyAsync(d_value, h_value.data(), (size_t)nfix * sizeof(double), cudaMemcpyHostToDevice, s));
+        pcq_text_scatter_kernel<<<(nfix + 255) / 256, 256, 0, s>>>(out_dev, d_index, d_value, nfix);
+        TEXT_TRY(cudaGetLastError());
+        g_pcq_launches.fetch_add(1, std::memory_order_relaxed);
+        TEXT_TRY(cudaStreamSynchronize(s));
+    }
+done:
+    if (d_fix) cudaFree(d_fix);
+    if (d_ctl) cudaFree(d_ctl);
+    if (d_index) cudaFree(d_index);
+    if (d_value) cudaFree(d_value);
+    return rc;
+}
+#undef TEXT_TRY
+
+}  // extern "C"

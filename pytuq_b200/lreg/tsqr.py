@@ -49,6 +49,10 @@ def r_factor_pc(pcrv, x, y, jdim=0, chunk_bytes=None):
     torch = _torch()
     _device.require_device()
     dev = _device.current_device()
+    from ..parallel import is_device_tensor
+    if is_device_tensor(x):        # resident samples: this route stages its chunks from the host (rare path)
+        x = x.cpu().numpy()
+        y = None if y is None else y.cpu().numpy()
     x = np.ascontiguousarray(x, dtype=np.float64)
     N, s = x.shape
     Y = None if y is None else np.ascontiguousarray(y, dtype=np.float64).reshape(N, -1)

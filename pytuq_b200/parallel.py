@@ -62,14 +62,64 @@ def _pinned_pair(nbytes):
     return bufs
 
 
+def is_device_tensor(a):
+    """True for a torch tensor that lives on a CUDA device (samples loaded by utils.io.loadtxt_device, or put
+    there by the caller): the fit then reads them where they are."""
+    return type(a).__module__.split(".")[0] == "torch" and bool(getattr(a, "is_cuda", False))
+
+
+def _resident(a, rows=None):
+    """float64, contiguous, 2-D view of a device tensor."""
+    import torch
+    t = a if a.dtype == torch.float64 else a.to(torch.float64)
+    if t.dim() == 1:
+        t = t.reshape(-1, 1)
+    assert t.dim() == 2 and (rows is None or t.shape[0] == rows)
+    return t.contiguous()
+
+
+def _suffstats_pc_resident(pcrv, x, y, jdim, distributed):
+    """K3 on samples that are already in HBM (torch CUDA tensors): one pcq_suffstats_dev call, no staging."""
+    import torch
+    from .lreg.stats import SuffStats
+    mindex = pcrv.mindices[jdim]
+    pcrv._check_orders(mindex)
+    xt = _resident(x)
+    N, s = xt.shape
+    assert s == pcrv.sdim
+    yt = None if y is None else _resident(y, N)
+    M = 0 if yt is None else yt.shape[1]
+    dev = xt.device.index
+    assert yt is None or yt.device == xt.device
+    plan = pcrv._plan(mindex, dev=dev)
+    K = mindex.shape[0]
+    S_t = torch.empty((K + M + 1, K + M + 1), dtype=torch.float64, device=xt.device)
+    with torch.cuda.device(xt.device):
+        stream = torch.cuda.current_stream()
+        _native.check(_native.lib().pcq_suffstats_dev(plan.handle, xt.data_ptr() if N else None, N, s,
+                                                      yt.data_ptr() if (M and N) else None, max(M, 1), M,
+                                                      S_t.data_ptr(), 0, stream.cuda_stream), "pcq_suffstats_dev")
+        if distributed and dist_info()[1] > 1:
+            import torch.distributed as dist
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(S_t, op=dist.ReduceOp.SUM)
+            else:
+                S_t = torch.from_numpy(allreduce_stats(S_t.cpu().numpy())).to(xt.device)
+        stream.synchronize()
+    pcrv._distributed_stats = bool(distributed)
+    return SuffStats(None, K, M, S_dev=S_t)
+
+
 def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
-    """K3 on host (numpy) inputs: the rows are streamed through two pinned staging buffers in L2-sized
+    """K3 on device-resident samples (torch CUDA tensors: read in place) or on host (numpy) inputs: the rows are streamed through two pinned staging buffers in L2-sized
     chunks (host memcpy and H2D of chunk i+1 overlap the Gram kernel of chunk i), the statistics are
     accumulated and stay on the device.  With ``distributed=True`` every rank passes its own row
     block (x, y) and the partial statistics are all-reduced on the device (NCCL)."""
     import torch
     from .lreg.stats import SuffStats
     _device.require_device()
+    if is_device_tensor(x):
+        return _suffstats_pc_resident(pcrv, x, y, jdim, distributed)
     mindex = pcrv.mindices[jdim]
     pcrv._check_orders(mindex)
     xin = np.ascontiguousarray(x, dtype=np.float64)
@@ -149,6 +199,21 @@ def residual_sums_pc(pcrv, x, y, col, jdim, cf):
     statistics identity  y^T y - 2 cf^T b + cf^T G cf  has cancelled (noise-free training data)."""
     _device.require_device()
     mindex = pcrv.mindices[jdim]
+    if is_device_tensor(x):
+        import torch
+        xt = _resident(x)
+        yt = _resident(y, xt.shape[0])
+        plan = pcrv._plan(mindex, dev=xt.device.index)
+        cf_t = torch.from_numpy(np.ascontiguousarray(cf, dtype=np.float64)).to(xt.device)
+        sums_t = torch.zeros(2, dtype=torch.float64, device=xt.device)
+        with torch.cuda.device(xt.device):
+            _native.check(_native.lib().pcq_residual_ss_dev(
+                plan.handle, xt.data_ptr(), xt.shape[0], xt.shape[1], yt.data_ptr() + 8 * int(col), yt.shape[1],
+                cf_t.data_ptr(), sums_t.data_ptr(), 0, torch.cuda.current_stream().cuda_stream), "pcq_residual_ss_dev")
+        sums = sums_t.cpu().numpy()
+        if dist_info()[1] > 1 and getattr(pcrv, "_distributed_stats", False):
+            sums = allreduce_stats(sums)
+        return float(sums[0]), float(sums[1])
     plan = pcrv._plan(mindex, dev=_device.current_device())
     xin = np.ascontiguousarray(x, dtype=np.float64)
     N, s = xin.shape

@@ -106,6 +106,41 @@ def loadtxt(fname, ndmin=0, threads=0):
     return np.atleast_1d(out) if ndmin == 1 else out
 
 
+def loadtxt_device(fname, device=None):
+    """The table of ``fname`` as a float64 ``torch`` tensor of shape (rows, cols) in the memory of CUDA device
+    ``device`` (default: the path's current device), converted ON the device from the file's text
+    (``pcq_text_open`` / ``pcq_text_parse_dev``, ``include/pcq.h``): no host parse and no upload of the binary
+    matrix.  Values are bit-identical to ``np.loadtxt(fname, ndmin=2)``.  ``pc_fit`` / ``lreg.fit`` /
+    ``PCRV.suffStats`` take such tensors in place of numpy arrays and read them where they are.
+
+    Plain decimal tables only (what ``savetxt`` writes): a file with ``#`` comments, inf/nan or another delimiter
+    raises ``ValueError`` naming the host reader ``loadtxt``; ragged rows and unconvertible tokens raise
+    ``ValueError`` as ``np.loadtxt`` does."""
+    import torch
+    from .. import _native, device as _device
+    _device.require_device()
+    dev = _device.current_device() if device is None else int(device)
+    if not os.path.exists(fname):
+        raise FileNotFoundError(f"{fname} not found.")
+    lib_ = _native.lib()
+    handle, rows, cols = C.c_void_p(), C.c_int64(), C.c_int64()
+    status = lib_.pcq_text_open(dev, os.fsencode(fname), C.byref(handle), C.byref(rows), C.byref(cols))
+    if status in (-1, -5):          # PCQ_ERR_ARG (ragged / unreadable), PCQ_ERR_UNSUPPORTED (not a plain table)
+        raise ValueError((lib_.pcq_last_error() or b"").decode(errors="replace"))
+    _native.check(status, "pcq_text_open")
+    try:
+        out = torch.empty((rows.value, cols.value), dtype=torch.float64, device=torch.device("cuda", dev))
+        with torch.cuda.device(out.device):
+            status = lib_.pcq_text_parse_dev(handle, out.data_ptr() if out.numel() else None, max(cols.value, 1),
+                                             torch.cuda.current_stream().cuda_stream)
+        if status in (-1, -5):
+            raise ValueError((lib_.pcq_last_error() or b"").decode(errors="replace"))
+        _native.check(status, "pcq_text_parse_dev")
+    finally:
+        lib_.pcq_text_close(handle)
+    return out
+
+
 def save(fname, X, threads=0):
     """``.npy`` -> ``np.save`` (binary, exact); anything else -> :func:`savetxt`."""
     if str(fname).endswith(".npy"):

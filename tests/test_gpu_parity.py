@@ -1128,3 +1128,106 @@ def test_shapes_of_baseline_configs_3_4_5_vs_reference():
     np.testing.assert_allclose(opc.computeSens(), g["main"], rtol=1e-8, atol=1e-12)
     np.testing.assert_allclose(opc.computeTotSens(), g["total"], rtol=1e-8, atol=1e-12)
     np.testing.assert_allclose(opc.function(c["x"][:64]), g["eval"], rtol=1e-10, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------- sample files -> HBM (pcq_text.cu)
+def _write(path, text):
+    with open(path, "wb") as f:
+        f.write(text if isinstance(text, bytes) else text.encode())
+    return str(path)
+
+
+def test_text_tables_are_converted_on_the_device_bit_for_bit(tmp_path):
+    """utils.io.loadtxt_device (pcq_text_open / pcq_text_parse_dev) against np.loadtxt: same shape, same bits, for
+    files written by np.savetxt and for hand-written layouts; what the device route declines or rejects."""
+    from pytuq_b200.utils import io
+    rng = np.random.default_rng(11)
+    tables = {
+        "samples": rng.standard_normal((5000, 20)),
+        "wide_range": rng.standard_normal((700, 7)) * 10.0 ** rng.integers(-300, 300, (700, 7)),   # subnormals -> fix-ups
+        "column": rng.uniform(-1, 1, (3000, 1)),
+        "one_value": np.array([[0.1]]),
+        "ties": ((2.0 * rng.integers(10 ** 8, 10 ** 9, 64) + 1) * 5.0 ** 10 / 2.0 ** 11 / 10.0 ** 10).reshape(16, 4),
+        "integers": np.arange(-50, 50).reshape(20, 5),
+        "edges": np.array([[5e-324, 1.7976931348623157e308, 2.2250738585072014e-308, -0.0, 1e22, 1e23]]),
+    }
+    for name, X in tables.items():
+        f = str(tmp_path / (name + ".txt"))
+        np.savetxt(f, X)
+        want = np.loadtxt(f, ndmin=2)
+        got = io.loadtxt_device(f)
+        assert got.is_cuda and tuple(got.shape) == want.shape, name
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), want.view(np.uint64)), name
+    # sizes around the 8 KB CTA partition and the 32-byte thread span: every cut position of a token
+    for n in (1, 2, 327, 328, 329, 655, 656, 1311):
+        X = rng.standard_normal((n, 1))
+        f = str(tmp_path / "cut.txt")
+        np.savetxt(f, X)
+        assert np.array_equal(io.loadtxt_device(f).cpu().numpy(), X), n
+    for shift in range(33):
+        f = _write(tmp_path / "shift.txt", " " * shift + "1.5 -2.25e3\n" + "\n" * (shift % 3) + "3 4")
+        assert np.array_equal(io.loadtxt_device(f).cpu().numpy(), [[1.5, -2250.0], [3.0, 4.0]]), shift
+    # hand-written layout: tabs, CRLF, blank lines, leading blanks, short forms, no newline at the end
+    f = _write(tmp_path / "layout.txt", "1 2\t3.5\r\n\r\n   \t \n-4e0 +5E-1 .25\n1. 00012 1e-400\n7 8 9")
+    want = np.loadtxt(f, ndmin=2)
+    got = io.loadtxt_device(f).cpu().numpy()
+    assert got.shape == (4, 3) and np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    f = _write(tmp_path / "empty.txt", "\n\n  \n")
+    assert tuple(io.loadtxt_device(f).shape) == (0, 0)
+    f = _write(tmp_path / "zero.txt", b"")
+    assert tuple(io.loadtxt_device(f).shape) == (0, 0)
+    # declined (host reader's job) and rejected inputs
+    for text in ("# header\n1 2\n", "1 nan\n", "1,2\n3,4\n", "1 inf\n"):
+        with pytest.raises(ValueError, match="host reader"):
+            io.loadtxt_device(_write(tmp_path / "declined.txt", text))
+        np.loadtxt(str(tmp_path / "declined.txt"), delimiter="," if "," in text else None)   # numpy / io.loadtxt read it
+    for text in ("1 2 3\n4 5\n", "1 2\n3 4 5 6\n", "1 2\n3 1e\n", "1 2\n3 1.2.3\n", "1 2\n3 --4\n"):
+        with pytest.raises(ValueError):
+            np.loadtxt(_write(tmp_path / "bad.txt", text))
+        with pytest.raises(ValueError):
+            io.loadtxt_device(str(tmp_path / "bad.txt"))
+    with pytest.raises(FileNotFoundError):
+        io.loadtxt_device(str(tmp_path / "missing.txt"))
+
+
+def test_fit_from_sample_files_resident_in_hbm():
+    """The uq_pc application's offline regime with the samples converted on the device and the fit reading them in
+    place (no host matrix at any point): same goldens as test_uqpc_app_replay_through_sample_files."""
+    import contextlib, io as _io, os
+    from conftest import GOLDEN
+    from pytuq_b200.utils import io
+    from pytuq_b200.workflows.fits import pc_fit
+    from pytuq_b200.lreg import anl, PCBasisEvaluator
+    gold = os.path.join(GOLDEN, "uqpc")
+    g = load_golden("uqpc")
+    germ = io.loadtxt_device(os.path.join(gold, "qtrain.txt"))
+    ytrain = io.loadtxt_device(os.path.join(gold, "ytrain.txt"))
+    assert germ.is_cuda and tuple(germ.shape) == (240, 3) and tuple(ytrain.shape) == (240, 2)
+    assert np.array_equal(germ.cpu().numpy(), np.loadtxt(os.path.join(gold, "qtrain.txt")))
+    for method in ("lsq", "anl", "bcs"):
+        with contextlib.redirect_stdout(_io.StringIO()):
+            opc, lregs = pc_fit(germ, ytrain, order=3, pctype="LU", method=method, eta=1e-6)
+        for iout in range(2):
+            assert np.array_equal(opc.mindices[iout], g[f"{method}__mi{iout}"]), (method, iout)
+            np.testing.assert_allclose(opc.coefs[iout], g[f"{method}__cf{iout}"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(opc.computeSens(), g[f"{method}__main"], rtol=1e-10, atol=1e-13)
+    # single-output fitter on resident samples, and noise-free data (the residual pass reads them in place too)
+    fit = anl()
+    fit.setBasisEvaluator(PCBasisEvaluator(0), (_pc_of_order(3, 3),))
+    fit.fit(germ, ytrain[:, 0])
+    np.testing.assert_allclose(fit.cf, g["anl__cf0"], rtol=1e-10, atol=1e-12)
+    import torch
+    pc = _pc_of_order(3, 3)
+    c = np.random.default_rng(3).standard_normal(20)
+    pc.setCfs([c])
+    yexact = torch.from_numpy(pc.evalPC(germ.cpu().numpy())).cuda()
+    fit = anl()
+    fit.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+    fit.fit(germ, yexact[:, 0])
+    np.testing.assert_allclose(fit.cf, c, rtol=0, atol=1e-11)
+    assert 0.0 <= float(fit.datavar) < 1e-12
+
+
+def _pc_of_order(order, dim, fam="LU"):
+    from pytuq_b200.rv.pcrv import PCRV
+    return PCRV(1, dim, fam, mi=orc.get_mi(order, dim))

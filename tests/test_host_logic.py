@@ -24,7 +24,7 @@ def _stats(A, y):
 def test_library_exports_every_declared_symbol():
     from pytuq_b200 import _native
     header = open(os.path.join(ROOT, "include", "pcq.h")).read()
-    declared = set(re.findall(r"\b(pcq_[a-z0-9_]+)\s*\(", header)) - {"pcq_plan", "pcq_status"}
+    declared = set(re.findall(r"\b(pcq_[a-z0-9_]+)\s*\(", header)) - {"pcq_plan", "pcq_status", "pcq_text"}
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     lib = ctypes.CDLL(_native.LIB_PATH)
     for name in declared:

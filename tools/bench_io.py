@@ -37,6 +37,28 @@ def main():
         t_us_r = best(lambda: got.__setitem__("us", io.loadtxt(f_np)), 3)
         t_us_r1 = best(lambda: got.__setitem__("us1", io.loadtxt(f_np, threads=1)), 1)
         size = os.path.getsize(f_np)
+        gpu = None
+        try:
+            import torch
+            have_gpu = torch.cuda.is_available()
+        except ImportError:
+            have_gpu = False
+        if have_gpu:
+            # text -> HBM on the device (pcq_text.cu) against host parse + upload of the binary matrix
+            def dev_route():
+                got["dev"] = io.loadtxt_device(f_np)
+                torch.cuda.synchronize()
+
+            def host_route():
+                got["up"] = torch.from_numpy(io.loadtxt(f_np, ndmin=2)).cuda()
+                torch.cuda.synchronize()
+            dev_route()
+            t_dev = best(dev_route, 3)
+            t_up = best(host_route, 3)
+            gpu = {"loadtxt_device_s": t_dev, "host_loadtxt_plus_upload_s": t_up, "speedup_vs_host_route": t_up / t_dev,
+                   "speedup_vs_numpy": None, "Mvalues_per_s": rows * cols / t_dev / 1e6,
+                   "text_GB_per_s": size / t_dev / 1e9,
+                   "values_identical": bool(torch.equal(got["dev"], got["up"]))}
     n = rows * cols
     print(json.dumps({
         "what": "np.savetxt / np.loadtxt (default options) vs pytuq_b200.utils.io on a %d x %d float64 matrix" % (rows, cols),
@@ -46,6 +68,7 @@ def main():
                                  and np.array_equal(got["us1"], x)),
         "savetxt": {"numpy_s": t_np_w, "native_s": t_us_w, "native_1thread_s": t_us_w1,
                     "speedup": t_np_w / t_us_w, "native_Mvalues_per_s": n / t_us_w / 1e6},
+        "to_hbm": gpu and dict(gpu, speedup_vs_numpy=t_np_r / gpu["loadtxt_device_s"]),
         "loadtxt": {"numpy_s": t_np_r, "native_s": t_us_r, "native_1thread_s": t_us_r1,
                     "speedup": t_np_r / t_us_r, "native_Mvalues_per_s": n / t_us_r / 1e6},
     }))
