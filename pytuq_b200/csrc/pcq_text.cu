@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cerrno>
+#include <mutex>
 #include <new>
 #include <cstdlib>
 #include <cstring>
@@ -148,7 +149,7 @@ pcq_text_parse_kernel(const unsigned char* __restrict__ text, const long long* _
         while (!text_is_space(text[i + n])) ++n;           // the '\n' padding behind the file ends the last token
         double v;
         if (pcq_parse_decimal_fast(reinterpret_cast<const char*>(text) + i, n, &v, d_pow10)) {
-            out[(token / cols) * ld + token % cols] = v;
+            out[ld == cols ? token : (token / cols) * ld + token % cols] = v;    // dense result: no division
         } else {
             const int slot = atomicAdd(fix_count, 1);
             if (slot < FIX_CAP) fix[slot] = FixItem{token, i};
@@ -175,20 +176,42 @@ struct DevGuard {
     }
 };
 
-constexpr size_t TEXT_STAGE_BYTES = (size_t)32 << 20;
+constexpr size_t TEXT_STAGE_BYTES = (size_t)64 << 20;
 
-// memcpy by a few host threads (one thread moves ~8 GB/s out of the page cache, the link takes ~50)
-void text_parallel_copy(char* dst, const char* src, size_t n) {
-    const int nthr = (int)std::min<size_t>(6, std::max<size_t>(1, std::thread::hardware_concurrency() / 2));
+// Reads [off, off + n) of the file into dst with a few host threads (pread: one kernel -> user copy per piece and no
+// page faults, unlike copying out of the mapping; one thread moves ~8 GB/s out of the page cache, the link ~50).
+bool text_parallel_read(int fd, char* dst, size_t off, size_t n) {
+    const int nthr = (int)std::min<size_t>(16, std::max<size_t>(1, std::thread::hardware_concurrency()));
     const size_t part = ((n + nthr - 1) / nthr + 4095) & ~(size_t)4095;
+    std::atomic<bool> ok{true};
+    auto piece = [&](size_t lo, size_t hi) {
+        while (lo < hi) {
+            const ssize_t got = pread(fd, dst + lo, hi - lo, (off_t)(off + lo));
+            if (got <= 0) {
+                if (got < 0 && errno == EINTR) continue;
+                ok = false;
+                return;
+            }
+            lo += (size_t)got;
+        }
+    };
     std::vector<std::thread> pool;
     for (int i = 1; i < nthr; ++i) {
         const size_t lo = std::min(n, part * i), hi = std::min(n, part * (i + 1));
-        if (hi > lo) pool.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+        if (hi > lo) pool.emplace_back(piece, lo, hi);
     }
-    memcpy(dst, src, std::min(n, part));
+    piece(0, std::min(n, part));
     for (auto& th : pool) th.join();
+    return ok.load();
 }
+
+// Two pinned staging buffers per process, allocated on first use and kept (cudaHostAlloc costs more than the copy of
+// a small file); the mutex serialises uploads of concurrent callers.
+struct TextStage {
+    std::mutex mu;
+    void* pin[2] = {nullptr, nullptr};
+};
+TextStage g_text_stage;
 
 locale_t text_c_locale() {
     static locale_t loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
@@ -246,9 +269,8 @@ int pcq_text_open(int device, const char* path, pcq_text** out, int64_t* rows, i
         }
         t->map = (const char*)m;
     }
-    close(fd);
     *rows = *cols = 0;
-    if (!t->nbytes) { *out = t; return PCQ_OK; }
+    if (!t->nbytes) { close(fd); *out = t; return PCQ_OK; }
 
     int rc = PCQ_OK;
     unsigned *d_tok = nullptr, *d_row = nullptr;
@@ -257,7 +279,6 @@ int pcq_text_open(int device, const char* path, pcq_text** out, int64_t* rows, i
     std::vector<long long> h_base;
     int h_flags[2] = {0, 0};
     long long total = 0, nrows = 0, ncols = 0;
-    void* pin[2] = {nullptr, nullptr};
     cudaEvent_t sent[2] = {nullptr, nullptr};
     t->nctas = (long long)((t->nbytes + TEXT_CTA_BYTES - 1) / TEXT_CTA_BYTES);
     t->padded = (size_t)t->nctas * TEXT_CTA_BYTES + TEXT_CTA_BYTES;     // one CTA of '\n' behind the file
@@ -272,24 +293,28 @@ int pcq_text_open(int device, const char* path, pcq_text** out, int64_t* rows, i
     } while (0)
     TEXT_TRY(cudaMalloc(&t->d_text, t->padded));
     TEXT_TRY(cudaMemsetAsync(t->d_text + (t->nbytes / 256) * 256, '\n', t->padded - (t->nbytes / 256) * 256, 0));
-    // the text goes over in 32 MB pieces: host threads copy piece i+1 from the page cache into one pinned buffer
-    // while the DMA engine sends piece i from the other (small files: one plain copy)
-    if (t->nbytes <= TEXT_STAGE_BYTES) {
-        TEXT_TRY(cudaMemcpyAsync(t->d_text, t->map, t->nbytes, cudaMemcpyHostToDevice, 0));
-    } else {
+    // the text goes over in 64 MB pieces: host threads read piece i+1 from the page cache into one pinned buffer
+    // while the DMA engine sends piece i from the other
+    {
+        std::lock_guard<std::mutex> lock(g_text_stage.mu);
         for (int b = 0; b < 2; ++b) {
-            TEXT_TRY(cudaHostAlloc(&pin[b], TEXT_STAGE_BYTES, cudaHostAllocDefault));
-            TEXT_TRY(cudaEventCreateWithFlags(&sent[b], cudaEventDisableTiming));
+            if (!g_text_stage.pin[b]) TEXT_TRY(cudaHostAlloc(&g_text_stage.pin[b], TEXT_STAGE_BYTES, cudaHostAllocDefault));
+            if (!sent[b]) TEXT_TRY(cudaEventCreateWithFlags(&sent[b], cudaEventDisableTiming));
         }
         int piece = 0;
         for (size_t off = 0; off < t->nbytes; off += TEXT_STAGE_BYTES, ++piece) {
             const int b = piece & 1;
             const size_t nb = std::min(TEXT_STAGE_BYTES, t->nbytes - off);
             if (piece >= 2) TEXT_TRY(cudaEventSynchronize(sent[b]));
-            text_parallel_copy((char*)pin[b], t->map + off, nb);
-            TEXT_TRY(cudaMemcpyAsync(t->d_text + off, pin[b], nb, cudaMemcpyHostToDevice, 0));
+            if (!text_parallel_read(fd, (char*)g_text_stage.pin[b], off, nb)) {
+                pcq_set_error("text_open: reading %s failed: %s", path, strerror(errno));
+                rc = PCQ_ERR_ARG;
+                goto done;
+            }
+            TEXT_TRY(cudaMemcpyAsync(t->d_text + off, g_text_stage.pin[b], nb, cudaMemcpyHostToDevice, 0));
             TEXT_TRY(cudaEventRecord(sent[b], 0));
         }
+        TEXT_TRY(cudaStreamSynchronize(0));      // the staging buffers are free again before the lock goes
     }
     TEXT_TRY(cudaMalloc(&d_tok, (size_t)t->nctas * sizeof(unsigned)));
     TEXT_TRY(cudaMalloc(&d_row, (size_t)t->nctas * sizeof(unsigned)));
@@ -329,11 +354,10 @@ int pcq_text_open(int device, const char* path, pcq_text** out, int64_t* rows, i
     t->rows = nrows;
     t->cols = ncols;
 done:
-    if (pin[0] || pin[1]) cudaStreamSynchronize(0);      // nothing may still read the staging buffers
-    for (int b = 0; b < 2; ++b) {
+    close(fd);
+    if (rc != PCQ_OK) cudaStreamSynchronize(0);          // nothing may still read the staging buffers
+    for (int b = 0; b < 2; ++b)
         if (sent[b]) cudaEventDestroy(sent[b]);
-        if (pin[b]) cudaFreeHost(pin[b]);
-    }
     if (d_tok) cudaFree(d_tok);
     if (d_row) cudaFree(d_row);
     if (d_flags) cudaFree(d_flags);
