@@ -28,6 +28,10 @@ from .. import _native, device as _device
 _SQRT3 = np.sqrt(3.)
 
 
+def _is_device_tensor(a):
+    return type(a).__module__.split(".")[0] == "torch" and bool(getattr(a, "is_cuda", False))
+
+
 class PC1d():
     r"""One-dimensional orthogonal-polynomial family: 'LU' (Legendre), 'nLU' (normalised
     Legendre), 'HG' (probabilists' Hermite), 'nHG' (the reference's scaled Hermite He_n/n!).
@@ -254,6 +258,8 @@ class PCRV(MRV):
 
     @staticmethod
     def _as_input(x):
+        if _is_device_tensor(x):       # resident samples on an entry point that returns host arrays
+            x = x.cpu().numpy()
         return np.ascontiguousarray(x, dtype=np.float64)
 
     # ------------------------------------------------------------------ K1
@@ -267,6 +273,8 @@ class PCRV(MRV):
         npc, sdim_ = mindex.shape
         assert(sdim_ == self.sdim)
         self._check_orders(mindex)
+        if _is_device_tensor(xi):
+            return self._evalBases_resident(xi, mindex)
         x = self._as_input(xi)
         ybases = np.empty((nxi, npc))
         plan = self._plan(mindex)
@@ -295,10 +303,12 @@ class PCRV(MRV):
         ``exact=False`` shares one basis product per term across outputs and uses FMA."""
         assert(self.sdim == x.shape[1])
         nsam = x.shape[0]
-        xin = self._as_input(x)
-        y = np.zeros((nsam, self.pdim))
         for mindex in self.mindices:
             self._check_orders(mindex)
+        if _is_device_tensor(x):
+            return self._evalPC_resident(x, exact)
+        xin = self._as_input(x)
+        y = np.zeros((nsam, self.pdim))
         lib = _native.lib()
         mode = 0 if exact else 1
         # outputs sharing one multi-index (the common case) go through one launch
@@ -316,6 +326,47 @@ class PCRV(MRV):
                 _native.check(lib.pcq_eval_pc(plan.handle, _native.ptr(xin), nsam, self.sdim,
                                               _native.ptr(cf), len(run), yptr, self.pdim, mode),
                               "pcq_eval_pc")
+        return y
+
+    # Samples that already live in HBM (torch CUDA tensors, e.g. from utils.io.loadtxt_device): same kernels through
+    # the device-pointer entry points, results stay on that device as torch tensors.
+    def _evalBases_resident(self, xi, mindex):
+        import torch
+        from ..parallel import _resident
+        xt = _resident(xi)
+        out = torch.empty((xt.shape[0], mindex.shape[0]), dtype=torch.float64, device=xt.device)
+        plan = self._plan(mindex, dev=xt.device.index)
+        with torch.cuda.device(xt.device):
+            _native.check(_native.lib().pcq_eval_bases_dev(plan.handle, xt.data_ptr(), xt.shape[0], self.sdim,
+                                                           out.data_ptr(), mindex.shape[0],
+                                                           torch.cuda.current_stream().cuda_stream),
+                          "pcq_eval_bases_dev")
+        return out
+
+    def _evalPC_resident(self, x, exact):
+        import torch
+        from ..parallel import _resident
+        xt = _resident(x)
+        nsam = xt.shape[0]
+        y = torch.zeros((nsam, self.pdim), dtype=torch.float64, device=xt.device)
+        mode = 0 if exact else 1
+        groups = {}
+        for j, mindex in enumerate(self.mindices):
+            groups.setdefault(id(mindex), []).append(j)
+        with torch.cuda.device(xt.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            for outs in groups.values():
+                mindex = self.mindices[outs[0]]
+                plan = self._plan(mindex, dev=xt.device.index)
+                _device.note_evalpc_work(plan, nsam, mindex.shape[0], len(outs), mode)
+                runs = [list(g) for _, g in itertools.groupby(outs, key=lambda j, c=itertools.count(): j - next(c))]
+                for run in runs:
+                    cf = torch.from_numpy(np.ascontiguousarray(np.stack([self.coefs[j] for j in run]),
+                                                               dtype=np.float64)).to(xt.device)
+                    if nsam:
+                        _native.check(_native.lib().pcq_eval_pc_dev(plan.handle, xt.data_ptr(), nsam, self.sdim,
+                                                                    cf.data_ptr(), len(run), y.data_ptr() + 8 * run[0],
+                                                                    self.pdim, mode, stream), "pcq_eval_pc_dev")
         return y
 
     def evalLinearForms(self, x, cfmat, jdim=0, exact=True, sumsq=False):

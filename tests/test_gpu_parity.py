@@ -1211,6 +1211,18 @@ def test_fit_from_sample_files_resident_in_hbm():
             assert np.array_equal(opc.mindices[iout], g[f"{method}__mi{iout}"]), (method, iout)
             np.testing.assert_allclose(opc.coefs[iout], g[f"{method}__cf{iout}"], rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(opc.computeSens(), g[f"{method}__main"], rtol=1e-10, atol=1e-13)
+        # evaluation on resident samples: same kernels through the device-pointer entry points, results stay in HBM
+        germ_h = germ.cpu().numpy()
+        for exact in (True, False):
+            yd = opc.evalPC(germ, exact=exact)
+            assert yd.is_cuda and np.array_equal(yd.cpu().numpy(), opc.evalPC(germ_h, exact=exact)), (method, exact)
+        np.testing.assert_allclose(opc.function(germ).cpu().numpy(), g[f"{method}__ytrain_pc"], rtol=1e-10, atol=1e-12)
+        Ad = opc.evalBases(germ, 1)
+        assert Ad.is_cuda and np.array_equal(Ad.cpu().numpy(), opc.evalBases(germ_h, 1))
+        lregs[0].setBasisEvaluator(PCBasisEvaluator(0), (opc,))
+        m_d, v_d, _ = lregs[0].predict(germ, msc=1)
+        m_h, v_h, _ = lregs[0].predict(germ_h, msc=1)
+        assert np.array_equal(m_d, m_h) and np.array_equal(v_d, v_h)
     # single-output fitter on resident samples, and noise-free data (the residual pass reads them in place too)
     fit = anl()
     fit.setBasisEvaluator(PCBasisEvaluator(0), (_pc_of_order(3, 3),))
