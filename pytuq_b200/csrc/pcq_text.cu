@@ -61,40 +61,70 @@ __device__ __forceinline__ bool text_first_in_line(const unsigned char* __restri
     return j < 0 || text_is_eol(text[j]);
 }
 
-// The 32 bytes of this thread -> bit masks of token starts; `bad` is set when a byte cannot belong to a decimal table.
-// The buffer is padded with '\n' to a multiple of the CTA size, so no bounds are needed.
-__device__ __forceinline__ unsigned text_token_starts(const unsigned char* __restrict__ text, long long b0, bool* bad) {
-    const uint4* v = reinterpret_cast<const uint4*>(text + b0);
-    const uint4 w0 = v[0], w1 = v[1];
+// Byte classes of four characters at a time (SIMD-in-a-word video instructions): 0xff per matching byte -> one
+// bit per byte.
+__device__ __forceinline__ unsigned text_bits4(unsigned bytemask) {
+    return ((bytemask & 0x01010101u) * 0x01020408u) >> 24;      // byte j -> bit j, no carries
+}
+__device__ __forceinline__ unsigned text_space4(unsigned w) {    // ' ' or 0x09..0x0d
+    return __vcmpeq4(w, 0x20202020u) | __vcmpltu4(__vsub4(w, 0x09090909u), 0x05050505u);
+}
+__device__ __forceinline__ unsigned text_eol4(unsigned w) {
+    return __vcmpeq4(w, 0x0a0a0a0au) | __vcmpeq4(w, 0x0d0d0d0du);
+}
+__device__ __forceinline__ unsigned text_numeric4(unsigned w) {  // 0-9 . - + e E
+    return __vcmpltu4(__vsub4(w, 0x30303030u), 0x0a0a0a0au) | __vcmpeq4(w, 0x2e2e2e2eu) | __vcmpeq4(w, 0x2d2d2d2du) |
+           __vcmpeq4(w, 0x2b2b2b2bu) | __vcmpeq4(w | 0x20202020u, 0x65656565u);
+}
+
+// The 32 bytes of this thread -> one bit per byte: blanks (incl. line ends), line ends, and "cannot belong to a
+// decimal table".  The buffer is padded with '\n' by a whole CTA, so no bounds are needed.
+struct TextMasks {
+    unsigned space, eol, bad;
+};
+template <bool WANT_BAD>
+__device__ __forceinline__ TextMasks text_classify(const uint4 w0, const uint4 w1) {
     const unsigned words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    unsigned char prev = b0 > 0 ? text[b0 - 1] : (unsigned char)'\n';
-    unsigned mask = 0;
-    bool any_bad = false;
+    TextMasks m{0u, 0u, 0u};
 #pragma unroll
-    for (int k = 0; k < TEXT_SPAN; ++k) {
-        const unsigned char c = (unsigned char)(words[k >> 2] >> (8 * (k & 3)));
-        const bool sp = text_is_space(c);
-        any_bad |= !sp && !text_is_numeric(c);
-        if (!sp && text_is_space(prev)) mask |= 1u << k;
-        prev = c;
+    for (int j = 0; j < 8; ++j) {
+        const unsigned sp = text_space4(words[j]);
+        m.space |= text_bits4(sp) << (4 * j);
+        m.eol |= text_bits4(text_eol4(words[j])) << (4 * j);
+        if (WANT_BAD) m.bad |= text_bits4(~(sp | text_numeric4(words[j]))) << (4 * j);
     }
-    *bad = any_bad;
-    return mask;
+    return m;
+}
+
+// Token start = non-blank byte behind a blank one.  prev_space: was the byte in front of the span a blank?
+__device__ __forceinline__ unsigned text_starts(unsigned space, bool prev_space) {
+    return ~space & ((space << 1) | (prev_space ? 1u : 0u));
+}
+
+// Is the token that starts at bit k of this span the first one of its line?  Decided from the span's masks when a
+// non-blank or a line end precedes it inside the span, else by walking back through the text.
+__device__ __forceinline__ bool text_first_in_line_m(const unsigned char* __restrict__ text, long long b0, int k,
+                                                     unsigned space, unsigned eol) {
+    const unsigned below = (~space | eol) & ((1u << k) - 1u);      // bytes in front that are not plain blanks
+    if (below) return (eol >> (31 - __clz(below))) & 1u;
+    return text_first_in_line(text, b0);                           // everything in front (in the span) is blank
 }
 
 __global__ void __launch_bounds__(TEXT_THREADS)
 pcq_text_scan_kernel(const unsigned char* __restrict__ text, unsigned* __restrict__ cta_tokens,
                      unsigned* __restrict__ cta_rows, int* __restrict__ flags) {
     const long long b0 = ((long long)blockIdx.x * TEXT_THREADS + threadIdx.x) * TEXT_SPAN;
-    bool bad;
-    unsigned mask = text_token_starts(text, b0, &bad);
+    const uint4* v = reinterpret_cast<const uint4*>(text + b0);
+    const TextMasks m = text_classify<true>(v[0], v[1]);
+    const bool prev_space = b0 == 0 || text_is_space(text[b0 - 1]);
+    unsigned mask = text_starts(m.space, prev_space);
     unsigned ntok = __popc(mask), nrow = 0;
     while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
-        nrow += text_first_in_line(text, b0 + k) ? 1u : 0u;
+        nrow += text_first_in_line_m(text, b0, k, m.space, m.eol) ? 1u : 0u;
     }
-    if (bad) atomicOr(&flags[0], 1);
+    if (m.bad) atomicOr(&flags[0], 1);
     __shared__ unsigned s_tok[TEXT_THREADS / 32], s_row[TEXT_THREADS / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -118,41 +148,75 @@ pcq_text_scan_kernel(const unsigned char* __restrict__ text, unsigned* __restric
     }
 }
 
+constexpr int TEXT_TAIL = 64;      // bytes of the next CTA's text staged too: tokens may run over the CTA's end
+
 __global__ void __launch_bounds__(TEXT_THREADS)
 pcq_text_parse_kernel(const unsigned char* __restrict__ text, const long long* __restrict__ cta_base, long long cols,
                       double* __restrict__ out, long long ld, FixItem* __restrict__ fix, int* __restrict__ fix_count,
                       int* __restrict__ flags) {
-    const long long b0 = ((long long)blockIdx.x * TEXT_THREADS + threadIdx.x) * TEXT_SPAN;
-    bool bad;
-    unsigned mask = text_token_starts(text, b0, &bad);
+    // the CTA's 8 KB of text (+ tail) in shared memory, and one blank-mask word per 32 bytes of it
+    __shared__ __align__(16) unsigned char s_text[TEXT_CTA_BYTES + TEXT_TAIL];
+    __shared__ unsigned s_space[TEXT_THREADS + TEXT_TAIL / TEXT_SPAN];
+    __shared__ unsigned s_warp[TEXT_THREADS / 32];
+    const int tid = threadIdx.x;
+    const long long cta0 = (long long)blockIdx.x * TEXT_CTA_BYTES;
+    const long long b0 = cta0 + (long long)tid * TEXT_SPAN;
+    const uint4* v = reinterpret_cast<const uint4*>(text + b0);
+    const uint4 w0 = v[0], w1 = v[1];
+    reinterpret_cast<uint4*>(s_text)[2 * tid] = w0;
+    reinterpret_cast<uint4*>(s_text)[2 * tid + 1] = w1;
+    const TextMasks m = text_classify<false>(w0, w1);
+    s_space[tid] = m.space;
+    if (tid < TEXT_TAIL / TEXT_SPAN) {
+        const uint4* tv = reinterpret_cast<const uint4*>(text + cta0 + TEXT_CTA_BYTES + tid * TEXT_SPAN);
+        const uint4 t0 = tv[0], t1 = tv[1];
+        reinterpret_cast<uint4*>(s_text + TEXT_CTA_BYTES)[2 * tid] = t0;
+        reinterpret_cast<uint4*>(s_text + TEXT_CTA_BYTES)[2 * tid + 1] = t1;
+        s_space[TEXT_THREADS + tid] = text_classify<false>(t0, t1).space;
+    }
+    const bool prev_space = b0 == 0 || text_is_space(text[b0 - 1]);
+    unsigned mask = text_starts(m.space, prev_space);
     // exclusive scan of the per-thread token counts over the CTA
     const unsigned ntok = __popc(mask);
     unsigned incl = ntok;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
     }
-    __shared__ unsigned s_warp[TEXT_THREADS / 32];
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     unsigned before = incl - ntok;
     for (int w = 0; w < warp; ++w) before += s_warp[w];
     long long token = cta_base[blockIdx.x] + before;
+    const bool dense = ld == cols;
     while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
-        const long long i = b0 + k;
-        if (text_first_in_line(text, i) && token % cols != 0) atomicOr(&flags[1], 1);
-        size_t n = 1;
-        while (!text_is_space(text[i + n])) ++n;           // the '\n' padding behind the file ends the last token
-        double v;
-        if (pcq_parse_decimal_fast(reinterpret_cast<const char*>(text) + i, n, &v, d_pow10)) {
-            out[ld == cols ? token : (token / cols) * ld + token % cols] = v;    // dense result: no division
+        if (text_first_in_line_m(text, b0, k, m.space, m.eol) && token % cols != 0) atomicOr(&flags[1], 1);
+        // end of the token: the next blank, looked up in the mask words of the staged text
+        const int start = tid * TEXT_SPAN + k;
+        int wi = (start + 1) >> 5;
+        unsigned sp = wi < TEXT_THREADS + TEXT_TAIL / TEXT_SPAN ? s_space[wi] & (~0u << ((start + 1) & 31)) : 0u;
+        while (!sp && ++wi < TEXT_THREADS + TEXT_TAIL / TEXT_SPAN) sp = s_space[wi];
+        double val;
+        bool ok;
+        if (sp) {
+            const int stop = wi * 32 + __ffs(sp) - 1;
+            ok = pcq_parse_decimal_fast(reinterpret_cast<const char*>(s_text) + start, (size_t)(stop - start), &val,
+                                        d_pow10);
+        } else {        // a token that runs past the staged tail: read it from global memory
+            const long long i = b0 + k;
+            size_t n = 1;
+            while (!text_is_space(text[i + n])) ++n;       // the '\n' padding behind the file ends the last token
+            ok = pcq_parse_decimal_fast(reinterpret_cast<const char*>(text) + i, n, &val, d_pow10);
+        }
+        if (ok) {
+            out[dense ? token : (token / cols) * ld + token % cols] = val;      // dense result: no division
         } else {
             const int slot = atomicAdd(fix_count, 1);
-            if (slot < FIX_CAP) fix[slot] = FixItem{token, i};
+            if (slot < FIX_CAP) fix[slot] = FixItem{token, b0 + k};
         }
         ++token;
     }
