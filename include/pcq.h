@@ -209,10 +209,10 @@ int pcq_sample_germ_dev(pcq_plan* plan, uint64_t seed, int64_t first_index, int6
  * there (csrc/pcq_text.cu), so the fit's inputs are born in HBM: no host parse, no upload of the binary
  * matrix.  Values are bit-identical to np.loadtxt's (the conversion is the one of pcq_io.h; the few
  * tokens it cannot decide on the device — ties, subnormals, > 19 digits — are converted by the host's
- * strtod and patched in).  Plain decimal tables only (what np.savetxt writes: numbers separated by
- * blanks, one row per line, blank lines allowed): '#' comments, inf/nan or other delimiters return
- * PCQ_ERR_UNSUPPORTED and belong to the host reader pcqio_open (pcq_io.h); ragged rows and
- * unconvertible tokens return PCQ_ERR_ARG.
+ * strtod and patched in, and so are inf / nan in numpy's spellings).  Whitespace-separated tables only
+ * (what np.savetxt writes: one row per line, blank lines allowed): a file with '#' comments returns
+ * PCQ_ERR_UNSUPPORTED and belongs to the host reader pcqio_open (pcq_io.h); ragged rows and tokens
+ * numpy would not convert return PCQ_ERR_ARG.
  *   pcq_text_open       maps the file, copies its bytes to `device`, counts *rows x *cols there;
  *   pcq_text_parse_dev  converts into out_dev (rows x cols, leading dimension ld >= cols) on `stream`
  *                       and returns once the result is complete (it synchronises the stream);

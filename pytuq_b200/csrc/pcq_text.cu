@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cerrno>
+#include <cmath>
 #include <mutex>
 #include <new>
 #include <cstdlib>
@@ -61,39 +62,24 @@ __device__ __forceinline__ bool text_first_in_line(const unsigned char* __restri
     return j < 0 || text_is_eol(text[j]);
 }
 
-// Byte classes of four characters at a time (SIMD-in-a-word video instructions): 0xff per matching byte -> one
-// bit per byte.
-__device__ __forceinline__ unsigned text_bits4(unsigned bytemask) {
-    return ((bytemask & 0x01010101u) * 0x01020408u) >> 24;      // byte j -> bit j, no carries
-}
-__device__ __forceinline__ unsigned text_space4(unsigned w) {    // ' ' or 0x09..0x0d
-    return __vcmpeq4(w, 0x20202020u) | __vcmpltu4(__vsub4(w, 0x09090909u), 0x05050505u);
-}
-__device__ __forceinline__ unsigned text_eol4(unsigned w) {
-    return __vcmpeq4(w, 0x0a0a0a0au) | __vcmpeq4(w, 0x0d0d0d0du);
-}
-__device__ __forceinline__ unsigned text_numeric4(unsigned w) {  // 0-9 . - + e E
-    return __vcmpltu4(__vsub4(w, 0x30303030u), 0x0a0a0a0au) | __vcmpeq4(w, 0x2e2e2e2eu) | __vcmpeq4(w, 0x2d2d2d2du) |
-           __vcmpeq4(w, 0x2b2b2b2bu) | __vcmpeq4(w | 0x20202020u, 0x65656565u);
+// Blank bytes (' ' and 0x09..0x0d) of four characters at a time with plain integer arithmetic: with bit 7 of every
+// byte forced on, a byte-wise subtraction cannot borrow from its neighbour, and bit 7 of the difference tells
+// "low seven bits >= n".  (The byte-wise __vcmp*4 intrinsics expand to several instructions each on sm_100a;
+// profiles/r01_m_text_summary.md.)  Bytes >= 0x80 are never blank.
+__device__ __forceinline__ unsigned text_space4(unsigned v) {
+    const unsigned a = v | 0x80808080u;
+    const unsigned ge9 = a - 0x09090909u, ge14 = a - 0x0e0e0e0eu;
+    const unsigned ne20 = ((v ^ 0x20202020u) | 0x80808080u) - 0x01010101u;      // bit 7 clear <=> low bits == 0x20
+    const unsigned sp7 = ((ge9 & ~ge14) | ~ne20) & ~v & 0x80808080u;
+    return ((sp7 >> 7) * 0x01020408u) >> 24;                                    // byte j -> bit j, no carries
 }
 
-// The 32 bytes of this thread -> one bit per byte: blanks (incl. line ends), line ends, and "cannot belong to a
-// decimal table".  The buffer is padded with '\n' by a whole CTA, so no bounds are needed.
-struct TextMasks {
-    unsigned space, eol, bad;
-};
-template <bool WANT_BAD>
-__device__ __forceinline__ TextMasks text_classify(const uint4 w0, const uint4 w1) {
-    const unsigned words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    TextMasks m{0u, 0u, 0u};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const unsigned sp = text_space4(words[j]);
-        m.space |= text_bits4(sp) << (4 * j);
-        m.eol |= text_bits4(text_eol4(words[j])) << (4 * j);
-        if (WANT_BAD) m.bad |= text_bits4(~(sp | text_numeric4(words[j]))) << (4 * j);
-    }
-    return m;
+// The 32 bytes of this thread -> one bit per blank byte (line ends included).  The buffer is padded with '\n' by a
+// whole CTA, so no bounds are needed.
+__device__ __forceinline__ unsigned text_space_mask(const uint4 w0, const uint4 w1) {
+    return text_space4(w0.x) | (text_space4(w0.y) << 4) | (text_space4(w0.z) << 8) | (text_space4(w0.w) << 12) |
+           (text_space4(w1.x) << 16) | (text_space4(w1.y) << 20) | (text_space4(w1.z) << 24) |
+           (text_space4(w1.w) << 28);
 }
 
 // Token start = non-blank byte behind a blank one.  prev_space: was the byte in front of the span a blank?
@@ -101,30 +87,23 @@ __device__ __forceinline__ unsigned text_starts(unsigned space, bool prev_space)
     return ~space & ((space << 1) | (prev_space ? 1u : 0u));
 }
 
-// Is the token that starts at bit k of this span the first one of its line?  Decided from the span's masks when a
-// non-blank or a line end precedes it inside the span, else by walking back through the text.
-__device__ __forceinline__ bool text_first_in_line_m(const unsigned char* __restrict__ text, long long b0, int k,
-                                                     unsigned space, unsigned eol) {
-    const unsigned below = (~space | eol) & ((1u << k) - 1u);      // bytes in front that are not plain blanks
-    if (below) return (eol >> (31 - __clz(below))) & 1u;
-    return text_first_in_line(text, b0);                           // everything in front (in the span) is blank
-}
-
 __global__ void __launch_bounds__(TEXT_THREADS)
 pcq_text_scan_kernel(const unsigned char* __restrict__ text, unsigned* __restrict__ cta_tokens,
                      unsigned* __restrict__ cta_rows, int* __restrict__ flags) {
     const long long b0 = ((long long)blockIdx.x * TEXT_THREADS + threadIdx.x) * TEXT_SPAN;
     const uint4* v = reinterpret_cast<const uint4*>(text + b0);
-    const TextMasks m = text_classify<true>(v[0], v[1]);
+    const unsigned space = text_space_mask(v[0], v[1]);
     const bool prev_space = b0 == 0 || text_is_space(text[b0 - 1]);
-    unsigned mask = text_starts(m.space, prev_space);
+    unsigned mask = text_starts(space, prev_space);
     unsigned ntok = __popc(mask), nrow = 0;
+    bool comment = false;
     while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
-        nrow += text_first_in_line_m(text, b0, k, m.space, m.eol) ? 1u : 0u;
+        nrow += text_first_in_line(text, b0 + k) ? 1u : 0u;
+        comment |= text[b0 + k] == '#';
     }
-    if (m.bad) atomicOr(&flags[0], 1);
+    if (comment) atomicOr(&flags[0], 1);
     __shared__ unsigned s_tok[TEXT_THREADS / 32], s_row[TEXT_THREADS / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -165,17 +144,17 @@ pcq_text_parse_kernel(const unsigned char* __restrict__ text, const long long* _
     const uint4 w0 = v[0], w1 = v[1];
     reinterpret_cast<uint4*>(s_text)[2 * tid] = w0;
     reinterpret_cast<uint4*>(s_text)[2 * tid + 1] = w1;
-    const TextMasks m = text_classify<false>(w0, w1);
-    s_space[tid] = m.space;
+    const unsigned space = text_space_mask(w0, w1);
+    s_space[tid] = space;
     if (tid < TEXT_TAIL / TEXT_SPAN) {
         const uint4* tv = reinterpret_cast<const uint4*>(text + cta0 + TEXT_CTA_BYTES + tid * TEXT_SPAN);
         const uint4 t0 = tv[0], t1 = tv[1];
         reinterpret_cast<uint4*>(s_text + TEXT_CTA_BYTES)[2 * tid] = t0;
         reinterpret_cast<uint4*>(s_text + TEXT_CTA_BYTES)[2 * tid + 1] = t1;
-        s_space[TEXT_THREADS + tid] = text_classify<false>(t0, t1).space;
+        s_space[TEXT_THREADS + tid] = text_space_mask(t0, t1);
     }
     const bool prev_space = b0 == 0 || text_is_space(text[b0 - 1]);
-    unsigned mask = text_starts(m.space, prev_space);
+    unsigned mask = text_starts(space, prev_space);
     // exclusive scan of the per-thread token counts over the CTA
     const unsigned ntok = __popc(mask);
     unsigned incl = ntok;
@@ -194,9 +173,15 @@ pcq_text_parse_kernel(const unsigned char* __restrict__ text, const long long* _
     while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
-        if (text_first_in_line_m(text, b0, k, m.space, m.eol) && token % cols != 0) atomicOr(&flags[1], 1);
-        // end of the token: the next blank, looked up in the mask words of the staged text
         const int start = tid * TEXT_SPAN + k;
+        // first token of its line?  Walk back over plain blanks (staged text, then global memory in front of the CTA)
+        {
+            int j = start - 1;
+            while (j >= 0 && !text_is_eol(s_text[j]) && text_is_space(s_text[j])) --j;
+            const bool first = j >= 0 ? text_is_eol(s_text[j]) : text_first_in_line(text, cta0);
+            if (first && token % cols != 0) atomicOr(&flags[1], 1);
+        }
+        // end of the token: the next blank, looked up in the mask words of the staged text
         int wi = (start + 1) >> 5;
         unsigned sp = wi < TEXT_THREADS + TEXT_TAIL / TEXT_SPAN ? s_space[wi] & (~0u << ((start + 1) & 31)) : 0u;
         while (!sp && ++wi < TEXT_THREADS + TEXT_TAIL / TEXT_SPAN) sp = s_space[wi];
@@ -280,6 +265,41 @@ TextStage g_text_stage;
 locale_t text_c_locale() {
     static locale_t loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
     return loc;
+}
+
+// A token the device handed back -> double with the acceptance rules of numpy's float converter (decimal literals
+// through the C locale's correctly rounded strtod; [+-]inf, [+-]infinity, [+-]nan in any case; nothing else: no hex,
+// no underscores).  0 = converted, 1 = not a number, 2 = contains '#'.
+int text_convert_on_host(const std::string& tok, double* out) {
+    if (tok.empty()) return 1;
+    bool numeric = true;
+    for (char c : tok) {
+        if (c == '#') return 2;
+        if (!((c >= '0' && c <= '9') || c == '.' || c == '+' || c == '-' || c == 'e' || c == 'E')) numeric = false;
+    }
+    if (numeric) {
+        char* stop = nullptr;
+        const double v = strtod_l(tok.c_str(), &stop, text_c_locale());
+        if (stop != tok.c_str() + tok.size()) return 1;
+        *out = v;
+        return 0;
+    }
+    std::string w;
+    for (char c : tok) w.push_back((char)tolower((unsigned char)c));
+    bool neg = false;
+    if (w[0] == '+' || w[0] == '-') {
+        neg = w[0] == '-';
+        w.erase(0, 1);
+    }
+    if (w == "inf" || w == "infinity") {
+        *out = neg ? -HUGE_VAL : HUGE_VAL;
+        return 0;
+    }
+    if (w == "nan") {
+        *out = neg ? -nan("") : nan("");
+        return 0;
+    }
+    return 1;
 }
 
 }  // namespace
@@ -393,8 +413,7 @@ int pcq_text_open(int device, const char* path, pcq_text** out, int64_t* rows, i
     TEXT_TRY(cudaMemcpy(h_row.data(), d_row, (size_t)t->nctas * sizeof(unsigned), cudaMemcpyDeviceToHost));
     TEXT_TRY(cudaMemcpy(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost));
     if (h_flags[0]) {
-        pcq_set_error("text_open: %s is not a plain decimal table (comments, inf/nan or another delimiter): "
-                      "use the host reader (pcqio_open)", path);
+        pcq_set_error("text_open: %s contains '#' comments: use the host reader (pcqio_open)", path);
         rc = PCQ_ERR_UNSUPPORTED;
         goto done;
     }
@@ -483,9 +502,14 @@ int pcq_text_parse_dev(pcq_text* t, double* out_dev, int64_t ld, void* stream) {
             size_t n = 0;
             while (p + n < end && !isspace((unsigned char)p[n])) ++n;
             std::string tok(p, n);
-            char* stop = nullptr;
-            const double v = strtod_l(tok.c_str(), &stop, text_c_locale());
-            if (stop != tok.c_str() + n || n == 0) {
+            double v = 0.0;
+            const int verdict = text_convert_on_host(tok, &v);
+            if (verdict == 2) {
+                pcq_set_error("text_parse: '#' inside the table: comments are the host reader's job (pcqio_open)");
+                rc = PCQ_ERR_UNSUPPORTED;
+                goto done;
+            }
+            if (verdict != 0) {
                 pcq_set_error("could not convert string '%.60s' to float64 (value %lld of the table)", tok.c_str(),
                               h_fix[(size_t)j].token);
                 rc = PCQ_ERR_ARG;

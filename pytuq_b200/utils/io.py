@@ -113,9 +113,9 @@ def loadtxt_device(fname, device=None):
     matrix.  Values are bit-identical to ``np.loadtxt(fname, ndmin=2)``.  ``pc_fit`` / ``lreg.fit`` /
     ``PCRV.suffStats`` take such tensors in place of numpy arrays and read them where they are.
 
-    Plain decimal tables only (what ``savetxt`` writes): a file with ``#`` comments, inf/nan or another delimiter
-    raises ``ValueError`` naming the host reader ``loadtxt``; ragged rows and unconvertible tokens raise
-    ``ValueError`` as ``np.loadtxt`` does."""
+    Whitespace-separated tables (what ``savetxt`` writes; inf / nan in numpy's spellings included): a file with
+    ``#`` comments raises ``ValueError`` naming the host reader ``loadtxt``; ragged rows and unconvertible tokens
+    raise ``ValueError`` as ``np.loadtxt`` does."""
     import torch
     from .. import _native, device as _device
     _device.require_device()

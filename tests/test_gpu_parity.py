@@ -1176,12 +1176,20 @@ def test_text_tables_are_converted_on_the_device_bit_for_bit(tmp_path):
     assert tuple(io.loadtxt_device(f).shape) == (0, 0)
     f = _write(tmp_path / "zero.txt", b"")
     assert tuple(io.loadtxt_device(f).shape) == (0, 0)
-    # declined (host reader's job) and rejected inputs
-    for text in ("# header\n1 2\n", "1 nan\n", "1,2\n3,4\n", "1 inf\n"):
+    # inf / nan: the device hands them back, the host converts them with numpy's rules, the result is patched in
+    f = _write(tmp_path / "special.txt", "1 nan -inf\n+Infinity 2 NaN\n-0 INF 3e0\n")
+    want = np.loadtxt(f, ndmin=2)
+    got = io.loadtxt_device(f).cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(np.nan_to_num(got, nan=7.0).view(np.uint64), np.nan_to_num(want, nan=7.0).view(np.uint64))
+    # declined: comments are the host reader's job
+    for text in ("# header\n1 2\n", "1 2 # tail\n3 4\n", "1 2\n#3 4\n"):
         with pytest.raises(ValueError, match="host reader"):
             io.loadtxt_device(_write(tmp_path / "declined.txt", text))
-        np.loadtxt(str(tmp_path / "declined.txt"), delimiter="," if "," in text else None)   # numpy / io.loadtxt read it
-    for text in ("1 2 3\n4 5\n", "1 2\n3 4 5 6\n", "1 2\n3 1e\n", "1 2\n3 1.2.3\n", "1 2\n3 --4\n"):
+        assert io.loadtxt(str(tmp_path / "declined.txt"), ndmin=2).shape[1] == 2
+    # rejected, as numpy rejects them
+    for text in ("1 2 3\n4 5\n", "1 2\n3 4 5 6\n", "1 2\n3 1e\n", "1 2\n3 1.2.3\n", "1 2\n3 --4\n", "1,2\n3,4\n",
+                 "1 2\n3 0x10\n", "1 2\n3 1_0\n", "1 2\n3 abc\n", "1 2\n3 na\n"):
         with pytest.raises(ValueError):
             np.loadtxt(_write(tmp_path / "bad.txt", text))
         with pytest.raises(ValueError):
