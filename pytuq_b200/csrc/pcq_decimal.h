@@ -41,11 +41,45 @@ PCQ_HD int pcq_clz64(uint64_t v) {
 #endif
 }
 
-// [+-]digits[.digits][e[+-]digits] with at most 19 significant digits -> w * 10^q -> one 64 x 128-bit product
-// with the truncated table entry.  The 53-bit result is certain unless the bits behind it are within the
-// product's error (< 2^66 of 2^139) of the half-way point; then, and for subnormal / overflowing results,
-// longer inputs or malformed tokens, it returns false and the libc route decides (or rejects the token).
+// (-1)^neg * w * 10^q -> binary64 with one 64 x 128-bit product and the truncated table entry.  The 53-bit result is
+// certain unless the bits behind it are within the product's error (< 2^66 of 2^139) of the half-way point; then,
+// and for subnormal / overflowing results or q outside the table, it returns false (the libc route decides).
 // `table` is the PCQIO_POW10 array of the side that calls (host copy or __device__ copy).
+PCQ_HD bool pcq_decimal_to_double(uint64_t w, int64_t q, bool neg, double* out, const pcqio_pow10* table) {
+    if (w == 0) {
+        *out = neg ? -0.0 : 0.0;
+        return true;
+    }
+    if (q < PCQIO_Q_MIN || q > PCQIO_Q_MAX) return false;
+    const int lz = pcq_clz64(w);
+    const pcqio_pow10 P = table[q - PCQIO_Q_MIN];
+    pcq_u192 r = pcq_mul_64x128(w << lz, P.hi, P.lo);
+    int e = P.e - lz;                           // value = r * 2^e, up to the table's truncation
+    if (!(r.r2 >> 63)) {
+        r.r2 = (r.r2 << 1) | (r.r1 >> 63);
+        r.r1 = (r.r1 << 1) | (r.r0 >> 63);
+        r.r0 <<= 1;
+        --e;
+    }
+    uint64_t m53 = r.r2 >> 11;
+    const uint64_t low = r.r2 & 0x7ff;
+    if (low == 0x3ff && r.r1 >= ~0ull - 8) return false;
+    if (low == 0x400 && r.r1 <= 8) return false;
+    if (low >= 0x400) ++m53;
+    int be = e + 139 + 52 + 1023;               // biased exponent of m53 * 2^(e+139)
+    if (m53 >> 53) {
+        m53 >>= 1;
+        ++be;
+    }
+    if (be < 1 || be > 2046) return false;
+    const uint64_t bits = ((uint64_t)neg << 63) | ((uint64_t)be << 52) | (m53 & ((1ull << 52) - 1));
+    memcpy(out, &bits, 8);
+    return true;
+}
+
+// [+-]digits[.digits][e[+-]digits] with at most 19 significant digits -> w * 10^q -> one 64 x 128-bit product
+// (pcq_decimal_to_double).  For longer inputs, malformed tokens and whatever the product cannot decide it returns
+// false and the libc route decides (or rejects the token).
 PCQ_HD bool pcq_parse_decimal_fast(const char* t, size_t n, double* out, const pcqio_pow10* table) {
     const char* p = t;
     const char* end = t + n;
@@ -92,34 +126,5 @@ PCQ_HD bool pcq_parse_decimal_fast(const char* t, size_t n, double* out, const p
         q += eneg ? -ex : ex;
     }
     if (p != end) return false;
-    if (w == 0) {
-        *out = neg ? -0.0 : 0.0;
-        return true;
-    }
-    if (q < PCQIO_Q_MIN || q > PCQIO_Q_MAX) return false;
-    const int lz = pcq_clz64(w);
-    const pcqio_pow10 P = table[q - PCQIO_Q_MIN];
-    pcq_u192 r = pcq_mul_64x128(w << lz, P.hi, P.lo);
-    int e = P.e - lz;                           // value = r * 2^e, up to the table's truncation
-    if (!(r.r2 >> 63)) {
-        r.r2 = (r.r2 << 1) | (r.r1 >> 63);
-        r.r1 = (r.r1 << 1) | (r.r0 >> 63);
-        r.r0 <<= 1;
-        --e;
-    }
-    uint64_t m53 = r.r2 >> 11;
-    const uint64_t low = r.r2 & 0x7ff;
-    if (low == 0x3ff && r.r1 >= ~0ull - 8) return false;
-    if (low == 0x400 && r.r1 <= 8) return false;
-    if (low >= 0x400) ++m53;
-    int be = e + 139 + 52 + 1023;               // biased exponent of m53 * 2^(e+139)
-    if (m53 >> 53) {
-        m53 >>= 1;
-        ++be;
-    }
-    if (be < 1 || be > 2046) return false;
-    const uint64_t bits = ((uint64_t)neg << 63) | ((uint64_t)be << 52) | (m53 & ((1ull << 52) - 1));
-    memcpy(out, &bits, 8);
-    return true;
+    return pcq_decimal_to_double(w, q, neg, out, table);
 }
-
