@@ -1172,6 +1172,16 @@ def test_text_tables_are_converted_on_the_device_bit_for_bit(tmp_path):
     want = np.loadtxt(f, ndmin=2)
     got = io.loadtxt_device(f).cpu().numpy()
     assert got.shape == (4, 3) and np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    # tokens longer than the 64 bytes staged behind a CTA's 8 KB, lying across that boundary: read from global memory
+    long_small = "0." + "0" * 140 + "125"           # few significant digits: converted on the device
+    long_digits = "1" + "234567890" * 11            # 100 digits: handed to the host
+    for pad in range(8192 - 80, 8192 - 20, 7):
+        rows = ["1.5 2.5"] * (pad // 8)
+        text = "\n".join(rows) + "\n" + " " * (pad - 8 * (pad // 8)) + long_small + " " + long_digits + "\n3 4\n"
+        f = _write(tmp_path / "long.txt", text)
+        want = np.loadtxt(f, ndmin=2)
+        got = io.loadtxt_device(f).cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint64), want.view(np.uint64)), pad
     f = _write(tmp_path / "empty.txt", "\n\n  \n")
     assert tuple(io.loadtxt_device(f).shape) == (0, 0)
     f = _write(tmp_path / "zero.txt", b"")
