@@ -66,6 +66,8 @@ def savetxt(fname, X, threads=0):
 
     A 1-D array is written one value per line and integer / float32 input is converted to float64 first, both
     as numpy does (``numpy/lib/_npyio_impl.py``, ``savetxt``)."""
+    if type(X).__module__.split(".")[0] == "torch":      # results that live in HBM (or any torch tensor) come to the host first
+        X = X.detach().cpu().numpy()
     X = np.asarray(X)
     if X.ndim == 0 or X.ndim > 2:
         raise ValueError("Expected 1D or 2D array, got %dD array instead" % X.ndim)

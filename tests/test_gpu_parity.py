@@ -1221,6 +1221,10 @@ def test_fit_from_sample_files_resident_in_hbm():
     germ = io.loadtxt_device(os.path.join(gold, "qtrain.txt"))
     ytrain = io.loadtxt_device(os.path.join(gold, "ytrain.txt"))
     assert germ.is_cuda and tuple(germ.shape) == (240, 3) and tuple(ytrain.shape) == (240, 2)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:           # and back: a resident tensor written in the same format
+        io.savetxt(os.path.join(d, "q.txt"), germ)
+        assert open(os.path.join(d, "q.txt"), "rb").read() == open(os.path.join(gold, "qtrain.txt"), "rb").read()
     assert np.array_equal(germ.cpu().numpy(), np.loadtxt(os.path.join(gold, "qtrain.txt")))
     for method in ("lsq", "anl", "bcs"):
         with contextlib.redirect_stdout(_io.StringIO()):

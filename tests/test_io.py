@@ -164,6 +164,14 @@ def test_errors_and_unsupported_inputs(tmp_path):
     assert lib.pcqio_close(None) == 0
 
 
+def test_savetxt_takes_torch_tensors(tmp_path):
+    import torch
+    X = np.random.default_rng(6).standard_normal((17, 3))
+    io.savetxt(str(tmp_path / "t.txt"), torch.from_numpy(X))
+    np.savetxt(str(tmp_path / "n.txt"), X)
+    assert open(tmp_path / "t.txt", "rb").read() == open(tmp_path / "n.txt", "rb").read()
+
+
 def test_save_load_pick_the_format_from_the_name(tmp_path):
     X = np.random.default_rng(5).standard_normal((50, 4))
     for name in ("x.npy", "x.txt", "x.dat"):
