@@ -55,6 +55,20 @@ def test_no_cpu_fallback_without_device():
     from pytuq_b200.linred.kle import KLE
     with pytest.raises(_native.PcqError):
         KLE().build(np.ones((4, 9)), plot=False)
+    from pytuq_b200.utils import io
+    with pytest.raises(_native.PcqError):          # the device reader does not quietly become the host reader
+        io.loadtxt_device(os.path.join(ROOT, "tests", "golden", "uqpc", "qtrain.txt"))
+
+
+def test_text_entry_points_reject_bad_arguments():
+    from pytuq_b200 import _native
+    lib = _native.lib()
+    rows, cols, h = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_void_p()
+    assert lib.pcq_text_open(0, None, ctypes.byref(h), ctypes.byref(rows), ctypes.byref(cols)) == -1
+    assert lib.pcq_text_open(-1, b"/nonexistent", ctypes.byref(h), ctypes.byref(rows), ctypes.byref(cols)) == -1
+    assert b"bad argument" in lib.pcq_last_error()
+    assert lib.pcq_text_parse_dev(None, None, 0, None) == -1
+    assert lib.pcq_text_close(None) == 0
 
 
 def test_c_abi_rejects_bad_arguments_before_touching_the_device():
