@@ -385,6 +385,32 @@ def main():
         kernels["K6_quadform_variance"] = {"rows": n6, "ms": ms, "samples_per_s": n6 / (ms * 1e-3),
                                            "TFLOPs_algorithmic": float(n6) * K * K / (ms * 1e-3) / 1e12, "bound": "tensor"}
         del Cm, v6
+        # samples read from their text file straight into HBM (csrc/pcq_text.cu): a side measurement of the
+        # on-disk format next to the path; it can never break the line
+        if world == 1:
+            try:
+                import tempfile
+                from pytuq_b200.utils import io as pio
+                with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmpd:
+                    ftxt = os.path.join(tmpd, "x.txt")
+                    pio.savetxt(ftxt, xh)
+                    nbytes = os.path.getsize(ftxt)
+                    pio.loadtxt_device(ftxt, device=local)
+                    tt = []
+                    for _ in range(2):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        xd = pio.loadtxt_device(ftxt, device=local)
+                        torch.cuda.synchronize()
+                        tt.append(time.perf_counter() - t0)
+                    same = bool(torch.equal(xd, x))
+                    del xd
+                kernels["text_to_hbm"] = {"rows": n, "cols": D, "text_bytes": nbytes, "ms": 1e3 * min(tt),
+                                          "values_per_s": n * D / min(tt), "text_GBps": nbytes / min(tt) / 1e9,
+                                          "bit_identical_to_the_resident_samples": same, "bound": "host-to-device copy of the text",
+                                          "api": "pytuq_b200.utils.io.loadtxt_device (pcq_text_open + pcq_text_parse_dev)"}
+            except Exception as exc:                     # noqa: BLE001
+                kernels["text_to_hbm"] = {"error": repr(exc)}
     peak = peaks.get("fp64_dmma_tflops")
     traffic = None
     try:   # DRAM bytes per step of the dominant kernel, from the committed ncu capture of this workload
