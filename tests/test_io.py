@@ -217,3 +217,36 @@ def test_germ_sample_files_of_the_uqpc_app_are_reproduced_byte_for_byte(tmp_path
     for name in ("ptrain.txt", "ytrain.txt", "qtrain.txt"):
         want = np.loadtxt(os.path.join(gold, name))
         assert np.array_equal(io.loadtxt(os.path.join(gold, name)), want)
+
+
+_sep = st.sampled_from([" ", "  ", "\t", " \t "])
+_eol = st.sampled_from(["\n", "\r\n", "\n\n", " \n", "\n \t\n"])
+_num = st.one_of(
+    st.floats(allow_nan=False, allow_infinity=False, width=64).map(repr),
+    st.floats(allow_nan=False, allow_infinity=False, width=64).map(lambda v: "%.18e" % v),
+    st.integers(-10 ** 25, 10 ** 25).map(str),
+    st.sampled_from(["inf", "-inf", "+Infinity", "nan", "NaN", ".5", "5.", "+0", "-0.0", "1E5", "1e-320", "00012"]),
+)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.integers(1, 5), st.integers(1, 6), st.data())
+def test_arbitrary_layouts_read_like_numpy(ncols, nrows, data):
+    import tempfile
+    lines = []
+    for _ in range(nrows):
+        toks = [data.draw(_num) for _ in range(ncols)]
+        seps = [data.draw(_sep) for _ in range(ncols - 1)]
+        line = data.draw(st.sampled_from(["", " ", "\t"])) + "".join(t + s for t, s in zip(toks, seps + [""]))
+        line += data.draw(st.sampled_from(["", "  # note 1 2 3", "#x"]))
+        lines.append(line + data.draw(_eol))
+    text = data.draw(st.sampled_from(["", "# head\n", "\n"])) + "".join(lines)
+    if data.draw(st.booleans()):
+        text = text.rstrip("\r\n \t")                      # no newline at the end
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "t.txt")
+        with open(f, "wb") as fh:
+            fh.write(text.encode())
+        want = np.loadtxt(f, ndmin=2)
+        got = io.loadtxt(f, ndmin=2)
+    assert _same_bits(_nan_payload_free(want), _nan_payload_free(got)), text
