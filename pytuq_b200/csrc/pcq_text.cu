@@ -2,16 +2,18 @@
 // to the device as bytes and converted there, so a fit that reads its samples from files never parses on the host
 // and never uploads the binary matrix (reference call sites apps/uqpc/uq_pc.py:232-265).
 //
-//   scan kernel   one thread per 32 bytes: token starts and first-tokens-of-a-line are counted per CTA, any byte
-//                 that is not part of a plain decimal table raises a flag (the host reader of pcq_io.h takes such
-//                 files: comments, inf/nan, other delimiters);
+//   scan kernel   one thread per 32 bytes: a blank mask of the span (carry-free word arithmetic), token starts and
+//                 first-tokens-of-a-line counted per CTA, '#' at a token start raises a flag (comments are the
+//                 host reader's job, pcq_io.h);
 //   host          exclusive scan of the per-CTA token counts (a few MB), rows x cols from the totals;
-//   parse kernel  same partition; a CTA-wide exclusive scan numbers the tokens, each token start converts its token
-//                 with pcq_parse_decimal_fast (pcq_decimal.h — the very function the host library uses) and stores
-//                 out[token / cols][token % cols]; the first token of every line must have index = 0 (mod cols),
-//                 which together with tokens = rows * cols proves the table is rectangular;
+//   parse kernel  same partition, the CTA's text staged in shared memory; a CTA-wide exclusive scan numbers the
+//                 tokens, their starts go into one shared list and thread j takes tokens j, j + 256, ...: lexed by
+//                 text_convert_token, converted by pcq_decimal_to_double (pcq_decimal.h — the very function the host
+//                 library uses) and stored at out[token / cols][token % cols]; the first token of every line must
+//                 have index = 0 (mod cols), which together with tokens = rows * cols proves the table is rectangular;
 //   fix-up        the few tokens whose rounding one 64 x 128-bit product cannot decide (ties, subnormals, > 19
-//                 digits) are listed by the kernel, converted by libc's strtod on the host and scattered back.
+//                 digits) or that are not decimal literals (inf, nan, junk) are listed by the kernel, converted on
+//                 the host with numpy's acceptance rules (libc's strtod) and scattered back.
 //
 // Both kernels are byte streams over the file: algorithmic traffic = file bytes read once per kernel + 8 bytes
 // written per value; the roof is HBM bandwidth (in practice the host -> device copy of the text dominates).
