@@ -3,9 +3,10 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-Workload (config.workload): BASELINE config 2/"target" -- Hermite PCE, d=20, order 3
-(K=1771 terms), basis evaluation + least-squares fit; 1.25e6 synthetic Gaussian samples
-per GPU (10M at 8 GPUs), weak scaling over the sample axis.
+Workload (config.workload): BASELINE.json's metric configuration -- Hermite PCE, d=20, order 3
+(K=1771 terms), basis evaluation + least-squares fit on N = 10M synthetic Gaussian samples.
+STRONG scaling: the 10M samples are the whole job at every GPU count (N=1: all 10M on one GPU;
+N GPUs: 10M/N contiguous rows per rank).  `--samples-per-gpu R` switches to weak scaling (R rows per rank).
 
 A step = one pass of the hot path over the rank's sample block:
     fused basis-evaluation + Gram/A^T y statistics (K3, DMMA)  ->  one all-reduce of the
@@ -27,14 +28,41 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # the CPU reference arm uses every core this process may run on: torchrun exports OMP_NUM_THREADS=1, and OpenBLAS
+    # sizes its thread pool from the environment when numpy/scipy are first imported -- so fix it before that import
+    _cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "GOTO_NUM_THREADS"):
+        os.environ[_v] = str(_cores)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D, P, FAMILY = 20, 3, "HG"
-N_PER_GPU = 1_250_000
-WORKLOAD = "C2 Hermite PCE d=20 p=3 K=1771, basis eval + lstsq fit, 1.25e6 Gaussian samples per GPU (10M at 8 GPUs)"
+N_TOTAL = 10_000_000
+WORKLOAD = "C2/target: Hermite PCE d=20 p=3 K=1771, basis eval + lstsq fit on N=10M Gaussian samples (strong scaling over 1/2/4/8 GPUs)"
+
+
+def shard_rows(n_total, rank, world):
+    base, extra = divmod(int(n_total), int(world))
+    return base + (1 if rank < extra else 0)
+
+
+def make_config(args, world, K):
+    """The `config` object of the JSON line; identical for the B200 arm and the reference arm."""
+    if args.samples_per_gpu:
+        n_total, scaling = args.samples_per_gpu * world, "weak"
+        workload = WORKLOAD.replace("N=10M", f"N={args.samples_per_gpu}/GPU").replace("strong", "weak")
+    else:
+        n_total, scaling = args.samples, "strong"
+        workload = WORKLOAD if n_total == N_TOTAL else WORKLOAD.replace("N=10M", f"N={n_total}")
+    per_gpu = -(-n_total // world)
+    cfg = {"workload": workload, "samples": int(n_total), "terms": int(K), "dim": D, "order": P, "family": FAMILY,
+           "parallelism": f"sample-sharded x{world}, one all-reduce of the packed statistics",
+           "l2": "inputs (x,y = %.0f MB per GPU) larger than the 126 MB L2; no explicit flush" % (per_gpu * (D + 1) * 8 / 1e6)}
+    return cfg, n_total, scaling
 
 
 def parse():
@@ -43,10 +71,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--samples-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--samples", type=int, default=N_TOTAL, help="total samples of the job (strong scaling)")
+    ap.add_argument("--samples-per-gpu", type=int, default=0, help="rows per rank: weak scaling instead")
     ap.add_argument("--cpu-samples", type=int, default=20000,
-                    help="rows of the workload the CPU baseline is timed on")
+                    help="rows of the workload one step of the CPU reference arm is timed on")
+    ap.add_argument("--cpu-probe-samples", type=int, default=100000,
+                    help="rows of the single larger pass that checks the CPU path scales linearly (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip K1/K2/peak side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
 
 
@@ -102,17 +134,69 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_reference_pass(x, y, mi):
-    """One pass of the reference's algorithm on the host: evalBases (Python loop over K x s,
-    rv/pcrv.py:413-442) + lsq.fita (scipy gelsd, lreg/lreg.py:328-339)."""
-    from oracle import pc_oracle as orc
-    t0 = time.perf_counter()
-    A = orc.eval_bases(x, mi, FAMILY)
-    t1 = time.perf_counter()
-    cf = orc.lsq_fit(A, y)
-    t2 = time.perf_counter()
-    return cf, t1 - t0, t2 - t1
+# ----------------------------------------------------------------------------- CPU reference arm
+class CpuReference:
+    """The reference's own CPU implementation of the path, timed on the host cores.
+
+    kind "reference": the UNMODIFIED PyTUQ copied to oracle/_ref (oracle/Makefile; matplotlib stubbed), driven through
+    its public API exactly as surrogates/pce.py:378-383 does -- lsq().setBasisEvaluator(closure over
+    PCRV.evalBases) -> evalBases (rv/pcrv.py:413-442) + lsq.fita (scipy gelsd, lreg/lreg.py:328-339).
+    kind "port": the numpy oracle restating the same two functions, only when oracle/_ref is absent.
+    BLAS threads are set explicitly (threadpoolctl) to the cores this process may use, so that torchrun's
+    OMP_NUM_THREADS=1 cannot skew the lstsq timing; evalBases is single-threaded Python + numpy in the reference."""
+
+    def __init__(self):
+        from oracle import ref_loader
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        try:
+            from threadpoolctl import threadpool_limits
+            self._limits = threadpool_limits(limits=self.cores)
+        except Exception:
+            self._limits = None
+        if ref_loader.available():
+            R = ref_loader.import_reference()
+            self.kind = "reference"
+            self.mi = R["get_mi"](P, D)
+            self._pcrv = R["PCRV"](1, D, FAMILY, mi=self.mi)
+            self._lsq = R["lsq"]
+        else:
+            from oracle import pc_oracle as orc
+            self.kind = "port"
+            self.mi = orc.get_mi(P, D)
+            self._orc = orc
+        self.K = self.mi.shape[0]
+
+    def blas_threads(self):
+        try:
+            from threadpoolctl import threadpool_info
+            return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+        except Exception:
+            return self.cores
+
+    def bases(self, x):
+        if self.kind == "reference":
+            return self._pcrv.evalBases(x, 0)
+        return self._orc.eval_bases(x, self.mi, FAMILY)
+
+    def one_pass(self, x, y):
+        """evalBases + lsq.fita on (x, y); returns (cf, seconds of evalBases, seconds of the lstsq)."""
+        t0 = time.perf_counter()
+        A = self.bases(x)
+        t1 = time.perf_counter()
+        if self.kind == "reference":
+            fit = self._lsq()
+            fit.fita(A, y)
+            cf = fit.cf
+        else:
+            cf = self._orc.lsq_fit(A, y)
+        t2 = time.perf_counter()
+        return cf, t1 - t0, t2 - t1
+
+    def describe(self, n, tb, tf):
+        what = ("unmodified PyTUQ (oracle/_ref) PCRV.evalBases + lsq.fita" if self.kind == "reference"
+                else "oracle port (numpy restatement of PCRV.evalBases + lsq.fita)")
+        return (f"{what} on {n} rows of the workload: basis {tb:.2f} s (single-threaded Python/numpy loop), "
+                f"lstsq {tf:.2f} s ({self.blas_threads()} BLAS threads of {self.cores} usable cores)")
 
 
 def synth_host(n, seed, mi):
@@ -122,51 +206,65 @@ def synth_host(n, seed, mi):
     return rng, x, c_true
 
 
-def host_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count() or 1
+def cpu_probe(ref, x, y, sizes):
+    """Per-unit CPU throughput at several row counts (the reference's cost is linear in N: K*s length-N
+    multiplies + an O(N K^2) SVD least squares) -> {rows: {...}}."""
+    out = {}
+    for n in sizes:
+        if n <= 0 or n > x.shape[0]:
+            continue
+        _, tb, tf = ref.one_pass(x[:n], y[:n])
+        out[str(n)] = {"basis_s": tb, "lstsq_s": tf, "evals_per_s": n * ref.K / (tb + tf)}
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot
-    travel to the GPU box) on a bounded sample of the same workload, all host threads."""
+    """--impl reference: the reference's own CPU implementation (oracle/_ref; the oracle port only when that copy is
+    absent) on a bounded sample of the SAME workload per step, all usable host cores, the requested steps/warm-up.
+    `value` is per-unit throughput (basis evaluations per second); 10M rows would need a 141.7 GB design matrix and
+    hours of SVD, so the 10M figure is the linear extrapolation stated in `extrapolated_seconds_at_full_size`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pc_oracle as orc
-    mi = orc.get_mi(P, D)
-    K = mi.shape[0]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    ref = CpuReference()
+    mi, K = ref.mi, ref.K
+    config, n_total, scaling = make_config(args, max(world, args.gpus), K)
     n = args.cpu_samples
-    _, x, c_true = synth_host(n, 2, mi)
+    nmax = max(n, args.cpu_probe_samples)
+    _, x, c_true = synth_host(nmax, 2, mi)
     rng = np.random.default_rng(99)
-    A = orc.eval_bases(x, mi, FAMILY)               # untimed: only to synthesise the targets
-    yfull = A @ c_true + 1e-2 * rng.standard_normal(n)
-    del A
+    y = np.empty(nmax)
+    for r0 in range(0, nmax, 20000):                 # untimed: only to synthesise the targets
+        y[r0:r0 + 20000] = ref.bases(x[r0:r0 + 20000]) @ c_true
+    y += 1e-2 * rng.standard_normal(nmax)
     times = []
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
-    for it in range(warm + steps):
-        cf, tb, tf = cpu_reference_pass(x, yfull, mi)
-        if it >= warm:
+    t_begin = time.perf_counter()
+    for it in range(args.warmup + args.steps):
+        cf, tb, tf = ref.one_pass(x[:n], y[:n])
+        if it >= args.warmup:
             times.append((tb, tf))
     tb = float(np.mean([t[0] for t in times])); tf = float(np.mean([t[1] for t in times]))
     value = n * K / (tb + tf)
-    cores = host_threads()
+    probe = cpu_probe(ref, x, y, sorted({n // 2, args.cpu_probe_samples} - {0, n}))
+    probe[str(n)] = {"basis_s": tb, "lstsq_s": tf, "evals_per_s": value}
+    err = float(np.max(np.abs(cf - c_true)))
+    unit = "basis evals/s (samples*terms)"
     line = {
-        "impl": "reference", "metric": "pc_basis_evals_per_s", "value": value, "unit": "basis evals/s (samples*terms)",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * (tb + tf),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{n} rows of the workload per step"},
+        "impl": "reference", "metric": "pc_basis_evals_per_s", "value": value, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tb + tf),
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config,
         "fit_seconds": tf, "basis_seconds": tb,
-        "cpu_baseline": {"value": value, "unit": "basis evals/s (samples*terms)", "cores": cores, "kind": "port",
-                         "sample": f"oracle port of evalBases+lsq.fita on {n} rows (basis {tb:.2f}s single-threaded "
-                                   f"numpy loop, lstsq {tf:.2f}s on {cores} BLAS threads)"},
-        "e2e": {"value": value, "unit": "basis evals/s (samples*terms)", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
+        "max_abs_coef_error_vs_truth": err,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": ref.cores, "kind": ref.kind,
+                         "sample": ref.describe(n, tb, tf) + f"; {args.steps} timed steps after {args.warmup} warm-up",
+                         "blas_threads": ref.blas_threads(),
+                         "linearity": probe,
+                         "extrapolated_seconds_at_full_size": n_total * K / value},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t_begin,
     }
     print(json.dumps(line), flush=True)
 
@@ -204,7 +302,8 @@ def main():
 
     mi = get_mi(P, D)
     K = mi.shape[0]
-    n = args.samples_per_gpu
+    config, n_total, scaling = make_config(args, world, K)
+    n = args.samples_per_gpu if args.samples_per_gpu else shard_rows(n_total, rank, world)
     pc = PCRV(1, D, FAMILY, mi=mi)
     plan = pc._plan(mi, dev=local)
 
@@ -269,7 +368,7 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     elapsed, k3_mean_ms = float(tmax[0]), float(tmax[1])
     ms_per_step = 1e3 * elapsed / args.steps
-    total_evals = float(n) * world * K
+    total_evals = float(n_total) * K
     value = total_evals / (elapsed / args.steps)
     err = float(np.max(np.abs(cf - c_true.cpu().numpy())))
 
@@ -393,7 +492,8 @@ def main():
                 from pytuq_b200.utils import io as pio
                 with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmpd:
                     ftxt = os.path.join(tmpd, "x.txt")
-                    pio.savetxt(ftxt, xh)
+                    nt = min(n, 1_250_000)
+                    pio.savetxt(ftxt, xh[:nt])
                     nbytes = os.path.getsize(ftxt)
                     pio.loadtxt_device(ftxt, device=local)
                     tt = []
@@ -403,22 +503,30 @@ def main():
                         xd = pio.loadtxt_device(ftxt, device=local)
                         torch.cuda.synchronize()
                         tt.append(time.perf_counter() - t0)
-                    same = bool(torch.equal(xd, x))
+                    same = bool(torch.equal(xd, x[:nt]))
                     del xd
-                kernels["text_to_hbm"] = {"rows": n, "cols": D, "text_bytes": nbytes, "ms": 1e3 * min(tt),
-                                          "values_per_s": n * D / min(tt), "text_GBps": nbytes / min(tt) / 1e9,
+                kernels["text_to_hbm"] = {"rows": nt, "cols": D, "text_bytes": nbytes, "ms": 1e3 * min(tt),
+                                          "values_per_s": nt * D / min(tt), "text_GBps": nbytes / min(tt) / 1e9,
                                           "bit_identical_to_the_resident_samples": same, "bound": "host-to-device copy of the text",
                                           "api": "pytuq_b200.utils.io.loadtxt_device (pcq_text_open + pcq_text_parse_dev)"}
             except Exception as exc:                     # noqa: BLE001
                 kernels["text_to_hbm"] = {"error": repr(exc)}
     peak = peaks.get("fp64_dmma_tflops")
-    traffic = None
-    try:   # DRAM bytes per step of the dominant kernel, from the committed ncu capture of this workload
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_j_k3_traffic.json")))
-        if n == N_PER_GPU:
-            traffic = tj["dram_bytes_per_step_main_kernel"]
-    except Exception:
-        pass
+    # DRAM bytes per step of the dominant kernel: NOT a live counter -- the committed ncu capture of this very
+    # command (bytes per sample x this rank's samples; the SYRK works chunk by chunk, so its traffic is linear in N)
+    traffic, traffic_source = None, None
+    for fn in ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
+            per_sample = tj.get("dram_bytes_per_sample_main_kernel",
+                                tj["dram_bytes_per_step_main_kernel"] / tj.get("samples_per_step", 1_250_000))
+            traffic = per_sample * n
+            traffic_source = (f"committed ncu capture profiles/{fn} (dram__bytes_read.sum + dram__bytes_write.sum of the "
+                              f"pcq_syrk_kernel launches of one step: {per_sample:.0f} B per sample) x {n} samples; "
+                              "not measured in this run")
+            break
+        except Exception:
+            continue
     mp = {}
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -434,27 +542,35 @@ def main():
             if tag in kernels:
                 kernels[tag]["frac_of_fp64_peak"] = kernels[tag]["TFLOPs_algorithmic"] / peaks["fp64_dfma_tflops"]
 
-    # ---------------- CPU baseline on a bounded sample (rank 0, N=1 only)
+    # ---------------- CPU baseline on a bounded sample (rank 0, N=1 only): the reference itself (oracle/_ref)
     cpu = None
-    if world == 1:
-        from oracle import pc_oracle as orc
-        nc = args.cpu_samples
-        xc = xh[:nc]
-        yc = yh[:nc]
-        _, tb, tf = cpu_reference_pass(xc, yc, mi)
-        cores = host_threads()
-        cpu = {"value": nc * K / (tb + tf), "unit": "basis evals/s (samples*terms)", "cores": cores, "kind": "port",
-               "sample": f"oracle port (numpy restatement of PCRV.evalBases + lsq.fita) on the first {nc} rows: "
-                         f"basis {tb:.2f} s (single-threaded numpy loop), lstsq {tf:.2f} s ({cores} BLAS threads)",
-               "basis_evals_per_s": nc * K / tb, "fit_seconds": tf}
+    if world == 1 and not args.no_cpu:
+        ref = CpuReference()
+        nc = min(args.cpu_samples, n)
+        npr = min(args.cpu_probe_samples, n)
+        probe = cpu_probe(ref, xh, yh, sorted({nc, npr} - {0}))
+        big = probe[str(max(nc, npr))]
+        tb, tf = big["basis_s"], big["lstsq_s"]
+        cpu = {"value": big["evals_per_s"], "unit": "basis evals/s (samples*terms)", "cores": ref.cores, "kind": ref.kind,
+               "sample": ref.describe(max(nc, npr), tb, tf), "blas_threads": ref.blas_threads(),
+               "basis_evals_per_s": max(nc, npr) * K / tb, "fit_seconds": tf, "linearity": probe,
+               "extrapolated_seconds_at_full_size": n_total * K / big["evals_per_s"],
+               "max_abs_coef_diff_vs_gpu_on_the_same_rows": None}
+        try:      # same rows through the drop-in: the coefficient parity of the two arms, for the record
+            chk = lsq()
+            chk.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+            chk.fit(xh[:nc], yh[:nc])
+            cf_ref, _, _ = ref.one_pass(xh[:nc], yh[:nc])
+            cpu["max_abs_coef_diff_vs_gpu_on_the_same_rows"] = float(np.max(np.abs(chk.cf - cf_ref)))
+        except Exception as exc:                         # noqa: BLE001
+            cpu["max_abs_coef_diff_vs_gpu_on_the_same_rows"] = repr(exc)
 
     line = {
         "metric": "pc_basis_evals_per_s", "value": value, "unit": "basis evals/s (samples*terms)",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "samples_per_gpu": n, "terms": K, "dim": D, "order": P,
-                   "parallelism": f"sample-sharded x{world}, one all-reduce of the packed statistics",
-                   "l2": "inputs (x,y = %.0f MB per GPU) larger than the 126 MB L2; no explicit flush" % ((n * (D + 1) * 8) / 1e6)},
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config,
+        "samples_per_gpu": n,
         "fit_seconds": ms_per_step * 1e-3,
         "breakdown_ms": {"k3_suffstats": k3_mean_ms, "allreduce": float(np.mean(ar_ms)),
                          "solve_kxk": 1e3 * float(np.mean(solve_s))},
@@ -465,11 +581,10 @@ def main():
                                "profiles/r01_j_k3_traffic.json)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if peak else None, "traffic": traffic,
-                     "traffic_note": "DRAM read+write bytes of the 18 pcq_syrk_kernel launches of one step (ncu, "
-                                     "profiles/r01_j_k3_traffic.json): the packed design matrix (17.9 GB, written once by the "
-                                     "pack kernel) is read 1.4x by the off-diagonal pass and once by the diagonal pass; the "
-                                     "kernels are tensor-pipe bound (DMMA pipe 96.6 %% active in the off-diagonal pass), DRAM "
-                                     "runs at ~0.35 TB/s; algorithmic input bytes = %d" % (8 * n * (D + 1)),
+                     "traffic_source": traffic_source,
+                     "traffic_note": "the packed design-matrix chunk (written once by the pack kernel) is re-read by the SYRK "
+                                     "passes; the kernels are tensor-pipe bound, DRAM runs far below its peak; "
+                                     "algorithmic input bytes = %d" % (8 * n * (D + 1)),
                      "achieved_note": "algorithmic flops of one step / duration of the whole pcq_suffstats_dev call "
                                       "(pack + SYRK + fix-up + mirror launches), CUDA events on the launching stream",
                      "algorithmic_flops_per_launch": flops,

@@ -229,7 +229,7 @@ int pcq_plan_destroy(pcq_plan* p) {
     pcq_spec_free(p->spec[0].load());
     pcq_spec_free(p->spec[1].load());
     cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
-    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_q); cudaFree(p->d_gtab); cudaFree(p->d_achunk);
+    cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_q); cudaFree(p->d_gtab[0]); cudaFree(p->d_gtab[1]); cudaFree(p->d_achunk);
     for (int i = 0; i < 2; ++i) {
         cudaFree(p->d_stage[i]); cudaFree(p->d_out[i]);
         if (p->h_pin[i]) cudaFreeHost(p->h_pin[i]);
@@ -477,19 +477,22 @@ int pcq_eval_bases(pcq_plan* p, const double* x, int64_t n, int64_t ldx, double*
         for (auto& th : pool) th.join();
         return PCQ_OK;
     };
+    // an error in the middle of the pipeline must not leave copies / kernels in flight on buffers the next call may
+    // reallocate
+    auto quiesce = [&](int status) { cudaStreamSynchronize(p->streams[0]); cudaStreamSynchronize(p->streams[1]); return status; };
     int c = 0;
     int64_t prev_r0 = 0, prev_nr = 0;
     for (int64_t r0 = 0; r0 < n; r0 += rows, ++c) {
         const int b = c & 1;
         const int64_t nr = std::min(rows, n - r0);
         cudaStream_t st = p->streams[b];
-        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
-        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * K * 8)) != PCQ_OK) return rc;
-        if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
-        if ((rc = pcq_launch_bases(p, p->d_stage[b], nr, s, p->d_out[b], K, st)) != PCQ_OK) return rc;
+        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return quiesce(rc);
+        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * K * 8)) != PCQ_OK) return quiesce(rc);
+        if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return quiesce(rc);
+        if ((rc = pcq_launch_bases(p, p->d_stage[b], nr, s, p->d_out[b], K, st)) != PCQ_OK) return quiesce(rc);
         PCQ_CUDA(cudaMemcpyAsync(p->h_pin[b], p->d_out[b], (size_t)nr * K * 8, cudaMemcpyDeviceToHost, st));
         PCQ_CUDA(cudaEventRecord(p->events[b], st));
-        if (c >= 1 && (rc = drain(b ^ 1, prev_r0, prev_nr)) != PCQ_OK) return rc;
+        if (c >= 1 && (rc = drain(b ^ 1, prev_r0, prev_nr)) != PCQ_OK) return quiesce(rc);
         prev_r0 = r0; prev_nr = nr;
     }
     return drain((c - 1) & 1, prev_r0, prev_nr);
@@ -510,6 +513,7 @@ int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const doub
     PCQ_CUDA(cudaMemcpyAsync(p->d_misc, cf, (size_t)m * K * 8, cudaMemcpyHostToDevice, p->streams[0]));
     PCQ_CUDA(cudaEventRecord(p->events[0], p->streams[0]));
     PCQ_CUDA(cudaStreamWaitEvent(p->streams[1], p->events[0], 0));
+    auto quiesce = [&](int status) { cudaStreamSynchronize(p->streams[0]); cudaStreamSynchronize(p->streams[1]); return status; };
     const int mo = (mode & 2) ? 1 : m;          // output columns per sample
     const int64_t rows = chunk_rows((int64_t)(s + mo) * 8, n);
     int c = 0;
@@ -517,12 +521,12 @@ int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const doub
         const int b = c & 1;
         const int64_t nr = std::min(rows, n - r0);
         cudaStream_t st = p->streams[b];
-        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return rc;
-        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * mo * 8)) != PCQ_OK) return rc;
-        if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return rc;
+        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return quiesce(rc);
+        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * mo * 8)) != PCQ_OK) return quiesce(rc);
+        if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return quiesce(rc);
         if ((rc = evalpc_any(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], mo, mode, st)) != PCQ_OK)
-            return rc;
-        if ((rc = copy_rows(y + r0 * ldy, ldy, p->d_out[b], mo, mo, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return rc;
+            return quiesce(rc);
+        if ((rc = copy_rows(y + r0 * ldy, ldy, p->d_out[b], mo, mo, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return quiesce(rc);
     }
     PCQ_CUDA(cudaStreamSynchronize(p->streams[0]));
     PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));
@@ -622,9 +626,14 @@ int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const do
     const int s = p->sdim;
     const int64_t L = (int64_t)p->nterms + m + 1;
     if ((rc = pcq_ensure_dev(&p->d_misc, &p->misc_bytes, (size_t)L * L * 8)) != PCQ_OK) return rc;
-    // copies go on stream 1 / 0 alternately, all Gram launches are ordered on stream 0 through
-    // events (they accumulate into the same S)
+    // all H2D copies go on stream 1, all Gram launches on stream 0 (they accumulate into the same S); the two
+    // are ordered through events: copied[b] (stream 1 -> 0) and p->events[b] (buffer b consumed, stream 0 -> 1)
     cudaStream_t sk = p->streams[0];
+    struct EventPair {
+        cudaEvent_t e[2] = {nullptr, nullptr};
+        ~EventPair() { for (auto ev : e) if (ev) cudaEventDestroy(ev); }
+    } copied;
+    for (auto& ev : copied.e) PCQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     ScratchLease lease(p->device, sk);
     if (n == 0) {
         if ((rc = pcq_launch_gram(p, p->num_sms, p->smem_optin, nullptr, 0, s, nullptr, 0, 0, nullptr,
@@ -643,11 +652,8 @@ int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const do
         if (c >= 2) PCQ_CUDA(cudaStreamWaitEvent(sc, p->events[b], 0));
         if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, sc)) != PCQ_OK) return rc;
         if (m > 0 && (rc = copy_rows(p->d_out[b], m, y + r0 * ldy, ldy, m, nr, cudaMemcpyHostToDevice, sc)) != PCQ_OK) return rc;
-        cudaEvent_t copied;
-        PCQ_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
-        PCQ_CUDA(cudaEventRecord(copied, sc));
-        PCQ_CUDA(cudaStreamWaitEvent(sk, copied, 0));
-        PCQ_CUDA(cudaEventDestroy(copied));
+        PCQ_CUDA(cudaEventRecord(copied.e[b], sc));
+        PCQ_CUDA(cudaStreamWaitEvent(sk, copied.e[b], 0));
         if ((rc = pcq_launch_gram(p, p->num_sms, p->smem_optin, p->d_stage[b], nr, s, nullptr, 0, 0,
                                   p->d_out[b], std::max(m, 1), m, p->d_misc, c > 0, &p->d_ws,
                                   &p->ws_bytes, &lease.d.zp, &lease.d.zp_bytes, sk)) != PCQ_OK)

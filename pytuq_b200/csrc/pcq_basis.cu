@@ -282,16 +282,17 @@ bool pcq_table_fits_smem(const pcq_plan* p) {
 
 // slot tables of n samples in global scratch, [slot][nc]; returns the table through *tab
 int pcq_launch_gtab(pcq_plan* p, const double* x, int64_t n, int64_t ldx, int64_t nc, double** tab, cudaStream_t st) {
-    int rc = pcq_ensure_dev(&p->d_gtab, &p->gtab_bytes, (size_t)p->nslots * nc * sizeof(double));
+    const int b = (st == p->streams[1] && st != nullptr) ? 1 : 0;     // table owned by the launching plan stream
+    int rc = pcq_ensure_dev(&p->d_gtab[b], &p->gtab_bytes[b], (size_t)p->nslots * nc * sizeof(double));
     if (rc != PCQ_OK) return rc;
     BasesParams P;
     memset(&P, 0, sizeof(P));
     P.x = x; P.n = n; P.ldx = ldx; P.sdim = p->sdim; P.pmax = p->pmax; P.nslots = p->nslots;
     P.rec_a = p->d_rec_a; P.rec_b = p->d_rec_b; P.p1 = p->d_p1;
     const int64_t want = (n * p->sdim + 255) / 256, cap = (int64_t)p->num_sms * 8;
-    pcq_gtab_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, p->d_gtab, nc);
+    pcq_gtab_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, p->d_gtab[b], nc);
     PCQ_LAUNCH_CHECK("pcq_gtab_kernel");
-    *tab = p->d_gtab;
+    *tab = p->d_gtab[b];
     return PCQ_OK;
 }
 

@@ -51,8 +51,10 @@ struct pcq_plan {
     double* d_ws = nullptr;
     size_t ws_bytes = 0;
     // large germ dimension: slot tables of a sample chunk in global memory, and a design-matrix chunk
-    double* d_gtab = nullptr;
-    size_t gtab_bytes = 0;
+    // (one table per plan stream: the host-pointer entry points alternate their chunks between streams[0] and
+    //  streams[1], and the table of chunk c must survive while chunk c+1 is being tabulated on the other stream)
+    double* d_gtab[2] = {nullptr, nullptr};
+    size_t gtab_bytes[2] = {0, 0};
     double* d_achunk = nullptr;
     size_t achunk_bytes = 0;
     // packed upper-triangular operand of the quadratic-form kernel (lazily grown)

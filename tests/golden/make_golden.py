@@ -207,6 +207,51 @@ def c1_full(R):
           f"{t1 - t0:.2f} s, lsq.fita {t2 - t1:.2f} s, anl.fita {t3 - t2:.2f} s on {os.cpu_count()} cores")
 
 
+def c2_inputs(n=20_000):
+    """BASELINE.json configs[1] / SURVEY 8(d) C2 synthetic inputs at reduced N (seed = config number):
+    Hermite d=20 p=3 (K=1771), Gaussian germ samples, decaying true coefficients, 1e-2 noise."""
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((n, 20))
+    cdraw = rng.standard_normal(1771)
+    noise = 1e-2 * rng.standard_normal(n)
+    return x, cdraw, noise
+
+
+def c2_shape(R):
+    """The headline shape (HG d=20 p=3 K=1771) with the unmodified reference: evalBases, lsq.fita
+    (lreg/lreg.py:328-339) and anl.fita (lreg/anl.py:69-105) on 2e4 samples.  y is stored (it is built from the
+    reference's own design matrix); x is regenerated from the seed by the test."""
+    import time
+    x, cdraw, noise = c2_inputs()
+    n = x.shape[0]
+    mi = R["get_mi"](3, 20)
+    c_true = cdraw / (1.0 + mi.sum(axis=1)) ** 2
+    pc = R["PCRV"](1, 20, "HG", mi=mi)
+    t0 = time.perf_counter()
+    A = pc.evalBases(x, 0)
+    t1 = time.perf_counter()
+    y = np.zeros(n)
+    for k in range(mi.shape[0]):               # term by term: no BLAS in the target
+        y = y + c_true[k] * A[:, k]
+    y = y + noise
+    t1b = time.perf_counter()
+    f_lsq = R["lsq"]()
+    f_lsq.fita(A, y)
+    t2 = time.perf_counter()
+    f_anl = R["anl"]()
+    f_anl.fita(A, y)
+    t3 = time.perf_counter()
+    pc.setCfs([f_lsq.cf])
+    rows = np.array([0, 1, n - 1])
+    out = dict(y=y, rows=rows, A_rows=A[rows], c_true=c_true, cf_lsq=f_lsq.cf, cf_anl=f_anl.cf,
+               anl_datavar=np.array(f_anl.datavar), anl_cov_diag=np.diag(f_anl.cf_cov).copy(),
+               mean=pc.computeMean(), var=pc.computeVar(), main=pc.computeSens(), total=pc.computeTotSens(),
+               ref_seconds=np.array([t1 - t0, t2 - t1b, t3 - t2]), ref_cores=np.array(os.cpu_count()))
+    np.savez_compressed(os.path.join(HERE, "c2_shape.npz"), **out)
+    print(f"c2_shape.npz  {os.path.getsize(os.path.join(HERE, 'c2_shape.npz')) / 1024:.1f} KiB; reference: evalBases "
+          f"{t1 - t0:.2f} s, lsq.fita {t2 - t1b:.2f} s, anl.fita {t3 - t2:.2f} s on {os.cpu_count()} cores")
+
+
 def shape_inputs(config):
     """Reduced-N synthetic inputs at the shapes of BASELINE.json configs 3, 4, 5; only elementwise
     numpy arithmetic, so the test regenerates them bit for bit from the seeds.  Needs get_mi from the caller."""
@@ -295,6 +340,8 @@ def main():
         return illcond(R)
     if len(sys.argv) > 1 and sys.argv[1] == "klsurr":
         return klsurr(R)
+    if len(sys.argv) > 1 and sys.argv[1] == "c2":
+        return c2_shape(R)
     PCRV, PC1d, get_mi = R["PCRV"], R["PC1d"], R["get_mi"]
     out = {}
 
@@ -450,6 +497,7 @@ def main():
     klsurr(R)
     uqpc(R)
     c1_full(R)
+    c2_shape(R)
     config_shapes(R)
 
 

@@ -277,6 +277,31 @@ def test_wide_germ_takes_the_global_table_route():
     assert abs(res["var"][0] / pc.computeVar()[0] - 1) < 0.05
 
 
+def test_wide_germ_across_host_chunks_on_both_plan_streams():
+    """The global-table route when N spans several host chunks: the host-pointer entry points alternate their
+    chunks between the plan's two streams, so each stream needs its own slot-table scratch (round-1 advisor
+    finding: one shared table was overwritten by chunk c+1 while chunk c was still reading it).  Rows of every
+    chunk, the last ones included, against the oracle."""
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(92)
+    d = 1000
+    mi = orc.get_mi(1, d)
+    K = mi.shape[0]
+    n_pc, n_a = 70_000, 26_000                # evalPC: 33520-row chunks; evalBases: 8380-row chunks
+    x = rng.uniform(-1, 1, (n_pc, d))
+    cf = rng.standard_normal(K) / np.sqrt(K)
+    pc = PCRV(1, d, "LU", mi=mi, cfs=[cf])
+    for _ in range(2):                        # twice: the second call starts with warm buffers
+        A = pc.evalBases(x[:n_a], 0)
+        rows = np.unique(np.concatenate([np.arange(0, n_a, 1733), np.arange(8370, 8390), np.arange(n_a - 48, n_a)]))
+        assert np.array_equal(A[rows], orc.eval_bases(x[rows], mi, "LU", np.full(d, 1)))
+        del A
+        y = pc.evalPC(x)
+        rows = np.unique(np.concatenate([np.arange(0, n_pc, 4999), np.arange(33500, 33540), np.arange(67030, 67050),
+                                         np.arange(n_pc - 48, n_pc)]))
+        assert np.array_equal(y[rows], orc.eval_pc(x[rows], [mi], [cf], "LU", np.full(d, 1)))
+
+
 def test_k4_gram_of_materialised_matrix():
     from pytuq_b200.lreg.stats import SuffStats
     rng = np.random.default_rng(8)
@@ -1066,6 +1091,44 @@ def test_full_size_baseline_config_1_vs_reference():
     np.testing.assert_allclose(pc.computeTotSens(), g["total"], rtol=1e-10, atol=1e-13)
     # surrogate evaluation equals the design matrix times the coefficients (sequential vs BLAS order)
     np.testing.assert_allclose(pc.evalPC(x[:4096])[:, 0], A[:4096] @ fits["lsq"].cf, rtol=1e-12, atol=1e-13)
+
+
+def test_headline_shape_c2_fit_vs_reference():
+    """The headline shape — Hermite PCE d=20 p=3 (K=1771), lsq and anl — against the unmodified reference run on the
+    same 2e4 Gaussian samples (tests/golden/c2_shape.npz, make_golden.py:c2_shape; lreg/lreg.py:328-339,
+    lreg/anl.py:69-105).  Basis values bit-identical, coefficients and Sobol indices within 1e-10."""
+    from conftest import golden_generator
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import lsq, anl, PCBasisEvaluator
+    g = load_golden("c2_shape")
+    x, _, _ = golden_generator().c2_inputs()
+    y = g["y"]
+    mi = orc.get_mi(3, 20)
+    pc = PCRV(1, 20, "HG", mi=mi)
+    A = pc.evalBases(x, 0)
+    assert A.shape == (20_000, 1771) and np.array_equal(A[g["rows"]], g["A_rows"])
+    scale = np.max(np.abs(g["cf_lsq"]))
+    fits = {}
+    for name, make in (("lsq", lsq), ("anl", anl)):
+        fused = make()
+        fused.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+        fused.fit(x, y)                       # K3: statistics without a design matrix
+        plain = make()                        # the reference idiom: a plain closure as the evaluator
+        plain.setBasisEvaluator(lambda xx, pars: pars[0].evalBases(xx, 0), (pc,))
+        plain.fit(x, y)
+        given = make()
+        given.fita(A, y)                      # K4: statistics of the caller's matrix
+        for f in (fused, plain, given):
+            np.testing.assert_allclose(f.cf, g[f"cf_{name}"], rtol=0, atol=1e-10 * scale)
+            assert np.array_equal(f.used, np.arange(1771))
+        fits[name] = fused
+    np.testing.assert_allclose(fits["anl"].datavar, g["anl_datavar"], rtol=1e-9)
+    np.testing.assert_allclose(np.diag(fits["anl"].cf_cov), g["anl_cov_diag"], rtol=1e-8)
+    pc.setCfs([fits["lsq"].cf])
+    np.testing.assert_allclose(pc.computeMean(), g["mean"], rtol=1e-10)
+    np.testing.assert_allclose(pc.computeVar(), g["var"], rtol=1e-10)
+    np.testing.assert_allclose(pc.computeSens(), g["main"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(pc.computeTotSens(), g["total"], rtol=1e-10, atol=1e-13)
 
 
 def test_shapes_of_baseline_configs_3_4_5_vs_reference():

@@ -167,6 +167,31 @@ def test_oracle_at_full_size_baseline_config_1():
     np.testing.assert_allclose(orc.sobol_total(mi, g["cf_lsq"], "LU"), g["total"][0], rtol=1e-12, atol=1e-15)
 
 
+def test_oracle_at_the_headline_shape_c2():
+    """BASELINE.json configs[1] shape (HG d=20 p=3 K=1771, lsq + anl on 2e4 Gaussian samples): the oracle against
+    the unmodified reference (tests/golden/c2_shape.npz, make_golden.py:c2_shape)."""
+    from conftest import golden_generator
+    g = load_golden("c2_shape")
+    x, cdraw, noise = golden_generator().c2_inputs()
+    mi = orc.get_mi(3, 20)
+    assert mi.shape == (1771, 20)
+    np.testing.assert_array_equal(g["c_true"], cdraw / (1.0 + mi.sum(axis=1)) ** 2)
+    A = orc.eval_bases(x, mi, "HG")
+    assert np.array_equal(A[g["rows"]], g["A_rows"])
+    y = np.zeros(x.shape[0])
+    for k in range(mi.shape[0]):
+        y = y + g["c_true"][k] * A[:, k]
+    assert np.array_equal(y + noise, g["y"])
+    scale = np.max(np.abs(g["cf_lsq"]))
+    np.testing.assert_allclose(orc.lsq_fit(A, g["y"]), g["cf_lsq"], rtol=0, atol=1e-12 * scale)
+    cf, cov, sig = orc.anl_fit(A, g["y"])
+    np.testing.assert_allclose(cf, g["cf_anl"], rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(sig, g["anl_datavar"], rtol=1e-11)
+    np.testing.assert_allclose(np.diag(cov), g["anl_cov_diag"], rtol=1e-10)
+    np.testing.assert_allclose(orc.sobol_main(mi, g["cf_lsq"], "HG"), g["main"][0], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(orc.sobol_total(mi, g["cf_lsq"], "HG"), g["total"][0], rtol=1e-12, atol=1e-15)
+
+
 def test_oracle_at_the_shapes_of_baseline_configs_3_4_5():
     """Oracle vs the unmodified reference at the (d, p, K) of BASELINE.json configs 3, 4, 5 with reduced sample
     counts (tests/golden/c{3,4,5}_shape.npz, make_golden.py:config_shapes).  C5's 25000 x 5456 design matrix is
