@@ -155,6 +155,21 @@ int pcq_quadform_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx
 int pcq_quadform(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
                  const double* c_host, int64_t ldc, double* v_host, int64_t ldv);
 
+/* ---- the same forms on a design matrix handed over by the caller (no plan) ---------------------------------
+ * lreg.predicta(Amat, msc) / compute_stdev(Amat) / predicta_samples(Amat) (lreg/lreg.py:112-198; the call pattern of
+ * apps/uqpc/uq_pc.py:313-315), where the reference forms Amat @ cf and || Amat chol(cf_cov) ||_row with numpy:
+ *   y (n x m, ldy)  = A (n x kcols, lda) CF^T,  CF m x kcols (ldcf)        skipped when m == 0
+ *   v[i * ldv]      = a_i^T C a_i,  C kcols x kcols symmetric (ldc; upper triangle read)   skipped when c == NULL
+ * Few vectors (m < 48, e.g. the mean) are HBM-bound row dot products; many vectors (predictive samples, the two
+ * GEMMs of msc = 2) and the quadratic form run on the FP64 tensor pipe through K6's kernels, the matrix chunk packed
+ * by pcq_qf_pack_matrix_kernel. */
+int pcq_matrix_forms_dev(int device, const double* a_dev, int64_t n, int64_t lda, int kcols,
+                         const double* cf_dev, int64_t ldcf, int m, double* y_dev, int64_t ldy,
+                         const double* c_dev, int64_t ldc, double* v_dev, int64_t ldv, void* stream);
+int pcq_matrix_forms(int device, const double* a_host, int64_t n, int64_t lda, int kcols,
+                     const double* cf_host, int64_t ldcf, int m, double* y_host, int64_t ldy,
+                     const double* c_host, int64_t ldc, double* v_host, int64_t ldv);
+
 /* Residual pass of one output: with r_n = y_n - sum_k cf[k] Psi_k(x_n) (surrogate through K2, fast mode),
  *   sums_dev[0] (+)= sum_n r_n^2      bcs_fit's final noise estimate, lreg/bcs.py:229
  *   sums_dev[1] (+)= sum_n y_n r_n    anl._compute_sigmahatsq, lreg/anl.py:61

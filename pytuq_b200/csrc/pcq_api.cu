@@ -386,7 +386,9 @@ namespace {
 // K4 has no plan: keep one workspace per device
 struct GramCtx { double* ws = nullptr; size_t ws_bytes = 0; double* stage[2] = {nullptr, nullptr};
                  size_t stage_bytes[2] = {0, 0}; double* s = nullptr; size_t s_bytes = 0;
-                 double* ys[2] = {nullptr, nullptr}; size_t ys_bytes[2] = {0, 0}; };
+                 double* ys[2] = {nullptr, nullptr}; size_t ys_bytes[2] = {0, 0};
+                 double* bq = nullptr; size_t bq_bytes = 0;        // packed B operand of the matrix forms
+                 double* out = nullptr; size_t out_bytes = 0; };   // results of the host-pointer matrix forms
 GramCtx g_gram_ctx[64];
 }
 
@@ -406,6 +408,69 @@ int pcq_gram_dev(int device, const double* a, int64_t n, int64_t lda, int kcols,
     ScratchLease lease(device, (cudaStream_t)stream);     // also guards the per-device K4 workspace
     return pcq_launch_gram(nullptr, num_sms, smem_optin, nullptr, n, 0, a, lda, kcols, y, ldy, m, s,
                            accumulate, &c.ws, &c.ws_bytes, &lease.d.zp, &lease.d.zp_bytes, (cudaStream_t)stream);
+}
+
+int pcq_matrix_forms_dev(int device, const double* a, int64_t n, int64_t lda, int kcols, const double* cf, int64_t ldcf,
+                         int m, double* y, int64_t ldy, const double* c, int64_t ldc, double* v, int64_t ldv,
+                         void* stream) {
+    if (device < 0 || device >= 64 || n < 0 || kcols <= 0 || m < 0 || lda < kcols || (n > 0 && !a) ||
+        (m > 0 && (!cf || !y || ldcf < kcols || ldy < m)) || (c && (!v || ldc < kcols || ldv < 1))) {
+        pcq_set_error("matrix_forms: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    if (n == 0) return PCQ_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) { pcq_set_error("matrix_forms: cudaSetDevice(%d) failed", device); return PCQ_ERR_NODEV; }
+    int num_sms = 0; size_t smem_optin = 0;
+    int rc = device_props(device, &num_sms, &smem_optin);
+    if (rc != PCQ_OK) return rc;
+    GramCtx& g = g_gram_ctx[device];
+    ScratchLease lease(device, (cudaStream_t)stream);     // also guards the per-device workspace
+    if (m > 0 && (rc = pcq_launch_linforms_matrix(num_sms, smem_optin, a, n, lda, kcols, cf, ldcf, m, y, ldy, &g.bq,
+                                                  &g.bq_bytes, &lease.d.zp, &lease.d.zp_bytes, (cudaStream_t)stream)) != PCQ_OK)
+        return rc;
+    if (c && (rc = pcq_launch_qform_matrix(num_sms, smem_optin, a, n, lda, kcols, c, ldc, v, ldv, &g.bq, &g.bq_bytes, &g.ws,
+                                           &g.ws_bytes, &lease.d.zp, &lease.d.zp_bytes, (cudaStream_t)stream)) != PCQ_OK)
+        return rc;
+    return PCQ_OK;
+}
+
+int pcq_matrix_forms(int device, const double* a, int64_t n, int64_t lda, int kcols, const double* cf, int64_t ldcf, int m,
+                     double* y, int64_t ldy, const double* c, int64_t ldc, double* v, int64_t ldv) {
+    if (device < 0 || device >= 64 || n < 0 || kcols <= 0 || m < 0 || lda < kcols || (n > 0 && !a) ||
+        (m > 0 && (!cf || !y || ldcf < kcols || ldy < m)) || (c && (!v || ldc < kcols || ldv < 1))) {
+        pcq_set_error("matrix_forms: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    if (n == 0) return PCQ_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) { pcq_set_error("matrix_forms: cudaSetDevice(%d) failed", device); return PCQ_ERR_NODEV; }
+    GramCtx& g = g_gram_ctx[device];
+    const int K = kcols;
+    int rc;
+    // operands: CF (m x K) and C (K x K) into the per-device S scratch; A chunk by chunk through the K4 staging buffer
+    const size_t opnd = ((size_t)m * K + (c ? (size_t)K * K : 0)) * 8;
+    if ((rc = pcq_ensure_dev(&g.s, &g.s_bytes, opnd ? opnd : 8)) != PCQ_OK) return rc;
+    double* d_cf = g.s;
+    double* d_c = g.s + (size_t)m * K;
+    if (m > 0) PCQ_CUDA(cudaMemcpy2D(d_cf, (size_t)K * 8, cf, (size_t)ldcf * 8, (size_t)K * 8, (size_t)m, cudaMemcpyHostToDevice));
+    if (c) PCQ_CUDA(cudaMemcpy2D(d_c, (size_t)K * 8, c, (size_t)ldc * 8, (size_t)K * 8, (size_t)K, cudaMemcpyHostToDevice));
+    const int64_t rows = chunk_rows((int64_t)(K + m + 1) * 8, n);
+    if ((rc = pcq_ensure_dev(&g.stage[0], &g.stage_bytes[0], (size_t)rows * K * 8)) != PCQ_OK) return rc;
+    if ((rc = pcq_ensure_dev(&g.out, &g.out_bytes, (size_t)rows * (m + 1) * 8)) != PCQ_OK) return rc;
+    double* d_y = g.out;
+    double* d_v = g.out + (size_t)rows * m;
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t nr = std::min(rows, n - r0);
+        PCQ_CUDA(cudaMemcpy2D(g.stage[0], (size_t)K * 8, a + r0 * lda, (size_t)lda * 8, (size_t)K * 8, (size_t)nr,
+                              cudaMemcpyHostToDevice));
+        if ((rc = pcq_matrix_forms_dev(device, g.stage[0], nr, K, K, m ? d_cf : nullptr, K, m, d_y, std::max(m, 1),
+                                       c ? d_c : nullptr, K, d_v, 1, nullptr)) != PCQ_OK)
+            return rc;
+        if (m > 0) PCQ_CUDA(cudaMemcpy2D(y + r0 * ldy, (size_t)ldy * 8, d_y, (size_t)m * 8, (size_t)m * 8, (size_t)nr, cudaMemcpyDeviceToHost));
+        if (c) PCQ_CUDA(cudaMemcpy2D(v + r0 * ldv, (size_t)ldv * 8, d_v, 8, 8, (size_t)nr, cudaMemcpyDeviceToHost));
+    }
+    return PCQ_OK;
 }
 
 int pcq_propagate_dev(pcq_plan* p, uint64_t seed, int64_t first_index, int64_t n,

@@ -126,6 +126,13 @@ int pcq_launch_qform(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const
                      int64_t ldv, double** bq, size_t* bq_bytes, double** ws, size_t* ws_bytes, double** zbuf,
                      size_t* zbuf_bytes, cudaStream_t st);
 bool pcq_linforms_applicable(const pcq_plan* p, int m);
+// the same contractions on a caller-supplied design matrix (no plan)
+int pcq_launch_qform_matrix(int num_sms, size_t smem_optin, const double* a, int64_t n, int64_t lda, int K, const double* c,
+                            int64_t ldc, double* v, int64_t ldv, double** bq, size_t* bq_bytes, double** ws,
+                            size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st);
+int pcq_launch_linforms_matrix(int num_sms, size_t smem_optin, const double* a, int64_t n, int64_t lda, int K,
+                               const double* cf, int64_t ldcf, int m, double* y, int64_t ldy, double** bq, size_t* bq_bytes,
+                               double** zbuf, size_t* zbuf_bytes, cudaStream_t st);
 int pcq_launch_linforms(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m, double* y,
                         int64_t ldy, double** bq, size_t* bq_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st);
 int pcq_launch_residual(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy,

@@ -112,6 +112,57 @@ __global__ void __launch_bounds__(256) pcq_lf_pack_cf_kernel(const double* __res
     }
 }
 
+
+// Caller-supplied design matrix A (n x K row-major, leading dimension lda, any alignment) -> Zq[i-block][sample (Nc)][8
+// terms], zero outside n x K.  Thread = (sample, term pair): a warp reads 512 contiguous bytes of a row and writes
+// eight 64-byte runs -- whole sectors both ways.
+__global__ void __launch_bounds__(256) pcq_qf_pack_matrix_kernel(const double* __restrict__ a, int64_t lda, int64_t n, int K,
+                                                                 int Kp, int64_t Nc, double* __restrict__ zq) {
+    const int pairs = Kp / 2;
+    const int64_t total = Nc * pairs;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / pairs;
+        const int j = (int)(e - row * pairs);
+        const int t0 = 2 * j;
+        double v0 = 0.0, v1 = 0.0;
+        if (row < n) {
+            if (t0 < K) v0 = __ldcs(a + row * lda + t0);
+            if (t0 + 1 < K) v1 = __ldcs(a + row * lda + t0 + 1);
+        }
+        const int ib = t0 >> 3, q = (t0 & 7) >> 1;
+        *reinterpret_cast<double2*>(zq + ((size_t)ib * Nc + row) * 8 + 2 * q) = make_double2(v0, v1);
+    }
+}
+
+// Y[i][j] = sum_k A[i][k] cf[j][k] for a FEW coefficient vectors (m <= 8 per pass): one warp per row, the row read
+// once with coalesced loads (HBM bound), fixed summation order (lane-strided partial sums, then a shuffle tree).
+template <int MB>
+__global__ void __launch_bounds__(256) pcq_matvec_rows_kernel(const double* __restrict__ a, int64_t lda, int64_t n, int K,
+                                                              const double* __restrict__ cf, int64_t ldcf, int m0, int m,
+                                                              double* __restrict__ y, int64_t ldy) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp; row < n; row += nwarps) {
+        double acc[MB];
+#pragma unroll
+        for (int j = 0; j < MB; ++j) acc[j] = 0.0;
+        for (int k = lane; k < K; k += 32) {
+            const double v = __ldcs(a + row * lda + k);
+#pragma unroll
+            for (int j = 0; j < MB; ++j)
+                if (m0 + j < m) acc[j] = fma(v, __ldg(cf + (size_t)(m0 + j) * ldcf + k), acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < MB; ++j) {
+            double t = acc[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0 && m0 + j < m) y[row * ldy + m0 + j] = t;
+        }
+    }
+}
+
 // LF = false: quadratic forms (triangular U, row-wise product epilogue).
 // LF = true:  linear forms Y = Psi C^T for many coefficient vectors (evalPC fast mode with M >= 64 outputs): same
 //             pipeline, every unit contracts all Kp terms and the epilogue stores the 128 x 128 tile of Y.
@@ -380,6 +431,102 @@ int pcq_launch_linforms(pcq_plan* p, const double* x, int64_t n, int64_t ldx, co
         Q.zq = *zbuf; Q.bq = *bq; Q.Nc = Nc; Q.Kp = Kp; Q.nJ = nJ; Q.ldb = Mp; Q.units = (Nc / 128) * nJ;
         Q.y = y + r0 * ldy; Q.ldy = ldy; Q.n = nr; Q.m = m;
         const int grid = (int)(Q.units < p->num_sms ? Q.units : p->num_sms);
+        pcq_qform_kernel<true><<<grid, SY_THREADS, smem, st>>>(Q);
+        PCQ_LAUNCH_CHECK("pcq_qform_kernel");
+    }
+    return PCQ_OK;
+}
+
+// ---- the same two contractions for a design matrix handed over by the caller (lreg.predicta / compute_stdev /
+// predicta_samples on Amat, lreg/lreg.py:112-198; apps/uqpc/uq_pc.py:313-315): no plan, A row-major in HBM.
+
+// v[i * ldv] = a_i^T C a_i
+int pcq_launch_qform_matrix(int num_sms, size_t smem_optin, const double* a, int64_t n, int64_t lda, int K, const double* c,
+                            int64_t ldc, double* v, int64_t ldv, double** bq, size_t* bq_bytes, double** ws,
+                            size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st) {
+    if (n == 0) return PCQ_OK;
+    const int Kp = (K + 127) / 128 * 128;
+    const int nJ = Kp / 128;
+    const size_t smem = syrk_smem_bytes(128);
+    if (smem > smem_optin) { pcq_set_error("quadform_matrix: pipeline does not fit in shared memory"); return PCQ_ERR_UNSUPPORTED; }
+    int rc = pcq_ensure_dev(bq, bq_bytes, (size_t)Kp * Kp * sizeof(double));
+    if (rc != PCQ_OK) return rc;
+    pcq_qf_pack_c_kernel<<<num_sms * 8, 256, 0, st>>>(c, ldc, K, Kp, *bq);
+    PCQ_LAUNCH_CHECK("pcq_qf_pack_c_kernel");
+    const char* env = getenv("PCQ_SYRK_CHUNK_MB");
+    const int64_t target = (int64_t)(env ? atoi(env) : 2048) << 20;
+    int64_t rows = (target / ((int64_t)Kp * 8)) / 128 * 128;
+    if (rows < 128) rows = 128;
+    const int64_t npad = (n + 127) / 128 * 128;
+    if (rows > npad) rows = npad;
+    if ((rc = pcq_ensure_dev(zbuf, zbuf_bytes, (size_t)rows * Kp * sizeof(double))) != PCQ_OK) return rc;
+    if ((rc = pcq_ensure_dev(ws, ws_bytes, (size_t)nJ * rows * sizeof(double))) != PCQ_OK) return rc;
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_qform_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t cap = (int64_t)num_sms * 8;
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t nr = (n - r0 < rows) ? n - r0 : rows;
+        const int64_t Nc = (nr + 127) / 128 * 128;
+        const int64_t wantp = (Nc * (Kp / 2) + 255) / 256;
+        pcq_qf_pack_matrix_kernel<<<(int)(wantp < cap * 4 ? wantp : cap * 4), 256, 0, st>>>(a + r0 * lda, lda, nr, K, Kp, Nc, *zbuf);
+        PCQ_LAUNCH_CHECK("pcq_qf_pack_matrix_kernel");
+        QformParams Q;
+        memset(&Q, 0, sizeof(Q));
+        Q.zq = *zbuf; Q.bq = *bq; Q.Nc = Nc; Q.Kp = Kp; Q.nJ = nJ; Q.ldb = Kp; Q.units = (Nc / 128) * nJ; Q.part = *ws;
+        const int grid = (int)(Q.units < num_sms ? Q.units : num_sms);
+        pcq_qform_kernel<false><<<grid, SY_THREADS, smem, st>>>(Q);
+        PCQ_LAUNCH_CHECK("pcq_qform_kernel");
+        const int64_t want = (nr + 255) / 256;
+        pcq_qf_reduce_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(*ws, Nc, nJ, nr, v + r0 * ldv, ldv);
+        PCQ_LAUNCH_CHECK("pcq_qf_reduce_kernel");
+    }
+    return PCQ_OK;
+}
+
+// Y (n x m, ldy) = A (n x K, lda) CF^T, CF m x K with leading dimension ldcf
+int pcq_launch_linforms_matrix(int num_sms, size_t smem_optin, const double* a, int64_t n, int64_t lda, int K,
+                               const double* cf, int64_t ldcf, int m, double* y, int64_t ldy, double** bq, size_t* bq_bytes,
+                               double** zbuf, size_t* zbuf_bytes, cudaStream_t st) {
+    if (n == 0 || m == 0) return PCQ_OK;
+    const int64_t cap = (int64_t)num_sms * 8;
+    const size_t smem = syrk_smem_bytes(128);
+    if (m < 48 || smem > smem_optin || ldcf != K) {
+        // few vectors (the mean of predicta: m = 1): HBM-bound row dot products, eight vectors per pass over A
+        const int64_t want = (n * 32 + 255) / 256;
+        const int grid = (int)(want < cap ? want : cap);
+        for (int m0 = 0; m0 < m; m0 += 8) {
+            const int mb = m - m0;
+            if (mb == 1) pcq_matvec_rows_kernel<1><<<grid, 256, 0, st>>>(a, lda, n, K, cf, ldcf, m0, m, y, ldy);
+            else if (mb <= 4) pcq_matvec_rows_kernel<4><<<grid, 256, 0, st>>>(a, lda, n, K, cf, ldcf, m0, m, y, ldy);
+            else pcq_matvec_rows_kernel<8><<<grid, 256, 0, st>>>(a, lda, n, K, cf, ldcf, m0, m, y, ldy);
+            PCQ_LAUNCH_CHECK("pcq_matvec_rows_kernel");
+        }
+        return PCQ_OK;
+    }
+    const int Kp = (K + 127) / 128 * 128, Mp = (m + 127) / 128 * 128;
+    const int nJ = Mp / 128;
+    int rc = pcq_ensure_dev(bq, bq_bytes, (size_t)Kp * Mp * sizeof(double));
+    if (rc != PCQ_OK) return rc;
+    pcq_lf_pack_cf_kernel<<<num_sms * 4, 256, 0, st>>>(cf, K, m, Kp, Mp, *bq);
+    PCQ_LAUNCH_CHECK("pcq_lf_pack_cf_kernel");
+    const char* env = getenv("PCQ_SYRK_CHUNK_MB");
+    const int64_t target = (int64_t)(env ? atoi(env) : 2048) << 20;
+    int64_t rows = (target / ((int64_t)Kp * 8)) / 128 * 128;
+    if (rows < 128) rows = 128;
+    const int64_t npad = (n + 127) / 128 * 128;
+    if (rows > npad) rows = npad;
+    if ((rc = pcq_ensure_dev(zbuf, zbuf_bytes, (size_t)rows * Kp * sizeof(double))) != PCQ_OK) return rc;
+    PCQ_CUDA(cudaFuncSetAttribute(pcq_qform_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t nr = (n - r0 < rows) ? n - r0 : rows;
+        const int64_t Nc = (nr + 127) / 128 * 128;
+        const int64_t wantp = (Nc * (Kp / 2) + 255) / 256;
+        pcq_qf_pack_matrix_kernel<<<(int)(wantp < cap * 4 ? wantp : cap * 4), 256, 0, st>>>(a + r0 * lda, lda, nr, K, Kp, Nc, *zbuf);
+        PCQ_LAUNCH_CHECK("pcq_qf_pack_matrix_kernel");
+        QformParams Q;
+        memset(&Q, 0, sizeof(Q));
+        Q.zq = *zbuf; Q.bq = *bq; Q.Nc = Nc; Q.Kp = Kp; Q.nJ = nJ; Q.ldb = Mp; Q.units = (Nc / 128) * nJ;
+        Q.y = y + r0 * ldy; Q.ldy = ldy; Q.n = nr; Q.m = m;
+        const int grid = (int)(Q.units < num_sms ? Q.units : num_sms);
         pcq_qform_kernel<true><<<grid, SY_THREADS, smem, st>>>(Q);
         PCQ_LAUNCH_CHECK("pcq_qform_kernel");
     }

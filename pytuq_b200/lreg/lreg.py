@@ -106,6 +106,38 @@ class lreg(fitbase):
         self.basisEval = basiseval
         self.basisEvalPars = basisevalpars
         self.basisEvaluatorSet = True
+        self._route = None
+
+    def _pc_route(self):
+        """(pcrv, jdim) when the basis evaluator is a PC design-matrix evaluator, else None.  Recognised are
+        PCBasisEvaluator and the reference idiom -- any callable (a plain function, the closure of
+        surrogates/pce.py:378-382, examples/ex_lreg_basiseval.py:55) whose ``pars[0]`` is a PCRV and whose result on
+        two probe points is bit-identical to ``pars[0].evalBases(x, j)`` for some output dimension j.  The probe is
+        repeated when the evaluator, the PCRV object or its number of terms changes."""
+        from ..rv.pcrv import PCRV
+        if isinstance(self.basisEval, PCBasisEvaluator):
+            return self.basisEvalPars[0], self.basisEval.jdim
+        pars = self.basisEvalPars
+        if not isinstance(pars, (tuple, list)) or len(pars) < 1 or not isinstance(pars[0], PCRV):
+            return None
+        pcrv = pars[0]
+        key = (id(self.basisEval), id(pcrv), tuple(m.shape[0] for m in pcrv.mindices))
+        cached = getattr(self, "_route", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        route = None
+        try:
+            xp = np.array([[0.3 + 0.05 * np.sin(1.0 + i) for i in range(pcrv.sdim)],
+                           [-0.45 + 0.07 * np.cos(2.0 + 3.0 * i) for i in range(pcrv.sdim)]])
+            out = np.asarray(self.basisEval(xp, pars))
+            for j in range(pcrv.pdim):
+                if out.shape == (2, pcrv.mindices[j].shape[0]) and np.array_equal(out, pcrv.evalBases(xp, j)):
+                    route = (pcrv, j)
+                    break
+        except Exception:
+            route = None
+        self._route = (key, route)
+        return route
 
     # -- fitting ------------------------------------------------------------------------
     def _fit_stats(self, stats):
@@ -119,8 +151,9 @@ class lreg(fitbase):
     def fit(self, x, y):
         r"""Fit with (x, y) pairs through the basis evaluator (lreg/lreg.py:62-71)."""
         assert(self.basisEvaluatorSet)
-        if isinstance(self.basisEval, PCBasisEvaluator):
-            stats = SuffStats.from_pc(self.basisEvalPars[0], x, y, self.basisEval.jdim)
+        route = self._pc_route()
+        if route is not None:
+            stats = SuffStats.from_pc(route[0], x, y, route[1])
             self._fit_stats(stats)
         else:
             Amat = self.basisEval(x, self.basisEvalPars)
@@ -149,9 +182,10 @@ class lreg(fitbase):
         quadratic form psi^T cf_cov psi -- on the tensor pipe (K6) for dense covariances with enough work,
         else as || Psi(x_n) F ||^2, cf_cov = F F^T, through K2's quadratic-form mode."""
         assert(self.basisEvaluatorSet)
-        if isinstance(self.basisEval, PCBasisEvaluator) and msc in (0, 1):
+        route = self._pc_route()
+        if route is not None and msc in (0, 1):
             assert(self.fitted)
-            pcrv, jdim = self.basisEvalPars[0], self.basisEval.jdim
+            pcrv, jdim = route
             if pcrv.mindices[jdim].shape[0] == self.cf.shape[0]:
                 ypred = pcrv.evalLinearForms(x, self.cf[None, :], jdim)[:, 0]
                 if msc == 0:
@@ -177,51 +211,82 @@ class lreg(fitbase):
         return self.predicta(Amat, msc=msc, pp=pp)
 
     def predict_samples(self, x, nsamples=100):
+        r"""Predictive samples at x (lreg/lreg.py:96-110).  With a PC basis evaluator the coefficient draws (numpy's
+        global stream, as in the reference) are pushed through evalPC's many-output mode: no design matrix."""
         assert(self.basisEvaluatorSet)
+        route = self._pc_route()
+        if route is not None and self.fitted and route[0].mindices[route[1]].shape[0] == self.cf.shape[0]:
+            assert(self.cf_cov is not None)
+            draws = np.random.multivariate_normal(self.cf, self.cf_cov, nsamples)
+            return route[0].evalLinearForms(x, draws, route[1], exact=False)
         Amat = self.basisEval(x, self.basisEvalPars)
         return self.predicta_samples(Amat, nsamples=nsamples)
 
     def predicta(self, Amat, msc=0, pp=False):
-        r"""(mean, variance | None, covariance | None) for an evaluated basis (lreg/lreg.py:112-143)."""
+        r"""(mean, variance | None, covariance | None) for an evaluated basis (lreg/lreg.py:112-143).  The matrix is
+        contracted on the device (``forms.matrix_forms``): mean = HBM-bound row dot products, variance = quadratic
+        form on the tensor pipe (K6 on the packed matrix), msc=2 = two linear-forms GEMMs."""
+        from .forms import matrix_forms, psd_part
+        from .. import device as _device
         assert(self.fitted)
-        ypred = Amat @ self.cf
-        ypred_var = ypred_cov = None
-        if msc == 2:
-            ypred_cov = (Amat @ self.cf_cov) @ Amat.T + int(pp) * self.datavar * np.eye(Amat.shape[0])
-            ypred_var = np.diag(ypred_cov)
-        elif msc == 1:
-            try:
-                ypred_var = self.compute_stdev(Amat, method='chol') ** 2
-            except np.linalg.LinAlgError:
-                ypred_var = self.compute_stdev(Amat, method='svd') ** 2
-            ypred_var += int(pp) * self.datavar
-        elif msc != 0:
+        _device.require_device()
+        if msc not in (0, 1, 2):
             print(f"msc={msc}, but needs to be 0,1, or 2. Exiting.")
             sys.exit()
+        ypred_var = ypred_cov = None
+        N = Amat.shape[0]
+        if msc == 1:
+            assert(self.cf_cov is not None)
+            if not np.any(self.cf_cov):
+                ypred = matrix_forms(Amat, self.cf[None, :])[0][:, 0]
+                ypred_var = np.zeros(N)
+            else:
+                Y, v = matrix_forms(Amat, self.cf[None, :], psd_part(self.cf_cov)[0])
+                ypred, ypred_var = Y[:, 0], np.maximum(v, 0.0)
+            ypred_var += int(pp) * self.datavar
+        else:
+            ypred = matrix_forms(Amat, self.cf[None, :])[0][:, 0]
+            if msc == 2:
+                T = matrix_forms(Amat, self.cf_cov.T)[0]              # Amat @ cf_cov       (N, K)
+                ypred_cov = matrix_forms(T, Amat)[0]                  # (Amat cf_cov) Amat^T (N, N)
+                ypred_cov += int(pp) * self.datavar * np.eye(N)
+                ypred_var = np.diag(ypred_cov)
         return ypred, ypred_var, ypred_cov
 
     def predicta_samples(self, Amat, nsamples=100):
+        r"""Amat @ (coefficient samples)^T (lreg/lreg.py:145-162): the draws come from numpy's global stream as in the
+        reference, the (N, K) x (K, nsamples) product runs on the device."""
+        from .forms import matrix_forms
         assert(self.fitted)
         assert(self.cf_cov is not None)
-        return Amat @ np.random.multivariate_normal(self.cf, self.cf_cov, nsamples).T
+        draws = np.random.multivariate_normal(self.cf, self.cf_cov, nsamples)
+        return matrix_forms(Amat, draws)[0]
 
     def compute_stdev(self, Amat, method="chol"):
-        r"""Pushed-forward standard deviation sqrt(diag(A C A^T)) (lreg/lreg.py:164-198)."""
+        r"""Pushed-forward standard deviation sqrt(diag(A C A^T)) (lreg/lreg.py:164-198).  Every method of the
+        reference is the square root of a quadratic form a^T C' a (C' = C; C + shift I for 'choleye'; u diag(s) u^T
+        for 'svd'), evaluated on the tensor pipe; 'chol' raises numpy's LinAlgError for a non-positive-definite
+        covariance exactly as np.linalg.cholesky does there."""
+        from .forms import matrix_forms, psd_part
+        from .. import device as _device
         assert(self.cf_cov is not None)
+        _device.require_device()
         C = self.cf_cov
         if method == "chol":
-            return np.linalg.norm(Amat @ np.linalg.cholesky(C), axis=1)
-        if method == "choleye":
+            Cq, pd = psd_part(C)
+            if not pd:
+                raise np.linalg.LinAlgError("Matrix is not positive definite")
+        elif method == "choleye":
             shift = abs(np.linalg.eigvalsh(C)[0]) + 1e-14
-            return np.linalg.norm(Amat @ np.linalg.cholesky(C + shift * np.eye(C.shape[0])), axis=1)
-        if method == "svd":
-            u, s, _ = np.linalg.svd(C, hermitian=True)
-            return np.linalg.norm((Amat @ u) @ np.sqrt(np.diag(s)), axis=1)
-        if method == "loop":
-            return np.sqrt(np.einsum('ij,ij->i', Amat @ C, Amat))
-        if method == "fullcov":
-            return np.sqrt(np.diag((Amat @ C) @ Amat.T))
-        return np.zeros(Amat.shape[0])
+            Cq = C + shift * np.eye(C.shape[0])
+        elif method == "svd":
+            u, sv, _ = np.linalg.svd(C, hermitian=True)
+            Cq = (u * sv) @ u.T
+        elif method in ("loop", "fullcov"):
+            return np.sqrt(matrix_forms(Amat, None, C)[1])
+        else:
+            return np.zeros(Amat.shape[0])
+        return np.sqrt(np.maximum(matrix_forms(Amat, None, Cq)[1], 0.0))
 
 
 class lsq(lreg):
@@ -281,10 +346,11 @@ class lsq(lreg):
 
     def fit(self, x, y):
         assert(self.basisEvaluatorSet)
-        if not isinstance(self.basisEval, PCBasisEvaluator):
+        route = self._pc_route()
+        if route is None:
             return self.fita(self.basisEval(x, self.basisEvalPars), y)
         from . import tsqr
-        pc, jdim = self.basisEvalPars[0], self.basisEval.jdim
+        pc, jdim = route
         K = pc.mindices[jdim].shape[0]
         N = np.shape(x)[0]
         if self.solver != 'qr' and (self.solver == 'gram' or N >= 4 * K):

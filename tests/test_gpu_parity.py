@@ -633,6 +633,93 @@ def test_fitters_vs_reference(fit_cases):
         assert l.predict(c["xt"])[1] is None
 
 
+def test_predictions_on_a_given_design_matrix_run_on_the_device(fit_cases):
+    """lreg.predicta / compute_stdev / predicta_samples on a caller-supplied Amat (lreg/lreg.py:112-198; the call
+    pattern of apps/uqpc/uq_pc.py:313-315) and the reference idiom of a plain function as basis evaluator
+    (examples/ex_lreg_basiseval.py:55, surrogates/pce.py:378-382): contracted on the device, compared with the
+    reference's numpy expressions evaluated here on the oracle's design matrix."""
+    import torch
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import anl, lsq, PCBasisEvaluator
+    from pytuq_b200 import _native
+    name, c = sorted(fit_cases.items())[0]
+    fam, mi = str(c["type"]), c["mi"]
+    pc = PCRV(1, mi.shape[1], fam, mi=mi)
+    a = anl()
+    a.setBasisEvaluator(lambda xx, pars: pars[0].evalBases(xx, 0), (pc,))      # plain closure: recognised
+    n0 = _native.lib().pcq_launch_count()
+    a.fit(c["x"], c["y"])
+    assert a._pc_route() == (pc, 0)
+    np.testing.assert_allclose(a.cf, c["anl_cf"], rtol=1e-10, atol=1e-12)
+    mean, var, _ = a.predict(c["xt"], msc=1)
+    np.testing.assert_allclose(mean, c["anl_pred_mean"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(var, c["anl_pred_var"], rtol=1e-7)
+    # an evaluator that is NOT the PC design matrix must not be mistaken for one
+    b = anl()
+    b.setBasisEvaluator(lambda xx, pars: 2.0 * pars[0].evalBases(xx, 0), (pc,))
+    assert b._pc_route() is None
+    b.fit(c["x"], c["y"])
+    np.testing.assert_allclose(2.0 * b.cf, c["anl_cf"], rtol=1e-9, atol=1e-12)
+
+    At = orc.eval_bases(c["xt"], mi, fam)
+    C, cf = a.cf_cov, a.cf
+    Lc = np.linalg.cholesky(C)
+    for msc in (0, 1, 2):
+        for pp in (False, True):
+            m, v, cov = a.predicta(At, msc=msc, pp=pp)
+            np.testing.assert_allclose(m, At @ cf, rtol=1e-12, atol=1e-13)
+            if msc == 0:
+                assert v is None and cov is None
+            elif msc == 1:
+                np.testing.assert_allclose(v, np.linalg.norm(At @ Lc, axis=1) ** 2 + int(pp) * a.datavar, rtol=1e-10)
+                assert cov is None
+            else:
+                ref = (At @ C) @ At.T + int(pp) * a.datavar * np.eye(At.shape[0])
+                np.testing.assert_allclose(cov, ref, rtol=1e-10, atol=1e-12 * np.abs(ref).max())
+                np.testing.assert_allclose(v, np.diag(ref), rtol=1e-10)
+    for method in ("chol", "choleye", "svd", "loop", "fullcov"):
+        np.testing.assert_allclose(a.compute_stdev(At, method=method), np.sqrt(np.einsum("ij,ij->i", At @ C, At)),
+                                   rtol=1e-7, err_msg=method)
+    assert not a.compute_stdev(At, method="none").any()
+    # a covariance that is not positive definite: 'chol' raises like numpy, predicta takes the reference's SVD route
+    Cbad = C.copy(); Cbad[0, 0] = -abs(Cbad[0, 0])
+    a2 = anl(); a2.cf, a2.cf_cov, a2.fitted, a2.datavar = cf, Cbad, True, 0.0
+    with pytest.raises(np.linalg.LinAlgError):
+        a2.compute_stdev(At, method="chol")
+    u, sv, _ = np.linalg.svd(Cbad, hermitian=True)
+    np.testing.assert_allclose(a2.predicta(At, msc=1)[1], np.linalg.norm((At @ u) @ np.sqrt(np.diag(sv)), axis=1) ** 2, rtol=1e-9)
+    # predictive samples: numpy's stream for the coefficient draws, the product on the device
+    np.random.seed(5); s_dev = a.predicta_samples(At, nsamples=70)
+    np.random.seed(5); s_ref = At @ np.random.multivariate_normal(cf, C, 70).T
+    np.testing.assert_allclose(s_dev, s_ref, rtol=1e-10, atol=1e-12)
+    np.random.seed(6); s_pc = a.predict_samples(c["xt"], nsamples=5)
+    np.random.seed(6); s_ref = At @ np.random.multivariate_normal(cf, C, 5).T
+    np.testing.assert_allclose(s_pc, s_ref, rtol=1e-10, atol=1e-12)
+    # larger, odd-shaped problem incl. leading dimension, many vectors (tensor-pipe route) and a device-resident matrix
+    rng = np.random.default_rng(8)
+    N, K, M = 3001, 203, 131
+    Abig = rng.standard_normal((N, K + 3))[:, :K]
+    Cb = rng.standard_normal((K, K)); Cb = Cb @ Cb.T / K
+    cfm = rng.standard_normal((M, K))
+    from pytuq_b200.lreg.forms import matrix_forms
+    Y, v = matrix_forms(Abig, cfm, Cb)
+    np.testing.assert_allclose(Y, Abig @ cfm.T, rtol=0, atol=1e-12 * np.abs(Abig @ cfm.T).max())
+    np.testing.assert_allclose(v, np.einsum("ij,ij->i", Abig @ Cb, Abig), rtol=1e-11)
+    Yd, vd = matrix_forms(torch.from_numpy(np.ascontiguousarray(Abig)).cuda(), cfm[:3], Cb)
+    np.testing.assert_allclose(Yd.cpu().numpy(), Abig @ cfm[:3].T, rtol=0, atol=1e-12 * np.abs(Abig @ cfm.T).max())
+    np.testing.assert_allclose(vd.cpu().numpy(), v, rtol=1e-13)
+    assert _native.lib().pcq_launch_count() > n0
+    m0, v0, _ = lsq_zero_cov_predicta(At, cf)
+    assert not v0.any()
+    np.testing.assert_allclose(m0, At @ cf, rtol=1e-12, atol=1e-13)
+
+
+def lsq_zero_cov_predicta(At, cf):
+    from pytuq_b200.lreg import lsq
+    l = lsq(); l.cf, l.cf_cov, l.fitted = cf, np.zeros((cf.shape[0],) * 2), True
+    return l.predicta(At, msc=1)
+
+
 def test_lsq_qr_route_on_illconditioned_systems():
     """8(f2): where the normal equations cannot follow the reference's SVD least squares, lsq switches to the
     QR statistic.  Golden coefficients come from the unmodified reference (tests/golden/lsq_illcond.npz)."""
