@@ -359,7 +359,7 @@ class lsq(lreg):
                 return
             if self.solver == 'gram':
                 return self._fit_stats(stats)
-        self._fit_r(tsqr.r_factor_pc(pc, x, y, jdim), K)
+        self._fit_r(tsqr.shared_r(tsqr.r_factor_pc(pc, x, y, jdim)), K)
 
     def fita(self, Amat, y):
         from . import tsqr

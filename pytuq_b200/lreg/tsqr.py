@@ -108,9 +108,20 @@ def allgather_r(R):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return R
     torch = _torch()
+    L = R.shape[1]
+    if R.shape[0] < L:          # a rank with fewer rows than columns: zero rows keep R^T R and make the shapes equal
+        R = torch.cat([R, torch.zeros((L - R.shape[0], L), dtype=R.dtype, device=R.device)])
     parts = [torch.empty_like(R) for _ in range(dist.get_world_size())]
     dist.all_gather(parts, R.contiguous())
     return combine_r(parts)
+
+
+def shared_r(R):
+    """R factor of the whole data set when the ranks hold row blocks (parallel.sharded_rows), else R itself."""
+    from .. import parallel
+    if parallel._sharded and parallel.dist_info()[1] > 1:
+        return allgather_r(R)
+    return R
 
 
 def lstsq_from_r(R, K, cond=1.0e-13):

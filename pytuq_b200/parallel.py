@@ -7,9 +7,33 @@ block to the packed statistics matrix S and performs ONE all-reduce (sum) of S -
 torch is used here only as plumbing (process group, device buffers); all arithmetic is in
 libpcq.
 """
+import contextlib
+
 import numpy as np
 
 from . import _native, device as _device
+
+# When set (and a process group with more than one rank is initialised) the (x, y) every rank passes to
+# lreg.fit / pc_fit / PCE.build are ITS ROW BLOCK of one global data set: the statistics pass all-reduces S and the
+# residual pass all-reduces its two sums, so every rank ends with the fit of the whole data set.  Off by default --
+# ranks that each hold the full data must not add their statistics up.
+_sharded = False
+
+
+def set_sharded_rows(flag=True):
+    global _sharded
+    _sharded = bool(flag)
+
+
+@contextlib.contextmanager
+def sharded_rows(flag=True):
+    """``with parallel.sharded_rows(): lsq.fit(x_block, y_block)`` -- see above."""
+    global _sharded
+    old, _sharded = _sharded, bool(flag)
+    try:
+        yield
+    finally:
+        _sharded = old
 
 
 def dist_info():
@@ -110,7 +134,7 @@ def _suffstats_pc_resident(pcrv, x, y, jdim, distributed):
     return SuffStats(None, K, M, S_dev=S_t)
 
 
-def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
+def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=None):
     """K3 on device-resident samples (torch CUDA tensors: read in place) or on host (numpy) inputs: the rows are streamed through two pinned staging buffers in L2-sized
     chunks (host memcpy and H2D of chunk i+1 overlap the Gram kernel of chunk i), the statistics are
     accumulated and stay on the device.  With ``distributed=True`` every rank passes its own row
@@ -118,6 +142,8 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=False):
     import torch
     from .lreg.stats import SuffStats
     _device.require_device()
+    if distributed is None:
+        distributed = _sharded and dist_info()[1] > 1
     if is_device_tensor(x):
         return _suffstats_pc_resident(pcrv, x, y, jdim, distributed)
     mindex = pcrv.mindices[jdim]

@@ -52,7 +52,7 @@ def pc_fit(x, y, order=3, pctype='LU', method='anl', **kwargs):
                 if C is not None:
                     batched = C.cpu().numpy()
         if batched is None:
-            batched = tsqr.lstsq_from_r(tsqr.r_factor_pc(pcrv, x, y, 0), K)[0]
+            batched = tsqr.lstsq_from_r(tsqr.shared_r(tsqr.r_factor_pc(pcrv, x, y, 0)), K)[0]
     else:
         stats = SuffStats.from_pc(pcrv, x, y, 0)
 

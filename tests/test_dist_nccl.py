@@ -1,0 +1,136 @@
+"""Multi-rank parity ON HARDWARE: two NCCL ranks (one per GPU) run the sample-sharded fit / propagation through the
+public API and the CUDA kernels, and the result is compared with the one-rank result and with the unmodified
+reference's golden coefficients (tests/golden/{c2_shape,c3_shape,workflow}.npz).  Skipped on a box with fewer than two
+GPUs (`gpurun --gpus 2 -- python -m pytest tests/test_dist_nccl.py -m gpu`); the CPU-side sharding logic is covered
+by tests/test_dist_gloo.py."""
+import contextlib
+import io
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    from conftest import load_golden, golden_generator
+    from oracle import pc_oracle as orc
+    from pytuq_b200 import parallel, device as pdev, _native
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200.lreg import lsq, anl, bcs, PCBasisEvaluator
+    from pytuq_b200.workflows.fits import pc_fit
+    torch.cuda.set_device(rank)
+    pdev.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        gen = golden_generator()
+        n0 = _native.lib().pcq_launch_count()
+
+        def fit(make, pc, x, y, sharded):
+            f = make()
+            f.setBasisEvaluator(PCBasisEvaluator(0), (pc,))
+            with contextlib.redirect_stdout(io.StringIO()):
+                if sharded:
+                    lo, hi = parallel.shard_bounds(x.shape[0], rank, world)
+                    with parallel.sharded_rows():
+                        f.fit(x[lo:hi], y[lo:hi])
+                else:
+                    f.fit(x, y)
+            return f
+
+        # --- C2 shape: lsq + anl (lreg/lreg.py:328-339, lreg/anl.py:69-105)
+        g = load_golden("c2_shape")
+        x, _, _ = gen.c2_inputs()
+        y = g["y"]
+        pc = PCRV(1, 20, "HG", mi=orc.get_mi(3, 20))
+        scale = np.max(np.abs(g["cf_lsq"]))
+        for name, make in (("lsq", lsq), ("anl", anl)):
+            one = fit(make, pc, x, y, False)
+            two = fit(make, pc, x, y, True)
+            np.testing.assert_allclose(two.cf, g[f"cf_{name}"], rtol=0, atol=1e-10 * scale)
+            np.testing.assert_allclose(two.cf, one.cf, rtol=0, atol=1e-12 * scale)
+            if name == "anl":
+                np.testing.assert_allclose(two.datavar, g["anl_datavar"], rtol=1e-9)
+                np.testing.assert_allclose(np.diag(two.cf_cov), g["anl_cov_diag"], rtol=1e-8)
+        # --- C3 shape: BCS on the sharded Gram (lreg/bcs.py:58-265), incl. the sharded residual pass
+        g, c = load_golden("c3_shape"), gen.shape_inputs(3)
+        mi = orc.get_mi(c["p"], c["d"])
+        pc3 = PCRV(1, c["d"], c["fam"], mi=mi)
+        A = pc3.evalBases(c["x"], 0)
+        y3 = gen.sparse_target(A, c["idx"], c["val"], c["noise"])
+        two = fit(lambda: bcs(eta=1e-8), pc3, c["x"], y3, True)
+        assert np.array_equal(two.used, g["used"])
+        np.testing.assert_allclose(two.cf, g["cf"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(np.reshape(two.datavar, -1), g["datavar"], rtol=1e-7)
+        lo, hi = parallel.shard_bounds(c["x"].shape[0], rank, world)
+        pc3._distributed_stats = True
+        full = np.zeros(mi.shape[0]); full[two.used] = two.cf
+        rss, ydr = parallel.residual_sums_pc(pc3, c["x"][lo:hi], y3[lo:hi], 0, 0, full)
+        r = y3 - A @ full
+        np.testing.assert_allclose([rss, ydr], [r @ r, y3 @ r], rtol=1e-9)
+        # --- multi-output pc_fit with one shared Gram (workflows/fits.py:47-64)
+        wf = load_golden("workflow")
+        xw, yw = wf["x"], wf["y"]
+        lo, hi = parallel.shard_bounds(xw.shape[0], rank, world)
+        for method in ("lsq", "anl", "bcs"):
+            with contextlib.redirect_stdout(io.StringIO()), parallel.sharded_rows():
+                opc, _ = pc_fit(xw[lo:hi], yw[lo:hi], order=3, pctype="LU", method=method)
+            for j in range(yw.shape[1]):
+                assert np.array_equal(opc.mindices[j], wf[f"{method}__mi{j}"]), method
+                np.testing.assert_allclose(opc.coefs[j], wf[f"{method}__cf{j}"], rtol=1e-10, atol=1e-12)
+        # --- propagation: the ranks draw disjoint blocks of ONE logical Philox stream
+        g4, c4 = load_golden("c4_shape"), gen.shape_inputs(4)
+        pc4 = PCRV(1, c4["d"], c4["fam"], mi=orc.get_mi(c4["p"], c4["d"]), cfs=c4["cf"])
+        both = pc4.propagate(400_001, seed=11)              # sharded over the two ranks + all-reduce
+        dist.barrier()
+        if rank == 0:
+            # the same stream on one rank: run outside the group's view by forcing world = 1
+            saved = parallel.dist_info
+            parallel.dist_info = lambda: (0, 1)
+            try:
+                single = pc4.propagate(400_001, seed=11)
+            finally:
+                parallel.dist_info = saved
+            np.testing.assert_allclose(both["sum"], single["sum"], rtol=1e-12)
+            np.testing.assert_allclose(both["sumsq"], single["sumsq"], rtol=1e-12)
+            assert both["min"][0] == single["min"][0] and both["max"][0] == single["max"][0]
+        assert _native.lib().pcq_launch_count() > n0
+        out.put((rank, "ok"))
+    except Exception as e:   # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()[-3000:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_nccl_sharded_fits_and_propagation_vs_reference():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
