@@ -167,7 +167,7 @@ def c5(scale):
     def solve():
         G_t, B_t = st.dev_system()
         return solve_normal_device(G_t, B_t, 1.0e-3)
-    t_solve, C = timed(solve)
+    t_solve, C = timed(solve, reps=2)      # the first call pays the cuSOLVER handle + workspace
     Cn = C.cpu().numpy()
     err = float(np.max(np.abs(Cn.T - C_true)))
     flops = float(n_total) * K * (K + 1) + 2.0 * n_total * K * M + 2.0 * n_total * M
