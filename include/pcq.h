@@ -88,6 +88,12 @@ int pcq_plan_specialize(pcq_plan* plan, int modes);
  * specialised ones are installed (pcq_plan_info(plan, 7) reports the installed modes, 8 the modes under way).
  * A failed build (no NVRTC) leaves the generic kernels in use.  pcq_plan_destroy waits for the thread. */
 int pcq_plan_specialize_async(pcq_plan* plan, int modes);
+/* Debugging aid, host only (no device needed): writes the CUDA source that pcq_plan_specialize compiles for the fast
+ * mode (Horner form over the multi-index trie, csrc/pcq_spec.cu) and trie positions [j0, j1) into buf; returns the
+ * length of the source (call with buf = NULL to size the buffer), < 0 on bad arguments. */
+int64_t pcq_debug_horner_source(int sdim, int nterms, const int32_t* mi, int pmax,
+                                const double* rec_a, const double* rec_b, const double* p1_scale,
+                                int j0, int j1, int spt, char* buf, int64_t bufsize);
 
 /* ---- K1: design matrix -----------------------------------------------------
  * A[n,k] = prod_i phi^{(i)}_{mi[k,i]}(x[n,i])          PCRV.evalBases, rv/pcrv.py:413-442

@@ -29,6 +29,8 @@ SIGNATURES = {
     "pcq_plan_info": (C.c_int64, [C.c_void_p, C.c_int]),
     "pcq_plan_specialize": (C.c_int, [C.c_void_p, C.c_int]),
     "pcq_plan_specialize_async": (C.c_int, [C.c_void_p, C.c_int]),
+    "pcq_debug_horner_source": (C.c_int64, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64]),
     "pcq_eval_bases_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                      C.c_int64, C.c_void_p]),
     "pcq_eval_bases": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),

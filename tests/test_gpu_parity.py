@@ -517,6 +517,46 @@ def test_k2_specialised_kernels_bitexact():
         np.testing.assert_allclose(b["mean"], a["mean"], rtol=1e-11, atol=1e-13)
 
 
+def test_k2_fast_specialised_kernels_in_horner_form():
+    """Fast-mode specialised evalPC = Horner form over the multi-index trie (csrc/pcq_spec.cu:gen_source_horner): one
+    DFMA per term, terms re-ordered -- values differ from the reference's summation order by rounding only
+    (rv/pcrv.py:486-497).  Checked against the bit-exact mode on downward-closed, sparse (not downward closed),
+    duplicated and multi-chunk multi-indices, with two outputs across several host chunks (both plan streams)."""
+    from pytuq_b200.rv.pcrv import PCRV
+    from pytuq_b200 import _native
+    rng = np.random.default_rng(123)
+    cases = [("HG", orc.get_mi(3, 20), 5000),                                   # C2 shape: 1771 terms, 2 chunks
+             ("LU", orc.get_mi(4, 12)[np.sort(rng.choice(1820, 700, replace=False))], 3000),   # sparse subset, no constant term guaranteed
+             (["LU", "HG", "nLU", "nHG", "LU"], np.vstack([orc.get_mi(3, 5)] * 2), 1000),     # duplicates, mixed families
+             ("HG", orc.get_mi(4, 20), 1500)]                                   # C4 shape: 10626 terms, 11 chunks
+    for types, mi, n in cases:
+        d = mi.shape[1]
+        K = mi.shape[0]
+        cfs = rng.standard_normal((2, K)) / (1.0 + mi.sum(axis=1)) ** 2
+        tlist = [types] * d if isinstance(types, str) else types
+        x = np.stack([rng.uniform(-1, 1, n) if t.endswith("LU") else rng.standard_normal(n) for t in tlist], axis=1)
+        pc = PCRV(2, d, types, mi=mi, cfs=cfs)
+        y_exact = pc.evalPC(x)
+        if not pc.specialize(exact=False, fast=True):
+            pytest.skip("NVRTC not available on this box")
+        assert _native.lib().pcq_plan_info(pc._plan(pc.mindices[0]).handle, 7) & 2
+        y_fast = pc.evalPC(x, exact=False)
+        scale = np.abs(cfs).sum(axis=1) * 0 + np.max(np.abs(y_exact), axis=0)
+        assert np.max(np.abs(y_fast - y_exact) / scale) < 1e-12, (types, K)
+        assert np.array_equal(pc.evalPC(x), y_exact)                            # exact mode untouched
+    # two outputs, N spanning three host chunks of the host-pointer route (alternating plan streams)
+    mi = orc.get_mi(3, 20)
+    cfs = rng.standard_normal((2, 1771)) / (1.0 + mi.sum(axis=1)) ** 2
+    pc = PCRV(2, 20, "HG", mi=mi, cfs=cfs)
+    pc.specialize(exact=False, fast=True)
+    n = 3_600_000
+    x = rng.standard_normal((n, 20))
+    y = pc.evalPC(x, exact=False)
+    rows = np.unique(np.concatenate([np.arange(0, n, 100_003), np.arange(1_597_000, 1_599_000, 7), np.arange(n - 100, n)]))
+    ref = orc.eval_pc(x[rows], [mi, mi], list(cfs), "HG")
+    assert np.max(np.abs(y[rows] - ref) / np.max(np.abs(ref), axis=0)) < 1e-12
+
+
 # ----------------------------------------------------------------------------- fitters and workflows
 def test_k2_specialised_cubins_are_cached_on_disk(monkeypatch, tmp_path):
     """Second build of the same plan (new process in real life; here: plan cache cleared) loads the cubins from
