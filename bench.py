@@ -295,6 +295,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     pdev.set_device(local)
+    pdev.set_devices([local])          # this arm counts GPUs by ranks: the public API must stay on the rank's own device
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _native.lib()

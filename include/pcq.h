@@ -253,6 +253,38 @@ int pcq_measure_peak(int device, int kind, double* result);
 /* number of kernel launches issued by this library since load (all threads) */
 int64_t pcq_launch_count(void);
 
+/* ---- pcq_group: one process, several GPUs, the same host-pointer calls -----------------------------------------
+ * SURVEY.md 8(b) (`ndev, devs` of the plan) / 8(e): the path shards over samples.  A group owns one plan per listed
+ * device; every call cuts the caller's rows into contiguous blocks (one per device) and runs them concurrently, one
+ * host thread per device.  evalBases / evalPC / quadratic forms / residual sums / propagation need no exchange
+ * (propagation blocks are disjoint index ranges of ONE logical Philox stream, so the result does not depend on the
+ * number of devices beyond summation order); the statistics pass leaves a partial S on every device and sums them
+ * on devices[0] in device order (peer copies over NVLink + an add kernel: deterministic) -- the path's one exchange
+ * step.  Same argument meaning and status codes as the single-plan calls above; this is what
+ * lreg.fit(x, y) / pc_fit / PCRV.evalPC / PCRV.propagate (lreg/lreg.py:62-71, workflows/fits.py:16-81,
+ * rv/pcrv.py:469-525) use in a plain Python process that sees more than one GPU. */
+typedef struct pcq_group pcq_group;
+int pcq_group_create(pcq_group** out, int ndev, const int* devices, int sdim, int nterms, const int32_t* mi,
+                     int pmax, const double* rec_a, const double* rec_b, const double* p1_scale);
+int pcq_group_destroy(pcq_group* group);
+int pcq_group_size(const pcq_group* group);
+int pcq_group_set_active(pcq_group* group, int n);               /* spread the next calls over the first n members */
+pcq_plan* pcq_group_plan(pcq_group* group, int member);          /* borrowed: the member's plan */
+int pcq_group_device(const pcq_group* group, int member);
+int pcq_group_specialize(pcq_group* group, int modes);           /* pcq_plan_specialize on every member */
+/* S = sum over all rows of [Psi|y|1]^T [Psi|y|1]; written to s_dev0 (device pointer on devices[0]) and / or s_host */
+int pcq_group_suffstats(pcq_group* group, const double* x_host, int64_t n, int64_t ldx,
+                        const double* y_host, int64_t ldy, int m, double* s_dev0, double* s_host);
+int pcq_group_eval_bases(pcq_group* group, const double* x_host, int64_t n, int64_t ldx, double* a_host, int64_t lda);
+int pcq_group_eval_pc(pcq_group* group, const double* x_host, int64_t n, int64_t ldx, const double* cf_host, int m,
+                      double* y_host, int64_t ldy, int mode);
+int pcq_group_quadform(pcq_group* group, const double* x_host, int64_t n, int64_t ldx, const double* c_host,
+                       int64_t ldc, double* v_host, int64_t ldv);
+int pcq_group_residual_ss(pcq_group* group, const double* x_host, int64_t n, int64_t ldx, const double* y_host,
+                          int64_t ldy, const double* cf_host, double* sums_host);
+int pcq_group_propagate(pcq_group* group, uint64_t seed, int64_t first_index, int64_t n,
+                        const int32_t* germ_kind, const double* cf_host, int m, double* sums_host, int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,25 @@ SIGNATURES = {
     "pcq_text_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pcq_text_parse_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pcq_text_close": (C.c_int, [C.c_void_p]),
+    "pcq_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pcq_group_destroy": (C.c_int, [C.c_void_p]),
+    "pcq_group_size": (C.c_int, [C.c_void_p]),
+    "pcq_group_set_active": (C.c_int, [C.c_void_p, C.c_int]),
+    "pcq_group_plan": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "pcq_group_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "pcq_group_specialize": (C.c_int, [C.c_void_p, C.c_int]),
+    "pcq_group_suffstats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                                      C.c_void_p, C.c_void_p]),
+    "pcq_group_eval_bases": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
+    "pcq_group_eval_pc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_int64, C.c_int]),
+    "pcq_group_quadform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_int64]),
+    "pcq_group_residual_ss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                        C.c_void_p]),
+    "pcq_group_propagate": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_int]),
     "pcq_measure_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
     "pcq_launch_count": (C.c_int64, []),
 }

@@ -94,6 +94,107 @@ def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None):
     return plan
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Several GPUs in ONE process (pcq_group, include/pcq.h): calls that take host (numpy) arrays are cut into row blocks,
+# one per device, when the process sees more than one GPU and the call is large enough to pay for the fan-out.
+# Policy: PCQ_DEVICES = "all" | "1" | "0,2,3" (explicit list; the first entry is where the K x K statistics land);
+# default "all" in a plain process and the rank's own device under torchrun (RANK / LOCAL_RANK in the environment),
+# where the sharding is over processes instead (parallel.sharded_rows).  set_devices() overrides the environment.
+_devices_override = None
+_groups = collections.OrderedDict()
+
+
+def set_devices(devices):
+    """Devices the host-array entry points may use in this process: a list of CUDA indices, or None for the
+    environment / default policy.  The first entry holds the reduced statistics and runs the K x K solves."""
+    global _devices_override
+    _devices_override = None if devices is None else [int(d) for d in devices]
+
+
+def devices():
+    """The device list the policy above yields right now (always at least [current_device()])."""
+    cur = current_device()
+    if _devices_override is not None:
+        devs = list(_devices_override)
+    else:
+        spec = os.environ.get("PCQ_DEVICES", "").strip().lower()
+        in_rank = int(os.environ.get("WORLD_SIZE", "1")) > 1 or "LOCAL_RANK" in os.environ
+        if spec in ("", "all"):
+            devs = [cur] if (in_rank and spec == "") else list(range(require_device()))
+        elif spec == "1":
+            devs = [cur]
+        else:
+            devs = [int(t) for t in spec.split(",") if t.strip() != ""]
+    if not devs:
+        devs = [cur]
+    if cur in devs:                       # the current device leads: statistics and solves stay where plans live
+        devs = [cur] + [d for d in devs if d != cur]
+    return devs
+
+
+class Group:
+    """Owner of one native pcq_group (one plan per device)."""
+
+    def __init__(self, handle, devs, sdim, nterms, pmax):
+        self.handle, self.devices = handle, list(devs)
+        self.sdim, self.nterms, self.pmax = sdim, nterms, pmax
+
+    def __len__(self):
+        return len(self.devices)
+
+    def close(self):
+        if self.handle:
+            _native.lib().pcq_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def get_group(mi, rec_a, rec_b, p1_scale, pmax, devs):
+    """Cached pcq_group for this content on this device list (created on first use)."""
+    require_device()
+    mi32 = np.ascontiguousarray(mi, dtype=np.int32)
+    rec_a = np.ascontiguousarray(rec_a, dtype=np.float64)
+    rec_b = np.ascontiguousarray(rec_b, dtype=np.float64)
+    p1_scale = np.ascontiguousarray(p1_scale, dtype=np.float64)
+    devs = [int(d) for d in devs]
+    key = (tuple(devs), mi32.shape, mi32.tobytes(), rec_a.tobytes(), rec_b.tobytes(), p1_scale.tobytes(), int(pmax))
+    with _lock:
+        grp = _groups.get(key)
+        if grp is not None:
+            _groups.move_to_end(key)
+            return grp
+    K, s = mi32.shape
+    handle = C.c_void_p()
+    darr = (C.c_int * len(devs))(*devs)
+    st = _native.lib().pcq_group_create(C.byref(handle), len(devs), darr, s, K, _native.ptr(mi32), int(pmax),
+                                        _native.ptr(rec_a), _native.ptr(rec_b), _native.ptr(p1_scale))
+    _native.check(st, "pcq_group_create")
+    grp = Group(handle, devs, s, K, int(pmax))
+    with _lock:
+        _groups[key] = grp
+        while len(_groups) > max(2, _PLAN_CACHE_MAX // 4):
+            _groups.popitem(last=False)
+    return grp
+
+
+def fan_out(work, unit, rows=None):
+    """Number of devices to spread a host-array call over: as many of devices() as the call has `unit`s of work (each
+    worth a few milliseconds on one GPU), at least 4096 rows per device; 1 means the single-plan path."""
+    nd = len(devices())
+    if nd == 1:
+        return 1
+    unit = float(unit) * float(os.environ.get("PCQ_FANOUT_SCALE", "1"))     # (tests shrink the unit to force the fan-out)
+    n = int(min(nd, max(1.0, float(work) / unit)))
+    if rows is not None:
+        n = min(n, max(1, int(rows) // 4096))
+    return max(n, 1)
+
+
 # A plan that keeps being evaluated (MCMC likelihoods, repeated surrogate sweeps) is worth compiling for: once the
 # generic evalPC kernel has processed this many sample-terms through one plan (~20 ms of kernel time), its
 # multi-index-specialised kernels are built on a BACKGROUND host thread (NVRTC, ~1 s per 2000 terms; cubins are
@@ -122,13 +223,15 @@ def clear_plans():
     waits for a background specialisation build that may still be running)."""
     with _lock:
         _plans.clear()
+        _groups.clear()
 
 
 def _close_all_at_exit():
     # destroy the cached plans (joining background builds) before the interpreter tears the CUDA runtime down
     with _lock:
-        plans = list(_plans.values())
+        plans = list(_plans.values()) + list(_groups.values())
         _plans.clear()
+        _groups.clear()
     for plan in plans:
         try:
             plan.close()

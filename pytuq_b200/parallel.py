@@ -159,11 +159,22 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=None):
         M = Y.shape[1]
     dev = _device.current_device()
     tdev = torch.device("cuda", dev)
-    plan = pcrv._plan(mindex, dev=dev)
     K = mindex.shape[0]
     L = K + M + 1
     lib = _native.lib()
     S_t = torch.empty((L, L), dtype=torch.float64, device=tdev)
+    # several GPUs in this process (and no process group sharding the rows already): the rows are cut into one block
+    # per device inside the C-ABI (pcq_group_suffstats: pinned pipelines per device, partial S summed on this device)
+    nuse = 1 if distributed else _device.fan_out(float(N) * K * (K + 2 * M + 1), 5e11, N)
+    if nuse > 1:
+        grp = pcrv._group(mindex, nuse)
+        assert grp.devices[0] == dev
+        torch.cuda.current_stream(tdev).synchronize()
+        _native.check(lib.pcq_group_suffstats(grp.handle, _native.ptr(xin), N, s, _native.ptr(Y), max(M, 1), M,
+                                              S_t.data_ptr(), None), "pcq_group_suffstats")
+        pcrv._distributed_stats = False
+        return SuffStats(None, K, M, S_dev=S_t)
+    plan = pcrv._plan(mindex, dev=dev)
     ncol = s + M
     rows = max(_STAGE_BYTES // (ncol * 8), 4096)
     pin = _pinned_pair(rows * ncol * 8)
@@ -240,12 +251,20 @@ def residual_sums_pc(pcrv, x, y, col, jdim, cf):
         if dist_info()[1] > 1 and getattr(pcrv, "_distributed_stats", False):
             sums = allreduce_stats(sums)
         return float(sums[0]), float(sums[1])
-    plan = pcrv._plan(mindex, dev=_device.current_device())
     xin = np.ascontiguousarray(x, dtype=np.float64)
     N, s = xin.shape
     Y = np.asarray(y, dtype=np.float64).reshape(N, -1)
     ycol = np.ascontiguousarray(Y[:, col])
     sums = np.zeros(2)
+    sharded = dist_info()[1] > 1 and getattr(pcrv, "_distributed_stats", False)
+    nuse = 1 if sharded else _device.fan_out(float(N) * mindex.shape[0], 4e9, N)
+    if nuse > 1:
+        _native.check(_native.lib().pcq_group_residual_ss(pcrv._group(mindex, nuse).handle, _native.ptr(xin), N, s,
+                                                          _native.ptr(ycol), 1,
+                                                          _native.ptr(np.ascontiguousarray(cf, dtype=np.float64)),
+                                                          _native.ptr(sums)), "pcq_group_residual_ss")
+        return float(sums[0]), float(sums[1])
+    plan = pcrv._plan(mindex, dev=_device.current_device())
     _native.check(_native.lib().pcq_residual_ss(plan.handle, _native.ptr(xin), N, s, _native.ptr(ycol), 1,
                                                 _native.ptr(np.ascontiguousarray(cf, dtype=np.float64)),
                                                 _native.ptr(sums)), "pcq_residual_ss")
@@ -287,17 +306,31 @@ def propagate(pcrv, nsam, seed=0, exact=False, return_samples=False, first_index
         pcrv._check_orders(mindex)
         groups.setdefault(id(mindex), []).append(j)
     kinds = pcrv._germ_kinds()
-    # multi-index-specialised kernels (NVRTC, ~0.3 ms of compile time per term and mode on the GPU box's
-    # host) save ~6.5e-13 s per sample-term: break-even near 5e8 samples per rank whatever K is; "auto"
-    # applies that threshold, True / False force it
-    if specialize is True or (specialize == "auto" and (hi - lo) >= 500_000_000):
+    # multi-index-specialised kernels (NVRTC, ~0.2 ms of compile time per term on the GPU box's host, cubins cached on
+    # disk afterwards) save ~8e-13 s per sample-term in fast mode: "auto" specialises from 1e12 sample-terms per rank
+    # (about a second of generic-kernel time), True / False force it
+    if specialize is True or (specialize == "auto" and float(hi - lo) * max(m.shape[0] for m in pcrv.mindices) >= 1.0e12):
         pcrv.specialize(exact=exact, fast=not exact)
     tdev = torch.device("cuda", dev)
     sums = np.zeros((pcrv.pdim, 4))
     ysam = np.empty((hi - lo, pcrv.pdim)) if return_samples else None
     lib = _native.lib()
     stream = torch.cuda.current_stream(tdev).cuda_stream
+    nuse = 1
+    if world == 1 and not return_samples:
+        nuse = _device.fan_out(float(nsam) * max(m.shape[0] for m in pcrv.mindices), 2e10, nsam)
     for outs in groups.values():
+        if nuse > 1:
+            # one process, several GPUs: disjoint index blocks of the one logical stream per device (pcq_group_propagate)
+            mindex = pcrv.mindices[outs[0]]
+            grp = pcrv._group(mindex, nuse)
+            cfh = np.ascontiguousarray(np.stack([pcrv.coefs[j] for j in outs]), dtype=np.float64)
+            part = np.zeros((len(outs), 4))
+            _native.check(lib.pcq_group_propagate(grp.handle, int(seed), int(first_index), int(nsam), _native.ptr(kinds),
+                                                  _native.ptr(cfh), len(outs), _native.ptr(part), 0 if exact else 1),
+                          "pcq_group_propagate")
+            sums[outs] = part
+            continue
         plan = pcrv._plan(pcrv.mindices[outs[0]], dev=dev)
         cf = torch.from_numpy(np.ascontiguousarray(np.stack([pcrv.coefs[j] for j in outs]))).to(tdev)
         dsums = torch.empty((len(outs), 4), dtype=torch.float64, device=tdev)

@@ -256,6 +256,22 @@ class PCRV(MRV):
             p1[i] = p.p1_scale
         return _device.get_plan(mindex, ra, rb, p1, pmax, device=dev)
 
+    def _group(self, mindex, nuse=None):
+        """pcq_group over device.devices() for this multi-index (several GPUs behind one host-array call), set to
+        spread the next calls over its first `nuse` members."""
+        devs = _device.devices()
+        pmax = int(np.max(mindex))
+        ra = np.zeros((pmax + 1, self.sdim))
+        rb = np.zeros((pmax + 1, self.sdim))
+        p1 = np.empty(self.sdim)
+        for i, p in enumerate(self.PC1ds):
+            ra[:, i], rb[:, i] = p.rec_tables(pmax)
+            p1[i] = p.p1_scale
+        grp = _device.get_group(mindex, ra, rb, p1, pmax, devs)
+        _native.check(_native.lib().pcq_group_set_active(grp.handle, len(devs) if nuse is None else int(nuse)),
+                      "pcq_group_set_active")
+        return grp
+
     @staticmethod
     def _as_input(x):
         if _is_device_tensor(x):       # resident samples on an entry point that returns host arrays
@@ -277,6 +293,11 @@ class PCRV(MRV):
             return self._evalBases_resident(xi, mindex)
         x = self._as_input(xi)
         ybases = np.empty((nxi, npc))
+        nuse = _device.fan_out(8.0 * nxi * npc, 128 << 20, nxi)       # PCIe bound: 128 MB of A per extra device
+        if nuse > 1:
+            _native.check(_native.lib().pcq_group_eval_bases(self._group(mindex, nuse).handle, _native.ptr(x), nxi,
+                                                             self.sdim, _native.ptr(ybases), npc), "pcq_group_eval_bases")
+            return ybases
         plan = self._plan(mindex)
         _native.check(_native.lib().pcq_eval_bases(plan.handle, _native.ptr(x), nxi, self.sdim,
                                                    _native.ptr(ybases), npc), "pcq_eval_bases")
@@ -317,15 +338,24 @@ class PCRV(MRV):
             groups.setdefault(id(mindex), []).append(j)
         for outs in groups.values():
             mindex = self.mindices[outs[0]]
-            plan = self._plan(mindex)
-            _device.note_evalpc_work(plan, nsam, mindex.shape[0], len(outs), mode)
+            nuse = _device.fan_out(float(nsam) * mindex.shape[0] * len(outs), 4e9, nsam)
+            if nuse > 1:
+                group = self._group(mindex, nuse)
+            else:
+                plan = self._plan(mindex)
+                _device.note_evalpc_work(plan, nsam, mindex.shape[0], len(outs), mode)
             runs = [list(g) for _, g in itertools.groupby(outs, key=lambda j, c=itertools.count(): j - next(c))]
             for run in runs:     # consecutive outputs -> adjacent columns of y
                 cf = np.ascontiguousarray(np.stack([self.coefs[j] for j in run]), dtype=np.float64)
                 yptr = y.ctypes.data + 8 * run[0]
-                _native.check(lib.pcq_eval_pc(plan.handle, _native.ptr(xin), nsam, self.sdim,
-                                              _native.ptr(cf), len(run), yptr, self.pdim, mode),
-                              "pcq_eval_pc")
+                if nuse > 1:
+                    _native.check(lib.pcq_group_eval_pc(group.handle, _native.ptr(xin), nsam, self.sdim,
+                                                        _native.ptr(cf), len(run), yptr, self.pdim, mode),
+                                  "pcq_group_eval_pc")
+                else:
+                    _native.check(lib.pcq_eval_pc(plan.handle, _native.ptr(xin), nsam, self.sdim,
+                                                  _native.ptr(cf), len(run), yptr, self.pdim, mode),
+                                  "pcq_eval_pc")
         return y
 
     # Samples that already live in HBM (torch CUDA tensors, e.g. from utils.io.loadtxt_device): same kernels through
@@ -382,9 +412,15 @@ class PCRV(MRV):
         nsam, M = xin.shape[0], cf.shape[0]
         out = np.zeros((nsam, 1 if sumsq else M))
         mode = (0 if exact and not sumsq else 1) | (2 if sumsq else 0)
-        _native.check(_native.lib().pcq_eval_pc(self._plan(mindex).handle, _native.ptr(xin), nsam, self.sdim,
-                                                _native.ptr(cf), M, _native.ptr(out), out.shape[1], mode),
-                      "pcq_eval_pc")
+        nuse = _device.fan_out(float(nsam) * mindex.shape[0] * M, 4e9, nsam)
+        if nuse > 1:
+            _native.check(_native.lib().pcq_group_eval_pc(self._group(mindex, nuse).handle, _native.ptr(xin), nsam,
+                                                          self.sdim, _native.ptr(cf), M, _native.ptr(out), out.shape[1],
+                                                          mode), "pcq_group_eval_pc")
+        else:
+            _native.check(_native.lib().pcq_eval_pc(self._plan(mindex).handle, _native.ptr(xin), nsam, self.sdim,
+                                                    _native.ptr(cf), M, _native.ptr(out), out.shape[1], mode),
+                          "pcq_eval_pc")
         return out[:, 0] if sumsq else out
 
     def evalQuadForm(self, x, Cmat, jdim=0):
@@ -401,8 +437,14 @@ class PCRV(MRV):
         out = np.zeros(nsam)
         if nsam:
             cm = np.ascontiguousarray(Cmat, dtype=np.float64)
-            _native.check(_native.lib().pcq_quadform(self._plan(mindex).handle, _native.ptr(xin), nsam, self.sdim,
-                                                     _native.ptr(cm), K, _native.ptr(out), 1), "pcq_quadform")
+            nuse = _device.fan_out(float(nsam) * K * K, 5e11, nsam)
+            if nuse > 1:
+                _native.check(_native.lib().pcq_group_quadform(self._group(mindex, nuse).handle, _native.ptr(xin), nsam,
+                                                               self.sdim, _native.ptr(cm), K, _native.ptr(out), 1),
+                              "pcq_group_quadform")
+            else:
+                _native.check(_native.lib().pcq_quadform(self._plan(mindex).handle, _native.ptr(xin), nsam, self.sdim,
+                                                         _native.ptr(cm), K, _native.ptr(out), 1), "pcq_quadform")
         return out
 
     def specialize(self, exact=True, fast=True):
@@ -420,6 +462,8 @@ class PCRV(MRV):
             seen.add(id(mindex))
             self._check_orders(mindex)
             st = _native.lib().pcq_plan_specialize(self._plan(mindex).handle, modes)
+            if st == 0 and len(_device.devices()) > 1:     # and on every GPU this process spreads host-array calls over
+                st = _native.lib().pcq_group_specialize(self._group(mindex).handle, modes)
             if st == -5:       # PCQ_ERR_UNSUPPORTED
                 ok = False
             else:
