@@ -68,7 +68,12 @@ class Plan:
 
 
 def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None):
-    """Returns the cached plan for this content, creating it on first use."""
+    """Returns the cached plan for this content, creating it on first use.
+
+    Threading: a plan (and a group) is NOT re-entrant -- its host-pointer entry points share per-plan staging
+    buffers, streams and events.  Two Python threads may use the library at the same time only on PCRVs with
+    different content (different plans); callers keep the returned object referenced for the duration of the native
+    call (the LRU below may otherwise destroy a handle another thread is still using)."""
     require_device()
     device = current_device() if device is None else int(device)
     mi32 = np.ascontiguousarray(mi, dtype=np.int32)

@@ -75,15 +75,24 @@ _STAGE_BYTES = 48 << 20        # host chunk = the Gram kernel's L2-sized sample 
 _pinned = {}
 
 
-def _pinned_pair(nbytes):
-    """Two reusable pinned staging buffers (double buffering of the H2D pipeline)."""
+def _pinned_pair(nbytes, dev):
+    """Two reusable pinned staging buffers per device (double buffering of the H2D pipeline)."""
     import torch
-    bufs = _pinned.get("bufs")
+    key = "bufs%d" % dev
+    bufs = _pinned.get(key)
     if bufs is None or bufs[0].numel() * 8 < nbytes:
         n = max(int(nbytes) // 8, 1)
         bufs = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
-        _pinned["bufs"] = bufs
+        _pinned[key] = bufs
     return bufs
+
+
+def _copy_stream(dev, tdev):
+    import torch
+    key = "stream%d" % dev
+    if key not in _pinned:
+        _pinned[key] = torch.cuda.Stream(device=tdev)
+    return _pinned[key]
 
 
 def is_device_tensor(a):
@@ -177,11 +186,16 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=None):
     plan = pcrv._plan(mindex, dev=dev)
     ncol = s + M
     rows = max(_STAGE_BYTES // (ncol * 8), 4096)
-    pin = _pinned_pair(rows * ncol * 8)
+    pin = _pinned_pair(rows * ncol * 8, dev)
     with torch.cuda.device(tdev):
         main = torch.cuda.current_stream()
-        copy_stream = _pinned.setdefault("stream%d" % dev, torch.cuda.Stream(device=tdev))
+        copy_stream = _copy_stream(dev, tdev)
         dbuf = [torch.empty(rows * ncol, dtype=torch.float64, device=tdev) for _ in range(2)]
+        # the staging tensors come from the caching allocator on the main stream: work still queued there on a recycled
+        # block must finish before the copy stream overwrites it
+        copy_stream.wait_stream(main)
+        for t in dbuf:
+            t.record_stream(copy_stream)
         copied = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
         if N == 0:

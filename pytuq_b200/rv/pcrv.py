@@ -418,7 +418,8 @@ class PCRV(MRV):
                                                           self.sdim, _native.ptr(cf), M, _native.ptr(out), out.shape[1],
                                                           mode), "pcq_group_eval_pc")
         else:
-            _native.check(_native.lib().pcq_eval_pc(self._plan(mindex).handle, _native.ptr(xin), nsam, self.sdim,
+            plan = self._plan(mindex)           # (kept referenced across the native call)
+            _native.check(_native.lib().pcq_eval_pc(plan.handle, _native.ptr(xin), nsam, self.sdim,
                                                     _native.ptr(cf), M, _native.ptr(out), out.shape[1], mode),
                           "pcq_eval_pc")
         return out[:, 0] if sumsq else out
@@ -443,7 +444,8 @@ class PCRV(MRV):
                                                                self.sdim, _native.ptr(cm), K, _native.ptr(out), 1),
                               "pcq_group_quadform")
             else:
-                _native.check(_native.lib().pcq_quadform(self._plan(mindex).handle, _native.ptr(xin), nsam, self.sdim,
+                plan = self._plan(mindex)
+                _native.check(_native.lib().pcq_quadform(plan.handle, _native.ptr(xin), nsam, self.sdim,
                                                          _native.ptr(cm), K, _native.ptr(out), 1), "pcq_quadform")
         return out
 
@@ -461,7 +463,8 @@ class PCRV(MRV):
                 continue
             seen.add(id(mindex))
             self._check_orders(mindex)
-            st = _native.lib().pcq_plan_specialize(self._plan(mindex).handle, modes)
+            plan = self._plan(mindex)
+            st = _native.lib().pcq_plan_specialize(plan.handle, modes)
             if st == 0 and len(_device.devices()) > 1:     # and on every GPU this process spreads host-array calls over
                 st = _native.lib().pcq_group_specialize(self._group(mindex).handle, modes)
             if st == -5:       # PCQ_ERR_UNSUPPORTED
