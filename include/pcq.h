@@ -253,6 +253,16 @@ int pcq_measure_peak(int device, int kind, double* result);
 /* number of kernel launches issued by this library since load (all threads) */
 int64_t pcq_launch_count(void);
 
+/* ---- QR statistic: R factor of a tall matrix by blocked Householder reflections (csrc/pcq_qr.cu) ----------------
+ * The sample-axis reduction of the least-squares route that has to follow the reference's SVD solve
+ * (scipy.linalg.lstsq(A, y, cond=1e-13), lreg/lreg.py:335) where the normal equations cannot: square,
+ * underdetermined, nearly collinear, rank-deficient systems.  z: m x L row-major on the device
+ * (leading dimension ldz), overwritten; r: L x L upper triangular (row-major, ldr), R^T R = Z^T Z to rounding,
+ * rows >= m are zero.  One call takes at most pcq_qr_max_rows(device) rows (its panel kernel is cooperative);
+ * longer matrices are chunked and the triangles combined by factorising [R_a; R_b] with the same call. */
+int64_t pcq_qr_max_rows(int device);
+int pcq_qr_r_dev(int device, double* z_dev, int64_t m, int64_t ldz, int L, double* r_dev, int64_t ldr, void* stream);
+
 /* ---- pcq_group: one process, several GPUs, the same host-pointer calls -----------------------------------------
  * SURVEY.md 8(b) (`ndev, devs` of the plan) / 8(e): the path shards over samples.  A group owns one plan per listed
  * device; every call cuts the caller's rows into contiguous blocks (one per device) and runs them concurrently, one

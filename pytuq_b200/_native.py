@@ -69,6 +69,8 @@ SIGNATURES = {
     "pcq_text_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pcq_text_parse_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pcq_text_close": (C.c_int, [C.c_void_p]),
+    "pcq_qr_max_rows": (C.c_int64, [C.c_int]),
+    "pcq_qr_r_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "pcq_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcq_group_destroy": (C.c_int, [C.c_void_p]),

@@ -3,19 +3,20 @@
 The Gram form squares the condition number, so ``lsq`` on square (N = K), underdetermined or nearly
 collinear systems cannot reproduce the reference's SVD least squares (``scipy.linalg.lstsq(A, y,
 cond=1e-13)``, lreg/lreg.py:335).  This module reduces the sample axis with orthogonal transformations
-instead: the augmented matrix  Z = [A | Y]  is processed in row chunks, each chunk stacked under the
-running triangular factor and re-factorised,
+instead: the augmented matrix  Z = [A | Y]  is processed in row chunks, each chunk factorised by the
+hand-written blocked Householder kernels of ``csrc/pcq_qr.cu`` (``pcq_qr_r_dev``: cooperative panel kernel, DMMA
+trailing updates), and the chunk triangles are combined pairwise in a balanced tree by factorising
+``[R_a; R_b]`` with the same kernels,
 
-    R  <-  qr([R ; Z_chunk]).R ,        R = [[R_A, Q^T Y], [0, rho]]   ((K+M) x (K+M), upper),
+    R = [[R_A, Q^T Y], [0, rho]]   ((K+M) x (K+M), upper),
 
 so that ``min ||A c - y||`` becomes the K x K problem ``min ||R_A c - Q^T y||`` with the SAME singular
 values as A; the truncated-SVD minimum-norm solution of that small problem is what gelsd returns for A.
 The design-matrix chunks are produced on the device by K1 (``pcq_eval_bases_dev`` writing straight into
-the left K columns of the chunk buffer); the chunk QR and the K x K SVD are plain library calls
-(cuSOLVER geqrf / gesvd through torch.linalg) -- this is the robustness route for ill-conditioned
-problems, not the throughput path (that is K3).  Shards combine by stacking their R factors
-(``combine_r``): same sharding as the Gram path, the all-reduce replaced by an all-gather of (K+M)^2
-doubles and one more QR.
+the left K columns of the chunk buffer).  Ranks that hold row blocks combine their triangles by a butterfly
+(log2(P) pairwise exchanges, both partners factorise the same stacked pair, so every rank ends with the
+identical R); a world size that is not a power of two falls back to an all-gather + tree.  The K x K SVD of R_A is
+a library call (cuSOLVER through torch.linalg), like the K x K Cholesky of the Gram route: not sample-parallel.
 """
 import numpy as np
 
@@ -30,21 +31,66 @@ def _torch():
 
 
 def _qr_r(Z):
+    """R factor (L x L, upper) of the device tensor Z (m x L, overwritten): pcq_qr_r_dev."""
     torch = _torch()
-    L = Z.shape[1]
-    if Z.shape[0] < L:       # fewer rows than columns: zero rows change nothing and keep R square
-        Z = torch.cat([Z, torch.zeros((L - Z.shape[0], L), dtype=Z.dtype, device=Z.device)])
-    return torch.linalg.qr(Z, mode="r").R
+    assert Z.is_cuda and Z.dtype == torch.float64 and Z.dim() == 2 and Z.stride(1) == 1
+    m, L = Z.shape
+    R = torch.empty((L, L), dtype=torch.float64, device=Z.device)
+    if m == 0:
+        return R.zero_()
+    lib = _native.lib()
+    dev = Z.device.index
+    cap = int(lib.pcq_qr_max_rows(dev))
+    if m > cap:                       # taller than one call takes: factor the pieces, then the stacked triangles
+        return combine_r([_qr_r(Z[r0:r0 + cap]) for r0 in range(0, m, cap)])
+    with torch.cuda.device(Z.device):
+        _native.check(lib.pcq_qr_r_dev(dev, Z.data_ptr(), m, Z.stride(0), L, R.data_ptr(), L,
+                                       torch.cuda.current_stream().cuda_stream), "pcq_qr_r_dev")
+    return R
 
 
-def combine_r(Rs):
-    """R factor of the row-stacked matrices whose R factors are given."""
+def combine_r(Rs, qr=None):
+    """R factor of the row-stacked matrices whose R factors are given: balanced pairwise tree, every node the
+    factorisation of two stacked triangles.  ``qr`` replaces the device kernel (host-logic tests on CPU)."""
     torch = _torch()
-    Rs = list(Rs)
-    return Rs[0] if len(Rs) == 1 else _qr_r(torch.cat(Rs))
+    qr = qr or _qr_r
+    level = list(Rs)
+    while len(level) > 1:
+        nxt = [qr(torch.cat([level[i], level[i + 1]])) for i in range(0, len(level) - 1, 2)]
+        if len(level) & 1:
+            nxt.append(level[-1])
+        level = nxt
+    return level[0]
 
 
-def r_factor_pc(pcrv, x, y, jdim=0, chunk_bytes=None):
+class _Tree:
+    """Streaming form of the balanced tree: chunk triangles arrive one by one, two triangles of the same height are
+    combined at once, so at most log2(#chunks) triangles are alive."""
+
+    def __init__(self):
+        self.levels = {}
+
+    def push(self, R):
+        h = 0
+        while h in self.levels:
+            torch = _torch()
+            R = _qr_r(torch.cat([self.levels.pop(h), R]))
+            h += 1
+        self.levels[h] = R
+
+    def result(self):
+        R = None
+        for h in sorted(self.levels):
+            R = self.levels[h] if R is None else _qr_r(_torch().cat([self.levels[h], R]))
+        return R
+
+
+def _chunk_rows(L, dev):
+    cap = int(_native.lib().pcq_qr_max_rows(dev))
+    return max(1, min(cap, int(_CHUNK_BYTES // (8 * L))))
+
+
+def r_factor_pc(pcrv, x, y, jdim=0, chunk_rows=None):
     """R factor of [Psi(x) | y] (device tensor, (K+M) x (K+M)); Psi comes from K1 chunk by chunk."""
     torch = _torch()
     _device.require_device()
@@ -62,10 +108,10 @@ def r_factor_pc(pcrv, x, y, jdim=0, chunk_bytes=None):
     plan = pcrv._plan(mi)
     lib = _native.lib()
     L = K + M
-    rows = max(L, int((chunk_bytes or _CHUNK_BYTES) // (8 * L)))
+    rows = chunk_rows or _chunk_rows(L, dev)
     tdev = torch.device("cuda", dev)
     stream = torch.cuda.current_stream(tdev).cuda_stream
-    R = None
+    tree = _Tree()
     for r0 in range(0, max(N, 1), rows):
         r1 = min(N, r0 + rows)
         nr = r1 - r0
@@ -75,11 +121,11 @@ def r_factor_pc(pcrv, x, y, jdim=0, chunk_bytes=None):
             _native.check(lib.pcq_eval_bases_dev(plan.handle, xs.data_ptr(), nr, s, Z.data_ptr(), L, stream))
             if M:
                 Z[:, K:] = torch.from_numpy(Y[r0:r1]).to(tdev)
-        R = _qr_r(Z if R is None else torch.cat([R, Z]))
-    return R
+        tree.push(_qr_r(Z))
+    return tree.result()
 
 
-def r_factor_matrix(Amat, y, chunk_bytes=None):
+def r_factor_matrix(Amat, y, chunk_rows=None):
     """R factor of [Amat | y] for a caller-supplied design matrix (host numpy)."""
     torch = _torch()
     _device.require_device()
@@ -89,31 +135,48 @@ def r_factor_matrix(Amat, y, chunk_bytes=None):
     Y = None if y is None else np.asarray(y, dtype=np.float64).reshape(N, -1)
     M = 0 if Y is None else Y.shape[1]
     L = K + M
-    rows = max(L, int((chunk_bytes or _CHUNK_BYTES) // (8 * L)))
+    rows = chunk_rows or _chunk_rows(L, dev)
     tdev = torch.device("cuda", dev)
-    R = None
+    tree = _Tree()
     for r0 in range(0, max(N, 1), rows):
         r1 = min(N, r0 + rows)
         Z = torch.empty((r1 - r0, L), dtype=torch.float64, device=tdev)
         Z[:, :K] = torch.from_numpy(np.ascontiguousarray(A[r0:r1])).to(tdev)
         if M:
             Z[:, K:] = torch.from_numpy(np.ascontiguousarray(Y[r0:r1])).to(tdev)
-        R = _qr_r(Z if R is None else torch.cat([R, Z]))
-    return R
+        tree.push(_qr_r(Z))
+    return tree.result()
 
 
-def allgather_r(R):
-    """Combines the R factors of all ranks of the default process group (every rank gets the result)."""
+def allgather_r(R, qr=None):
+    """Combines the R factors of all ranks of the default process group; every rank gets the same result.
+    Power-of-two worlds: butterfly -- log2(P) rounds, rank r and r ^ step exchange their triangles and both factorise
+    [R_low_rank; R_high_rank] (same input, same kernels: identical output).  Otherwise all-gather + tree."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return R
     torch = _torch()
-    L = R.shape[1]
-    if R.shape[0] < L:          # a rank with fewer rows than columns: zero rows keep R^T R and make the shapes equal
-        R = torch.cat([R, torch.zeros((L - R.shape[0], L), dtype=R.dtype, device=R.device)])
-    parts = [torch.empty_like(R) for _ in range(dist.get_world_size())]
-    dist.all_gather(parts, R.contiguous())
-    return combine_r(parts)
+    qr = qr or _qr_r
+    world, rank = dist.get_world_size(), dist.get_rank()
+    R = R.contiguous()
+    if world & (world - 1) == 0:
+        step = 1
+        while step < world:
+            partner = rank ^ step
+            other = torch.empty_like(R)
+            if rank < partner:
+                dist.send(R, partner)
+                dist.recv(other, partner)
+                R = qr(torch.cat([R, other]))
+            else:
+                dist.recv(other, partner)
+                dist.send(R, partner)
+                R = qr(torch.cat([other, R]))
+            step <<= 1
+        return R
+    parts = [torch.empty_like(R) for _ in range(world)]
+    dist.all_gather(parts, R)
+    return combine_r(parts, qr=qr)
 
 
 def shared_r(R):

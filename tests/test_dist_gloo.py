@@ -55,7 +55,11 @@ def _worker(rank, world, port, out):
         # QR statistic (8(f2)): R factors of the row shards combine to the R factor of the whole matrix
         from pytuq_b200.lreg import tsqr
         Z = torch.from_numpy(np.hstack([A, Y[:, :1]]))
-        R = tsqr.allgather_r(torch.linalg.qr(Z[lo:hi], mode="r").R)
+        host_qr = lambda M_: torch.linalg.qr(M_, mode="r").R       # (the device kernel is covered by the -m gpu tests)
+        R = tsqr.allgather_r(torch.linalg.qr(Z[lo:hi], mode="r").R, qr=host_qr)
+        parts = [torch.linalg.qr(Z[i::3], mode="r").R for i in range(3)]
+        Rt = tsqr.combine_r(parts, qr=host_qr)                      # odd count: balanced tree with a bye
+        np.testing.assert_allclose((Rt.T @ Rt).numpy(), (Z.T @ Z).numpy(), rtol=1e-12, atol=1e-10)
         Rf = torch.linalg.qr(Z, mode="r").R
         np.testing.assert_allclose((R.T @ R).numpy(), (Rf.T @ Rf).numpy(), rtol=1e-12, atol=1e-10)
         cq, sv, rank_ = tsqr.lstsq_from_r(R, mi.shape[0])

@@ -68,6 +68,23 @@ def _worker(rank, world, port, out):
             if name == "anl":
                 np.testing.assert_allclose(two.datavar, g["anl_datavar"], rtol=1e-9)
                 np.testing.assert_allclose(np.diag(two.cf_cov), g["anl_cov_diag"], rtol=1e-8)
+        # --- the QR route (lreg/lreg.py:335 on ill-conditioned systems): chunk triangles from the Householder kernels,
+        #     the two ranks' triangles combined by the butterfly exchange -- identical R on both ranks
+        from pytuq_b200.lreg import tsqr
+        ill = load_golden("lsq_illcond")
+        for case in ("collinear_hg_d3p5", "rankdef_lu_d3p2"):
+            xi, yi, mii = ill[f"{case}__x"], ill[f"{case}__y"], ill[f"{case}__mi"]
+            pci = PCRV(1, xi.shape[1], str(ill[f"{case}__type"]), mi=mii)
+            f = lsq(solver="qr")
+            f.setBasisEvaluator(PCBasisEvaluator(0), (pci,))
+            lo, hi = parallel.shard_bounds(xi.shape[0], rank, world)
+            with parallel.sharded_rows():
+                f.fit(xi[lo:hi], yi[lo:hi])
+            np.testing.assert_allclose(f.cf, ill[f"{case}__lsq_cf"], rtol=0, atol=1e-9 * np.max(np.abs(ill[f"{case}__lsq_cf"])))
+            t = torch.from_numpy(f.cf.copy()).cuda()
+            both = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(both, t)
+            assert torch.equal(both[0], both[1])
         # --- C3 shape: BCS on the sharded Gram (lreg/bcs.py:58-265), incl. the sharded residual pass
         g, c = load_golden("c3_shape"), gen.shape_inputs(3)
         mi = orc.get_mi(c["p"], c["d"])

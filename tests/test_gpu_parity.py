@@ -761,6 +761,61 @@ def lsq_zero_cov_predicta(At, cf):
     return l.predicta(At, msc=1)
 
 
+def test_householder_qr_kernels_give_the_r_factor():
+    """pcq_qr_r_dev (csrc/pcq_qr.cu): hand-written blocked Householder QR.  R^T R = Z^T Z, |R| equals LAPACK's R up
+    to row signs, the singular values of R are those of Z even when Z is ill-conditioned or rank deficient (the
+    reason this route exists: lreg/lreg.py:335), for tall / square / wide shapes, ragged panel widths, rows beyond
+    one cooperative launch, leading dimensions, and the tree that combines chunk triangles."""
+    import torch
+    from pytuq_b200 import _native
+    from pytuq_b200.lreg import tsqr
+    lib = _native.lib()
+    dev = torch.device("cuda", 0)
+    cap = int(lib.pcq_qr_max_rows(0))
+    assert cap >= 256
+    rng = np.random.default_rng(2024)
+    n0 = lib.pcq_launch_count()
+    for (m, L, kind) in [(1, 1, "rand"), (5, 9, "rand"), (40, 40, "rand"), (70, 33, "rand"), (300, 64, "rand"),
+                         (1000, 97, "rand"), (5000, 130, "graded"), (3000, 200, "rankdef"), (cap + 1000, 70, "rand"),
+                         (20000, 333, "graded")]:
+        Z = rng.standard_normal((m, L))
+        if kind == "graded":                       # condition number ~1e12
+            Z = Z * np.logspace(0, -12, L)[None, :]
+            Z[:, 1::7] += Z[:, 0:1]
+        if kind == "rankdef":
+            Z[:, 5] = Z[:, 3]
+            Z[:, L - 1] = 2.0 * Z[:, 0] - Z[:, 1]
+        Zt = torch.from_numpy(Z).to(dev)
+        pad = torch.full((m, L + 3), 7.0, dtype=torch.float64, device=dev)      # a leading dimension > L
+        pad[:, :L] = Zt
+        for src in (Zt.clone(), pad[:, :L]):
+            R = tsqr._qr_r(src).cpu().numpy()
+            assert R.shape == (L, L) and np.array_equal(R, np.triu(R))
+            G = Z.T @ Z
+            sc = np.sqrt(np.outer(np.diag(G), np.diag(G))) + 1e-300
+            assert np.max(np.abs(R.T @ R - G) / sc) < 1e-13, (m, L, kind)
+            sv = np.linalg.svd(Z, compute_uv=False)
+            svr = np.linalg.svd(R, compute_uv=False)
+            np.testing.assert_allclose(svr[:len(sv)], sv, rtol=0, atol=1e-13 * sv[0], err_msg=str((m, L, kind)))
+            if kind == "rand" and m >= L:
+                Rref = np.linalg.qr(Z, mode="r")
+                np.testing.assert_allclose(np.abs(R), np.abs(Rref), rtol=1e-9, atol=1e-12 * np.abs(Rref).max())
+            if m < L:
+                assert not R[m:].any()
+        assert torch.equal(pad[:, L:], torch.full((m, 3), 7.0, dtype=torch.float64, device=dev))   # nothing outside
+    # chunked factorisation through the balanced tree equals the one-shot factor (up to signs)
+    Z = rng.standard_normal((9000, 60))
+    chunks = [torch.from_numpy(Z[i:i + 1300]).to(dev) for i in range(0, 9000, 1300)]       # 7 triangles: tree with byes
+    Rt = tsqr.combine_r([tsqr._qr_r(c) for c in chunks]).cpu().numpy()
+    R1 = tsqr._qr_r(torch.from_numpy(Z).to(dev)).cpu().numpy()
+    np.testing.assert_allclose(np.abs(Rt), np.abs(R1), rtol=1e-10, atol=1e-12)
+    tree = tsqr._Tree()
+    for c in [torch.from_numpy(Z[i:i + 1300]).to(dev) for i in range(0, 9000, 1300)]:
+        tree.push(tsqr._qr_r(c))
+    np.testing.assert_allclose(np.abs(tree.result().cpu().numpy()), np.abs(R1), rtol=1e-10, atol=1e-12)
+    assert lib.pcq_launch_count() > n0
+
+
 def test_lsq_qr_route_on_illconditioned_systems():
     """8(f2): where the normal equations cannot follow the reference's SVD least squares, lsq switches to the
     QR statistic.  Golden coefficients come from the unmodified reference (tests/golden/lsq_illcond.npz)."""
@@ -797,7 +852,7 @@ def test_lsq_qr_route_on_illconditioned_systems():
     Y = rng.standard_normal((1500, 2))
     pc = PCRV(1, 4, "LU", mi=mi)
     R1 = tsqr.r_factor_pc(pc, x, Y, 0).cpu().numpy()
-    R2 = tsqr.r_factor_pc(pc, x, Y, 0, chunk_bytes=8 * 37 * 100).cpu().numpy()
+    R2 = tsqr.r_factor_pc(pc, x, Y, 0, chunk_rows=100).cpu().numpy()
     assert rel_err(R2.T @ R2, R1.T @ R1) < 1e-12
     Z = np.hstack([orc.eval_bases(x, mi, "LU"), Y])
     assert rel_err(R1.T @ R1, Z.T @ Z) < 1e-12
