@@ -584,10 +584,10 @@ def main():
         "breakdown_ms": {"k3_suffstats": k3_mean_ms, "allreduce": float(np.mean(ar_ms)),
                          "solve_kxk": 1e3 * float(np.mean(solve_s))},
         "max_abs_coef_error_vs_truth": err,
-        "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; per chunk one launch over the "
-                               "off-diagonal tiles, 86.3 % of the step, and one over the upper-triangle sub-blocks of the diagonal tiles, "
-                               "9.6 %; the rest is pcq_pack_bases_kernel 2.6 %, fix-up/mirror 0.4 %, K x K solve 1 %; "
-                               "profiles/r01_j_k3_traffic.json)",
+        "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; per 2 GB chunk one launch over "
+                               "the off-diagonal tiles, 87.5 % of the step, and one over the upper-triangle sub-blocks of the diagonal "
+                               "tiles, 9.6 %; the rest is pcq_pack_bases_kernel 2.5 %, fix-up/mirror 0.4 %, K x K solve 0.2 %; "
+                               "profiles/r02_k3_traffic.json, profiles/r02_launches_bench.csv)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if peak else None, "traffic": traffic,
                      "traffic_source": traffic_source,
