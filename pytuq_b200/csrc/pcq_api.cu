@@ -229,7 +229,6 @@ int pcq_plan_destroy(pcq_plan* p) {
     pcq_spec_free(p->spec[0].load());
     pcq_spec_free(p->spec[1].load());
     cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
-    pcq_horner_free(p->horner);
     cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_q); cudaFree(p->d_gtab[0]); cudaFree(p->d_gtab[1]); cudaFree(p->d_achunk);
     for (int i = 0; i < 2; ++i) {
         cudaFree(p->d_stage[i]); cudaFree(p->d_out[i]);

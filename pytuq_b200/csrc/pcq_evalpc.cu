@@ -703,11 +703,6 @@ int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, cons
         }
         return PCQ_OK;
     }
-    if (fast && m <= 8) {
-        // not specialised (yet): the Horner interpreter -- one table gather + one DFMA per term (pcq_horner.cu)
-        const int rc = pcq_launch_evalpc_horner(p, x, n, ldx, cf, m, y, ldy, P.sumsq, st);
-        if (rc != PCQ_ERR_UNSUPPORTED) return rc;
-    }
     return launch_evalpc_any<false>(p, P, mode, st, nullptr);
 }
 
@@ -731,7 +726,7 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
     P.seed = seed; P.first_index = first; P.germ_kind = dkind;
     const int fast = mode & 1;
     const bool bigdim = !pcq_table_fits_smem(p);
-    if ((p->spec[fast].load(std::memory_order_acquire) && m <= 8) || bigdim || (fast && m <= 8 && pcq_horner_ready(p))) {
+    if ((p->spec[fast].load(std::memory_order_acquire) && m <= 8) || bigdim) {
         // materialised-germ path: germ chunk -> HBM (160 B per sample, far below the evaluation cost) ->
         // specialised evalPC (or, for a germ too wide for shared-memory tables, the global-table evalPC) ->
         // power sums; chunks of 4M samples (64k for wide germs), sums combined on the device
@@ -751,8 +746,13 @@ int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
             const int64_t ldc = y ? ldy : m;
             if (nr > 0) {
                 if ((rc = pcq_launch_germ(p, seed, first + r0, nr, germ_kind, p->d_stage[0], s, st)) != PCQ_OK) return rc;
-                // (routes to the specialised kernels, the global-table kernel of wide germs or the Horner interpreter)
-                if ((rc = pcq_launch_evalpc(p, p->d_stage[0], nr, s, cf, m, yc, ldc, mode & 1, st)) != PCQ_OK) return rc;
+                if (bigdim) {
+                    if ((rc = pcq_launch_evalpc(p, p->d_stage[0], nr, s, cf, m, yc, ldc, mode & 1, st)) != PCQ_OK) return rc;
+                } else {
+                    for (int j = 0; j < m; ++j)
+                        if ((rc = pcq_spec_launch(p, fast, p->d_stage[0], nr, s, cf + (size_t)j * p->nterms, yc + j, ldc, st)) != PCQ_OK)
+                            return rc;
+                }
             }
             pcq_moments_kernel<<<mgrid, 256, 0, st>>>(yc, nr, ldc, m, part);
             PCQ_LAUNCH_CHECK("pcq_moments_kernel");

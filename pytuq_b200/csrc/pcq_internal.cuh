@@ -47,9 +47,6 @@ struct pcq_plan {
     std::atomic<pcq_spec*> spec[2]{};
     std::thread spec_thread;                  // background build started by pcq_plan_specialize_async
     std::atomic<int> spec_building{0};        // modes being built in the background (bit 0 exact, bit 1 fast)
-    // fast-mode evalPC through the Horner interpreter (csrc/pcq_horner.cu): record stream built on first use
-    struct pcq_horner* horner = nullptr;
-    int horner_state = 0;                     // 0 not built, 1 ready, 2 not applicable to this multi-index
     // Gram workspace (lazily grown)
     double* d_ws = nullptr;
     size_t ws_bytes = 0;
@@ -112,12 +109,6 @@ bool pcq_table_fits_smem(const pcq_plan* p);
 int pcq_launch_gtab(pcq_plan* p, const double* x, int64_t n, int64_t ldx, int64_t nc, double** tab, cudaStream_t st);
 int pcq_launch_evalpc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf,
                       int m, double* y, int64_t ldy, int mode, cudaStream_t st);
-// fast-mode evalPC in Horner form without run-time compilation (pcq_horner.cu); PCQ_ERR_UNSUPPORTED = not applicable
-struct pcq_horner;
-void pcq_horner_free(pcq_horner* h);
-bool pcq_horner_ready(pcq_plan* p);
-int pcq_launch_evalpc_horner(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* cf, int m, double* y,
-                             int64_t ldy, int sumsq, cudaStream_t st);
 // generator == plan (fused, p != nullptr) or materialised A (a != nullptr)
 int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n,
                     int64_t ldx, const double* a, int64_t lda, int kcols, const double* y,

@@ -517,54 +517,6 @@ def test_k2_specialised_kernels_bitexact():
         np.testing.assert_allclose(b["mean"], a["mean"], rtol=1e-11, atol=1e-13)
 
 
-def test_k2_fast_mode_generic_horner_interpreter(monkeypatch):
-    """Fast-mode evalPC of a plan that is not specialised = the Horner interpreter (csrc/pcq_horner.cu): the trie
-    flattened into a record stream, one table gather + one DFMA per term.  Against the bit-exact mode (rounding-level
-    differences only, rv/pcrv.py:486-497) on downward-closed, sparse, duplicated, mixed-family and many-chunk
-    multi-indices, 1..8 outputs, the sum-of-squares form, a trie deeper than the register stack (falls back to the
-    term-by-term kernel) and through propagate."""
-    from pytuq_b200.rv.pcrv import PCRV
-    from pytuq_b200 import _native
-    monkeypatch.setenv("PCQ_AUTO_SPECIALIZE", "0")
-    rng = np.random.default_rng(321)
-    deep = np.zeros((40, 12), dtype=np.int64)
-    for r in range(1, 40):
-        deep[r, rng.choice(12, int(rng.integers(1, 10)), replace=False)] = 1          # up to 9 non-zero orders per term
-    cases = [("HG", orc.get_mi(3, 20), 3000, 1), ("LU", orc.get_mi(4, 12)[np.sort(rng.choice(1820, 700, replace=False))], 2000, 3),
-             (["LU", "HG", "nLU", "nHG", "LU"], np.vstack([orc.get_mi(3, 5)] * 2), 1000, 8), ("HG", orc.get_mi(4, 20), 700, 2),
-             ("LU", orc.get_mi(2, 50), 1500, 5), ("LU", deep, 500, 2), ("HG", orc.get_mi(6, 2), 999, 1), ("LU", np.zeros((1, 3), dtype=np.int64), 10, 1)]
-    for types, mi, n, M in cases:
-        d, K = mi.shape[1], mi.shape[0]
-        cfs = rng.standard_normal((M, K)) / (1.0 + mi.sum(axis=1)) ** 2
-        tlist = [types] * d if isinstance(types, str) else types
-        x = np.stack([rng.uniform(-1, 1, n) if t.endswith("LU") else rng.standard_normal(n) for t in tlist], axis=1)
-        pc = PCRV(M, d, types, mi=mi, cfs=cfs)
-        y_exact = pc.evalPC(x)
-        l0 = _native.lib().pcq_launch_count()
-        y_fast = pc.evalPC(x, exact=False)
-        assert _native.lib().pcq_launch_count() > l0
-        assert _native.lib().pcq_plan_info(pc._plan(pc.mindices[0]).handle, 7) == 0          # not specialised
-        scale = np.maximum(np.max(np.abs(y_exact), axis=0), 1e-300)
-        assert np.max(np.abs(y_fast - y_exact) / scale) < 1e-12, (types, K, M)
-        v = pc.evalLinearForms(x, cfs, 0, sumsq=True)
-        np.testing.assert_allclose(v, (y_exact ** 2).sum(axis=1), rtol=1e-11, atol=1e-13 * np.max(np.abs(v)) + 1e-300)
-    # the interpreter and the term-by-term kernel agree (PCQ_K2_NO_HORNER switches the former off)
-    pc = PCRV(2, 20, "HG", mi=orc.get_mi(3, 20), cfs=rng.standard_normal((2, 1771)))
-    x = rng.standard_normal((4097, 20))
-    y_h = pc.evalPC(x, exact=False)
-    monkeypatch.setenv("PCQ_K2_NO_HORNER", "1")
-    from pytuq_b200 import device as pdev
-    pdev.clear_plans()
-    y_t = pc.evalPC(x, exact=False)
-    monkeypatch.delenv("PCQ_K2_NO_HORNER")
-    pdev.clear_plans()
-    np.testing.assert_allclose(y_h, y_t, rtol=1e-11, atol=1e-12)
-    a = pc.propagate(300_000, seed=21, exact=False, specialize=False)
-    b = pc.propagate(300_000, seed=21, exact=True, specialize=False)
-    np.testing.assert_allclose(a["sum"], b["sum"], rtol=1e-10)
-    np.testing.assert_allclose(a["sumsq"], b["sumsq"], rtol=1e-10)
-
-
 def test_k2_fast_specialised_kernels_in_horner_form():
     """Fast-mode specialised evalPC = Horner form over the multi-index trie (csrc/pcq_spec.cu:gen_source_horner): one
     DFMA per term, terms re-ordered -- values differ from the reference's summation order by rounding only
