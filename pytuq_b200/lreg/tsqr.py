@@ -164,14 +164,10 @@ def allgather_r(R, qr=None):
         while step < world:
             partner = rank ^ step
             other = torch.empty_like(R)
-            if rank < partner:
-                dist.send(R, partner)
-                dist.recv(other, partner)
-                R = qr(torch.cat([R, other]))
-            else:
-                dist.recv(other, partner)
-                dist.send(R, partner)
-                R = qr(torch.cat([other, R]))
+            ops = [dist.P2POp(dist.isend, R, partner), dist.P2POp(dist.irecv, other, partner)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            R = qr(torch.cat([R, other] if rank < partner else [other, R]))
             step <<= 1
         return R
     parts = [torch.empty_like(R) for _ in range(world)]
