@@ -253,6 +253,37 @@ class lreg(fitbase):
                 ypred_var = np.diag(ypred_cov)
         return ypred, ypred_var, ypred_cov
 
+    def predict_plot(self, aa_list, yy_list, labels=None, colors=None):
+        r"""Diagonal plots of fit vs data and |residual| vs predictive standard deviation for several (A, y) sets
+        (lreg/lreg.py:201-240): the predictions run on the device (``predicta(msc=1)``); drawing needs matplotlib,
+        which this package does not depend on otherwise."""
+        nlist = len(aa_list)
+        assert(nlist == len(yy_list))
+        preds, stds = [], []
+        for aa in aa_list:
+            yy_pred, yy_pred_var, _ = self.predicta(aa, msc=1)
+            preds.append(yy_pred)
+            stds.append(np.sqrt(yy_pred_var))
+        labels = [f'Set {i+1}' for i in range(nlist)] if labels is None else labels
+        colors = (['b', 'g', 'r', 'c', 'm', 'y'] * nlist)[:nlist] if colors is None else colors
+        assert(len(labels) == nlist and len(colors) == nlist)
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError as exc:
+            raise ImportError("lreg.predict_plot draws with matplotlib, which is not installed") from exc
+        for fname, xs, ys, errs, axl in (
+                ('fitdiag.png', yy_list, preds, stds, ('Data', 'Fit')),
+                ('resid_vs_std.png', [np.abs(p - y) for y, p in zip(yy_list, preds)], stds, None, ('|Residual|', 'Fit StDev'))):
+            fig, ax = plt.subplots(figsize=(8, 8))
+            for i in range(nlist):
+                ax.errorbar(xs[i], ys[i], yerr=None if errs is None else errs[i], fmt='o', color=colors[i], label=labels[i])
+            lo = min(float(np.min(v)) for v in list(xs) + list(ys))
+            hi = max(float(np.max(v)) for v in list(xs) + list(ys))
+            ax.plot([lo, hi], [lo, hi], 'k--', lw=1)
+            ax.set_xlabel(axl[0]); ax.set_ylabel(axl[1]); ax.legend()
+            fig.savefig(fname)
+            plt.close(fig)
+
     def predicta_samples(self, Amat, nsamples=100):
         r"""Amat @ (coefficient samples)^T (lreg/lreg.py:145-162): the draws come from numpy's global stream as in the
         reference, the (N, K) x (K, nsamples) product runs on the device."""
