@@ -52,7 +52,7 @@ def test_reference_example_prints_the_same_numbers_on_the_drop_in(example, tmp_p
     launches = [ln for ln in out_d.splitlines() if ln.startswith("PCQ_LAUNCHES")]
     if rc_d == 0:
         assert launches, "the drop-in run did not report its kernel launches"
-        if example not in ("ex_pcbasis1d.py",):
+        if example not in ("ex_pcbasis1d.py", "ex_quad.py"):       # (quadrature rules are host-only work)
             assert int(launches[0].split()[1]) > 0, "no CUDA kernel was launched by the drop-in run"
     a, la = _numbers(out_r)
     b, lb = _numbers(out_d)
