@@ -70,8 +70,10 @@ __global__ void __launch_bounds__(QR_ROWS) qr_panel_kernel(PanelParams P) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[QR_ROWS / 32][QR_NB];
     __shared__ double s_sum[2 * QR_NB];     // [0..NB): dots of the pivot column, [NB..2NB): Gram column of the reflectors
+    __shared__ double s_red[4][2 * QR_NB];
     __shared__ double s_w[QR_NB];
     __shared__ double s_sc[2];              // scale, beta
+    static_assert(QR_ROWS == 4 * 2 * QR_NB, "the partial-sum reduction maps four threads to each of the 2*NB values");
     const int tid = threadIdx.x;
     const int jb = P.jb;
     const int64_t row = (int64_t)P.j0 + (int64_t)blockIdx.x * QR_ROWS + tid;
@@ -119,12 +121,16 @@ __global__ void __launch_bounds__(QR_ROWS) qr_panel_kernel(PanelParams P) {
         }
         __threadfence();
         grid.sync();
-        // every CTA reduces the partials in block order (identical result everywhere)
-        if (tid < 2 * QR_NB) {
+        // every CTA reduces the partials in a fixed order (identical result everywhere): four threads per value, each
+        // over every fourth block, then the four partial sums in order
+        {
+            const int v = tid & (2 * QR_NB - 1), q = tid >> 6;       // QR_ROWS = 4 * 2 * QR_NB
             double t = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) t += P.part[((size_t)par * gridDim.x + b) * (2 * QR_NB) + tid];
-            s_sum[tid] = t;
+            for (unsigned b = q; b < gridDim.x; b += 4) t += P.part[((size_t)par * gridDim.x + b) * (2 * QR_NB) + v];
+            s_red[q][v] = t;
         }
+        __syncthreads();
+        if (tid < 2 * QR_NB) s_sum[tid] = ((s_red[0][tid] + s_red[1][tid]) + s_red[2][tid]) + s_red[3][tid];
         __syncthreads();
         // T column jj-1 (CTA 0): T[0:jj-1, jj-1] = -tau * T[0:jj-1, 0:jj-1] * (V[:,0:jj-1]^T v_{jj-1}),  T[jj-1][jj-1] = tau
         if (blockIdx.x == 0 && jj >= 1 && tid == 0) {
