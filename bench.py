@@ -598,7 +598,9 @@ def main():
                                       "(pack + SYRK + fix-up + mirror launches), CUDA events on the launching stream",
                      "algorithmic_flops_per_launch": flops,
                      "peak_source": "FP64 DMMA m8n8k4 register-chain micro-benchmark run live on this GPU "
-                                    "(pcq_measure_peak); MEASURED_PEAKS.json has no FP64 figure"},
+                                    "(pcq_measure_peak); MEASURED_PEAKS.json has no FP64 figure -- the same measurement looped "
+                                    "for 4 s with a clock record is committed as profiles/r02_fp64_peaks.json (DMMA 36.95 burst / "
+                                    "36.85 sustained, DFMA 36.49 / 36.42 TFLOP/s at 1965 MHz, no throttle reason)"},
         "peaks_measured_live": peaks,
         "kernels": kernels,
         "cpu_baseline": cpu,
