@@ -1,41 +1,44 @@
-"""Minimal ``Function`` wrapper PCRV.setFunction hands out (reference: func/func.py:14-56,
-82-99, 185-208).  Only the members the PC path and its callers use are provided; the
-reference's function algebra and test-function zoo are out of scope."""
+"""The small ``Function`` object ``PCRV.setFunction`` / ``KLSurr.setFunction`` hand out: a named callable on a box domain
+(the members of the reference's func/func.py:14-56, 82-99, 185-208 that the PC path and its callers use).  The
+reference's function algebra, gradients, plotting and test-function zoo are out of scope."""
 import numpy as np
 
 
 class Function():
+    dmax = 10.0            # half-width of the default domain
+
     def __init__(self, name='Base'):
-        self.dim = None
-        self.outdim = None
-        self.domain = None
         self.name = name
         self.eval = None
-        self.dmax = 10.0
+        self.dim = self.outdim = self.domain = None
+        self.dmax = Function.dmax
+
+    def __repr__(self):
+        return f"Function({self.name}, dim={self.dim}, outdim={self.outdim})"
 
     def __call__(self, x):
         if self.eval is None:
             raise NotImplementedError("Function evaluation is not implemented in the base class.")
         return self.eval(x)
 
-    def __repr__(self):
-        return f"Function({self.name}, dim={self.dim}, outdim={self.outdim})"
-
     def setCall(self, eval):
+        """Installs the callable x (N, d) -> (N, o)."""
         self.eval = eval
 
     def call1d(self, odim=0):
-        return lambda x: self.__call__(x)[:, odim]
+        """The odim-th output as a function of its own."""
+        return lambda x: self(x)[:, odim]
 
     def setDimDom(self, domain=None, dimension=None):
-        if domain is None:
-            assert dimension is not None
-            self.dim = int(dimension)
-            self.domain = np.tile(np.array([-self.dmax, self.dmax]), (self.dim, 1))
-        else:
-            assert dimension is None
-            self.dim = domain.shape[0]
+        """Either a (d, 2) box, or a dimension (the box is then [-dmax, dmax]^d)."""
+        assert (domain is None) != (dimension is None)
+        if domain is not None:
             self.domain = domain
+            self.dim = domain.shape[0]
+        else:
+            self.dim = int(dimension)
+            self.domain = np.repeat(np.array([[-self.dmax, self.dmax]]), self.dim, axis=0)
 
     def inDomain(self, x):
-        return bool(np.all(x >= self.domain[:, 0]) and np.all(x <= self.domain[:, 1]))
+        lo, hi = self.domain[:, 0], self.domain[:, 1]
+        return bool((x >= lo).all() and (x <= hi).all())

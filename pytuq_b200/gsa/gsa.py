@@ -1,6 +1,11 @@
-"""PC-based Sobol sensitivity analysis (drop-in for ``PCSobol``, reference gsa/gsa.py:383-457).
-The sampling estimators that share the reference's file (SamSobol, Moat, Linreg) do not
-touch the PC path and are out of scope."""
+"""PC-based Sobol sensitivity analysis: drop-in for ``PCSobol`` (reference gsa/gsa.py:383-457).
+
+Workflow of the reference class, kept call for call: ``sample(N)`` draws the germ of a total-order PC and maps it to
+the input box, the caller evaluates the model there, ``compute(y)`` regresses the PC on (germ, y) and reads the
+main / total / joint indices off the coefficients.  Here the regression is the fused statistics pass (K3) -- the
+design matrix the reference builds in ``compute`` never exists -- and the indices come from the vectorised
+``PCRV.compute*Sens``.  The sampling-based estimators that share the reference's file (SamSobol, Moat, Linreg,
+model_sens) never touch the PC path and are out of scope."""
 import numpy as np
 
 from ..lreg.lreg import lsq, PCBasisEvaluator
@@ -9,18 +14,23 @@ from ..utils.mindex import get_mi
 
 
 def scale01ToDom(xx, dom):
-    """[0,1]^d -> domain (reference: utils/maps.py:7-22)."""
-    if np.any(xx < 0.0) or np.any(xx > 1.0):
+    """Affine map of points of the unit cube onto the box ``dom`` (d, 2) (reference: utils/maps.py:7-22)."""
+    unit = np.asarray(xx)
+    if (unit < 0.0).any() or (unit > 1.0).any():
         print("Warning: some elements are outside the [0,1] range.")
-    return xx * np.abs(dom[:, 1] - dom[:, 0]) + np.min(dom, axis=1)
+    lower = np.min(dom, axis=1)
+    width = np.abs(dom[:, 1] - dom[:, 0])
+    return lower + unit * width
 
 
 class SensMethod():
+    """Common state of the sensitivity estimators: the input box and one result slot per index family."""
+
     def __init__(self, dom, sens_names):
         self.dom = dom
-        self.dim = dom.shape[0]
+        self.dim = len(dom)
         self.sens_names = sens_names
-        self.sens = dict((k, [None] * self.dim) for k in self.sens_names)
+        self.sens = {name: [None] * self.dim for name in sens_names}
 
     def sample(self, nsam):
         raise NotImplementedError("Sampling for sensitivity is not implemented in the base class.")
@@ -30,34 +40,35 @@ class SensMethod():
 
 
 class PCSobol(SensMethod):
-    r"""Samples the germ, fits a PC by least squares (fused statistics, no design matrix)
-    and reads main / total / joint Sobol indices off the coefficients."""
+    r"""Sobol indices from a regression PC surrogate (Sudret 2008).  Attributes after ``sample`` / ``compute`` as in the
+    reference: ``pcrv``, ``nsam``, ``germ_sam (N, d)``, ``xsam (N, d)``, ``sens`` with keys main, total, jointt."""
 
     def __init__(self, dom, pctype='LU', order=3):
         print("Initializing PCSobol Sensitivity Method")
         self.sens_names = ['main', 'total', 'jointt']
-        super().__init__(dom, self.sens_names)
-        self.pctype = pctype
-        self.order = order
+        SensMethod.__init__(self, dom, self.sens_names)
+        self.pctype, self.order = pctype, order
+
+    def _inputs_of(self, germ):
+        """Germ samples -> model inputs: each coordinate through its own germ CDF onto [0, 1], then onto the box."""
+        unit = np.column_stack([pc1.germCdf(germ[:, i]) for i, pc1 in enumerate(self.pcrv.PC1ds)])
+        return scale01ToDom(unit, self.dom)
 
     def sample(self, nsam):
         print("Sampling PCSobol Sensitivity Method")
-        self.pcrv = PCRV(1, self.dim, self.pctype, mi=get_mi(self.order, self.dim))
         self.nsam = nsam
-        self.germ_sam = self.pcrv.sampleGerm(nsam=self.nsam)
-        unif_sam = np.zeros((self.nsam, self.dim))
-        for idim in range(self.dim):
-            unif_sam[:, idim] = self.pcrv.PC1ds[idim].germCdf(self.germ_sam[:, idim])
-        self.xsam = scale01ToDom(unif_sam, self.dom)
+        self.pcrv = PCRV(1, self.dim, self.pctype, mi=get_mi(self.order, self.dim))
+        self.germ_sam = self.pcrv.sampleGerm(nsam=nsam)
+        self.xsam = self._inputs_of(self.germ_sam)
         return self.xsam
 
     def compute(self, ysam):
         assert(ysam.shape[0] == self.nsam)
-        fitter = lsq()
-        fitter.setBasisEvaluator(PCBasisEvaluator(0), (self.pcrv,))
-        fitter.fit(self.germ_sam, ysam)
-        self.pcrv.setCfs([fitter.cf])
-        self.sens['main'] = self.pcrv.computeSens()[0]
-        self.sens['total'] = self.pcrv.computeTotSens()[0]
-        self.sens['jointt'] = self.pcrv.computeJointSens()[0]
+        regression = lsq()
+        regression.setBasisEvaluator(PCBasisEvaluator(0), (self.pcrv,))
+        regression.fit(self.germ_sam, ysam)                    # statistics pass on the device, no design matrix
+        self.pcrv.setCfs([regression.cf])
+        for key, indices in (('main', self.pcrv.computeSens), ('total', self.pcrv.computeTotSens),
+                             ('jointt', self.pcrv.computeJointSens)):
+            self.sens[key] = indices()[0]
         return self.sens

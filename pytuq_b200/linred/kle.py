@@ -1,42 +1,48 @@
-"""Karhunen-Loeve expansion (reference: linred/kle.py:9-84).  Covariance (one GEMM), symmetric
+"""Karhunen-Loeve expansion of an ensemble of fields (reference: linred/kle.py:9-84).
+
+The field lives on N grid points with trapezoidal quadrature weights w (1/2 at the two ends), M samples.  The modes
+are the eigenvectors of the weighted covariance  diag(sqrt w) C diag(sqrt w), mapped back by 1/sqrt(w); the latent
+features are the weighted projections on the modes scaled to unit variance.  Covariance GEMM, symmetric
 eigendecomposition (cuSOLVER syevd through torch.linalg.eigh) and projection run on the device."""
 import numpy as np
 
-from .linred import LinRed, _dev, _mm
+from .. import device as _device
+from .linred import LinRed, _mm
 
 
 class KLE(LinRed):
     def __init__(self):
-        super().__init__()
-        self.weights2 = None
+        LinRed.__init__(self)
+        self.weights2 = None          # quadrature weights (the reference keeps them under this name)
 
     def build(self, data, plot=True):
         r"""data (N, M): N conditions (grid points), M samples.  ``plot`` is accepted and ignored."""
         import torch
-        nx, nsam = data.shape
-        d = _dev()
-        D = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).to(d)
-        mean = D.mean(dim=1)
-        Dc = D - mean[:, None]
-        cov = (Dc @ Dc.T) / (nsam - 1)                     # np.cov(data), kle.py:43
+        _device.require_device()
+        where = torch.device("cuda", _device.current_device())
+        npts, nsam = data.shape
+        quad = np.ones(npts)
+        quad[[0, -1]] = 0.5
+        self.weights2 = quad
 
-        self.mean = mean.cpu().numpy()
-        self.weights2 = np.ones(nx)                        # trapezoidal rule weights, kle.py:46-49
-        self.weights2[0] = 0.5
-        self.weights2[-1] = 0.5
-        weights = np.sqrt(self.weights2)
-        w_t = torch.from_numpy(weights).to(d)
-
-        eigval, eigvec = torch.linalg.eigh(torch.outer(w_t, w_t) * cov)
-        self.eigval = eigval.flip(0).cpu().numpy()
-        self.modes = (eigvec.flip(1) / w_t[:, None]).cpu().numpy()      # nx, neig
+        field = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).to(where)
+        centre = field.mean(dim=1)
+        dev = field - centre[:, None]
+        root_w = torch.from_numpy(np.sqrt(quad)).to(where)
+        weighted = dev * root_w[:, None]
+        # eigenpairs of the weighted sample covariance (np.cov normalisation: M - 1), largest first
+        lam, vec = torch.linalg.eigh((weighted @ weighted.T) / (nsam - 1))
+        self.mean = centre.cpu().numpy()
+        self.eigval = lam.flip(0).cpu().numpy()
+        self.modes = (vec.flip(1) / root_w[:, None]).cpu().numpy()
         self.built = True
         self.eigval_clip()
         self.xi = self.project(data)
 
     def project(self, data, subtract_mean=True):
-        r"""data (N, M) -> (M, K) with the trapezoidal inner product (kle.py:67-82)."""
+        r"""data (N, M) -> (M, K): quadrature-weighted inner products with the modes, scaled by 1 / sqrt(eigval)."""
         assert(self.built)
-        nmodes = self.modes.shape[1]
-        return _mm(data.T - int(subtract_mean) * self.mean,
-                   self.modes * self.weights2.reshape(-1, 1)) / np.sqrt(self.eigval[:nmodes])
+        kept = self.modes.shape[1]
+        rows = data.T - self.mean if subtract_mean else data.T
+        basis = (self.modes * self.weights2[:, np.newaxis]) / np.sqrt(self.eigval[:kept])
+        return _mm(rows, basis)
