@@ -77,11 +77,13 @@ int pcq_plan_destroy(pcq_plan* plan);
  *          8 modes being built in the background */
 int64_t pcq_plan_info(const pcq_plan* plan, int what);
 
-/* Opt-in: compiles (NVRTC, at run time) evalPC kernels specialised for this plan's multi-index -- the
- * term list unrolled into straight-line code with the 1-D tables in registers.  Bit-identical to the
- * generic kernels in exact mode and 3-4x faster, but costs ~3 ms of compile time per term, so it pays
- * only for large propagation jobs or many repeated evaluations (MCMC).  modes: bit 0 exact, bit 1 fast.
- * Once built, pcq_eval_pc(_dev) (up to 8 outputs, no quadratic-form mode) and pcq_propagate_dev use them.
+/* Opt-in: compiles (NVRTC, at run time) evalPC kernels specialised for this plan's multi-index, the 1-D tables in
+ * registers, no shared-memory gathers.  modes: bit 0 exact -- the term list unrolled in k order with the reference's
+ * rounding sequence (rv/pcrv.py:486-497): bit-identical to the generic kernels, 4.7x faster at K = 1771; bit 1 fast
+ * -- Horner form over the multi-index trie, one fused multiply-add per term, terms re-ordered: rounding-level
+ * differences only, 11.5x the generic kernel.  ~0.2 ms of compile time per term on 16 host threads, cubins cached on
+ * disk ($PCQ_SPEC_CACHE_DIR), so it pays for propagation jobs and repeated evaluations (MCMC).  Once built,
+ * pcq_eval_pc(_dev) (up to 8 outputs, no quadratic-form mode) and pcq_propagate(_dev) use them.
  * Returns PCQ_ERR_UNSUPPORTED when libnvrtc is not available; the generic kernels stay in use. */
 int pcq_plan_specialize(pcq_plan* plan, int modes);
 /* Same build on a background host thread: returns at once, evaluations keep using the generic kernels until the
