@@ -66,7 +66,6 @@ def bcs_fit_stats(stats, sigma2=None, eta=1.e-8, adaptive=0, optimal=1, scale=0.
 
     itermax = 100
     mlhist = np.empty(itermax)
-    allterms = np.arange(M)
     for count in range(itermax):
         ss = S.copy()
         qq = Q.copy()
@@ -75,9 +74,15 @@ def bcs_fit_stats(stats, sigma2=None, eta=1.e-8, adaptive=0, optimal=1, scale=0.
         theta = qq ** 2 - ss
 
         ml = np.full(M, -np.inf)
-        positive = np.where(theta > 0)[0]
+        # membership masks instead of sorted-set operations (same candidate sets in the same ascending order, a
+        # third of the iteration's time at K ~ 1300): pos_of[k] = position of term k in `index`, -1 outside the model
+        positive = theta > 0
+        pos_of = np.full(M, -1)
+        pos_of[index] = np.arange(len(index))
+        inside = pos_of >= 0
         # in the model and theta > 0: candidates for re-estimation
-        ire, _, which = np.intersect1d(positive, index, return_indices=True)
+        ire = np.flatnonzero(positive & inside)
+        which = pos_of[ire]
         if len(ire) > 0:
             anew = ss[ire] ** 2 / theta[ire] + nugget
             delta = (alpha[which] - anew) / (anew * alpha[which])
@@ -86,14 +91,15 @@ def bcs_fit_stats(stats, sigma2=None, eta=1.e-8, adaptive=0, optimal=1, scale=0.
             else:
                 ml[ire] = Q[ire] ** 2 * delta / (S[ire] * delta + 1) - np.log(1 + S[ire] * delta)
         # outside the model and theta > 0: candidates for addition
-        iad = np.setdiff1d(positive, ire)
+        iad = np.flatnonzero(positive & ~inside)
         if len(iad) > 0:
             if (S[iad] <= 0.0).any():
                 ml[iad] = -1.e+80
             else:
                 ml[iad] = (Q[iad] ** 2 - S[iad]) / S[iad] + np.log(S[iad] / (Q[iad] ** 2))
         # in the model and theta <= 0: candidates for deletion
-        ide, _, which = np.intersect1d(np.setdiff1d(allterms, positive), index, return_indices=True)
+        ide = np.flatnonzero(~positive & inside)
+        which = pos_of[ide]
         if len(ide) > 0:
             ml[ide] = Q[ide] ** 2 / (S[ide] - alpha[which]) - np.log(1. - S[ide] / alpha[which])
 
