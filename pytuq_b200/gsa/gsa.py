@@ -6,11 +6,31 @@ main / total / joint indices off the coefficients.  Here the regression is the f
 design matrix the reference builds in ``compute`` never exists -- and the indices come from the vectorised
 ``PCRV.compute*Sens``.  The sampling-based estimators that share the reference's file (SamSobol, Moat, Linreg,
 model_sens) never touch the PC path and are out of scope."""
+import sys
+
 import numpy as np
 
-from ..lreg.lreg import lsq, PCBasisEvaluator
+from ..lreg.lreg import lsq, PCBasisEvaluator, solve_normal_device, solve_normal
+from ..lreg.stats import SuffStats
 from ..rv.pcrv import PCRV
 from ..utils.mindex import get_mi
+
+
+def model_sens(model, model_params, domain, method='SamSobol', nsam=100, plot=True, **kwargs):
+    r"""Main and total sensitivities of a multi-output model ``model(x, params) -> (N, o)``, each (o, d)
+    (reference gsa/gsa.py:21-66).  Only ``method='PCSobol'`` -- the PC path -- is provided here; the sampling estimators
+    (SamSobol, LinReg, Moat) are outside this package.  Where the reference regresses output by output on the same
+    design matrix, all outputs share ONE statistics pass here (``PCSobol.compute_all``).  ``plot`` is accepted and
+    ignored (no matplotlib dependency)."""
+    if method != "PCSobol":
+        if method in ("SamSobol", "LinReg", "Moat"):
+            raise NotImplementedError(f"model_sens: method '{method}' is a sampling estimator outside the PC path of this package")
+        print(f'Sensitivity method {method} is unknown. Exiting.')
+        sys.exit()
+    estimator = PCSobol(domain, **kwargs)
+    xsam = estimator.sample(nsam)
+    ysam = model(xsam, model_params)
+    return estimator.compute_all(ysam)
 
 
 def scale01ToDom(xx, dom):
@@ -72,3 +92,22 @@ class PCSobol(SensMethod):
                              ('jointt', self.pcrv.computeJointSens)):
             self.sens[key] = indices()[0]
         return self.sens
+
+    def compute_all(self, ysam):
+        r"""Main and total indices of ALL outputs ``ysam (N, o)`` at once, each (o, d): one fused statistics pass with
+        the o outputs as right-hand sides, one batched K x K solve, the vectorised index formulas on the (o, K)
+        coefficient matrix.  Same numbers as calling ``compute`` per column (what the reference's model_sens does)."""
+        ysam = np.asarray(ysam, dtype=np.float64).reshape(self.nsam, -1)
+        nout = ysam.shape[1]
+        stats = SuffStats.from_pc(self.pcrv, self.germ_sam, ysam, 0)
+        system = stats.dev_system()
+        coef = solve_normal_device(system[0], system[1], 1.0e-6) if system is not None else None
+        coef = solve_normal(stats.G, stats.B()) if coef is None else coef.cpu().numpy()          # (K, o)
+        for i in range(nout):
+            print(f'Output # {i+1}')
+        mindex = self.pcrv.mindices[0]
+        multi = PCRV(nout, self.dim, self.pctype, mi=mindex, cfs=np.ascontiguousarray(coef.T))
+        self.pcrv.setCfs([np.ascontiguousarray(coef[:, -1])])      # state after the reference's loop: the last output
+        self.sens['main'], self.sens['total'] = multi.computeSens()[-1], multi.computeTotSens()[-1]
+        self.sens['jointt'] = self.pcrv.computeJointSens()[0]
+        return multi.computeSens(), multi.computeTotSens()

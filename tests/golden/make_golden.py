@@ -207,6 +207,33 @@ def c1_full(R):
           f"{t1 - t0:.2f} s, lsq.fita {t2 - t1:.2f} s, anl.fita {t3 - t2:.2f} s on {os.cpu_count()} cores")
 
 
+def gsa_model(x, params):
+    """Two-output test model of the PCSobol golden (an Ishigami-like function and a polynomial)."""
+    a, b = params
+    y0 = np.sin(x[:, 0]) + a * np.sin(x[:, 1]) ** 2 + b * x[:, 2] ** 4 * np.sin(x[:, 0])
+    y1 = x[:, 0] * x[:, 1] + 0.5 * x[:, 2] ** 2 - 0.3 * x[:, 1]
+    return np.stack([y0, y1], axis=1)
+
+
+def gsa_golden(R):
+    """model_sens(method='PCSobol') of the unmodified reference (gsa/gsa.py:21-66, 383-457) on a 3-D, two-output model;
+    numpy's global stream seeded, so the drop-in draws the same germ.  Written to gsa.npz."""
+    import io, contextlib
+    from pytuq.gsa.gsa import model_sens, PCSobol
+    dom = np.array([[-np.pi, np.pi]] * 3)
+    np.random.seed(31)
+    with contextlib.redirect_stdout(io.StringIO()):
+        main, tot = model_sens(gsa_model, (7.0, 0.1), dom, method="PCSobol", nsam=4000, plot=False, pctype="LU", order=5)
+    np.random.seed(31)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sm = PCSobol(dom, pctype="LU", order=5)
+        xs = sm.sample(4000)
+        sens = sm.compute(gsa_model(xs, (7.0, 0.1))[:, 0])
+    np.savez_compressed(os.path.join(HERE, "gsa.npz"), main=main, total=tot, xsam_head=xs[:8], xsam_sum=np.array(xs.sum()),
+                        jointt0=sens["jointt"], main0=sens["main"])
+    print(f"gsa.npz  {os.path.getsize(os.path.join(HERE, 'gsa.npz')) / 1024:.1f} KiB")
+
+
 def c2_inputs(n=20_000):
     """BASELINE.json configs[1] / SURVEY 8(d) C2 synthetic inputs at reduced N (seed = config number):
     Hermite d=20 p=3 (K=1771), Gaussian germ samples, decaying true coefficients, 1e-2 noise."""
@@ -342,6 +369,8 @@ def main():
         return klsurr(R)
     if len(sys.argv) > 1 and sys.argv[1] == "c2":
         return c2_shape(R)
+    if len(sys.argv) > 1 and sys.argv[1] == "gsa":
+        return gsa_golden(R)
     PCRV, PC1d, get_mi = R["PCRV"], R["PC1d"], R["get_mi"]
     out = {}
 
@@ -498,6 +527,7 @@ def main():
     uqpc(R)
     c1_full(R)
     c2_shape(R)
+    gsa_golden(R)
     config_shapes(R)
 
 

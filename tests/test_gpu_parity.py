@@ -981,6 +981,34 @@ def test_pc_fit_workflow_vs_reference():
         np.testing.assert_allclose(pc.function(x[:16]), g[f"{method}__eval"], rtol=1e-10, atol=1e-12)
 
 
+def test_model_sens_pcsobol_batched_vs_reference():
+    """gsa.model_sens(method='PCSobol') (reference gsa/gsa.py:21-66): same germ from numpy's stream, all outputs fitted
+    in ONE statistics pass, against the unmodified reference's per-output loop (tests/golden/gsa.npz)."""
+    import contextlib, io
+    from conftest import golden_generator
+    from pytuq_b200.gsa.gsa import model_sens, PCSobol
+    gen = golden_generator()
+    g = load_golden("gsa")
+    dom = np.array([[-np.pi, np.pi]] * 3)
+    np.random.seed(31)
+    with contextlib.redirect_stdout(io.StringIO()):
+        main, tot = model_sens(gen.gsa_model, (7.0, 0.1), dom, method="PCSobol", nsam=4000, plot=False, pctype="LU", order=5)
+    assert main.shape == (2, 3) and tot.shape == (2, 3)
+    np.testing.assert_allclose(main, g["main"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(tot, g["total"], rtol=1e-9, atol=1e-12)
+    np.random.seed(31)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sm = PCSobol(dom, pctype="LU", order=5)
+        xs = sm.sample(4000)
+        sens = sm.compute(gen.gsa_model(xs, (7.0, 0.1))[:, 0])
+    np.testing.assert_allclose(xs[:8], g["xsam_head"], rtol=1e-14)
+    np.testing.assert_allclose(xs.sum(), g["xsam_sum"], rtol=1e-12)
+    np.testing.assert_allclose(sens["main"], g["main0"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(sens["jointt"], g["jointt0"], rtol=1e-9, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        model_sens(gen.gsa_model, (7.0, 0.1), dom, method="SamSobol", nsam=10, plot=False)
+
+
 def test_pce_and_pcsobol():
     import contextlib, io
     from pytuq_b200.surrogates.pce import PCE
