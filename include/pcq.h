@@ -264,6 +264,13 @@ int64_t pcq_launch_count(void);
  * longer matrices are chunked and the triangles combined by factorising [R_a; R_b] with the same call. */
 int64_t pcq_qr_max_rows(int device);
 int pcq_qr_r_dev(int device, double* z_dev, int64_t m, int64_t ldz, int L, double* r_dev, int64_t ldr, void* stream);
+/* One-sided Jacobi SVD of the small (n x n) factor the QR route ends in (csrc/pcq_svd.cu): in  g = A^T (row-major,
+ * contiguous); out  g = (U Sigma)^T (row j = sigma_j u_j^T), vt = V^T, sigma (n, unsorted), A = U Sigma V^T.  Sweeps of
+ * a round-robin tournament (one kernel launch per round, one CTA per column pair) until no pair is further than tol
+ * from orthogonal (or max_sweeps); small singular values come out to high relative accuracy, which the reference's
+ * rank cut-off (cond = 1e-13, lreg/lreg.py:335) needs.  Synchronises the stream once per sweep. */
+int pcq_svd_jacobi_dev(int device, double* g_dev, int n, double* vt_dev, double* sigma_dev, int max_sweeps, double tol,
+                       int* sweeps, void* stream);
 
 /* ---- pcq_group: one process, several GPUs, the same host-pointer calls -----------------------------------------
  * SURVEY.md 8(b) (`ndev, devs` of the plan) / 8(e): the path shards over samples.  A group owns one plan per listed

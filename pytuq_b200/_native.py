@@ -71,6 +71,8 @@ SIGNATURES = {
     "pcq_text_close": (C.c_int, [C.c_void_p]),
     "pcq_qr_max_rows": (C.c_int64, [C.c_int]),
     "pcq_qr_r_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pcq_svd_jacobi_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                     C.POINTER(C.c_int), C.c_void_p]),
     "pcq_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcq_group_destroy": (C.c_int, [C.c_void_p]),

@@ -183,17 +183,50 @@ def shared_r(R):
     return R
 
 
+def svd_jacobi(A):
+    """(U Sigma)^T, V^T, sigma of the square device tensor A by the one-sided Jacobi kernels (pcq_svd_jacobi_dev);
+    sigma is unsorted, A = U diag(sigma) V^T with row j of the first result = sigma_j u_j^T."""
+    import ctypes
+    torch = _torch()
+    n = A.shape[0]
+    G = A.t().contiguous()
+    Vt = torch.empty((n, n), dtype=torch.float64, device=A.device)
+    sig = torch.empty(n, dtype=torch.float64, device=A.device)
+    sweeps = ctypes.c_int(0)
+    if n:
+        with torch.cuda.device(A.device):
+            _native.check(_native.lib().pcq_svd_jacobi_dev(A.device.index, G.data_ptr(), n, Vt.data_ptr(), sig.data_ptr(), 60,
+                                                           1.0e-15, ctypes.byref(sweeps),
+                                                           torch.cuda.current_stream().cuda_stream), "pcq_svd_jacobi_dev")
+    return G, Vt, sig, sweeps.value
+
+
 def lstsq_from_r(R, K, cond=1.0e-13):
     """Minimum-norm least-squares solution from the R factor of [A | Y]: singular values of R_A (= those of
-    A) below ``cond * s_max`` are treated as zero, like gelsd.  Returns (C (K x M) numpy, singular values,
-    effective rank)."""
+    A) below ``cond * s_max`` are treated as zero, like gelsd.  The SVD of the K x K factor is the hand-written
+    one-sided Jacobi (``svd_jacobi``); with  R_A = U S V^T  and  B = U S,  C = V S^-2 B^T (Q^T Y)  on the kept part,
+    the two products on the device through the linear-forms kernels.  Returns (C (K x M) numpy, singular values
+    (descending), effective rank)."""
+    from .forms import matrix_forms
     torch = _torch()
-    RA = R[:K, :K]
-    Q = R[:K, K:]
-    U, S, Vh = torch.linalg.svd(RA)
-    smax = float(S[0]) if S.numel() else 0.0
-    keep = S > cond * smax
+    M = R.shape[1] - K
+    if not R.is_cuda:
+        # host tensors: only the GPU-less host-logic tests of the collective plumbing come here (tests/test_dist_gloo.py)
+        U, S, Vh = torch.linalg.svd(R[:K, :K])
+        s = S.numpy()
+        keep = s > cond * (float(s[0]) if s.size else 0.0)
+        Wh = (U.T @ R[:K, K:])[keep] / S[keep, None]
+        return (Vh[keep].T @ Wh).numpy(), s, int(keep.sum())
+    Bt, Vt, sig, _ = svd_jacobi(R[:K, :K])
+    s = sig.cpu().numpy()
+    smax = float(s.max()) if s.size else 0.0
+    keep = s > cond * smax
     rank = int(keep.sum())
-    W = (U.T @ Q)[keep] / S[keep, None]
-    C = Vh[keep].T @ W
-    return C.cpu().numpy(), S.cpu().numpy(), rank
+    if M == 0 or K == 0:
+        return np.zeros((K, M)), np.sort(s)[::-1], rank
+    Q = R[:K, K:]
+    W = matrix_forms(Bt, Q.t().contiguous())[0]                     # (K, M): row j = sigma_j u_j^T (Q^T Y)
+    scale = torch.from_numpy(np.where(keep, 1.0 / np.maximum(s, 1e-300) ** 2, 0.0)).to(W.device)
+    W = W * scale[:, None]
+    C = matrix_forms(Vt.t().contiguous(), W.t().contiguous())[0]    # V (S^-2 B^T Q^T Y)
+    return C.cpu().numpy(), np.sort(s)[::-1], rank

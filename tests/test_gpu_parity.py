@@ -816,6 +816,38 @@ def test_householder_qr_kernels_give_the_r_factor():
     assert lib.pcq_launch_count() > n0
 
 
+def test_jacobi_svd_kernels():
+    """pcq_svd_jacobi_dev (csrc/pcq_svd.cu): one-sided Jacobi SVD of the small factor of the QR route.  Singular values
+    against LAPACK to high RELATIVE accuracy on well-conditioned, graded (cond 1e14), rank-deficient and odd-sized
+    matrices; A = U S V^T reconstructed; V orthogonal."""
+    import torch
+    from pytuq_b200.lreg import tsqr
+    rng = np.random.default_rng(77)
+    for n, kind in [(1, "rand"), (2, "rand"), (7, "rand"), (64, "rand"), (131, "graded"), (200, "rankdef"), (333, "triu"), (600, "rand")]:
+        A = rng.standard_normal((n, n))
+        if kind == "graded":
+            A = A * np.logspace(0, -14, n)[None, :]
+        if kind == "rankdef":
+            A[:, 5] = A[:, 3]; A[:, 17] = 0.0
+        if kind == "triu":
+            A = np.triu(A) * np.logspace(0, -6, n)[None, :]
+        Bt, Vt, sig, sweeps = tsqr.svd_jacobi(torch.from_numpy(A).cuda())
+        Bt, Vt, sig = Bt.cpu().numpy(), Vt.cpu().numpy(), sig.cpu().numpy()
+        assert 0 <= sweeps < 60 or n == 1
+        ref = np.linalg.svd(A, compute_uv=False)
+        got = np.sort(sig)[::-1]
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13 * ref[0], err_msg=kind)
+        if kind == "graded":          # column scaling: Jacobi keeps the small ones accurate relative to THEMSELVES
+            big = ref > 1e-13 * ref[0]
+            np.testing.assert_allclose(got[big], ref[big], rtol=1e-9)
+        np.testing.assert_allclose(Vt @ Vt.T, np.eye(n), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(Bt.T @ Vt, A, rtol=0, atol=1e-12 * max(1.0, np.abs(A).max()))      # A = (U S) V^T
+        # the columns of U S are orthogonal
+        Gm = Bt @ Bt.T
+        off = Gm - np.diag(np.diag(Gm))
+        assert np.max(np.abs(off)) <= 1e-12 * max(np.max(np.diag(Gm)), 1e-300), kind
+
+
 def test_lsq_qr_route_on_illconditioned_systems():
     """8(f2): where the normal equations cannot follow the reference's SVD least squares, lsq switches to the
     QR statistic.  Golden coefficients come from the unmodified reference (tests/golden/lsq_illcond.npz)."""
