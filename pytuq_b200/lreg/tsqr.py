@@ -226,7 +226,9 @@ def lstsq_from_r(R, K, cond=1.0e-13):
         return np.zeros((K, M)), np.sort(s)[::-1], rank
     Q = R[:K, K:]
     W = matrix_forms(Bt, Q.t().contiguous())[0]                     # (K, M): row j = sigma_j u_j^T (Q^T Y)
-    scale = torch.from_numpy(np.where(keep, 1.0 / np.maximum(s, 1e-300) ** 2, 0.0)).to(W.device)
+    inv2 = np.zeros_like(s)
+    inv2[keep] = 1.0 / s[keep] ** 2
+    scale = torch.from_numpy(inv2).to(W.device)
     W = W * scale[:, None]
     C = matrix_forms(Vt.t().contiguous(), W.t().contiguous())[0]    # V (S^-2 B^T Q^T Y)
     return C.cpu().numpy(), np.sort(s)[::-1], rank

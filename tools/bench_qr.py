@@ -27,3 +27,13 @@ for (m, L) in [(cap, 1772), (cap, 1002), (20000, 1772), (cap, 257), (3544, 1772)
     fl = 2.0 * m * L * L - 2.0 / 3.0 * L ** 3
     print(json.dumps(dict(rows=m, cols=L, pcq_qr_ms=min(ts), cusolver_geqrf_ms=min(tl), pcq_TFLOPs=fl / min(ts) / 1e9,
                           rel_diff_RtR=err)), flush=True)
+
+# the K x K SVD that ends the QR route: one-sided Jacobi kernels (csrc/pcq_svd.cu) against cuSOLVER (torch.linalg.svd)
+for n in (257, 1002, 1772):
+    Z = torch.randn((4 * n, n), dtype=torch.float64, device=dev)
+    R = tsqr._qr_r(Z.clone())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); Bt, Vt, sig, sweeps = tsqr.svd_jacobi(R); torch.cuda.synchronize(); tj = time.perf_counter() - t0
+    t0 = time.perf_counter(); S2 = torch.linalg.svd(R).S; torch.cuda.synchronize(); tl = time.perf_counter() - t0
+    err = float((sig.sort(descending=True).values - S2).abs().max() / S2[0])
+    print(json.dumps(dict(svd_n=n, jacobi_ms=1e3 * tj, sweeps=sweeps, cusolver_svd_ms=1e3 * tl, rel_diff_sigma=err)), flush=True)
