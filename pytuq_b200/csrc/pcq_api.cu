@@ -578,21 +578,69 @@ int pcq_eval_pc(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const doub
     PCQ_CUDA(cudaMemcpyAsync(p->d_misc, cf, (size_t)m * K * 8, cudaMemcpyHostToDevice, p->streams[0]));
     PCQ_CUDA(cudaEventRecord(p->events[0], p->streams[0]));
     PCQ_CUDA(cudaStreamWaitEvent(p->streams[1], p->events[0], 0));
-    auto quiesce = [&](int status) { cudaStreamSynchronize(p->streams[0]); cudaStreamSynchronize(p->streams[1]); return status; };
     const int mo = (mode & 2) ? 1 : m;          // output columns per sample
-    const int64_t rows = chunk_rows((int64_t)(s + mo) * 8, n);
+    // The call is bound by getting x to the device (8 s bytes per sample against ~1 ns of kernel time).  A copy
+    // straight from the caller's pageable array is staged by the driver on ONE thread (~9 GB/s); here a few host
+    // threads gather each chunk into one of two pinned buffers (which also packs a strided x) and the DMA engine
+    // sends it while the next chunk is being gathered: ~2.5x the rate.  Results return through pinned memory too.
+    const int64_t rows = std::min<int64_t>(std::max<int64_t>(((int64_t)32 << 20) / ((int64_t)(s + mo) * 8), 1024), n);
+    const size_t in_bytes = (size_t)rows * s * 8, out_bytes = (size_t)rows * mo * 8;
+    for (int b = 0; b < 2; ++b) {
+        if (p->pin_bytes[b] < in_bytes + out_bytes) {
+            if (p->h_pin[b]) cudaFreeHost(p->h_pin[b]);
+            p->h_pin[b] = nullptr; p->pin_bytes[b] = 0;
+            if (cudaHostAlloc((void**)&p->h_pin[b], in_bytes + out_bytes, cudaHostAllocDefault) != cudaSuccess) {
+                pcq_set_error("eval_pc: pinned staging allocation of %zu bytes failed", in_bytes + out_bytes);
+                return PCQ_ERR_ALLOC;
+            }
+            p->pin_bytes[b] = in_bytes + out_bytes;
+        }
+        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], in_bytes)) != PCQ_OK) return rc;
+        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], out_bytes)) != PCQ_OK) return rc;
+    }
+    auto quiesce = [&](int status) { cudaStreamSynchronize(p->streams[0]); cudaStreamSynchronize(p->streams[1]); return status; };
+    auto parallel_rows = [&](int64_t nr, size_t bytes, auto&& body) {     // body(lo, hi) over row ranges, a few threads
+        const int nthreads = bytes >= ((size_t)4 << 20) ? 4 : 1;
+        if (nthreads == 1) { body((int64_t)0, nr); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back([&, t] { body(nr * t / nthreads, nr * (t + 1) / nthreads); });
+        for (auto& th : pool) th.join();
+    };
+    auto drain = [&](int b, int64_t r0, int64_t nr) -> int {               // results of buffer b -> caller rows [r0, r0+nr)
+        PCQ_CUDA(cudaEventSynchronize(p->events[b]));
+        const double* src = p->h_pin[b] + (size_t)rows * s;
+        parallel_rows(nr, (size_t)nr * mo * 8, [&](int64_t lo, int64_t hi) {
+            if (ldy == mo) memcpy(y + (r0 + lo) * ldy, src + lo * mo, (size_t)(hi - lo) * mo * 8);
+            else for (int64_t r = lo; r < hi; ++r) memcpy(y + (r0 + r) * ldy, src + r * mo, (size_t)mo * 8);
+        });
+        return PCQ_OK;
+    };
     int c = 0;
+    int64_t prev_r0 = 0, prev_nr = 0;
     for (int64_t r0 = 0; r0 < n; r0 += rows, ++c) {
         const int b = c & 1;
         const int64_t nr = std::min(rows, n - r0);
         cudaStream_t st = p->streams[b];
-        if ((rc = pcq_ensure_dev(&p->d_stage[b], &p->stage_bytes[b], (size_t)rows * s * 8)) != PCQ_OK) return quiesce(rc);
-        if ((rc = pcq_ensure_dev(&p->d_out[b], &p->out_bytes[b], (size_t)rows * mo * 8)) != PCQ_OK) return quiesce(rc);
-        if ((rc = copy_rows(p->d_stage[b], s, x + r0 * ldx, ldx, s, nr, cudaMemcpyHostToDevice, st)) != PCQ_OK) return quiesce(rc);
-        if ((rc = evalpc_any(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], mo, mode, st)) != PCQ_OK)
-            return quiesce(rc);
-        if ((rc = copy_rows(y + r0 * ldy, ldy, p->d_out[b], mo, mo, nr, cudaMemcpyDeviceToHost, st)) != PCQ_OK) return quiesce(rc);
+        // buffer b was last used by chunk c-2, whose results were drained (after its event) in iteration c-1
+        double* hx = p->h_pin[b];
+        parallel_rows(nr, (size_t)nr * s * 8, [&](int64_t lo, int64_t hi) {
+            if (ldx == s) memcpy(hx + lo * s, x + (r0 + lo) * ldx, (size_t)(hi - lo) * s * 8);
+            else for (int64_t r = lo; r < hi; ++r) memcpy(hx + r * s, x + (r0 + r) * ldx, (size_t)s * 8);
+        });
+        if (cudaMemcpyAsync(p->d_stage[b], hx, (size_t)nr * s * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            pcq_set_error("eval_pc: host-to-device copy failed");
+            return quiesce(PCQ_ERR_CUDA);
+        }
+        if ((rc = evalpc_any(p, p->d_stage[b], nr, s, p->d_misc, m, p->d_out[b], mo, mode, st)) != PCQ_OK) return quiesce(rc);
+        if (cudaMemcpyAsync(p->h_pin[b] + (size_t)rows * s, p->d_out[b], (size_t)nr * mo * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaEventRecord(p->events[b], st) != cudaSuccess) {
+            pcq_set_error("eval_pc: device-to-host copy failed");
+            return quiesce(PCQ_ERR_CUDA);
+        }
+        if (c >= 1 && (rc = drain(b ^ 1, prev_r0, prev_nr)) != PCQ_OK) return quiesce(rc);
+        prev_r0 = r0; prev_nr = nr;
     }
+    if ((rc = drain((c - 1) & 1, prev_r0, prev_nr)) != PCQ_OK) return quiesce(rc);
     PCQ_CUDA(cudaStreamSynchronize(p->streams[0]));
     PCQ_CUDA(cudaStreamSynchronize(p->streams[1]));
     return PCQ_OK;
