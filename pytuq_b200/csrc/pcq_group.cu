@@ -144,6 +144,7 @@ int member_suffstats(Member& M, const double* x, int64_t ldx, const double* y, i
 template <typename F>
 int run_members(pcq_group* g, F fn) {
     const int nd = g->active;
+    struct Share { Share(int n) { g_pcq_host_thread_div.store(n); } ~Share() { g_pcq_host_thread_div.store(1); } } share(nd);
     std::vector<std::thread> pool;
     for (int i = 0; i < nd; ++i) {
         pool.emplace_back([g, i, &fn] {

@@ -76,6 +76,7 @@ struct pcq_plan {
 // error plumbing --------------------------------------------------------------
 void pcq_set_error(const char* fmt, ...);
 extern std::atomic<long long> g_pcq_launches;
+extern std::atomic<int> g_pcq_host_thread_div;      // > 1 while a pcq_group call runs one host pipeline per device
 
 #define PCQ_CUDA(call)                                                            \
     do {                                                                          \
