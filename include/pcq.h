@@ -145,6 +145,27 @@ int pcq_eval_pc(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
  *   y may be NULL when m == 0.
  *   s_out  L x L, row-major, leading dimension L.
  */
+/* Moment form of K3 (csrc/pcq_moment.cu).  The entries of Psi^T Psi are linear combinations of the sums
+ *     m_gamma = sum_n prod_i phi^{(i)}_{gamma_i}(x[n,i]),   |gamma| <= 2 * (highest total order of the multi-index),
+ * through the linearisation phi_a phi_b = sum_k c_abk phi_k of each 1-D family (d = 20, p = 3: 230 230 moments instead of
+ * 1 569 106 Gram entries).  Once a plan has the recurrence tables up to that order, pcq_suffstats(_dev) computes the
+ * moments as staircase GEMMs on the FP64 tensor pipe (N |Gamma| multiply-adds instead of N K^2 / 2, operands generated
+ * in shared memory) and reconstructs S from them, whenever that is estimated faster than the pack + SYRK form and
+ * n >= PCQ_MOMENT_MIN_N (65536).  Same S up to rounding (1e-15 relative to sqrt(S_ii S_jj)); it replaces the same
+ * reference lines (lreg/anl.py:78,83, lreg/bcs.py:83-100, lreg/lreg.py:328-339).  PCQ_GRAM_MOMENT=0 disables it, =1
+ * uses it for every n.
+ *   nord       >= 2 * max_k sum_i mi[k,i]
+ *   rec_a_ext  (nord+1) x s, rec_a_ext[n*s+i] = PC1d_i.a(n);  rec_b_ext likewise   (rv/pcrv.py:755-777)
+ */
+int pcq_plan_enable_moments(pcq_plan* plan, int nord, const double* rec_a_ext, const double* rec_b_ext);
+/* Debugging aid, host only (no device needed): plans the moment form for this multi-index and m outputs, executes the
+ * planned units on the CPU exactly as the kernel does and reconstructs S (L x L, L = nterms + m + 1) into s_out (may be
+ * NULL: plan only).  info[0..7] = moments, units, estimated cycles per 16-sample block, multiply-adds per sample,
+ * functions / sub-functions of the largest unit, usable flag, tree nodes. */
+int pcq_debug_moments_host(int sdim, int nterms, const int32_t* mi, int nord, const double* rec_a_ext,
+                           const double* rec_b_ext, const double* p1_scale, const double* x, int64_t n, int64_t ldx,
+                           const double* y, int64_t ldy, int m, double* s_out, double* info);
+
 int64_t pcq_suffstats_dim(const pcq_plan* plan, int m);   /* returns L */
 int pcq_suffstats_dev(pcq_plan* plan, const double* x_dev, int64_t n, int64_t ldx,
                       const double* y_dev, int64_t ldy, int m,
@@ -287,6 +308,7 @@ int pcq_group_create(pcq_group** out, int ndev, const int* devices, int sdim, in
                      int pmax, const double* rec_a, const double* rec_b, const double* p1_scale);
 int pcq_group_destroy(pcq_group* group);
 int pcq_group_size(const pcq_group* group);
+int pcq_group_enable_moments(pcq_group* group, int nord, const double* rec_a_ext, const double* rec_b_ext);   /* every member plan */
 int pcq_group_set_active(pcq_group* group, int n);               /* spread the next calls over the first n members */
 pcq_plan* pcq_group_plan(pcq_group* group, int member);          /* borrowed: the member's plan */
 int pcq_group_device(const pcq_group* group, int member);

@@ -31,6 +31,11 @@ SIGNATURES = {
     "pcq_plan_specialize_async": (C.c_int, [C.c_void_p, C.c_int]),
     "pcq_debug_horner_source": (C.c_int64, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64]),
+    "pcq_plan_enable_moments": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "pcq_group_enable_moments": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "pcq_debug_moments_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                         C.c_void_p]),
     "pcq_eval_bases_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                      C.c_int64, C.c_void_p]),
     "pcq_eval_bases": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),

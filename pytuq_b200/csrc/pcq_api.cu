@@ -11,6 +11,7 @@
 #include <thread>
 
 std::atomic<long long> g_pcq_launches{0};
+std::atomic<int> g_pcq_host_thread_div{1};      // see pcq_host_threads()
 
 namespace {
 thread_local char g_err[512] = "";
@@ -71,7 +72,6 @@ int copy_rows(double* dst, int64_t ld_dst, const double* src, int64_t ld_src, in
 // most the hardware concurrency; measured on the 16-core GPU box: evalBases host-to-host 14.6 / 21.0 / 24.3 GB/s and
 // evalPC of 1e7 samples 0.092 / 0.075 / 0.072 s with 4 / 8 / 16 threads).  Divided among the members of a pcq_group
 // call, which run one such pipeline per device at the same time.
-std::atomic<int> g_pcq_host_thread_div{1};
 int pcq_host_threads() {
     static int n = 0;
     if (n == 0) {
@@ -246,6 +246,7 @@ int pcq_plan_destroy(pcq_plan* p) {
     if (p->spec_thread.joinable()) p->spec_thread.join();
     pcq_spec_free(p->spec[0].load());
     pcq_spec_free(p->spec[1].load());
+    pcq_mom_free(p);
     cudaFree(p->d_rec_a); cudaFree(p->d_rec_b); cudaFree(p->d_p1); cudaFree(p->d_kinds);
     cudaFree(p->d_desc4); cudaFree(p->d_descw); cudaFree(p->d_flags); cudaFree(p->d_ws); cudaFree(p->d_misc); cudaFree(p->d_q); cudaFree(p->d_gtab[0]); cudaFree(p->d_gtab[1]); cudaFree(p->d_achunk);
     for (int i = 0; i < 2; ++i) {

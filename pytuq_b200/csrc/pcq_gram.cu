@@ -693,6 +693,12 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
         }
         return PCQ_OK;
     }
+    if (n > 0 && a == nullptr && p->mom) {
+        // moment form (pcq_moment.cu): N |Gamma| instead of N K^2 / 2 multiply-adds where the planner expects a gain
+        bool handled = false;
+        const int rc = pcq_launch_moments(p, x, n, ldx, y, ldy, m, s, accumulate, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled);
+        if (handled || rc != PCQ_OK) return rc;
+    }
     {
         const char* e = getenv("PCQ_GRAM_SYRK");
         if (n > 0 && !(e && atoi(e) == 0)) {

@@ -226,6 +226,15 @@ int pcq_group_destroy(pcq_group* g) {
 
 int pcq_group_size(const pcq_group* g) { return g ? (int)g->m.size() : PCQ_ERR_ARG; }
 
+int pcq_group_enable_moments(pcq_group* g, int nord, const double* rec_a_ext, const double* rec_b_ext) {
+    if (!g) { pcq_set_error("group_enable_moments: group is null"); return PCQ_ERR_ARG; }
+    for (auto& mem : g->m) {
+        const int rc = pcq_plan_enable_moments(mem.plan, nord, rec_a_ext, rec_b_ext);
+        if (rc != PCQ_OK) return rc;
+    }
+    return PCQ_OK;
+}
+
 int pcq_group_set_active(pcq_group* g, int n) {
     if (!g || n < 1 || n > (int)g->m.size()) { pcq_set_error("group_set_active: 1 <= n <= size"); return PCQ_ERR_ARG; }
     g->active = n;

@@ -69,6 +69,7 @@ struct pcq_plan {
     size_t pin_bytes[2] = {0, 0};
     double* d_misc = nullptr;      // coefficients / S matrix for host-pointer calls
     size_t misc_bytes = 0;
+    void* mom = nullptr;           // moment form of K3 (pcq_moment.cu): extended recurrences + per-output-count plans
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t events[2] = {nullptr, nullptr};
 };
@@ -120,6 +121,11 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
                     const double* a, int64_t lda, int kcols, const double* y, int64_t ldy, int m, double* s,
                     int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes,
                     cudaStream_t st, bool* handled);
+// moment form of the same statistics (pcq_moment.cu); *handled = false when it does not apply or would be slower
+int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy, int m,
+                       double* s, int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes,
+                       cudaStream_t st, bool* handled);
+void pcq_mom_free(pcq_plan* p);
 int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
                          const int32_t* germ_kind, const double* cf, int m, double* sums,
                          double* y, int64_t ldy, int mode, cudaStream_t st);

@@ -67,8 +67,21 @@ class Plan:
             pass
 
 
-def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None):
-    """Returns the cached plan for this content, creating it on first use.
+def _enable_moments(obj, fn_name, ext):
+    """Hands the recurrence tables up to twice the total order to a plan / group (moment form of K3, include/pcq.h:
+    pcq_plan_enable_moments); once per object."""
+    if ext is None or getattr(obj, "_moments", False):
+        return
+    nord, ra, rb = ext
+    ra = np.ascontiguousarray(ra, dtype=np.float64)
+    rb = np.ascontiguousarray(rb, dtype=np.float64)
+    _native.check(getattr(_native.lib(), fn_name)(obj.handle, int(nord), _native.ptr(ra), _native.ptr(rb)), fn_name)
+    obj._moments = True
+
+
+def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None, ext=None):
+    """Returns the cached plan for this content, creating it on first use.  ext = (nord, rec_a_ext, rec_b_ext) enables
+    the moment form of the sufficient statistics on it.
 
     Threading: a plan (and a group) is NOT re-entrant -- its host-pointer entry points share per-plan staging
     buffers, streams and events.  Two Python threads may use the library at the same time only on PCRVs with
@@ -85,6 +98,7 @@ def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None):
         plan = _plans.get(key)
         if plan is not None:
             _plans.move_to_end(key)
+            _enable_moments(plan, "pcq_plan_enable_moments", ext)
             return plan
     K, s = mi32.shape
     handle = C.c_void_p()
@@ -92,6 +106,7 @@ def get_plan(mi, rec_a, rec_b, p1_scale, pmax, device=None):
                                        _native.ptr(rec_a), _native.ptr(rec_b), _native.ptr(p1_scale))
     _native.check(st, "pcq_plan_create")
     plan = Plan(handle, s, K, int(pmax), device)
+    _enable_moments(plan, "pcq_plan_enable_moments", ext)
     with _lock:
         _plans[key] = plan
         while len(_plans) > _PLAN_CACHE_MAX:
@@ -159,8 +174,8 @@ class Group:
             pass
 
 
-def get_group(mi, rec_a, rec_b, p1_scale, pmax, devs):
-    """Cached pcq_group for this content on this device list (created on first use)."""
+def get_group(mi, rec_a, rec_b, p1_scale, pmax, devs, ext=None):
+    """Cached pcq_group for this content on this device list (created on first use); ext as in get_plan."""
     require_device()
     mi32 = np.ascontiguousarray(mi, dtype=np.int32)
     rec_a = np.ascontiguousarray(rec_a, dtype=np.float64)
@@ -172,6 +187,7 @@ def get_group(mi, rec_a, rec_b, p1_scale, pmax, devs):
         grp = _groups.get(key)
         if grp is not None:
             _groups.move_to_end(key)
+            _enable_moments(grp, "pcq_group_enable_moments", ext)
             return grp
     K, s = mi32.shape
     handle = C.c_void_p()
@@ -180,6 +196,7 @@ def get_group(mi, rec_a, rec_b, p1_scale, pmax, devs):
                                         _native.ptr(rec_a), _native.ptr(rec_b), _native.ptr(p1_scale))
     _native.check(st, "pcq_group_create")
     grp = Group(handle, devs, s, K, int(pmax))
+    _enable_moments(grp, "pcq_group_enable_moments", ext)
     with _lock:
         _groups[key] = grp
         while len(_groups) > max(2, _PLAN_CACHE_MAX // 4):

@@ -246,6 +246,18 @@ class PCRV(MRV):
         if np.min(mindex) < 0:
             raise IndexError("negative order in multi-index")
 
+    def _moment_tables(self, mindex):
+        """(nord, a_n, b_n up to nord = twice the highest total order) for the moment form of the sufficient statistics
+        (include/pcq.h: pcq_plan_enable_moments), or None where that form cannot apply."""
+        nord = 2 * int(np.max(np.sum(mindex, axis=1)))
+        if nord < 2 or nord > 32 or not (2 <= self.sdim <= 64):
+            return None
+        ra = np.zeros((nord + 1, self.sdim))
+        rb = np.zeros((nord + 1, self.sdim))
+        for i, p in enumerate(self.PC1ds):
+            ra[:, i], rb[:, i] = p.rec_tables(nord)
+        return nord, ra, rb
+
     def _plan(self, mindex, dev=None):
         pmax = int(np.max(mindex))
         ra = np.zeros((pmax + 1, self.sdim))
@@ -254,7 +266,7 @@ class PCRV(MRV):
         for i, p in enumerate(self.PC1ds):
             ra[:, i], rb[:, i] = p.rec_tables(pmax)
             p1[i] = p.p1_scale
-        return _device.get_plan(mindex, ra, rb, p1, pmax, device=dev)
+        return _device.get_plan(mindex, ra, rb, p1, pmax, device=dev, ext=self._moment_tables(mindex))
 
     def _group(self, mindex, nuse=None):
         """pcq_group over device.devices() for this multi-index (several GPUs behind one host-array call), set to
@@ -267,7 +279,7 @@ class PCRV(MRV):
         for i, p in enumerate(self.PC1ds):
             ra[:, i], rb[:, i] = p.rec_tables(pmax)
             p1[i] = p.p1_scale
-        grp = _device.get_group(mindex, ra, rb, p1, pmax, devs)
+        grp = _device.get_group(mindex, ra, rb, p1, pmax, devs, ext=self._moment_tables(mindex))
         _native.check(_native.lib().pcq_group_set_active(grp.handle, len(devs) if nuse is None else int(nuse)),
                       "pcq_group_set_active")
         return grp
