@@ -151,7 +151,7 @@ int pcq_eval_pc(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
  * 1 569 106 Gram entries).  Once a plan has the recurrence tables up to that order, pcq_suffstats(_dev) computes the
  * moments as staircase GEMMs on the FP64 tensor pipe (N |Gamma| multiply-adds instead of N K^2 / 2, operands generated
  * in shared memory) and reconstructs S from them, whenever that is estimated faster than the pack + SYRK form and
- * n >= PCQ_MOMENT_MIN_N (65536).  Same S up to rounding (1e-15 relative to sqrt(S_ii S_jj)); it replaces the same
+ * n >= PCQ_MOMENT_MIN_N (32768).  Same S up to rounding (1e-15 relative to sqrt(S_ii S_jj)); it replaces the same
  * reference lines (lreg/anl.py:78,83, lreg/bcs.py:83-100, lreg/lreg.py:328-339).  PCQ_GRAM_MOMENT=0 disables it, =1
  * uses it for every n.
  *   nord       >= 2 * max_k sum_i mi[k,i]

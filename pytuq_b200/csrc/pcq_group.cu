@@ -49,7 +49,7 @@ struct pcq_group {
 
 namespace {
 
-constexpr size_t GROUP_STAGE_BYTES = (size_t)48 << 20;
+constexpr size_t GROUP_STAGE_BYTES = (size_t)128 << 20;
 
 __global__ void __launch_bounds__(256) pcq_group_add_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

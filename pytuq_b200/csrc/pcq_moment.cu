@@ -497,8 +497,10 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
         UnitBuild& U = ub[u];
         const double half = 64.0 * MOM_CLS[U.cls][0] * MOM_CLS[U.cls][1];      // DMMA cycles of one warp per block
         macs[u] = MOM_TASKS * half;
-        const double gen = 150.0 + 30.0 * (double)((U.subs.size() * 8 + 255) / 256) * 0.5 + 12.0 * H.B0;
-        fin[u] = {2.0 * std::max(half, gen) + 100.0, (int)u, U.cls};
+        // cycles of one 16-sample block: both warps of a scheduler at the measured DMMA-pipe share of the class
+        // (profiles/r02_moment_notes.md: 0.68 / 0.69 / 0.53 / 0.41 / 0.25 active)
+        static const double eff[MOM_NCLS] = {0.66, 0.66, 0.52, 0.40, 0.24};
+        fin[u] = {2.0 * half / eff[U.cls], (int)u, U.cls};
     }
     std::stable_sort(fin.begin(), fin.end(), [](const Fin& a, const Fin& b) { return a.cls != b.cls ? a.cls < b.cls : a.cost > b.cost; });
     for (const Fin& f : fin) {
@@ -1108,7 +1110,7 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
     if (!ms || mode == 0 || n <= 0 || m > MOM_MAXOUT) return PCQ_OK;
     if (mode < 0) {
         const char* e2 = getenv("PCQ_MOMENT_MIN_N");
-        if (n < (e2 ? atoll(e2) : 65536)) return PCQ_OK;
+        if (n < (e2 ? atoll(e2) : 32768)) return PCQ_OK;
     }
     MomDev* D;
     {
@@ -1130,10 +1132,13 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
     if (!D->ready) return PCQ_OK;
     const MomHost& H = D->H;
     if (mode < 0) {
-        // cycles per sample and SM: this form (planner estimate per 16-sample block) against pack + SYRK at 0.89 of the DMMA rate
+        // cycles per sample and SM of the two forms (pack + SYRK at 0.89 of the DMMA rate), and this form's cost that
+        // does not depend on n (reconstruction ~0.3 ns per Gram entry, a dozen small launches)
         const double L = (double)p->nterms + m + 1;
-        const double syrk = (L * L / 2 * 1.04) / 64.0 / 0.89;
-        if (H.clk_per_block / MOM_BS * 1.15 > syrk) return PCQ_OK;
+        const double syrk = (L * L / 2 * 1.04) / 64.0 / 0.89, mine = H.clk_per_block / MOM_BS;
+        const double hz = 1.9e9 * p->num_sms;
+        const double fixed = 0.31e-9 * (double)p->nterms * p->nterms + 1.5e-4;
+        if (mine * 1.1 > syrk || (double)n * (syrk - mine) / hz < 1.25 * fixed) return PCQ_OK;
     }
     *handled = true;
 
