@@ -9,15 +9,18 @@ STRONG scaling: the 10M samples are the whole job at every GPU count (N=1: all 1
 N GPUs: 10M/N contiguous rows per rank).  `--samples-per-gpu R` switches to weak scaling (R rows per rank).
 
 A step = one pass of the hot path over the rank's sample block:
-    fused basis-evaluation + Gram/A^T y statistics (K3, DMMA)  ->  one all-reduce of the
-    packed statistics (N>1)  ->  K x K normal-equation solve (cuSOLVER Cholesky on the device, a plain
+    fused basis-evaluation + Gram/A^T y statistics (K3, DMMA; in moment form -- csrc/pcq_moment.cu -- where that is
+    faster, as at this shape)  ->  one all-reduce of the statistics (N>1)  ->  K x K normal-equation solve (cuSOLVER Cholesky on the device, a plain
     library call: the factorisation is not sample-parallel)  ->  coefficients.
 `value` is basis evaluations (samples x terms) per second for that whole step with x, y
 already resident in HBM; `e2e` is the same metric through the public API
 (`lsq.fit(x, y)` with numpy host arrays: pinned double-buffered H2D of x, y and D2H of the
 coefficients inside the timed region).  `roofline` is for the dominant kernel (K3) against the FP64 tensor (DMMA)
-peak measured live on the same GPU (MEASURED_PEAKS.json has no FP64 number); the K1
-(materialised A) and K2 (evalPC) kernels are reported in `kernels` with their own roofs.
+peak measured live on the same GPU (MEASURED_PEAKS.json has no FP64 number): `achieved` counts the multiply-adds the
+DMMA pipe EXECUTES in the moment form (the pipe's utilisation); the same step counted with the dense N K^2 flops of
+SURVEY 8(d) is `dense_equivalent` (above the roof: the moment form does ~5x fewer multiply-adds), and the dense pack +
+SYRK form itself is timed beside it in `kernels.K3_pack_syrk_form`.  The K1 (materialised A) and K2 (evalPC) kernels are
+reported in `kernels` with their own roofs.
 """
 import argparse
 import ctypes
@@ -407,8 +410,12 @@ def main():
         return
 
     # ---------------- roofline of the dominant kernel + side kernels (rank 0)
-    flops = float(n) * K * (K + 1) + 2.0 * n * K * 1 + 2.0 * n * 1
-    achieved = flops / (k3_mean_ms * 1e-3) / 1e12
+    flops = float(n) * K * (K + 1) + 2.0 * n * K * 1 + 2.0 * n * 1          # dense form, SURVEY 8(d)
+    minfo = (ctypes.c_double * 8)()
+    _native.check(lib.pcq_moment_info(plan.handle, 1, n, minfo))
+    moment_form = bool(minfo[5])
+    flops_exec = 2.0 * n * minfo[2] if moment_form else flops              # multiply-adds the DMMA pipe executes
+    achieved = flops_exec / (k3_mean_ms * 1e-3) / 1e12
     peaks = {}
     kernels = {}
     if not args.no_extras:
@@ -419,6 +426,27 @@ def main():
                 _native.check(lib.pcq_measure_peak(local, kind, ctypes.byref(v)))
                 best = max(best, v.value)
             peaks[name] = best
+        # K3 in its dense form (pack + SYRK, PCQ_GRAM_MOMENT=0) on the same resident samples: the N K^2 contraction
+        # the moment form replaces, against the same DMMA roof
+        if moment_form:
+            os.environ["PCQ_GRAM_MOMENT"] = "0"
+            try:
+                ts = []
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                S2 = torch.empty_like(S)
+                for it in range(3):
+                    e0.record()
+                    _native.check(lib.pcq_suffstats_dev(plan.handle, x.data_ptr(), n, D, y.data_ptr(), 1, 1, S2.data_ptr(), 0, stream))
+                    e1.record(); e1.synchronize()
+                    if it >= 1:
+                        ts.append(e0.elapsed_time(e1))
+                dgn = torch.sqrt(torch.abs(torch.diagonal(S2)))
+                kernels["K3_pack_syrk_form"] = {"rows": n, "ms": float(np.mean(ts)), "TFLOPs_algorithmic": flops / (np.mean(ts) * 1e-3) / 1e12,
+                                                "bound": "tensor", "max_rel_diff_of_the_statistics_vs_moment_form":
+                                                float(torch.max(torch.abs(S2 - S) / torch.outer(dgn, dgn)))}
+                del S2
+            finally:
+                os.environ.pop("PCQ_GRAM_MOMENT", None)
         # K1: materialised design matrix, device resident (N*K*8 bytes must fit: use 2^19 rows = 7.4 GB)
         n1 = 1 << 19
         A = torch.empty((n1, K), dtype=torch.float64, device=dev)
@@ -522,14 +550,14 @@ def main():
     # DRAM bytes per step of the dominant kernel: NOT a live counter -- the committed ncu capture of this very
     # command (bytes per sample x this rank's samples; the SYRK works chunk by chunk, so its traffic is linear in N)
     traffic, traffic_source = None, None
-    for fn in ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
+    for fn in (("r02_moment_traffic.json",) if moment_form else ()) + ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
             per_sample = tj.get("dram_bytes_per_sample_main_kernel",
                                 tj["dram_bytes_per_step_main_kernel"] / tj.get("samples_per_step", 1_250_000))
             traffic = per_sample * n
             traffic_source = (f"committed ncu capture profiles/{fn} (dram__bytes_read.sum + dram__bytes_write.sum of the "
-                              f"pcq_syrk_kernel launches of one step: {per_sample:.0f} B per sample) x {n} samples; "
+                              f"{'pcq_mom_kernel' if 'moment' in fn else 'pcq_syrk_kernel'} launches of one step: {per_sample:.0f} B per sample) x {n} samples; "
                               "not measured in this run")
             break
         except Exception:
@@ -574,6 +602,45 @@ def main():
         except Exception as exc:                         # noqa: BLE001
             cpu["max_abs_coef_diff_vs_gpu_on_the_same_rows"] = repr(exc)
 
+    peak_source = ("FP64 DMMA m8n8k4 register-chain micro-benchmark run live on this GPU "
+                   "(pcq_measure_peak); MEASURED_PEAKS.json has no FP64 figure -- the same measurement looped "
+                   "for 4 s with a clock record is committed as profiles/r02_fp64_peaks.json (DMMA 36.95 burst / "
+                   "36.85 sustained, DFMA 36.49 / 36.42 TFLOP/s at 1965 MHz, no throttle reason)")
+    if moment_form:
+        roofline = {"bound": "tensor",
+                    "kernel": "pcq_mom_kernel<FM,FN> (K3 in moment form, csrc/pcq_moment.cu: the %d moments the Gram entries are linear "
+                              "combinations of, as staircase GEMMs on DMMA -- %.0f executed multiply-adds per sample instead of "
+                              "K(K+1)/2 + ... = %.0f; five launches, one per task shape, fed by pcq_mom_table_kernel; then "
+                              "fix-up and the K x K reconstruction; launch list profiles/r02_moment_launches.csv)"
+                              % (int(minfo[0]), minfo[2], flops / (2.0 * n)),
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
+                    "achieved_note": "multiply-adds EXECUTED on the DMMA pipe (planner count, fragment padding included) x 2 / "
+                                     "duration of the whole pcq_suffstats_dev call (table + moment kernels + fix-up + "
+                                     "reconstruction launches), CUDA events on the launching stream: the pipe utilisation",
+                    "executed_flops_per_launch": flops_exec,
+                    "algorithmic_minimum_flops": 2.0 * n * minfo[0],
+                    "algorithmic_minimum_frac": (2.0 * n * minfo[0] / (k3_mean_ms * 1e-3) / 1e12 / peak) if peak else None,
+                    "dense_equivalent": {"flops_per_launch_survey_8d": flops, "TFLOPs": flops / (k3_mean_ms * 1e-3) / 1e12,
+                                         "frac": (flops / (k3_mean_ms * 1e-3) / 1e12 / peak) if peak else None,
+                                         "note": "the step counted with the dense N K (K+1) flops of SURVEY 8(d): above the DMMA roof "
+                                                 "because the moment form needs ~5x fewer multiply-adds for the same statistics; the "
+                                                 "dense form itself (pack + SYRK) is kernels.K3_pack_syrk_form"},
+                    "traffic": traffic, "traffic_source": traffic_source,
+                    "traffic_note": "x, y are read once by the table kernel, which writes %d B per sample of 1-D values; every "
+                                    "unit (53 at this shape) streams that table once through L2; algorithmic input bytes = %d"
+                                    % (int(minfo[6]), 8 * n * (D + 1)),
+                    "peak_source": peak_source}
+    else:
+        roofline = {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; "
+                                                 "profiles/r02_k3_traffic.json, profiles/r02_launches_bench.csv)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                    "traffic_source": traffic_source,
+                    "achieved_note": "algorithmic flops of one step / duration of the whole pcq_suffstats_dev call "
+                                     "(pack + SYRK + fix-up + mirror launches), CUDA events on the launching stream",
+                    "algorithmic_flops_per_launch": flops,
+                    "peak_source": peak_source}
+
     line = {
         "metric": "pc_basis_evals_per_s", "value": value, "unit": "basis evals/s (samples*terms)",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -584,23 +651,7 @@ def main():
         "breakdown_ms": {"k3_suffstats": k3_mean_ms, "allreduce": float(np.mean(ar_ms)),
                          "solve_kxk": 1e3 * float(np.mean(solve_s))},
         "max_abs_coef_error_vs_truth": err,
-        "roofline": {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; per 2 GB chunk one launch over "
-                               "the off-diagonal tiles, 87.5 % of the step, and one over the upper-triangle sub-blocks of the diagonal "
-                               "tiles, 9.6 %; the rest is pcq_pack_bases_kernel 2.5 %, fix-up/mirror 0.4 %, K x K solve 0.2 %; "
-                               "profiles/r02_k3_traffic.json, profiles/r02_launches_bench.csv)",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": (achieved / peak) if peak else None, "traffic": traffic,
-                     "traffic_source": traffic_source,
-                     "traffic_note": "the packed design-matrix chunk (written once by the pack kernel) is re-read by the SYRK "
-                                     "passes; the kernels are tensor-pipe bound, DRAM runs far below its peak; "
-                                     "algorithmic input bytes = %d" % (8 * n * (D + 1)),
-                     "achieved_note": "algorithmic flops of one step / duration of the whole pcq_suffstats_dev call "
-                                      "(pack + SYRK + fix-up + mirror launches), CUDA events on the launching stream",
-                     "algorithmic_flops_per_launch": flops,
-                     "peak_source": "FP64 DMMA m8n8k4 register-chain micro-benchmark run live on this GPU "
-                                    "(pcq_measure_peak); MEASURED_PEAKS.json has no FP64 figure -- the same measurement looped "
-                                    "for 4 s with a clock record is committed as profiles/r02_fp64_peaks.json (DMMA 36.95 burst / "
-                                    "36.85 sustained, DFMA 36.49 / 36.42 TFLOP/s at 1965 MHz, no throttle reason)"},
+        "roofline": roofline,
         "peaks_measured_live": peaks,
         "kernels": kernels,
         "cpu_baseline": cpu,

@@ -158,6 +158,10 @@ int pcq_eval_pc(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
  *   rec_a_ext  (nord+1) x s, rec_a_ext[n*s+i] = PC1d_i.a(n);  rec_b_ext likewise   (rv/pcrv.py:755-777)
  */
 int pcq_plan_enable_moments(pcq_plan* plan, int nord, const double* rec_a_ext, const double* rec_b_ext);
+/* Query: info[0..6] = moments, units, DMMA multiply-adds executed per sample, estimated cycles per sample and SM, usable
+ * flag, 1 if pcq_suffstats(_dev) would take the moment form for n samples and m outputs right now, bytes per sample of
+ * the 1-D value table the form keeps in scratch.  All zero when the plan has no moment tables. */
+int pcq_moment_info(pcq_plan* plan, int m, int64_t n, double* info);
 /* Debugging aid, host only (no device needed): plans the moment form for this multi-index and m outputs, executes the
  * planned units on the CPU exactly as the kernel does and reconstructs S (L x L, L = nterms + m + 1) into s_out (may be
  * NULL: plan only).  info[0..7] = moments, units, estimated cycles per 16-sample block, multiply-adds per sample,

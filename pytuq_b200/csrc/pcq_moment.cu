@@ -1099,6 +1099,63 @@ extern "C" int pcq_plan_enable_moments(pcq_plan* p, int nord, const double* rec_
     return PCQ_OK;
 }
 
+namespace {
+// device plan of this output count, built on first use
+int mom_get_dev(pcq_plan* p, MomState* ms, int m, MomDev** out) {
+    std::lock_guard<std::mutex> lock(ms->mu);
+    if (!ms->dev[m]) {
+        MomDev* D = new MomDev();
+        mom_build(D->H, p->sdim, p->nterms, p->h_mi.data(), ms->nord, ms->rec_a.data(), ms->rec_b.data(), p->h_p1.data(), m);
+        if (D->H.why.empty()) {
+            if (mom_smem_bytes(D->H.nt, (D->H.nsub_max + 63) & ~63, (D->H.nf_max + 7) & ~7) > p->smem_optin) D->H.why = "shared memory";
+            else {
+                const int rc = mom_upload(*D);
+                if (rc != PCQ_OK) { delete D; return rc; }
+            }
+        }
+        ms->dev[m] = D;
+    }
+    *out = ms->dev[m];
+    return PCQ_OK;
+}
+
+// cycles per sample and SM of the two forms (pack + SYRK at 0.89 of the DMMA rate) and this form's cost that does not
+// depend on n (reconstruction ~0.3 ns per Gram entry, a dozen small launches): true when the moment form is expected
+// to be faster for n samples
+bool mom_pays(const pcq_plan* p, const MomHost& H, int m, int64_t n) {
+    const double L = (double)p->nterms + m + 1;
+    const double syrk = (L * L / 2 * 1.04) / 64.0 / 0.89, mine = H.clk_per_block / MOM_BS;
+    const double hz = 1.9e9 * p->num_sms;
+    const double fixed = 0.31e-9 * (double)p->nterms * p->nterms + 1.5e-4;
+    return mine * 1.1 <= syrk && (double)n * (syrk - mine) / hz >= 1.25 * fixed;
+}
+}  // namespace
+
+extern "C" int pcq_moment_info(pcq_plan* p, int m, int64_t n, double* info) {
+    if (!p || m < 0 || !info) { pcq_set_error("moment_info: bad argument"); return PCQ_ERR_ARG; }
+    for (int i = 0; i < 8; ++i) info[i] = 0.0;
+    MomState* ms = static_cast<MomState*>(p->mom);
+    if (!ms || m > MOM_MAXOUT) return PCQ_OK;
+    MomDev* D = nullptr;
+    {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(p->device);
+        const int rc = mom_get_dev(p, ms, m, &D);
+        if (prev >= 0) cudaSetDevice(prev);
+        if (rc != PCQ_OK) return rc;
+    }
+    const MomHost& H = D->H;
+    info[0] = (double)H.nmom; info[1] = (double)H.units.size(); info[2] = H.mac_slots; info[3] = H.clk_per_block / MOM_BS;
+    info[4] = D->ready ? 1.0 : 0.0;
+    const char* env = getenv("PCQ_GRAM_MOMENT");
+    const int mode = env ? atoi(env) : -1;
+    const char* e2 = getenv("PCQ_MOMENT_MIN_N");
+    info[5] = (D->ready && mode != 0 && n > 0 && (mode > 0 || (n >= (e2 ? atoll(e2) : 32768) && mom_pays(p, H, m, n)))) ? 1.0 : 0.0;
+    info[6] = 8.0 * H.nt;
+    return PCQ_OK;
+}
+
 // S (+)= statistics of n samples through the moment form; *handled = false when the route does not apply (the caller
 // falls back to the SYRK form).  PCQ_GRAM_MOMENT = 0 never, 1 whenever a plan exists, unset: when it is estimated faster.
 int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy, int m,
@@ -1112,34 +1169,14 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
         const char* e2 = getenv("PCQ_MOMENT_MIN_N");
         if (n < (e2 ? atoll(e2) : 32768)) return PCQ_OK;
     }
-    MomDev* D;
+    MomDev* D = nullptr;
     {
-        std::lock_guard<std::mutex> lock(ms->mu);
-        if (!ms->dev[m]) {
-            D = new MomDev();
-            mom_build(D->H, p->sdim, p->nterms, p->h_mi.data(), ms->nord, ms->rec_a.data(), ms->rec_b.data(), p->h_p1.data(), m);
-            if (D->H.why.empty()) {
-                if (mom_smem_bytes(D->H.nt, (D->H.nsub_max + 63) & ~63, (D->H.nf_max + 7) & ~7) > p->smem_optin) D->H.why = "shared memory";
-                else {
-                    const int rc = mom_upload(*D);
-                    if (rc != PCQ_OK) { delete D; return rc; }
-                }
-            }
-            ms->dev[m] = D;
-        }
-        D = ms->dev[m];
+        const int rcd = mom_get_dev(p, ms, m, &D);
+        if (rcd != PCQ_OK) return rcd;
     }
     if (!D->ready) return PCQ_OK;
     const MomHost& H = D->H;
-    if (mode < 0) {
-        // cycles per sample and SM of the two forms (pack + SYRK at 0.89 of the DMMA rate), and this form's cost that
-        // does not depend on n (reconstruction ~0.3 ns per Gram entry, a dozen small launches)
-        const double L = (double)p->nterms + m + 1;
-        const double syrk = (L * L / 2 * 1.04) / 64.0 / 0.89, mine = H.clk_per_block / MOM_BS;
-        const double hz = 1.9e9 * p->num_sms;
-        const double fixed = 0.31e-9 * (double)p->nterms * p->nterms + 1.5e-4;
-        if (mine * 1.1 > syrk || (double)n * (syrk - mine) / hz < 1.25 * fixed) return PCQ_OK;
-    }
+    if (mode < 0 && !mom_pays(p, H, m, n)) return PCQ_OK;
     *handled = true;
 
     const int nunits = (int)H.units.size();
