@@ -32,6 +32,7 @@
 namespace {
 
 using Desc = std::array<uint16_t, MOM_WS>;
+constexpr int MOM_SUBBATCH = 64;    // sub-function rows per batch of the kernel's pass (32 rows x MOM_VB per 256 threads)
 constexpr int MOM_BS_HOST = 16;     // samples per block: descriptors are stored as BYTE offsets of 16-sample rows (x 128)
 
 struct MomHost {
@@ -513,19 +514,31 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
         mu.nsub = (int)U.subs.size();
         mu.task_off = (int)H.tasks.size();
         mu.ntasks = (int)U.tasks.size();
-        int wsub = 1;
+        // sub-function rows: the zero and the constant function first, the others by falling factor count (stable), so
+        // that each batch of 64 rows of the kernel's sub-function pass multiplies only as many factors as its rows have
+        // (wsub packs the factor count of batch b in bits 4b .. 4b+3)
         std::vector<Desc> byid(U.subs.size());
         for (const auto& kv : U.subs) byid[kv.second] = kv.first;
-        for (const Desc& d : byid) {
-            int w = 0;
-            for (int q = 0; q < MOM_WS; ++q) { H.subdesc.push_back((uint16_t)(d[q] * (MOM_BS_HOST * 8))); if (d[q] != 0) w = q + 1; }
-            wsub = std::max(wsub, w);
+        auto nnz_of = [](const Desc& d) { int w = 1; for (int q = 0; q < MOM_WS; ++q) if (d[q] != 0) w = q + 1; return w; };
+        std::vector<int> ord(byid.size());
+        for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
+        std::stable_sort(ord.begin() + std::min<size_t>(2, ord.size()), ord.end(), [&](int a, int b) { return nnz_of(byid[a]) > nnz_of(byid[b]); });
+        std::vector<int> newid(byid.size());
+        for (size_t i = 0; i < ord.size(); ++i) newid[ord[i]] = (int)i;
+        uint32_t wpack = 0;
+        for (size_t i = 0; i < ord.size(); ++i) {
+            const Desc& d = byid[ord[i]];
+            for (int q = 0; q < MOM_WS; ++q) H.subdesc.push_back((uint16_t)(d[q] * (MOM_BS_HOST * 8)));
+            const int b = (int)(i / MOM_SUBBATCH);
+            const uint32_t w = (uint32_t)nnz_of(d);
+            if (((wpack >> (4 * b)) & 15u) < w) wpack = (wpack & ~(15u << (4 * b))) | (w << (4 * b));
         }
-        mu.wsub = wsub;
+        mu.wsub = (int32_t)wpack;
         mu.cls = U.cls;
         for (size_t sI = 0; sI < U.segs.size(); ++sI)
             for (const auto& fdesc : U.segs[sI].fn)
-                H.funcdesc.push_back((uint32_t)U.subs.at(fdesc.first) * (MOM_BS_HOST * 8) | ((uint32_t)U.subs.at(fdesc.second) * (MOM_BS_HOST * 8) << 16));
+                H.funcdesc.push_back((uint32_t)newid[U.subs.at(fdesc.first)] * (MOM_BS_HOST * 8) |
+                                     ((uint32_t)newid[U.subs.at(fdesc.second)] * (MOM_BS_HOST * 8) << 16));
         for (int t = 0; t < MOM_TASKS; ++t) {
             MomTask mt;
             MomTaskOut to;
@@ -578,7 +591,8 @@ void host_moments(const MomHost& H, const double* x, int64_t n, int64_t ldx, con
         for (const MomUnit& U : H.units) {
             for (int q = 0; q < U.nsub; ++q) {
                 double v = 1.0;
-                for (int k = 0; k < U.wsub; ++k) v *= T[H.subdesc[(size_t)(U.sub_off + q) * MOM_WS + k] / (MOM_BS_HOST * 8)];
+                const int wq = (int)(((uint32_t)U.wsub >> (4 * (q / MOM_SUBBATCH))) & 15u);
+                for (int k = 0; k < wq; ++k) v *= T[H.subdesc[(size_t)(U.sub_off + q) * MOM_WS + k] / (MOM_BS_HOST * 8)];
                 V[q] = v;
             }
             for (int f = 0; f < U.nfunc; ++f) {
@@ -780,7 +794,8 @@ __global__ void __launch_bounds__(256, 1) pcq_mom_kernel(MomParams P) {
         if (item >= nitems) break;
         const int u = item / P.nsplit, part = item - u * P.nsplit;
         const MomUnit U = P.units[P.unit0 + u];
-        const int nsub = U.nsub, wsub = U.wsub;
+        const int nsub = U.nsub;
+        const uint32_t wpack = (uint32_t)U.wsub;
         const int nsp = (nsub + 32 * MOM_VB - 1) / (32 * MOM_VB) * (32 * MOM_VB);      // the sub-function pass runs whole batches
         for (int i = tid; i < U.nfunc; i += 256) fdesc[i] = P.funcdesc[U.func_off + i];
         for (int i = tid; i < nsp * MOM_WS; i += 256) sdesc[i] = i < nsub * MOM_WS ? P.subdesc[(size_t)U.sub_off * MOM_WS + i] : (uint16_t)0;
@@ -827,19 +842,26 @@ __global__ void __launch_bounds__(256, 1) pcq_mom_kernel(MomParams P) {
             const uint32_t tb = aT + st * tbytes + sp * 16;
             uint32_t sd = aSD + (tid >> 3) * (MOM_WS * 2);
             uint32_t vo = aV + (k & 1u) * vbytes + (tid >> 3) * (MOM_BS * 8) + ((((sp >> 2) ^ (tid >> 3)) & 1) << 6) + (sp & 3) * 16;
-            for (int i0 = 0; i0 < nsub; i0 += 32 * MOM_VB, sd += 32 * MOM_VB * MOM_WS * 2, vo += 32 * MOM_VB * MOM_BS * 8) {
+            uint32_t wp = wpack;
+            for (int i0 = 0; i0 < nsub; i0 += 32 * MOM_VB, sd += 32 * MOM_VB * MOM_WS * 2, vo += 32 * MOM_VB * MOM_BS * 8, wp >>= 4) {
+                const int wsub = (int)(wp & 15u);            // factors of this batch's rows
                 uint4 dd[MOM_VB];
                 double2 v[MOM_VB];
 #pragma unroll
                 for (int q = 0; q < MOM_VB; ++q) dd[q] = lds128u(sd + q * (32 * MOM_WS * 2));
 #pragma unroll
                 for (int q = 0; q < MOM_VB; ++q) v[q] = lds128(tb + off_of(dd[q], 0));
+                // factors two at a time: their product does not wait for v
 #pragma unroll
-                for (int f = 1; f < MOM_WS; ++f) {
+                for (int f = 1; f < MOM_WS; f += 2) {
                     if (f < wsub) {
-                        double2 t[MOM_VB];
+                        double2 t[MOM_VB], w2[MOM_VB];
 #pragma unroll
                         for (int q = 0; q < MOM_VB; ++q) t[q] = lds128(tb + off_of(dd[q], f));
+#pragma unroll
+                        for (int q = 0; q < MOM_VB; ++q) w2[q] = lds128(tb + ((f + 1 < MOM_WS) ? off_of(dd[q], (f + 1 < MOM_WS) ? f + 1 : f) : 0u));
+#pragma unroll
+                        for (int q = 0; q < MOM_VB; ++q) { t[q].x *= w2[q].x; t[q].y *= w2[q].y; }
 #pragma unroll
                         for (int q = 0; q < MOM_VB; ++q) { v[q].x *= t[q].x; v[q].y *= t[q].y; }
                     }
