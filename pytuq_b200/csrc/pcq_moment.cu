@@ -67,7 +67,7 @@ struct MomHost {
 int build_node(std::vector<MomNode>& nodes, int lo, int hi) {
     const int idx = (int)nodes.size();
     nodes.push_back({lo, hi, hi, -1, -1});
-    if (hi - lo >= 2) {
+    if (hi - lo > MOM_LEAF) {
         const int mid = lo + (hi - lo + 1) / 2;
         nodes[idx].mid = mid;
         const int ca = build_node(nodes, lo, mid);
@@ -179,7 +179,7 @@ struct Planner {
 
     void make_functions(Seg& sg) {
         const MomNode nd = H.nodes[sg.node];
-        const bool leaf = (nd.hi - nd.lo == 1);
+        const bool leaf = (nd.ca < 0);
         int d0, d1;
         if (sg.side == 0) { d0 = nd.lo; d1 = leaf ? nd.hi : nd.mid; }
         else { d0 = nd.mid; d1 = nd.hi; }
@@ -191,11 +191,9 @@ struct Planner {
             Desc s1 = trivial(), s2 = trivial();
             if (i >= sg.count) { sg.fn[i] = {zero(), trivial()}; continue; }
             if (md > 0) {
-                if (sg.side == 0 && leaf) {
-                    ks[0] = sg.start + i + 1;              // a leaf's rows are psi_1 .. psi_B of its dimension
-                } else if (sg.side == 0) {
+                if (sg.side == 0 && !leaf) {
                     unrank(H.cnt, md, sg.sel, (int64_t)sg.start + i, ks.data());
-                } else {
+                } else {                                   // columns, and a leaf's rows: all non-constant functions by (order, lex)
                     const int64_t colidx = (int64_t)sg.start + i + 1;
                     int b = 1;
                     while (H.cum[(size_t)md * MOM_CSTR + b] <= colidx) ++b;
@@ -408,14 +406,19 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
     int64_t total = 0;
     for (int v = 0; v < nn; ++v) {
         const MomNode nd = H.nodes[v];
-        const bool leaf = (nd.hi - nd.lo == 1);
+        const bool leaf = (nd.ca < 0);
         const int mA = nd.mid - nd.lo, mB = nd.hi - nd.mid;
         for (int cls = 0; cls < 2; ++cls) {
             const int B = cls ? H.B1 : H.B0;
             int64_t off = 0;
-            for (int a = 1; a <= (leaf ? B : B - 1); ++a) {
-                int64_t nc = leaf ? 1 : H.cum[(size_t)mB * MOM_CSTR + (B - a)] - 1;
-                const int64_t nr = leaf ? 1 : H.cnt[(size_t)mA * MOM_CSTR + a];
+            if (leaf) {
+                off = H.cum[(size_t)(nd.hi - nd.lo) * MOM_CSTR + B] - 1;
+                H.ncols[((size_t)v * 2 + cls) * MOM_CSTR + 1] = 1;
+                if (off > ((int64_t)1 << 30)) { H.why = "too many moments"; return; }
+            }
+            for (int a = 1; !leaf && a <= B - 1; ++a) {
+                int64_t nc = H.cum[(size_t)mB * MOM_CSTR + (B - a)] - 1;
+                const int64_t nr = H.cnt[(size_t)mA * MOM_CSTR + a];
                 if (nc > ((int64_t)1 << 30) || nr > ((int64_t)1 << 30)) { H.why = "too many moments"; return; }
                 H.bandoff[((size_t)v * 2 + cls) * MOM_CSTR + a] = off;
                 H.ncols[((size_t)v * 2 + cls) * MOM_CSTR + a] = (int32_t)nc;
@@ -435,13 +438,13 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
     std::vector<Bundle> bundles;
     for (int v = 0; v < nn; ++v) {
         const MomNode nd = H.nodes[v];
-        const bool leaf = (nd.hi - nd.lo == 1);
+        const bool leaf = (nd.ca < 0);
         const int mA = nd.mid - nd.lo;
         for (int cls = 0; cls < 2; ++cls) {
             const int B = cls ? H.B1 : H.B0;
             for (int w = 0; w < (cls ? m : 1); ++w)
-                for (int a = 1; a <= (leaf ? 1 : B - 1); ++a) {      // a leaf is one band: rows psi_1 .. psi_B, one column
-                    const int64_t nr = leaf ? B : H.cnt[(size_t)mA * MOM_CSTR + a];
+                for (int a = 1; a <= (leaf ? 1 : B - 1); ++a) {      // a leaf is one band: all its functions, one column
+                    const int64_t nr = leaf ? H.cum[(size_t)(nd.hi - nd.lo) * MOM_CSTR + B] - 1 : H.cnt[(size_t)mA * MOM_CSTR + a];
                     const int64_t nc = H.ncols[((size_t)v * 2 + cls) * MOM_CSTR + a];
                     if (nr <= 0 || nc <= 0) continue;
                     const int64_t base = H.base[(size_t)v * 2 + cls] + (cls ? (int64_t)w * H.wsize[v] : 0) +
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(256, 1) pcq_mom_kernel(MomParams P) {
         const MomUnit U = P.units[P.unit0 + u];
         const int nsub = U.nsub;
         const uint32_t wpack = (uint32_t)U.wsub;
-        const int nsp = (nsub + 32 * MOM_VB - 1) / (32 * MOM_VB) * (32 * MOM_VB);      // the sub-function pass runs whole batches
+        const int nsp = (nsub + 127) & ~127;      // the sub-function pass runs whole batches (64 or 128 rows)
         for (int i = tid; i < U.nfunc; i += 256) fdesc[i] = P.funcdesc[U.func_off + i];
         for (int i = tid; i < nsp * MOM_WS; i += 256) sdesc[i] = i < nsub * MOM_WS ? P.subdesc[(size_t)U.sub_off * MOM_WS + i] : (uint16_t)0;
         if (tid < MOM_TASKS) tk[tid] = P.tasks[U.task_off + tid];
@@ -836,6 +839,7 @@ __global__ void __launch_bounds__(256, 1) pcq_mom_kernel(MomParams P) {
 
         // sub-functions of block number k of this item (ring position cnt + k): item = (sub-function, sample pair),
         // MOM_VB items in flight; descriptors hold byte offsets of the table rows
+        constexpr int VB = (FM * FN >= 32) ? 2 : 4;      // sub-function items a thread keeps in flight: what the accumulators leave room for
         auto gen_v = [&](uint32_t k) {
             const uint32_t c = cnt + k, st = c % MOM_NST;
             mbar_wait(full + st, (c / MOM_NST) & 1u);
@@ -843,31 +847,32 @@ __global__ void __launch_bounds__(256, 1) pcq_mom_kernel(MomParams P) {
             uint32_t sd = aSD + (tid >> 3) * (MOM_WS * 2);
             uint32_t vo = aV + (k & 1u) * vbytes + (tid >> 3) * (MOM_BS * 8) + ((((sp >> 2) ^ (tid >> 3)) & 1) << 6) + (sp & 3) * 16;
             uint32_t wp = wpack;
-            for (int i0 = 0; i0 < nsub; i0 += 32 * MOM_VB, sd += 32 * MOM_VB * MOM_WS * 2, vo += 32 * MOM_VB * MOM_BS * 8, wp >>= 4) {
-                const int wsub = (int)(wp & 15u);            // factors of this batch's rows
-                uint4 dd[MOM_VB];
-                double2 v[MOM_VB];
+            for (int i0 = 0; i0 < nsub; i0 += 32 * VB, sd += 32 * VB * MOM_WS * 2, vo += 32 * VB * MOM_BS * 8, wp >>= (VB == 4 ? 8 : 4)) {
+                int wsub = (int)(wp & 15u);                  // factors of this batch's rows (planner batches of 64)
+                if (VB == 4) { const int w1 = (int)((wp >> 4) & 15u); wsub = w1 > wsub ? w1 : wsub; }
+                uint4 dd[VB];
+                double2 v[VB];
 #pragma unroll
-                for (int q = 0; q < MOM_VB; ++q) dd[q] = lds128u(sd + q * (32 * MOM_WS * 2));
+                for (int q = 0; q < VB; ++q) dd[q] = lds128u(sd + q * (32 * MOM_WS * 2));
 #pragma unroll
-                for (int q = 0; q < MOM_VB; ++q) v[q] = lds128(tb + off_of(dd[q], 0));
+                for (int q = 0; q < VB; ++q) v[q] = lds128(tb + off_of(dd[q], 0));
                 // factors two at a time: their product does not wait for v
 #pragma unroll
                 for (int f = 1; f < MOM_WS; f += 2) {
                     if (f < wsub) {
-                        double2 t[MOM_VB], w2[MOM_VB];
+                        double2 t[VB], w2[VB];
 #pragma unroll
-                        for (int q = 0; q < MOM_VB; ++q) t[q] = lds128(tb + off_of(dd[q], f));
+                        for (int q = 0; q < VB; ++q) t[q] = lds128(tb + off_of(dd[q], f));
 #pragma unroll
-                        for (int q = 0; q < MOM_VB; ++q) w2[q] = lds128(tb + ((f + 1 < MOM_WS) ? off_of(dd[q], (f + 1 < MOM_WS) ? f + 1 : f) : 0u));
+                        for (int q = 0; q < VB; ++q) w2[q] = lds128(tb + ((f + 1 < MOM_WS) ? off_of(dd[q], (f + 1 < MOM_WS) ? f + 1 : f) : 0u));
 #pragma unroll
-                        for (int q = 0; q < MOM_VB; ++q) { t[q].x *= w2[q].x; t[q].y *= w2[q].y; }
+                        for (int q = 0; q < VB; ++q) { t[q].x *= w2[q].x; t[q].y *= w2[q].y; }
 #pragma unroll
-                        for (int q = 0; q < MOM_VB; ++q) { v[q].x *= t[q].x; v[q].y *= t[q].y; }
+                        for (int q = 0; q < VB; ++q) { v[q].x *= t[q].x; v[q].y *= t[q].y; }
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < MOM_VB; ++q) sts128(vo + q * (32 * MOM_BS * 8), v[q].x, v[q].y);     // 32 rows on: same parity
+                for (int q = 0; q < VB; ++q) sts128(vo + q * (32 * MOM_BS * 8), v[q].x, v[q].y);     // 32 rows on: same parity
             }
         };
         // the DMMAs of block number k for this warp's task; every function value is the product of its two
@@ -1129,7 +1134,7 @@ int mom_get_dev(pcq_plan* p, MomState* ms, int m, MomDev** out) {
         MomDev* D = new MomDev();
         mom_build(D->H, p->sdim, p->nterms, p->h_mi.data(), ms->nord, ms->rec_a.data(), ms->rec_b.data(), p->h_p1.data(), m);
         if (D->H.why.empty()) {
-            if (mom_smem_bytes(D->H.nt, (D->H.nsub_max + 63) & ~63, (D->H.nf_max + 7) & ~7) > p->smem_optin) D->H.why = "shared memory";
+            if (mom_smem_bytes(D->H.nt, (D->H.nsub_max + 127) & ~127, (D->H.nf_max + 7) & ~7) > p->smem_optin) D->H.why = "shared memory";
             else {
                 const int rc = mom_upload(*D);
                 if (rc != PCQ_OK) { delete D; return rc; }
@@ -1232,7 +1237,7 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
     }
     rc = pcq_ensure_dev(ws, ws_bytes, (size_t)cls_item0[MOM_NCLS] * MOM_TASKS * 2048 * 8);
     if (rc != PCQ_OK) return rc;
-    const int nfcap = (H.nf_max + 7) & ~7, nsubcap = (H.nsub_max + 63) & ~63;
+    const int nfcap = (H.nf_max + 7) & ~7, nsubcap = (H.nsub_max + 127) & ~127;
     const size_t smem = mom_smem_bytes(H.nt, nsubcap, nfcap);
 
     for (int64_t r0 = 0; r0 < n; r0 += rows) {

@@ -9,7 +9,8 @@
 //     m_(pi|kappa) = sum_n P_pi(x_n[A]) Q_kappa(x_n[B]),
 // rows = product functions of the dimensions in A, columns = product functions of the dimensions in B, a staircase
 // (rows of order a meet the columns of order <= 2 pt - a).  Moments whose support lies in one half are the same problem
-// on that half: a binary tree of nodes over the dimensions, each node a staircase GEMM, leaves = single dimensions.
+// on that half: a binary tree of nodes over the dimensions, each node a staircase GEMM; a leaf (<= 5 dimensions) pairs
+// all its functions with the constant 1.
 // A^T y, A^T 1 are moments weighted by y (order <= pt).
 #pragma once
 #include <stdint.h>
@@ -30,7 +31,8 @@ constexpr int MOM_CSTR = MOM_MAXORD + 1;
 #define MOM_HD inline
 #endif
 
-struct MomNode { int lo, mid, hi, ca, cb; };   // dimensions [lo, mid) | [mid, hi); a leaf has hi - lo == 1 (mid == hi)
+constexpr int MOM_LEAF = 5;        // a node over at most this many dimensions is a leaf
+struct MomNode { int lo, mid, hi, ca, cb; };   // dimensions [lo, mid) | [mid, hi); a leaf (ca < 0, mid == hi) keeps all its functions as rows of one column
 
 // class 0: plain moments, budget B0 = 2 pt;  class 1: moments weighted by output w, budget B1 = pt
 struct MomGeom {
@@ -63,7 +65,12 @@ MOM_HD int64_t mom_loc(const MomGeom& g, const int* dims, const int* ks, int ne,
         const MomNode nd = g.nodes[node];
         const int64_t base = g.base[node * 2 + cls] + (cls ? (int64_t)w * g.wsize[node] : 0);
         const int64_t* bo = g.bandoff + ((size_t)node * 2 + cls) * MOM_CSTR;
-        if (nd.hi - nd.lo == 1) return base + bo[ks[0]];
+        if (nd.ca < 0) {            // leaf: rows = its non-constant functions by (order, lexicographic), one column
+            int a = 0;
+            for (int e = 0; e < ne; ++e) a += ks[e];
+            const int m = nd.hi - nd.lo;
+            return base + g.cum[m * MOM_CSTR + (a - 1)] - 1 + mom_lexrank(g.cnt, dims, ks, ne, nd.lo, m, a);
+        }
         int na = 0;
         while (na < ne && dims[na] < nd.mid) ++na;
         if (na == ne) { node = nd.ca; continue; }
