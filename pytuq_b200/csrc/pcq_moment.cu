@@ -215,13 +215,24 @@ struct Planner {
 
     // one band: countM x countN moments at `base`, element (i, j) -> base + i sm + j sn
     void band(std::vector<Bundle>& out, int node, int a, int w, int64_t nrows, int64_t ncols, int64_t base) {
-        // orientation: rows on the M side (<= 32 per task) or on the N side (<= 64 per task), fewer tasks wins
+        // orientation: rows on the M side (<= 32 per task) or on the N side (<= 64 per task, <= 128 where the M side
+        // has at most 16), fewer tasks wins
+        auto tiles = [](int64_t m8_, int64_t n8_, int64_t& TM_, int64_t& TN_, int& ncap) {
+            TM_ = (m8_ + 3) / 4;
+            const int64_t fmax = (m8_ + TM_ - 1) / TM_;
+            ncap = fmax <= 2 ? 16 : 8;
+            TN_ = (n8_ + ncap - 1) / ncap;
+        };
         const int64_t r8 = (nrows + 7) / 8, c8 = (ncols + 7) / 8;
-        const int64_t t_rm = ((r8 + 3) / 4) * ((c8 + 7) / 8), t_cm = ((c8 + 3) / 4) * ((r8 + 7) / 8);
-        const bool rows_on_m = t_rm <= t_cm;
+        int64_t tm1, tn1, tm2, tn2;
+        int cap1, cap2;
+        tiles(r8, c8, tm1, tn1, cap1);
+        tiles(c8, r8, tm2, tn2, cap2);
+        const bool rows_on_m = tm1 * tn1 <= tm2 * tn2;
         const int64_t cm = rows_on_m ? nrows : ncols, cn = rows_on_m ? ncols : nrows;
         const int64_t m8 = (cm + 7) / 8, n8 = (cn + 7) / 8;
-        const int64_t TM = (m8 + 3) / 4, TN = (n8 + 7) / 8;
+        const int64_t TM = rows_on_m ? tm1 : tm2, TN = rows_on_m ? tn1 : tn2;
+        const int ncap = rows_on_m ? cap1 : cap2;
         const int32_t sm = rows_on_m ? (int32_t)ncols : 1, sn = rows_on_m ? 1 : (int32_t)ncols;
         auto part = [](int64_t total8, int64_t parts, int64_t t, int64_t& off8, int& len8) {
             const int64_t q = total8 / parts, r = total8 % parts;
@@ -233,9 +244,9 @@ struct Planner {
             int64_t best = INT64_MAX;
             for (int a_ = 1; a_ <= 8; ++a_)
                 for (int b_ = 1; a_ * b_ <= 8; ++b_) {
-                    if (a_ > TM || b_ > TN || 32 * a_ + 64 * b_ > MOM_NF) continue;
+                    if (a_ > TM || b_ > TN || 32 * a_ + 8 * ncap * b_ > MOM_NF) continue;
                     const int64_t nb = ((TM + a_ - 1) / a_) * ((TN + b_ - 1) / b_);
-                    const int64_t key = nb * 1024 + (32 * a_ + 64 * b_);
+                    const int64_t key = nb * 4096 + (32 * a_ + 8 * ncap * b_);
                     if (key < best) { best = key; um = a_; un = b_; }
                 }
         }
@@ -472,18 +483,34 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
         if (!placed) {
             ub.emplace_back();
             if (!try_add(ub.back(), B, H.zero_slot)) {
-                // a block of tasks whose sub-functions do not fit: one task per unit always does
+                // a block of tasks whose sub-functions do not fit one unit: halves of it, recursively
                 ub.pop_back();
-                for (const BTask& t : B.tasks) {
-                    Bundle one;
-                    one.cls = B.cls;
-                    one.segs = {B.segs[t.segM], B.segs[t.segN]};
-                    BTask t1 = t;
-                    t1.segM = 0; t1.segN = 1;
-                    one.tasks = {t1};
+                std::vector<Bundle> stack{B};
+                while (!stack.empty()) {
+                    Bundle cur = std::move(stack.back());
+                    stack.pop_back();
                     ub.emplace_back();
-                    if (!try_add(ub.back(), one, H.zero_slot)) { H.why = "a task does not fit a unit"; return; }
-                    open.push_back((int)ub.size() - 1);
+                    if (try_add(ub.back(), cur, H.zero_slot)) {
+                        if (ub.back().tasks.size() < (size_t)MOM_TASKS) open.push_back((int)ub.size() - 1);
+                        continue;
+                    }
+                    ub.pop_back();
+                    if (cur.tasks.size() < 2) { H.why = "a task does not fit a unit"; return; }
+                    for (int half = 0; half < 2; ++half) {
+                        Bundle part;
+                        part.cls = cur.cls;
+                        std::vector<int> map(cur.segs.size(), -1);
+                        const size_t lo = half ? cur.tasks.size() / 2 : 0, hi = half ? cur.tasks.size() : cur.tasks.size() / 2;
+                        for (size_t t = lo; t < hi; ++t) {
+                            BTask q = cur.tasks[t];
+                            for (int* sg : {&q.segM, &q.segN}) {
+                                if (map[*sg] < 0) { map[*sg] = (int)part.segs.size(); part.segs.push_back(cur.segs[*sg]); }
+                                *sg = map[*sg];
+                            }
+                            part.tasks.push_back(q);
+                        }
+                        stack.push_back(std::move(part));
+                    }
                 }
                 continue;
             }
@@ -503,7 +530,7 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
         macs[u] = MOM_TASKS * half;
         // cycles of one 16-sample block: both warps of a scheduler at the measured DMMA-pipe share of the class
         // (profiles/r02_moment_notes.md: 0.68 / 0.69 / 0.53 / 0.41 / 0.25 active)
-        static const double eff[MOM_NCLS] = {0.66, 0.66, 0.52, 0.40, 0.24};
+        static const double eff[MOM_NCLS] = {0.70, 0.66, 0.60, 0.45, 0.24};
         fin[u] = {2.0 * half / eff[U.cls], (int)u, U.cls};
     }
     std::stable_sort(fin.begin(), fin.end(), [](const Fin& a, const Fin& b) { return a.cls != b.cls ? a.cls < b.cls : a.cost > b.cost; });
@@ -943,19 +970,19 @@ __global__ void __launch_bounds__(256, 1) pcq_mom_kernel(MomParams P) {
 #pragma unroll
             for (int j = 0; j < FN; ++j)
                 if (i < fm && j < fn)
-                    *reinterpret_cast<double2*>(w + (i * 8 + g) * 64 + j * 8 + 2 * tig) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    *reinterpret_cast<double2*>(w + (i * 8 + g) * (FN * 8) + j * 8 + 2 * tig) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
 }
 
 // moments of one task = its partial tiles summed over the sample parts, in part order; grid (nunits * 8)
 __global__ void __launch_bounds__(256) pcq_mom_fixup_kernel(const MomUnit* units, const MomTaskOut* touts, const double* ws,
-                                                            int unit0, int item0, int nsplit, int accumulate, double* mom) {
+                                                            int unit0, int item0, int nsplit, int stride, int accumulate, double* mom) {
     const int u = blockIdx.x >> 3, slot = blockIdx.x & 7;
     const MomTaskOut to = touts[units[unit0 + u].task_off + slot];
     const int total = to.vm * to.vn;
     for (int e = threadIdx.x; e < total; e += 256) {
         const int i = e / to.vn, j = e - i * to.vn;
-        const double* w = ws + (((size_t)item0 + (size_t)u * nsplit) * MOM_TASKS + slot) * 2048 + i * 64 + j;
+        const double* w = ws + (((size_t)item0 + (size_t)u * nsplit) * MOM_TASKS + slot) * 2048 + i * stride + j;
         double sum = 0.0;
         for (int q = 0; q < nsplit; ++q) sum += w[(size_t)q * MOM_TASKS * 2048];
         double* dst = mom + to.base + (int64_t)i * to.sm + (int64_t)j * to.sn;
@@ -1270,14 +1297,14 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
             switch (c) {
                 case 0: rc = launch(pcq_mom_kernel<4, 8>); break;
                 case 1: rc = launch(pcq_mom_kernel<3, 8>); break;
-                case 2: rc = launch(pcq_mom_kernel<2, 8>); break;
-                case 3: rc = launch(pcq_mom_kernel<1, 8>); break;
+                case 2: rc = launch(pcq_mom_kernel<2, 16>); break;
+                case 3: rc = launch(pcq_mom_kernel<1, 16>); break;
                 default: rc = launch(pcq_mom_kernel<1, 2>); break;
             }
             if (rc != PCQ_OK) return rc;
             PCQ_LAUNCH_CHECK("pcq_mom_kernel");
             pcq_mom_fixup_kernel<<<nu * MOM_TASKS, 256, 0, st>>>(D->units, D->touts, *ws, cls_unit0[c], cls_item0[c], cls_split[c],
-                                                                  r0 > 0 ? 1 : 0, D->mom);
+                                                                  8 * MOM_CLS[c][1], r0 > 0 ? 1 : 0, D->mom);
             PCQ_LAUNCH_CHECK("pcq_mom_fixup_kernel");
         }
     }

@@ -18,7 +18,7 @@
 constexpr int MOM_MAXORD = 32;     // 2 pt <= MOM_MAXORD
 constexpr int MOM_MAXDIM = 32;     // germ dimension (a thread tabulates two (dimension, sample) items of a 16-sample block)
 constexpr int MOM_WS = 8;          // table slots per sub-function descriptor
-constexpr int MOM_NF = 512;        // functions (rows + columns) of one unit
+constexpr int MOM_NF = 1280;       // functions (rows + columns) of one unit
 constexpr int MOM_NSUB = 384;      // distinct sub-functions of one unit
 constexpr int MOM_NT = 256;        // table slots: 1 + 2 pt s, the weights, the zero slot
 constexpr int MOM_TASKS = 8;       // warp tasks per unit
@@ -92,7 +92,7 @@ struct MomUnit { int32_t func_off, nfunc, sub_off, nsub, task_off, ntasks, wsub,
 // Task shapes the kernel is compiled for (row fragments x column fragments of 8): all tasks of a unit run as the unit's
 // class, padded with zero functions.  Sub-function 0 of every unit is the zero function, 1 the constant one.
 constexpr int MOM_NCLS = 5;
-constexpr int MOM_CLS[MOM_NCLS][2] = {{4, 8}, {3, 8}, {2, 8}, {1, 8}, {1, 2}};
+constexpr int MOM_CLS[MOM_NCLS][2] = {{4, 8}, {3, 8}, {2, 16}, {1, 16}, {1, 2}};
 
 // One Gram entry from the moments: terms i and j as sparse (dimension, order) lists in ascending dimension.
 //   lin[((d (pt+1) + a) (pt+1) + b) (B0+1) + k] = c^{(d)}_{abk},  psi_a psi_b = sum_k c_{abk} psi_k  in dimension d

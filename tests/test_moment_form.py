@@ -109,7 +109,7 @@ def test_plan_of_the_headline_shape():
     rc, _, info = _host_stats_plan_only(mi, ["HG"] * 20, 1)
     assert rc == 0 and info[6] == 1.0
     assert int(info[0]) == comb(26, 6) - 1 + comb(23, 3) - 1
-    assert info[4] <= 512 and info[5] <= 384
+    assert info[4] <= 1280 and info[5] <= 384
     assert info[3] < 0.3 * mi.shape[0] ** 2 / 2          # executed multiply-adds per sample against K^2 / 2
 
 
