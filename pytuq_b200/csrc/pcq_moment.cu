@@ -1098,8 +1098,17 @@ struct MomDev {
     MomUnit* units = nullptr; MomTask* tasks = nullptr; MomTaskOut* touts = nullptr; uint32_t* funcdesc = nullptr; uint16_t* subdesc = nullptr;
     double* mom = nullptr; double* yy = nullptr; double* yypart = nullptr; unsigned int* counter = nullptr;
     bool ready = false;
+    // the class kernels of a chunk run on their own streams (forked from / joined to the caller's), so that the tail of
+    // one launch is filled by the CTAs of the next
+    cudaStream_t cs[MOM_NCLS] = {};
+    cudaEvent_t fork = nullptr, join[MOM_NCLS] = {};
     std::vector<void*> owned;
-    ~MomDev() { for (void* q : owned) cudaFree(q); }
+    ~MomDev() {
+        for (void* q : owned) cudaFree(q);
+        for (auto st : cs) if (st) cudaStreamDestroy(st);
+        if (fork) cudaEventDestroy(fork);
+        for (auto e : join) if (e) cudaEventDestroy(e);
+    }
 };
 
 struct MomState {
@@ -1131,6 +1140,11 @@ int mom_upload(MomDev& D) {
     PCQ_CUDA(cudaMalloc((void**)&D.yy, MOM_YV * 8)); D.owned.push_back(D.yy);
     PCQ_CUDA(cudaMalloc((void**)&D.yypart, (size_t)1024 * MOM_YV * 8)); D.owned.push_back(D.yypart);
     PCQ_CUDA(cudaMalloc((void**)&D.counter, 64)); D.owned.push_back(D.counter);
+    for (int c = 0; c < MOM_NCLS; ++c) {
+        PCQ_CUDA(cudaStreamCreateWithFlags(&D.cs[c], cudaStreamNonBlocking));
+        PCQ_CUDA(cudaEventCreateWithFlags(&D.join[c], cudaEventDisableTiming));
+    }
+    PCQ_CUDA(cudaEventCreateWithFlags(&D.fork, cudaEventDisableTiming));
     D.ready = true;
     return PCQ_OK;
 }
@@ -1236,7 +1250,7 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
     const int nunits = (int)H.units.size();
     // sample chunks: the table of 1-D values of a chunk (8 nt bytes per sample) lives in the scratch buffer
     const char* cenv = getenv("PCQ_MOMENT_CHUNK_MB");
-    const int64_t target = (int64_t)(cenv ? atoi(cenv) : 2048) << 20;
+    const int64_t target = (int64_t)(cenv ? atoi(cenv) : 6144) << 20;
     int64_t rows = std::max<int64_t>(MOM_BS, target / ((int64_t)H.nt * 8) / MOM_BS * MOM_BS);
     {
         const int64_t nchunks = (n + rows - 1) / rows;
@@ -1254,7 +1268,7 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
         for (int c = 0; c < MOM_NCLS; ++c) {
             int nu = 0;
             while (u0 + nu < nunits && H.units[u0 + nu].cls == c) ++nu;
-            int sp = nu ? (4 * p->num_sms + nu - 1) / nu : 1;
+            int sp = nu ? (6 * p->num_sms + nu - 1) / nu : 1;
             if (senv) sp = atoi(senv);
             sp = (int)std::max<int64_t>(1, std::min<int64_t>(sp, nb_chunk / 24));
             cls_unit0[c] = u0; cls_split[c] = sp; cls_item0[c] = it0;
@@ -1284,14 +1298,17 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
         P.tab = *zbuf; P.nblocks = nblocks; P.nt = H.nt;
         P.units = D->units; P.tasks = D->tasks; P.funcdesc = D->funcdesc; P.subdesc = D->subdesc;
         P.nfcap = nfcap; P.nsubcap = nsubcap; P.ws = *ws;
+        PCQ_CUDA(cudaEventRecord(D->fork, st));
         for (int c = 0; c < MOM_NCLS; ++c) {
             const int nu = cls_unit0[c + 1] - cls_unit0[c];
             if (nu == 0) continue;
+            cudaStream_t sc = D->cs[c];
+            PCQ_CUDA(cudaStreamWaitEvent(sc, D->fork, 0));
             P.unit0 = cls_unit0[c]; P.nunits = nu; P.nsplit = cls_split[c]; P.item0 = cls_item0[c]; P.counter = D->counter + c;
             const int grid = std::min(p->num_sms, nu * P.nsplit);
             auto launch = [&](auto kern) -> int {
                 PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<grid, 256, smem, st>>>(P);
+                kern<<<grid, 256, smem, sc>>>(P);
                 return PCQ_OK;
             };
             switch (c) {
@@ -1303,9 +1320,11 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
             }
             if (rc != PCQ_OK) return rc;
             PCQ_LAUNCH_CHECK("pcq_mom_kernel");
-            pcq_mom_fixup_kernel<<<nu * MOM_TASKS, 256, 0, st>>>(D->units, D->touts, *ws, cls_unit0[c], cls_item0[c], cls_split[c],
+            pcq_mom_fixup_kernel<<<nu * MOM_TASKS, 256, 0, sc>>>(D->units, D->touts, *ws, cls_unit0[c], cls_item0[c], cls_split[c],
                                                                   8 * MOM_CLS[c][1], r0 > 0 ? 1 : 0, D->mom);
             PCQ_LAUNCH_CHECK("pcq_mom_fixup_kernel");
+            PCQ_CUDA(cudaEventRecord(D->join[c], sc));
+            PCQ_CUDA(cudaStreamWaitEvent(st, D->join[c], 0));
         }
     }
     if (m > 0) {
