@@ -550,7 +550,7 @@ def main():
     # DRAM bytes per step of the dominant kernel: NOT a live counter -- the committed ncu capture of this very
     # command (bytes per sample x this rank's samples; the SYRK works chunk by chunk, so its traffic is linear in N)
     traffic, traffic_source = None, None
-    for fn in (("r02_moment_traffic.json",) if moment_form else ()) + ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
+    for fn in (("r02_n_moment_traffic.json", "r02_moment_traffic.json") if moment_form else ()) + ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
             per_sample = tj.get("dram_bytes_per_sample_main_kernel",
@@ -610,9 +610,10 @@ def main():
         roofline = {"bound": "tensor",
                     "kernel": "pcq_mom_kernel<FM,FN> (K3 in moment form, csrc/pcq_moment.cu: the %d moments the Gram entries are linear "
                               "combinations of, as staircase GEMMs on DMMA -- %.0f executed multiply-adds per sample instead of "
-                              "K(K+1)/2 + ... = %.0f; five launches, one per task shape, fed by pcq_mom_table_kernel; then "
-                              "fix-up and the K x K reconstruction; launch list profiles/r02_moment_launches.csv)"
-                              % (int(minfo[0]), minfo[2], flops / (2.0 * n)),
+                              "K(K+1)/2 + ... = %.0f; %d units of eight warp tasks; per 6 GB table chunk one launch per task "
+                              "shape on forked streams, fed by pcq_mom_table_kernel; then fix-up and the K x K reconstruction; "
+                              "launch list profiles/r02_n_moment_launches.csv)"
+                              % (int(minfo[0]), minfo[2], flops / (2.0 * n), int(minfo[1])),
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
                     "achieved_note": "multiply-adds EXECUTED on the DMMA pipe (planner count, fragment padding included) x 2 / "
                                      "duration of the whole pcq_suffstats_dev call (table + moment kernels + fix-up + "
@@ -627,8 +628,8 @@ def main():
                                                  "dense form itself (pack + SYRK) is kernels.K3_pack_syrk_form"},
                     "traffic": traffic, "traffic_source": traffic_source,
                     "traffic_note": "x, y are read once by the table kernel, which writes %d B per sample of 1-D values; every "
-                                    "unit (53 at this shape) streams that table once through L2; algorithmic input bytes = %d"
-                                    % (int(minfo[6]), 8 * n * (D + 1)),
+                                    "unit (%d at this shape) streams that table once through L2; algorithmic input bytes = %d"
+                                    % (int(minfo[6]), int(minfo[1]), 8 * n * (D + 1)),
                     "peak_source": peak_source}
     else:
         roofline = {"bound": "tensor", "kernel": "pcq_syrk_kernel (K3: DMMA SYRK over the packed design matrix, TMA-fed; "

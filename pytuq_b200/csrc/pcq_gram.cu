@@ -24,6 +24,7 @@
 //   pcq_gram_kernel       generic: any width, and a materialised A; plain generate / barrier / DMMA
 //                         phases
 #include "pcq_internal.cuh"
+#include "pcq_moment.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -696,8 +697,23 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
     if (n > 0 && a == nullptr && p->mom) {
         // moment form (pcq_moment.cu): N |Gamma| instead of N K^2 / 2 multiply-adds where the planner expects a gain
         bool handled = false;
-        const int rc = pcq_launch_moments(p, x, n, ldx, y, ldy, m, s, accumulate, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled);
+        int rc = pcq_launch_moments(p, x, n, ldx, y, ldy, m, s, accumulate, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled);
         if (handled || rc != PCQ_OK) return rc;
+        // more outputs than the moment form carries (pc_fit of a field, C5): G, A^T 1 and N in moment form, the output
+        // columns (A^T Y, Y^T Y, Y^T 1) by the SYRK over the tile columns that hold them
+        const char* he = getenv("PCQ_GRAM_HYBRID");
+        if (m > MOM_MAXOUT && y && he && atoi(he) != 0) {      // off until confirmed on the GPU
+            rc = pcq_launch_moments(p, x, n, ldx, nullptr, 0, 0, s, accumulate, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled, m);
+            if (rc != PCQ_OK) return rc;
+            if (handled) {
+                bool h2 = false;
+                rc = pcq_launch_syrk(p, num_sms, smem_optin, x, n, ldx, nullptr, 0, 0, y, ldy, m, s, accumulate, ws, ws_bytes,
+                                     zbuf, zbuf_bytes, st, &h2, true);
+                if (rc != PCQ_OK) return rc;
+                if (!h2) { pcq_set_error("suffstats: SYRK pipeline unavailable for the output columns"); return PCQ_ERR_UNSUPPORTED; }
+                return PCQ_OK;
+            }
+        }
     }
     {
         const char* e = getenv("PCQ_GRAM_SYRK");

@@ -120,11 +120,13 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
 int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n, int64_t ldx,
                     const double* a, int64_t lda, int kcols, const double* y, int64_t ldy, int m, double* s,
                     int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes,
-                    cudaStream_t st, bool* handled);
+                    cudaStream_t st, bool* handled, bool rect = false);
+// rect: only the output columns of S (A^T Y, Y^T Y, Y^T 1) -- the part the moment form leaves when it serves G alone
 // moment form of the same statistics (pcq_moment.cu); *handled = false when it does not apply or would be slower
 int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy, int m,
                        double* s, int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes,
-                       cudaStream_t st, bool* handled);
+                       cudaStream_t st, bool* handled, int layout_m = -1);
+// layout_m >= 0 with m == 0: G, A^T 1 and N only, written into an S laid out for layout_m outputs (L = K + layout_m + 1)
 void pcq_mom_free(pcq_plan* p);
 int pcq_launch_propagate(pcq_plan* p, uint64_t seed, int64_t first, int64_t n,
                          const int32_t* germ_kind, const double* cf, int m, double* sums,

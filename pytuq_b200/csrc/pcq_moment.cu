@@ -1037,6 +1037,7 @@ struct MomRecon {
     const double* lin; const double* mom; const double* yy;    // yy: MOM_YV sums of the outputs
     const int16_t* tdim; const uint8_t* tord; const uint8_t* tnnz;
     int K, M, W;
+    int ML;                // outputs S is laid out for (L = K + ML + 1); M of them (0 or ML) are served here
     double nsamples;
     double* S; int accumulate;
 };
@@ -1044,7 +1045,7 @@ struct MomRecon {
 __global__ void __launch_bounds__(256) pcq_mom_pairs_kernel(MomRecon R) {
     const int j = blockIdx.x * 16 + (threadIdx.x & 15), i = blockIdx.y * 16 + (threadIdx.x >> 4);
     if (i > j || j >= R.K) return;
-    const int L = R.K + R.M + 1;
+    const int L = R.K + R.ML + 1;
     const double v = mom_pair(R.g, R.lin, R.mom, R.nsamples, R.tdim + (size_t)i * R.W, R.tord + (size_t)i * R.W, R.tnnz[i],
                               R.tdim + (size_t)j * R.W, R.tord + (size_t)j * R.W, R.tnnz[j]);
     double* a = R.S + (size_t)i * L + j;
@@ -1058,7 +1059,7 @@ __global__ void __launch_bounds__(256) pcq_mom_pairs_kernel(MomRecon R) {
 // the y and 1 columns / rows and the (M + 1) x (M + 1) corner
 __global__ void __launch_bounds__(256) pcq_mom_edges_kernel(MomRecon R) {
     const int k = blockIdx.x * 256 + threadIdx.x;
-    const int K = R.K, M = R.M, L = K + M + 1;
+    const int K = R.K, M = R.M, L = K + R.ML + 1;
     auto put = [&](int r, int c, double v) {
         double* a = R.S + (size_t)r * L + c;
         *a = (R.accumulate ? *a : 0.0) + v;
@@ -1203,7 +1204,9 @@ extern "C" int pcq_moment_info(pcq_plan* p, int m, int64_t n, double* info) {
     if (!p || m < 0 || !info) { pcq_set_error("moment_info: bad argument"); return PCQ_ERR_ARG; }
     for (int i = 0; i < 8; ++i) info[i] = 0.0;
     MomState* ms = static_cast<MomState*>(p->mom);
-    if (!ms || m > MOM_MAXOUT) return PCQ_OK;
+    if (!ms) return PCQ_OK;
+    const int mlay = m;
+    if (m > MOM_MAXOUT) m = 0;      // hybrid: G in moment form, the output columns by the SYRK (pcq_launch_gram)
     MomDev* D = nullptr;
     {
         int prev = -1;
@@ -1221,14 +1224,17 @@ extern "C" int pcq_moment_info(pcq_plan* p, int m, int64_t n, double* info) {
     const char* e2 = getenv("PCQ_MOMENT_MIN_N");
     info[5] = (D->ready && mode != 0 && n > 0 && (mode > 0 || (n >= (e2 ? atoll(e2) : 32768) && mom_pays(p, H, m, n)))) ? 1.0 : 0.0;
     info[6] = 8.0 * H.nt;
+    info[7] = mlay > MOM_MAXOUT ? 1.0 : 0.0;
     return PCQ_OK;
 }
 
 // S (+)= statistics of n samples through the moment form; *handled = false when the route does not apply (the caller
 // falls back to the SYRK form).  PCQ_GRAM_MOMENT = 0 never, 1 whenever a plan exists, unset: when it is estimated faster.
 int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy, int m,
-                       double* s_out, int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st, bool* handled) {
+                       double* s_out, int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes, cudaStream_t st, bool* handled,
+                       int layout_m) {
     *handled = false;
+    if (layout_m >= 0 && m != 0) { pcq_set_error("moments: layout_m goes with m == 0"); return PCQ_ERR_ARG; }
     MomState* ms = static_cast<MomState*>(p->mom);
     const char* env = getenv("PCQ_GRAM_MOMENT");
     const int mode = env ? atoi(env) : -1;
@@ -1340,7 +1346,7 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
     R.g.nodes = D->nodes; R.g.base = D->base; R.g.wsize = D->wsize; R.g.bandoff = D->bandoff; R.g.ncols = D->ncols;
     R.g.cnt = D->cnt; R.g.cum = D->cum;
     R.lin = D->lin; R.mom = D->mom; R.yy = D->yy; R.tdim = D->tdim; R.tord = D->tord; R.tnnz = D->tnnz;
-    R.K = H.nterms; R.M = m; R.W = H.width; R.nsamples = (double)n; R.S = s_out; R.accumulate = accumulate;
+    R.K = H.nterms; R.M = m; R.ML = layout_m >= 0 ? layout_m : m; R.W = H.width; R.nsamples = (double)n; R.S = s_out; R.accumulate = accumulate;
     const int nb16 = (H.nterms + 15) / 16;
     pcq_mom_pairs_kernel<<<dim3(nb16, nb16), 256, 0, st>>>(R);
     PCQ_LAUNCH_CHECK("pcq_mom_pairs_kernel");

@@ -37,7 +37,10 @@ namespace {
 struct SyrkParams {
     const double* zp;
     int Lp, L, ntile, ntri, nsplit;   // ntri: tiles of THIS launch (all, off-diagonal only, or diagonal only)
-    int kind;                         // 0 all upper-triangle tiles, 1 off-diagonal tiles, 2 diagonal tiles
+    int kind;                         // 0 all upper-triangle tiles, 1 off-diagonal tiles, 2 diagonal tiles,
+                                      // 3 + t0: the tile columns J >= t0 only (I <= J), full tiles ("rect" mode)
+    int cmin;                         // rect mode: only entries in columns >= cmin are written, and of the last column
+                                      // (the ones) only the rows in [cmin, L - 1): the rest of S belongs to the moment form
     int64_t nstages;       // stages (of STAGE_SAMPLES samples) in this chunk
     double* s_out;
     int accumulate;
@@ -184,9 +187,21 @@ __global__ void __launch_bounds__(256) pcq_pack_matrix_kernel(PackParams P) {
 }
 
 // ------------------------------------------------------------------------------------------ syrk
+// rect mode (cmin > 0): is entry (row, c) of S this launch's to write?
+__device__ __forceinline__ bool syrk_keeps(const SyrkParams& P, int row, int c) {
+    if (P.cmin <= 0) return true;
+    return c >= P.cmin && (c < P.L - 1 || (row >= P.cmin && row < P.L - 1));
+}
 __device__ __forceinline__ void tile_of(int kind, int t, int ntile, int& I, int& J) {
     if (kind == 2) { I = J = t; return; }
     if (kind == 0) { tile_decode(t, ntile, I, J); return; }
+    if (kind >= 3) {                          // column J holds J + 1 tiles, columns from t0 on
+        int j = kind - 3, rem = t;
+        while (rem > j) { rem -= j + 1; ++j; }
+        I = rem;
+        J = j;
+        return;
+    }
     int i = 0, rem = t;                       // off-diagonal: row i holds ntile - 1 - i tiles
     while (rem >= ntile - 1 - i) { rem -= ntile - 1 - i; ++i; }
     I = i;
@@ -376,8 +391,8 @@ __global__ void __launch_bounds__(SY_THREADS, 1) pcq_syrk_kernel(SyrkParams P) {
                         const int row = ti * ST + rl, c = tj * ST + cl;
                         if (row < P.L) {
                             double* dst = P.s_out + (size_t)row * P.L + c;
-                            if (c < P.L) dst[0] = (P.accumulate ? dst[0] : 0.0) + acc[i][j][0];
-                            if (c + 1 < P.L) dst[1] = (P.accumulate ? dst[1] : 0.0) + acc[i][j][1];
+                            if (c < P.L && syrk_keeps(P, row, c)) dst[0] = (P.accumulate ? dst[0] : 0.0) + acc[i][j][0];
+                            if (c + 1 < P.L && syrk_keeps(P, row, c + 1)) dst[1] = (P.accumulate ? dst[1] : 0.0) + acc[i][j][1];
                         }
                     }
                 }
@@ -397,7 +412,7 @@ __global__ void __launch_bounds__(256) pcq_syrk_fixup_kernel(SyrkParams P) {
     for (int e = blockIdx.y * PER + threadIdx.x; e < (blockIdx.y + 1) * PER; e += 256) {
         const int r = e / ST, c = e - r * ST;
         const int row = I * ST + r, cc = J * ST + c;
-        if (row >= P.L || cc >= P.L || row > cc) continue;      // the mirror kernel fills the lower triangle
+        if (row >= P.L || cc >= P.L || row > cc || !syrk_keeps(P, row, cc)) continue;      // the mirror kernel fills the lower triangle
         double sum = 0.0;
         for (int q = 0; q < P.nsplit; ++q) sum += w[(size_t)q * ST * ST + e];
         double* dst = P.s_out + (size_t)row * P.L + cc;
@@ -446,7 +461,7 @@ int choose_split(int ntri, int grid, int64_t nstages) {
 int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x, int64_t n, int64_t ldx,
                     const double* a, int64_t lda, int kcols, const double* y, int64_t ldy, int m, double* s,
                     int accumulate, double** ws, size_t* ws_bytes, double** zbuf, size_t* zbuf_bytes,
-                    cudaStream_t st, bool* handled) {
+                    cudaStream_t st, bool* handled, bool rect) {
     *handled = false;
     const bool fused = (a == nullptr);
     const int kb = fused ? p->nterms : kcols;
@@ -529,13 +544,18 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
         // launch gets its own number of sample parts, so both fill the SMs in whole waves
         // (K = 1771: 91 tiles x 13 parts = 7.99 waves, 14 diagonal tiles x 21 parts = 1.99 waves).
         const char* denv = getenv("PCQ_SYRK_DIAG");
-        const bool split_diag = ST == 128 && !(denv && atoi(denv) == 0);
+        const bool split_diag = ST == 128 && !(denv && atoi(denv) == 0) && !rect;
         struct Pass { int kind, ntiles; bool diagh; int wstiles; };     // ntiles: scheduling units per part
         Pass passes[2];
         int npass = 0;
         if (split_diag) {
             if (ntri - ntile > 0) passes[npass++] = {1, ntri - ntile, false, ntri - ntile};
             passes[npass++] = {2, (10 * ntile + 7) / 8, true, ntile};
+        } else if (rect) {
+            // the y columns against everything (A^T Y, Y^T Y, Y^T 1): tile columns from the one holding column kb on
+            const int t0 = kb / ST;
+            const int nt = ntri - t0 * (t0 + 1) / 2;
+            passes[npass++] = {3 + t0, nt, false, nt};
         } else {
             passes[npass++] = {0, ntri, false, ntri};
         }
@@ -560,6 +580,7 @@ int pcq_launch_syrk(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
             P.zp = *zbuf; P.Lp = Lp; P.L = L; P.ntile = ntile; P.ntri = passes[q].ntiles; P.kind = passes[q].kind;
             P.nstages = nstages; P.nsplit = nsplit[q];
             P.s_out = s; P.accumulate = (accumulate || r0 > 0) ? 1 : 0;
+            P.cmin = rect ? kb : 0;
             if (P.nsplit > 1) {
                 P.ws = *ws + ws_off;
                 ws_off += (size_t)passes[q].wstiles * P.nsplit * ST * ST;
