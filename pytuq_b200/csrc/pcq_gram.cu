@@ -702,7 +702,7 @@ int pcq_launch_gram(pcq_plan* p, int num_sms, size_t smem_optin, const double* x
         // more outputs than the moment form carries (pc_fit of a field, C5): G, A^T 1 and N in moment form, the output
         // columns (A^T Y, Y^T Y, Y^T 1) by the SYRK over the tile columns that hold them
         const char* he = getenv("PCQ_GRAM_HYBRID");
-        if (m > MOM_MAXOUT && y && he && atoi(he) != 0) {      // off until confirmed on the GPU
+        if (m > MOM_MAXOUT && y && !(he && atoi(he) == 0)) {
             rc = pcq_launch_moments(p, x, n, ldx, nullptr, 0, 0, s, accumulate, ws, ws_bytes, zbuf, zbuf_bytes, st, &handled, m);
             if (rc != PCQ_OK) return rc;
             if (handled) {

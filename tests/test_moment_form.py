@@ -245,3 +245,30 @@ def test_full_size_agreement_of_the_two_forms():
     assert _rel(Sm, Ss) < 1e-12
     sol = np.linalg.solve(Sm[:K, :K], Sm[:K, K])
     assert np.max(np.abs(sol - cf)) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fam,d,p,m,n", [("HG", 3, 2, 9, 5003), ("LU", 6, 3, 20, 7777), ("HG", 8, 3, 130, 30001),
+                                         ("nLU", 5, 4, 300, 4099)])
+def test_more_outputs_than_the_moment_form_carries(fam, d, p, m, n, monkeypatch):
+    """m > MOM_MAXOUT: G, A^T 1 and N in moment form, the output columns (A^T Y, Y^T Y, Y^T 1) by the SYRK over the
+    tile columns that hold them (pcq_launch_gram's hybrid route; workflows/fits.py:47-64 with a field of outputs) --
+    against Z^T Z of the oracle's design matrix, in one call, accumulated over two calls, and with the dense form."""
+    from pytuq_b200.rv.pcrv import PCRV
+    rng = np.random.default_rng(n + m)
+    fams = [fam] * d
+    mi = orc.get_mi(p, d)
+    pc = PCRV(1, d, fam, mi=mi)
+    x = _sample(rng, fams, n)
+    y = rng.standard_normal((n, m))
+    Z = np.concatenate([_design(x, mi, fams), y, np.ones((n, 1))], axis=1)
+    Sref = Z.T @ Z
+    S1 = _dev_stats(pc, mi, x, y, m, "1")
+    assert not np.isnan(S1).any()
+    assert _rel(S1, Sref) < 1e-12
+    np.testing.assert_array_equal(S1, S1.T)
+    assert _rel(_dev_stats(pc, mi, x, y, m, "1", accumulate_in_two=True, ldx=d + 1), Sref) < 1e-12
+    monkeypatch.setenv("PCQ_SYRK_TILE", "96")
+    assert _rel(_dev_stats(pc, mi, x, y, m, "1"), Sref) < 1e-12
+    monkeypatch.delenv("PCQ_SYRK_TILE")
+    assert _rel(_dev_stats(pc, mi, x, y, m, "0"), Sref) < 1e-12
