@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -529,8 +530,8 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
         const double half = 64.0 * MOM_CLS[U.cls][0] * MOM_CLS[U.cls][1];      // DMMA cycles of one warp per block
         macs[u] = MOM_TASKS * half;
         // cycles of one 16-sample block: both warps of a scheduler at the measured DMMA-pipe share of the class
-        // (profiles/r02_moment_notes.md: 0.68 / 0.69 / 0.53 / 0.41 / 0.25 active)
-        static const double eff[MOM_NCLS] = {0.70, 0.66, 0.60, 0.45, 0.24};
+        // (warp-specialised kernels, cycle counters of PCQ_MOMENT_DBG at C2: profiles/r02_moment_notes.md)
+        static const double eff[MOM_NCLS] = {0.847, 0.78, 0.77, 0.54, 0.30};
         fin[u] = {2.0 * half / eff[U.cls], (int)u, U.cls};
     }
     std::stable_sort(fin.begin(), fin.end(), [](const Fin& a, const Fin& b) { return a.cls != b.cls ? a.cls < b.cls : a.cost > b.cost; });
@@ -590,6 +591,13 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
         H.nsub_max = std::max(H.nsub_max, mu.nsub);
         H.clk_per_block += f.cost;
         H.mac_slots += macs[f.idx];
+        if (getenv("PCQ_MOMENT_VERBOSE")) {
+            double useful = 0.0, frag = 0.0;
+            for (const BTask& bt : U.tasks) { useful += (double)bt.out.vm * bt.out.vn; frag += 64.0 * bt.fm * bt.fn; }
+            fprintf(stderr, "unit %3d class (%d,%2d) tasks %d funcs %4d subs %3d  moments %7.0f  fragment slots %7.0f  executed %7.0f  est. cycles/block %7.0f\n",
+                    (int)H.units.size() - 1, MOM_CLS[U.cls][0], MOM_CLS[U.cls][1], (int)U.tasks.size(), U.nfunc, (int)U.subs.size(),
+                    useful, frag, macs[f.idx], f.cost);
+        }
     }
 }
 
@@ -788,6 +796,8 @@ struct MomParams {
     const MomUnit* units; const MomTask* tasks; const uint32_t* funcdesc; const uint16_t* subdesc;
     int nunits, nsplit, nfcap, nsubcap;      // units of this launch's class, sample parts per unit
     int unit0, item0;                        // first unit of the class; work items (unit, part) before it in ws
+    int nvb;                                 // warp-specialised kernel: V buffers in its ring (2 or 3)
+    unsigned long long* dbg;                 // PCQ_MOMENT_DBG: cycle counters of one consumer / one producer thread per CTA
     unsigned int* counter;
     double* ws;            // [work item][8 warps][32 x 64]
 };
@@ -971,6 +981,230 @@ __global__ void __launch_bounds__(256, 1) pcq_mom_kernel(MomParams P) {
             for (int j = 0; j < FN; ++j)
                 if (i < fm && j < fn)
                     *reinterpret_cast<double2*>(w + (i * 8 + g) * (FN * 8) + j * 8 + 2 * tig) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Warp-specialised form of the same kernel (PCQ_MOMENT_WS, default where its shared memory fits): 12 warps.
+//   warps 8-11 (one per scheduler, 72 registers after setmaxnreg) GENERATE the sub-function values of block k + 1 .. into
+//   a ring of V buffers; warps 0-7 (216 registers) only multiply: both warps of a scheduler issue DMMAs all the time,
+//   instead of one generating while the other multiplies.  Hand-over by mbarriers (vfull: 128 producer arrivals,
+//   vempty: one arrival per consumer warp); the CTA-wide barrier is only used between work items.
+constexpr int MOM_WS_THREADS = 384;
+// register budgets after setmaxnreg: the consumers can only take what the producers give back to the CTA's pool,
+// 8 x 32 x RC + 4 x 32 x RP <= 384 x 168 (more and the TRY_ALLOC of the consumers never returns)
+constexpr int MOM_WS_RC = 216, MOM_WS_RP = 72;
+static_assert(2 * MOM_WS_RC + MOM_WS_RP <= 3 * 168 && MOM_WS_RC % 8 == 0 && MOM_WS_RP % 8 == 0, "setmaxnreg budgets exceed the CTA's registers");
+constexpr int MOM_PVB = 4;           // sub-function items a producer thread keeps in flight
+inline size_t mom_ws_smem_bytes(int nt, int nsubcap, int nfcap, int nvb) {
+    return (size_t)(MOM_NST * nt + nvb * nsubcap) * MOM_BS * 8 + (size_t)nfcap * 4 + (size_t)nsubcap * MOM_WS * 2 +
+           MOM_TASKS * sizeof(MomTask) + (MOM_NST + 6) * 8 + 16;
+}
+
+template <int FM, int FN>
+__global__ void __launch_bounds__(MOM_WS_THREADS, 1) pcq_mom_ws_kernel(MomParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* T = reinterpret_cast<double*>(smem_raw);                 // [MOM_NST][nt][16]
+    double* V = T + (size_t)MOM_NST * P.nt * MOM_BS;                  // [nvb][nsubcap][16]
+    uint32_t* fdesc = reinterpret_cast<uint32_t*>(V + (size_t)P.nvb * P.nsubcap * MOM_BS);
+    uint16_t* sdesc = reinterpret_cast<uint16_t*>(fdesc + P.nfcap);
+    MomTask* tk = reinterpret_cast<MomTask*>(sdesc + (size_t)P.nsubcap * MOM_WS);
+    uint64_t* tfull = reinterpret_cast<uint64_t*>(tk + MOM_TASKS);
+    uint64_t* vfull = tfull + MOM_NST;
+    uint64_t* vempty = vfull + 3;
+    int* sh = reinterpret_cast<int*>(vempty + 3);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp >= 8;
+    const uint32_t tbytes = (uint32_t)P.nt * MOM_BS * 8, vbytes = (uint32_t)P.nsubcap * MOM_BS * 8;
+    if (tid == 0) {
+        for (int k = 0; k < MOM_NST; ++k) mbar_init(tfull + k, 1);
+        for (int k = 0; k < 3; ++k) { mbar_init(vfull + k, 128); mbar_init(vempty + k, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int nitems = P.nunits * P.nsplit;
+    const uint32_t aT = smem_u32(T), aV = smem_u32(V), aSD = smem_u32(sdesc);
+    // ring positions, advanced identically by both roles: table stage / its use count, V buffer / its use count
+    uint32_t tst = 0, tu = 0, vb = 0, vu = 0;
+
+    // next work item and its descriptors; both roles run this at the same points (CTA barrier 0 counts arrivals, the
+    // two role loops below are separate code so that each gets the register budget of its setmaxnreg)
+    struct Item { int item, nsub; uint32_t wsub, nblk; int64_t b0; };
+    auto next_item = [&]() -> Item {
+        Item it;
+        asm volatile("bar.sync 0, 384;" ::: "memory");
+        if (tid == 0) sh[0] = (int)atomicAdd(P.counter, 1u);
+        asm volatile("bar.sync 0, 384;" ::: "memory");
+        it.item = sh[0];
+        it.nsub = 0; it.wsub = 0; it.nblk = 0; it.b0 = 0;
+        if (it.item >= nitems) return it;
+        const int u = it.item / P.nsplit, part = it.item - u * P.nsplit;
+        const MomUnit U = P.units[P.unit0 + u];
+        it.nsub = U.nsub;
+        it.wsub = (uint32_t)U.wsub;
+        const int nsp = (U.nsub + 127) & ~127;
+        for (int i = tid; i < U.nfunc; i += MOM_WS_THREADS) fdesc[i] = P.funcdesc[U.func_off + i];
+        for (int i = tid; i < nsp * MOM_WS; i += MOM_WS_THREADS) sdesc[i] = i < U.nsub * MOM_WS ? P.subdesc[(size_t)U.sub_off * MOM_WS + i] : (uint16_t)0;
+        if (tid < MOM_TASKS) tk[tid] = P.tasks[U.task_off + tid];
+        it.b0 = (int64_t)part * P.nblocks / P.nsplit;
+        it.nblk = (uint32_t)((int64_t)(part + 1) * P.nblocks / P.nsplit - it.b0);
+        asm volatile("bar.sync 0, 384;" ::: "memory");
+        return it;
+    };
+
+    if (producer) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MOM_WS_RP));
+        const int ptid = tid - 256, sp = ptid & 7, prow = ptid >> 3;      // sample pair, row of a 16-row pass
+        for (;;) {
+            const Item it = next_item();
+            if (it.item >= nitems) break;
+            const int nsub = it.nsub;
+            const uint32_t nblk = it.nblk;
+            const int64_t b0 = it.b0;
+            if (ptid == 0) {
+                for (uint32_t k = 0; k < MOM_NST && k < nblk; ++k) {
+                    const uint32_t st = (tst + k) % MOM_NST;
+                    mbar_expect_tx(tfull + st, tbytes);
+                    tma_bulk_g2s(reinterpret_cast<unsigned char*>(T) + (size_t)st * tbytes, P.tab + (size_t)(b0 + k) * P.nt * MOM_BS, tbytes, tfull + st);
+                }
+            }
+            long long pe = 0, pt = 0, p0 = P.dbg ? clock64() : 0;
+            for (uint32_t k = 0; k < nblk; ++k) {
+                if (P.dbg) {
+                    const long long a = clock64();
+                    if (vu > 0) mbar_wait(vempty + vb, (vu - 1) & 1u);
+                    const long long b = clock64();
+                    mbar_wait(tfull + tst, tu & 1u);
+                    pe += b - a; pt += clock64() - b;
+                } else {
+                if (vu > 0) mbar_wait(vempty + vb, (vu - 1) & 1u);        // the consumers are done with this buffer's last use
+                mbar_wait(tfull + tst, tu & 1u);
+                }
+                const uint32_t tb = aT + tst * tbytes + sp * 16;
+                uint32_t sd = aSD + prow * (MOM_WS * 2);
+                uint32_t vo = aV + vb * vbytes + prow * (MOM_BS * 8) + ((((sp >> 2) ^ prow) & 1) << 6) + (sp & 3) * 16;
+                // planner batches of 64 rows (one factor count each) = two passes of 16 rows x MOM_PVB
+                for (int i0 = 0; i0 < nsub; i0 += 16 * MOM_PVB, sd += 16 * MOM_PVB * MOM_WS * 2, vo += 16 * MOM_PVB * MOM_BS * 8) {
+                    const int wsub = (int)((it.wsub >> (4 * (i0 >> 6))) & 15u);
+                    uint4 dd[MOM_PVB];
+                    double2 v[MOM_PVB];
+#pragma unroll
+                    for (int q = 0; q < MOM_PVB; ++q) dd[q] = lds128u(sd + q * (16 * MOM_WS * 2));
+#pragma unroll
+                    for (int q = 0; q < MOM_PVB; ++q) v[q] = lds128(tb + off_of(dd[q], 0));
+#pragma unroll
+                    for (int f = 1; f < MOM_WS; f += 2) {
+                        if (f < wsub) {
+                            double2 t[MOM_PVB], w2[MOM_PVB];
+#pragma unroll
+                            for (int q = 0; q < MOM_PVB; ++q) t[q] = lds128(tb + off_of(dd[q], f));
+#pragma unroll
+                            for (int q = 0; q < MOM_PVB; ++q) w2[q] = lds128(tb + ((f + 1 < MOM_WS) ? off_of(dd[q], (f + 1 < MOM_WS) ? f + 1 : f) : 0u));
+#pragma unroll
+                            for (int q = 0; q < MOM_PVB; ++q) { t[q].x *= w2[q].x; t[q].y *= w2[q].y; }
+#pragma unroll
+                            for (int q = 0; q < MOM_PVB; ++q) { v[q].x *= t[q].x; v[q].y *= t[q].y; }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < MOM_PVB; ++q) sts128(vo + q * (16 * MOM_BS * 8), v[q].x, v[q].y);      // 16 rows on: same parity
+                }
+                mbar_arrive(vfull + vb);
+                // the table stage is free once all four producer warps have read it
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (ptid == 0 && k + MOM_NST < nblk) {
+                    mbar_expect_tx(tfull + tst, tbytes);
+                    tma_bulk_g2s(reinterpret_cast<unsigned char*>(T) + (size_t)tst * tbytes, P.tab + (size_t)(b0 + k + MOM_NST) * P.nt * MOM_BS, tbytes, tfull + tst);
+                }
+                if (++tst == MOM_NST) { tst = 0; ++tu; }
+                if (++vb == (uint32_t)P.nvb) { vb = 0; ++vu; }
+            }
+            if (P.dbg && ptid == 0) {
+                atomicAdd(P.dbg + 3, (unsigned long long)(clock64() - p0));
+                atomicAdd(P.dbg + 4, (unsigned long long)pe);
+                atomicAdd(P.dbg + 5, (unsigned long long)pt);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MOM_WS_RC));
+        const int g = lane >> 2, tig = lane & 3;
+        for (;;) {
+            const Item it = next_item();
+            if (it.item >= nitems) break;
+            const uint32_t nblk = it.nblk;
+            const MomTask mt = tk[warp];
+            const int fm = mt.fm, fn = mt.fn;
+            uint32_t a1[FM], a2[FM], c1[FN], c2[FN];
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const uint32_t d = i < fm ? fdesc[mt.moff + i * 8 + g] : 0u;
+                a1[i] = aV + vrow_half0(d & 0xffffu) + tig * 16;
+                a2[i] = aV + vrow_half0(d >> 16) + tig * 16;
+            }
+#pragma unroll
+            for (int j = 0; j < FN; ++j) {
+                const uint32_t d = j < fn ? fdesc[mt.noff + j * 8 + g] : 0u;
+                c1[j] = aV + vrow_half0(d & 0xffffu) + tig * 16;
+                c2[j] = aV + vrow_half0(d >> 16) + tig * 16;
+            }
+            double acc[FM][FN][2];
+#pragma unroll
+            for (int i = 0; i < FM; ++i)
+#pragma unroll
+                for (int j = 0; j < FN; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+            long long tw = 0, t0 = P.dbg ? clock64() : 0;
+            for (uint32_t k = 0; k < nblk; ++k) {
+                if (P.dbg) { const long long a = clock64(); mbar_wait(vfull + vb, vu & 1u); tw += clock64() - a; }
+                else mbar_wait(vfull + vb, vu & 1u);
+                const uint32_t bo = vb * vbytes;
+                constexpr int JB = FN < 4 ? FN : (FM <= 2 ? 8 : 4);      // column fragments per batch of loads: more where the accumulators leave room
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t hx = (uint32_t)h << 6;
+                    double2 af[FM];
+#pragma unroll
+                    for (int i = 0; i < FM; ++i) {
+                        const double2 p = lds128((a1[i] ^ hx) + bo), q = lds128((a2[i] ^ hx) + bo);
+                        af[i] = make_double2(p.x * q.x, p.y * q.y);
+                    }
+#pragma unroll
+                    for (int jb = 0; jb < FN; jb += JB) {
+                        double2 bf[JB];
+#pragma unroll
+                        for (int j = 0; j < JB; ++j) {
+                            const double2 p = lds128((c1[jb + j] ^ hx) + bo), q = lds128((c2[jb + j] ^ hx) + bo);
+                            bf[j] = make_double2(p.x * q.x, p.y * q.y);
+                        }
+#pragma unroll
+                        for (int i = 0; i < FM; ++i)
+#pragma unroll
+                            for (int j = 0; j < JB; ++j) dmma(acc[i][jb + j][0], acc[i][jb + j][1], af[i].x, bf[j].x);
+#pragma unroll
+                        for (int i = 0; i < FM; ++i)
+#pragma unroll
+                            for (int j = 0; j < JB; ++j) dmma(acc[i][jb + j][0], acc[i][jb + j][1], af[i].y, bf[j].y);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(vempty + vb);
+                if (++vb == (uint32_t)P.nvb) { vb = 0; ++vu; }
+            }
+            if (P.dbg && tid == 0) {
+                atomicAdd(P.dbg + 0, (unsigned long long)(clock64() - t0));
+                atomicAdd(P.dbg + 1, (unsigned long long)tw);
+                atomicAdd(P.dbg + 2, (unsigned long long)nblk);
+            }
+            double* w = P.ws + ((size_t)(P.item0 + it.item) * MOM_TASKS + warp) * 2048;
+#pragma unroll
+            for (int i = 0; i < FM; ++i)
+#pragma unroll
+                for (int j = 0; j < FN; ++j)
+                    if (i < fm && j < fn)
+                        *reinterpret_cast<double2*>(w + (i * 8 + g) * (FN * 8) + j * 8 + 2 * tig) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
     }
 }
 
@@ -1228,6 +1462,8 @@ extern "C" int pcq_moment_info(pcq_plan* p, int m, int64_t n, double* info) {
     return PCQ_OK;
 }
 
+static unsigned long long* dbg_buf = nullptr;      // PCQ_MOMENT_DBG: managed cycle counters, 8 per task shape
+
 // S (+)= statistics of n samples through the moment form; *handled = false when the route does not apply (the caller
 // falls back to the SYRK form).  PCQ_GRAM_MOMENT = 0 never, 1 whenever a plan exists, unset: when it is estimated faster.
 int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const double* y, int64_t ldy, int m,
@@ -1286,6 +1522,21 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
     if (rc != PCQ_OK) return rc;
     const int nfcap = (H.nf_max + 7) & ~7, nsubcap = (H.nsub_max + 127) & ~127;
     const size_t smem = mom_smem_bytes(H.nt, nsubcap, nfcap);
+    // warp-specialised kernels (default; PCQ_MOMENT_WS=0: the 8-warp kernels, 2: two V buffers): three V buffers where
+    // they fit, else two
+    bool use_ws = false;
+    int nvb = 3;
+    size_t smem_ws = 0;
+    {
+        const char* we = getenv("PCQ_MOMENT_WS");
+        const int wmode = we ? atoi(we) : 1;
+        if (wmode != 0) {
+            if (wmode == 2) nvb = 2;
+            if (mom_ws_smem_bytes(H.nt, nsubcap, nfcap, nvb) > p->smem_optin) nvb = 2;
+            smem_ws = mom_ws_smem_bytes(H.nt, nsubcap, nfcap, nvb);
+            use_ws = smem_ws <= p->smem_optin;
+        }
+    }
 
     for (int64_t r0 = 0; r0 < n; r0 += rows) {
         const int64_t nr = std::min(rows, n - r0);
@@ -1304,25 +1555,33 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
         P.tab = *zbuf; P.nblocks = nblocks; P.nt = H.nt;
         P.units = D->units; P.tasks = D->tasks; P.funcdesc = D->funcdesc; P.subdesc = D->subdesc;
         P.nfcap = nfcap; P.nsubcap = nsubcap; P.ws = *ws;
+        P.nvb = nvb;
+        if (getenv("PCQ_MOMENT_DBG") && !dbg_buf) { cudaMallocManaged(&dbg_buf, 8 * MOM_NCLS * sizeof(unsigned long long)); memset(dbg_buf, 0, 8 * MOM_NCLS * sizeof(unsigned long long)); }
         PCQ_CUDA(cudaEventRecord(D->fork, st));
         for (int c = 0; c < MOM_NCLS; ++c) {
             const int nu = cls_unit0[c + 1] - cls_unit0[c];
             if (nu == 0) continue;
             cudaStream_t sc = D->cs[c];
             PCQ_CUDA(cudaStreamWaitEvent(sc, D->fork, 0));
+            P.dbg = getenv("PCQ_MOMENT_DBG") ? dbg_buf + 8 * c : nullptr;
             P.unit0 = cls_unit0[c]; P.nunits = nu; P.nsplit = cls_split[c]; P.item0 = cls_item0[c]; P.counter = D->counter + c;
             const int grid = std::min(p->num_sms, nu * P.nsplit);
-            auto launch = [&](auto kern) -> int {
+            auto launch = [&](auto kern, auto kern_ws) -> int {
+                if (use_ws) {
+                    PCQ_CUDA(cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+                    kern_ws<<<grid, MOM_WS_THREADS, smem_ws, sc>>>(P);
+                    return PCQ_OK;
+                }
                 PCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<grid, 256, smem, sc>>>(P);
                 return PCQ_OK;
             };
             switch (c) {
-                case 0: rc = launch(pcq_mom_kernel<4, 8>); break;
-                case 1: rc = launch(pcq_mom_kernel<3, 8>); break;
-                case 2: rc = launch(pcq_mom_kernel<2, 16>); break;
-                case 3: rc = launch(pcq_mom_kernel<1, 16>); break;
-                default: rc = launch(pcq_mom_kernel<1, 2>); break;
+                case 0: rc = launch(pcq_mom_kernel<4, 8>, pcq_mom_ws_kernel<4, 8>); break;
+                case 1: rc = launch(pcq_mom_kernel<3, 8>, pcq_mom_ws_kernel<3, 8>); break;
+                case 2: rc = launch(pcq_mom_kernel<2, 16>, pcq_mom_ws_kernel<2, 16>); break;
+                case 3: rc = launch(pcq_mom_kernel<1, 16>, pcq_mom_ws_kernel<1, 16>); break;
+                default: rc = launch(pcq_mom_kernel<1, 2>, pcq_mom_ws_kernel<1, 2>); break;
             }
             if (rc != PCQ_OK) return rc;
             PCQ_LAUNCH_CHECK("pcq_mom_kernel");
@@ -1331,6 +1590,17 @@ int pcq_launch_moments(pcq_plan* p, const double* x, int64_t n, int64_t ldx, con
             PCQ_LAUNCH_CHECK("pcq_mom_fixup_kernel");
             PCQ_CUDA(cudaEventRecord(D->join[c], sc));
             PCQ_CUDA(cudaStreamWaitEvent(st, D->join[c], 0));
+        }
+    }
+    if (getenv("PCQ_MOMENT_DBG")) {
+        cudaStreamSynchronize(st);
+        for (int c = 0; c < MOM_NCLS && dbg_buf; ++c) {
+            unsigned long long* d = dbg_buf + 8 * c;
+            if (d[2] == 0) continue;
+            fprintf(stderr, "moment dbg class (%d,%2d): blocks %llu  consumer cycles/block %.0f (waiting for V %.0f)  producer cycles/block %.0f "
+                            "(waiting for a free V buffer %.0f, for the table %.0f)\n", MOM_CLS[c][0], MOM_CLS[c][1], d[2],
+                    (double)d[0] / d[2], (double)d[1] / d[2], (double)d[3] / d[2], (double)d[4] / d[2], (double)d[5] / d[2]);
+            for (int q = 0; q < 8; ++q) d[q] = 0;
         }
     }
     if (m > 0) {
