@@ -550,14 +550,14 @@ def main():
     # DRAM bytes per step of the dominant kernel: NOT a live counter -- the committed ncu capture of this very
     # command (bytes per sample x this rank's samples; the SYRK works chunk by chunk, so its traffic is linear in N)
     traffic, traffic_source = None, None
-    for fn in (("r02_n_moment_traffic.json", "r02_moment_traffic.json") if moment_form else ()) + ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
+    for fn in (("r02_p_moment_traffic.json", "r02_n_moment_traffic.json", "r02_moment_traffic.json") if moment_form else ()) + ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
             per_sample = tj.get("dram_bytes_per_sample_main_kernel",
                                 tj["dram_bytes_per_step_main_kernel"] / tj.get("samples_per_step", 1_250_000))
             traffic = per_sample * n
             traffic_source = (f"committed ncu capture profiles/{fn} (dram__bytes_read.sum + dram__bytes_write.sum of the "
-                              f"{'pcq_mom_kernel' if 'moment' in fn else 'pcq_syrk_kernel'} launches of one step: {per_sample:.0f} B per sample) x {n} samples; "
+                              f"{'pcq_mom_ws_kernel' if 'moment' in fn else 'pcq_syrk_kernel'} launches of one step: {per_sample:.0f} B per sample) x {n} samples; "
                               "not measured in this run")
             break
         except Exception:
@@ -608,11 +608,11 @@ def main():
                    "36.85 sustained, DFMA 36.49 / 36.42 TFLOP/s at 1965 MHz, no throttle reason)")
     if moment_form:
         roofline = {"bound": "tensor",
-                    "kernel": "pcq_mom_kernel<FM,FN> (K3 in moment form, csrc/pcq_moment.cu: the %d moments the Gram entries are linear "
+                    "kernel": "pcq_mom_ws_kernel<FM,FN> (K3 in moment form, csrc/pcq_moment.cu, warp-specialised: 4 producer warps generate the operands in shared memory, 8 consumer warps issue the DMMAs; the %d moments the Gram entries are linear "
                               "combinations of, as staircase GEMMs on DMMA -- %.0f executed multiply-adds per sample instead of "
                               "K(K+1)/2 + ... = %.0f; %d units of eight warp tasks; per 6 GB table chunk one launch per task "
                               "shape on forked streams, fed by pcq_mom_table_kernel; then fix-up and the K x K reconstruction; "
-                              "launch list profiles/r02_n_moment_launches.csv)"
+                              "launch list profiles/r02_p_moment_launches.csv)"
                               % (int(minfo[0]), minfo[2], flops / (2.0 * n), int(minfo[1])),
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
                     "achieved_note": "multiply-adds EXECUTED on the DMMA pipe (planner count, fragment padding included) x 2 / "

@@ -468,56 +468,83 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
     }
     if (P.fail) { H.why = "a sub-function has more than 8 factors"; return; }
 
-    // bundles -> units: full bundles alone, partial ones first-fit (largest first) into the few units still open
+    // bundles -> units: full bundles alone; partial ones first-fit (largest first) into the few units still open, whole
+    // if they fit (their tasks share row / column functions), else task by task, so that only the last unit of a
+    // shape is left with idle warps
     std::vector<int> order(bundles.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bundles[a].tasks.size() > bundles[b].tasks.size(); });
     std::vector<UnitBuild> ub;
     std::vector<int> open;
-    for (int bi : order) {
-        const Bundle& B = bundles[bi];
-        bool placed = false;
-        if (B.tasks.size() < (size_t)MOM_TASKS) {
-            for (size_t q = open.size() > 6 ? open.size() - 6 : 0; q < open.size() && !placed; ++q)
-                placed = try_add(ub[open[q]], B, H.zero_slot);
+    auto sub_bundle = [](const Bundle& cur, size_t lo, size_t hi) {
+        Bundle part;
+        part.cls = cur.cls;
+        std::vector<int> map(cur.segs.size(), -1);
+        for (size_t t = lo; t < hi; ++t) {
+            BTask q = cur.tasks[t];
+            for (int* sg : {&q.segM, &q.segN}) {
+                if (map[*sg] < 0) { map[*sg] = (int)part.segs.size(); part.segs.push_back(cur.segs[*sg]); }
+                *sg = map[*sg];
+            }
+            part.tasks.push_back(q);
         }
-        if (!placed) {
+        return part;
+    };
+    auto close_full = [&]() {
+        open.erase(std::remove_if(open.begin(), open.end(), [&](int u) { return ub[u].tasks.size() >= (size_t)MOM_TASKS; }), open.end());
+    };
+    // a new unit for the bundle; halves of it, recursively, where its sub-functions do not fit one unit
+    auto place_new = [&](const Bundle& B) -> bool {
+        std::vector<Bundle> stack{B};
+        while (!stack.empty()) {
+            Bundle cur = std::move(stack.back());
+            stack.pop_back();
             ub.emplace_back();
-            if (!try_add(ub.back(), B, H.zero_slot)) {
-                // a block of tasks whose sub-functions do not fit one unit: halves of it, recursively
-                ub.pop_back();
-                std::vector<Bundle> stack{B};
-                while (!stack.empty()) {
-                    Bundle cur = std::move(stack.back());
-                    stack.pop_back();
-                    ub.emplace_back();
-                    if (try_add(ub.back(), cur, H.zero_slot)) {
-                        if (ub.back().tasks.size() < (size_t)MOM_TASKS) open.push_back((int)ub.size() - 1);
-                        continue;
-                    }
-                    ub.pop_back();
-                    if (cur.tasks.size() < 2) { H.why = "a task does not fit a unit"; return; }
-                    for (int half = 0; half < 2; ++half) {
-                        Bundle part;
-                        part.cls = cur.cls;
-                        std::vector<int> map(cur.segs.size(), -1);
-                        const size_t lo = half ? cur.tasks.size() / 2 : 0, hi = half ? cur.tasks.size() : cur.tasks.size() / 2;
-                        for (size_t t = lo; t < hi; ++t) {
-                            BTask q = cur.tasks[t];
-                            for (int* sg : {&q.segM, &q.segN}) {
-                                if (map[*sg] < 0) { map[*sg] = (int)part.segs.size(); part.segs.push_back(cur.segs[*sg]); }
-                                *sg = map[*sg];
-                            }
-                            part.tasks.push_back(q);
-                        }
-                        stack.push_back(std::move(part));
-                    }
-                }
+            if (try_add(ub.back(), cur, H.zero_slot)) {
+                if (ub.back().tasks.size() < (size_t)MOM_TASKS) open.push_back((int)ub.size() - 1);
                 continue;
             }
-            if (ub.back().tasks.size() < (size_t)MOM_TASKS) open.push_back((int)ub.size() - 1);
+            ub.pop_back();
+            if (cur.tasks.size() < 2) return false;
+            stack.push_back(sub_bundle(cur, cur.tasks.size() / 2, cur.tasks.size()));
+            stack.push_back(sub_bundle(cur, 0, cur.tasks.size() / 2));
         }
-        open.erase(std::remove_if(open.begin(), open.end(), [&](int u) { return ub[u].tasks.size() >= (size_t)MOM_TASKS; }), open.end());
+        return true;
+    };
+    auto first_fit = [&](const Bundle& B) -> bool {
+        for (size_t q = open.size() > 6 ? open.size() - 6 : 0; q < open.size(); ++q)
+            if (try_add(ub[open[q]], B, H.zero_slot)) return true;
+        return false;
+    };
+    for (int bi : order) {
+        const Bundle& B = bundles[bi];
+        if (B.tasks.size() >= (size_t)MOM_TASKS || !first_fit(B)) {
+            bool any_open_same_class = false;
+            for (size_t q = open.size() > 6 ? open.size() - 6 : 0; q < open.size(); ++q) any_open_same_class |= ub[open[q]].cls == B.cls;
+            if (B.tasks.size() < (size_t)MOM_TASKS && B.tasks.size() > 1 && any_open_same_class) {
+                // task by task into the open units; what is left starts a new unit together
+                std::vector<size_t> left;
+                for (size_t t = 0; t < B.tasks.size(); ++t) {
+                    if (!first_fit(sub_bundle(B, t, t + 1))) left.push_back(t);
+                    close_full();
+                }
+                if (!left.empty()) {
+                    Bundle rest;
+                    rest.cls = B.cls;
+                    std::vector<int> map(B.segs.size(), -1);
+                    for (size_t t : left) {
+                        BTask q = B.tasks[t];
+                        for (int* sg : {&q.segM, &q.segN}) {
+                            if (map[*sg] < 0) { map[*sg] = (int)rest.segs.size(); rest.segs.push_back(B.segs[*sg]); }
+                            *sg = map[*sg];
+                        }
+                        rest.tasks.push_back(q);
+                    }
+                    if (!place_new(rest)) { H.why = "a task does not fit a unit"; return; }
+                }
+            } else if (!place_new(B)) { H.why = "a task does not fit a unit"; return; }
+        }
+        close_full();
     }
 
     // finalise: warp slots (four costliest tasks on warps 0-3, the rest on 4-7: the two warp groups issue their
@@ -528,11 +555,13 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
     for (size_t u = 0; u < ub.size(); ++u) {
         UnitBuild& U = ub[u];
         const double half = 64.0 * MOM_CLS[U.cls][0] * MOM_CLS[U.cls][1];      // DMMA cycles of one warp per block
-        macs[u] = MOM_TASKS * half;
+        macs[u] = (double)U.tasks.size() * half;          // warps without a task issue no DMMA
         // cycles of one 16-sample block: both warps of a scheduler at the measured DMMA-pipe share of the class
         // (warp-specialised kernels, cycle counters of PCQ_MOMENT_DBG at C2: profiles/r02_moment_notes.md)
         static const double eff[MOM_NCLS] = {0.847, 0.78, 0.77, 0.54, 0.30};
-        fin[u] = {2.0 * half / eff[U.cls], (int)u, U.cls};
+        // a unit with at most four tasks has one warp per scheduler (slots 0-3): half the DMMAs per scheduler
+        fin[u] = {(U.tasks.size() <= 4 ? 1.1 : 2.0) * half / eff[U.cls], (int)u, U.cls};
+
     }
     std::stable_sort(fin.begin(), fin.end(), [](const Fin& a, const Fin& b) { return a.cls != b.cls ? a.cls < b.cls : a.cost > b.cost; });
     for (const Fin& f : fin) {
@@ -1161,8 +1190,9 @@ __global__ void __launch_bounds__(MOM_WS_THREADS, 1) pcq_mom_ws_kernel(MomParams
                 else mbar_wait(vfull + vb, vu & 1u);
                 const uint32_t bo = vb * vbytes;
                 constexpr int JB = FN < 4 ? FN : (FM <= 2 ? 8 : 4);      // column fragments per batch of loads: more where the accumulators leave room
+                // a warp without a task (the last unit of a shape) leaves the pipe to the other warp of its scheduler
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < (fm ? 2 : 0); ++h) {
                     const uint32_t hx = (uint32_t)h << 6;
                     double2 af[FM];
 #pragma unroll

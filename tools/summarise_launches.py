@@ -36,7 +36,7 @@ def main():
         a["n"] += 1
         for f in ("ms", "rd", "wr"):
             a[f] += k.get(f, 0.0)
-    main_k = {n: a for n, a in agg.items() if n.startswith("pcq_mom_kernel") or n.startswith("pcq_syrk_kernel")}
+    main_k = {n: a for n, a in agg.items() if n.startswith("pcq_mom_kernel") or n.startswith("pcq_mom_ws_kernel") or n.startswith("pcq_syrk_kernel")}
     main_bytes = sum(a["rd"] + a["wr"] for a in main_k.values())
     all_bytes = sum(a["rd"] + a["wr"] for a in agg.values())
     total_ms = sum(a["ms"] for a in agg.values())
