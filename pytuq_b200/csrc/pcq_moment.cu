@@ -359,7 +359,7 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
     H.zero_slot = H.nslots + m;
     H.nt = H.zero_slot + 1;
     if (pt < 1) { H.why = "constant basis"; return; }
-    if (s < 2 || s > MOM_MAXDIM) { H.why = "germ dimension outside [2, 32]"; return; }
+    if (s < 2 || s > MOM_MAXDIM) { H.why = "germ dimension outside [2, 64]"; return; }
     if (H.B0 > MOM_MAXORD || nord < H.B0) { H.why = "order too high for the tabulated recurrence"; return; }
     if (H.nt > MOM_NT) { H.why = "1-D table too large for shared memory"; return; }
     if (m > MOM_MAXOUT) { H.why = "too many outputs"; return; }

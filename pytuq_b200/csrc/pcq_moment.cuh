@@ -16,7 +16,7 @@
 #include <stdint.h>
 
 constexpr int MOM_MAXORD = 32;     // 2 pt <= MOM_MAXORD
-constexpr int MOM_MAXDIM = 32;     // germ dimension (a thread tabulates two (dimension, sample) items of a 16-sample block)
+constexpr int MOM_MAXDIM = 64;     // germ dimension (the table of 1-D values must also fit MOM_NT slots: 1 + 2 pt s + m + 1)
 constexpr int MOM_WS = 8;          // table slots per sub-function descriptor
 constexpr int MOM_NF = 1280;       // functions (rows + columns) of one unit
 constexpr int MOM_NSUB = 384;      // distinct sub-functions of one unit

@@ -67,7 +67,7 @@ def _rel(S, Sref):
 
 
 CASES = [("LU", 2, 2, 1), ("HG", 3, 2, 2), ("LU", 4, 3, 1), (["LU", "HG", "nLU", "nHG", "LU"], 5, 3, 2), ("HG", 7, 2, 0),
-         ("nLU", 6, 3, 1), ("nHG", 3, 4, 3), ("HG", 8, 3, 1), ("LU", 2, 7, 1)]
+         ("nLU", 6, 3, 1), ("nHG", 3, 4, 3), ("HG", 8, 3, 1), ("LU", 2, 7, 1), ("LU", 40, 2, 1), ("HG", 33, 1, 2)]
 
 
 @pytest.mark.parametrize("fam,d,p,m", CASES)
@@ -128,8 +128,8 @@ def _host_stats_plan_only(mi, fams, m):
 
 def test_refusals():
     """Shapes the form does not serve are refused (the caller keeps the pack + SYRK form): one dimension, more than
-    32 dimensions, a constant basis."""
-    for mi, fams in [(np.arange(4).reshape(-1, 1), ["LU"]), (orc.get_mi(1, 40), ["LU"] * 40), (np.zeros((1, 3), dtype=int), ["HG"] * 3)]:
+    64 dimensions, a constant basis."""
+    for mi, fams in [(np.arange(4).reshape(-1, 1), ["LU"]), (orc.get_mi(1, 70), ["LU"] * 70), (np.zeros((1, 3), dtype=int), ["HG"] * 3)]:
         rc, _, info = _host_stats_plan_only(mi, fams, 1)
         assert rc == -5 and info[6] == 0.0
 
@@ -170,7 +170,7 @@ def _dev_stats(pc, mi, x, y, m, mode, accumulate_in_two=False, ldx=None):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fam,d,p,m,n", [("LU", 2, 2, 1, 1), ("LU", 2, 2, 1, 1000), ("HG", 3, 2, 2, 5003), ("LU", 4, 3, 1, 20000),
-                                         ("nLU", 6, 3, 0, 7777), ("nHG", 3, 4, 3, 15), ("HG", 8, 3, 1, 30001),
+                                         ("nLU", 6, 3, 0, 7777), ("nHG", 3, 4, 3, 15), ("HG", 8, 3, 1, 30001), ("LU", 50, 2, 1, 9001),
                                          (["LU", "HG", "nLU", "nHG", "LU"], 5, 3, 2, 4097)])
 def test_kernels_vs_oracle(fam, d, p, m, n):
     from pytuq_b200.rv.pcrv import PCRV
