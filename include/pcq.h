@@ -161,7 +161,13 @@ int pcq_plan_enable_moments(pcq_plan* plan, int nord, const double* rec_a_ext, c
 /* Query: info[0..6] = moments, units, DMMA multiply-adds executed per sample, estimated cycles per sample and SM, usable
  * flag, 1 if pcq_suffstats(_dev) would take the moment form for n samples and m outputs right now, bytes per sample of
  * the 1-D value table the form keeps in scratch.  All zero when the plan has no moment tables. */
-int pcq_moment_info(pcq_plan* plan, int m, int64_t n, double* info);
+int pcq_moment_info(pcq_plan* plan, int m, int64_t n, double* info);   /* info[7] = 1: more than 8 outputs, hybrid route */
+
+/* Host helper of the staging pipelines (the callers of lreg.fit hand over pageable numpy arrays, lreg/lreg.py:62-71):
+ * rows x width doubles from src (row stride ld_src) to dst (row stride ld_dst), both HOST memory, split over
+ * PCQ_HOST_THREADS threads (default 16) when the block is at least 8 MB.  Pageable -> pinned at ~24 GB/s on the 16-core
+ * GPU box where one thread reaches ~10. */
+int pcq_host_copy_rows(double* dst, int64_t ld_dst, const double* src, int64_t ld_src, int64_t width, int64_t rows);
 /* Debugging aid, host only (no device needed): plans the moment form for this multi-index and m outputs, executes the
  * planned units on the CPU exactly as the kernel does and reconstructs S (L x L, L = nterms + m + 1) into s_out (may be
  * NULL: plan only).  info[0..7] = moments, units, estimated cycles per 16-sample block, multiply-adds per sample,

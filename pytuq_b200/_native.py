@@ -33,6 +33,7 @@ SIGNATURES = {
                                             C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64]),
     "pcq_plan_enable_moments": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pcq_moment_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "pcq_host_copy_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "pcq_group_enable_moments": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pcq_debug_moments_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,

@@ -798,6 +798,29 @@ int pcq_suffstats(pcq_plan* p, const double* x, int64_t n, int64_t ldx, const do
     return PCQ_OK;
 }
 
+int pcq_host_copy_rows(double* dst, int64_t ld_dst, const double* src, int64_t ld_src, int64_t width, int64_t rows) {
+    if (rows < 0 || width < 0 || (rows > 0 && width > 0 && (!dst || !src)) || ld_dst < width || ld_src < width) {
+        pcq_set_error("host_copy_rows: bad argument");
+        return PCQ_ERR_ARG;
+    }
+    if (rows == 0 || width == 0) return PCQ_OK;
+    const int nthreads = (int64_t)rows * width * 8 >= (8 << 20) ? (int)std::min<int64_t>(pcq_host_threads(), rows) : 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t lo = rows * t / nthreads, hi = rows * (t + 1) / nthreads;
+        auto work = [=]() {
+            if (ld_dst == width && ld_src == width) {
+                memcpy(dst + lo * width, src + lo * width, (size_t)(hi - lo) * width * 8);
+            } else {
+                for (int64_t r = lo; r < hi; ++r) memcpy(dst + r * ld_dst, src + r * ld_src, (size_t)width * 8);
+            }
+        };
+        if (nthreads == 1) work(); else pool.emplace_back(work);
+    }
+    for (auto& th : pool) th.join();
+    return PCQ_OK;
+}
+
 int pcq_gram(int device, const double* a, int64_t n, int64_t lda, int kcols, const double* y,
              int64_t ldy, int m, double* s_host) {
     if (device < 0 || device >= 64 || n < 0 || kcols <= 0 || m < 0 || !s_host || (n > 0 && !a) ||

@@ -8,6 +8,8 @@ torch is used here only as plumbing (process group, device buffers); all arithme
 libpcq.
 """
 import contextlib
+import os
+import time
 
 import numpy as np
 
@@ -71,7 +73,8 @@ def allreduce_stats(S):
     return t.numpy()
 
 
-_STAGE_BYTES = 128 << 20       # host chunk: large enough that the per-call cost of the statistics kernels (launch tail,
+_GROUP_STAGES = 8              # stages per call of the statistics kernels once the pipeline has ramped up (1, 2, 4, 8, 8, ..)
+_STAGE_BYTES = 64 << 20       # host chunk: large enough that the per-call cost of the statistics kernels (launch tail,
                                # moment reconstruction ~1 ms at K = 1771) stays below a few per cent
 _pinned = {}
 
@@ -188,58 +191,95 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=None):
     ncol = s + M
     rows = max(_STAGE_BYTES // (ncol * 8), 4096)
     pin = _pinned_pair(rows * ncol * 8, dev)
+    # Host rows travel stage by stage (two pinned buffers) into one of two device GROUP buffers; the statistics kernels
+    # run once per group, not per stage: their per-call cost (launch tails of the task-shape kernels, the K x K
+    # reconstruction of the moment form) is paid a handful of times per fit.  Groups ramp up (1, 2, 4, .. _GROUP_STAGES
+    # stages) so that the first kernels start after one stage while the copies stay ahead of the kernels.
+    stages, r0 = [], 0
+    while r0 < N:
+        stages.append((r0, min(rows, N - r0)))
+        r0 += stages[-1][1]
+    groups, i, size = [], 0, 1
+    while i < len(stages):
+        groups.append(stages[i:i + size])
+        i += size
+        size = min(2 * size, _GROUP_STAGES)
+    grows = max([sum(nr for _, nr in g) for g in groups], default=0)
+    threaded_copy = os.environ.get("PCQ_PY_HOST_COPY", "threads") != "numpy"
+    trace = {"wait_pinned": 0.0, "host_copy": 0.0, "enqueue_h2d": 0.0, "launch_call": 0.0} if os.environ.get("PCQ_PY_TRACE") else None
     with torch.cuda.device(tdev):
         main = torch.cuda.current_stream()
         copy_stream = _copy_stream(dev, tdev)
-        dbuf = [torch.empty(rows * ncol, dtype=torch.float64, device=tdev) for _ in range(2)]
-        # the staging tensors come from the caching allocator on the main stream: work still queued there on a recycled
+        gbuf = [torch.empty(max(grows, 1) * ncol, dtype=torch.float64, device=tdev) for _ in range(min(2, max(len(groups), 1)))]
+        # the group buffers come from the caching allocator on the main stream: work still queued there on a recycled
         # block must finish before the copy stream overwrites it
         copy_stream.wait_stream(main)
-        for t in dbuf:
+        for t in gbuf:
             t.record_stream(copy_stream)
-        copied = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]        # H2D out of pinned buffer b finished
+        filled = [torch.cuda.Event() for _ in range(2)]        # every stage of the group in buffer gb has arrived
+        consumed = [torch.cuda.Event() for _ in range(2)]      # the kernels of the group in buffer gb are done
         if N == 0:
             _native.check(lib.pcq_suffstats_dev(plan.handle, None, 0, s, None, max(M, 1), M, S_t.data_ptr(), 0,
                                                 main.cuda_stream), "pcq_suffstats_dev")
-        # chunk schedule: the first host memcpy + H2D cannot overlap anything, so the pipeline ramps up
-        # (1/8, 1/4, 1/2 of a stage) before it settles on full stages
-        bounds, r0 = [], 0
-        for frac in (8, 4, 2):
-            if N - r0 > rows:
-                bounds.append((r0, max(rows // frac, 4096)))
-                r0 += bounds[-1][1]
-        while r0 < N:
-            bounds.append((r0, min(rows, N - r0)))
-            r0 += bounds[-1][1]
         c = 0
-        for r0, nr in bounds:
-            b = c & 1
-            if c >= 2:
-                consumed[b].synchronize()          # staging buffer b free again (host and device side)
-            hx = pin[b][:nr * s].view(nr, s)
-            np.copyto(hx.numpy(), xin[r0:r0 + nr])
-            if M:
-                hy = pin[b][nr * s:nr * ncol].view(nr, M)
-                np.copyto(hy.numpy(), Y[r0:r0 + nr])
-            with torch.cuda.stream(copy_stream):
-                dbuf[b][:nr * ncol].copy_(pin[b][:nr * ncol], non_blocking=True)
-                copied[b].record(copy_stream)
-            main.wait_event(copied[b])
-            xd = dbuf[b].data_ptr()
-            yd = xd + nr * s * 8 if M else None
-            _native.check(lib.pcq_suffstats_dev(plan.handle, xd, nr, s, yd, max(M, 1), M, S_t.data_ptr(),
-                                                1 if c > 0 else 0, main.cuda_stream), "pcq_suffstats_dev")
-            consumed[b].record(main)
-            copy_stream.wait_event(consumed[b])    # next H2D into buffer b waits for the kernel
-            c += 1
+        for gi, grp_stages in enumerate(groups):
+            gb = gi & 1
+            gn = sum(nr for _, nr in grp_stages)
+            gx = gbuf[gb][:gn * s].view(gn, s)
+            gy = gbuf[gb][gn * s:gn * ncol].view(gn, M) if M else None
+            if gi >= 2:
+                copy_stream.wait_event(consumed[gb])       # the kernels of group gi - 2 have read this buffer
+            off = 0
+            for r0, nr in grp_stages:
+                b = c & 1
+                _t0 = time.perf_counter() if trace is not None else 0.0
+                if c >= 2:
+                    copied[b].synchronize()                # pinned buffer b free again
+                _t1 = time.perf_counter() if trace is not None else 0.0
+                hx = pin[b][:nr * s].view(nr, s)
+                hy = pin[b][nr * s:nr * ncol].view(nr, M) if M else None
+                if threaded_copy:
+                    _native.check(lib.pcq_host_copy_rows(hx.data_ptr(), s, xin[r0:r0 + nr].ctypes.data, s, s, nr), "pcq_host_copy_rows")
+                    if M:
+                        _native.check(lib.pcq_host_copy_rows(hy.data_ptr(), M, Y[r0:r0 + nr].ctypes.data, M, M, nr), "pcq_host_copy_rows")
+                else:
+                    np.copyto(hx.numpy(), xin[r0:r0 + nr])
+                    if M:
+                        np.copyto(hy.numpy(), Y[r0:r0 + nr])
+                _t2 = time.perf_counter() if trace is not None else 0.0
+                with torch.cuda.stream(copy_stream):
+                    gx[off:off + nr].copy_(hx, non_blocking=True)
+                    if M:
+                        gy[off:off + nr].copy_(hy, non_blocking=True)
+                    copied[b].record(copy_stream)
+                if trace is not None:
+                    _t3 = time.perf_counter()
+                    trace["wait_pinned"] += _t1 - _t0
+                    trace["host_copy"] += _t2 - _t1
+                    trace["enqueue_h2d"] += _t3 - _t2
+                off += nr
+                c += 1
+            filled[gb].record(copy_stream)
+            main.wait_event(filled[gb])
+            _t4 = time.perf_counter() if trace is not None else 0.0
+            _native.check(lib.pcq_suffstats_dev(plan.handle, gx.data_ptr(), gn, s, gy.data_ptr() if M else None, max(M, 1), M,
+                                                S_t.data_ptr(), 1 if gi > 0 else 0, main.cuda_stream), "pcq_suffstats_dev")
+            consumed[gb].record(main)
+            if trace is not None:
+                trace["launch_call"] += time.perf_counter() - _t4
         if distributed and dist_info()[1] > 1:
             import torch.distributed as dist
             if dist.get_backend() == "nccl":
                 dist.all_reduce(S_t, op=dist.ReduceOp.SUM)
             else:
                 S_t = torch.from_numpy(allreduce_stats(S_t.cpu().numpy())).to(tdev)
+        _t5 = time.perf_counter()
         main.synchronize()
+        if trace is not None:
+            trace["final_sync"] = time.perf_counter() - _t5
+            trace["groups"] = [sum(nr for _, nr in g) for g in groups]
+            print("suffstats_pc host path (seconds):", trace, flush=True)
     pcrv._distributed_stats = bool(distributed)
     return SuffStats(None, K, M, S_dev=S_t)
 
