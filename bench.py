@@ -550,7 +550,7 @@ def main():
     # DRAM bytes per step of the dominant kernel: NOT a live counter -- the committed ncu capture of this very
     # command (bytes per sample x this rank's samples; the SYRK works chunk by chunk, so its traffic is linear in N)
     traffic, traffic_source = None, None
-    for fn in (("r02_p_moment_traffic.json", "r02_n_moment_traffic.json", "r02_moment_traffic.json") if moment_form else ()) + ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
+    for fn in (("r02_q_moment_traffic.json", "r02_p_moment_traffic.json", "r02_n_moment_traffic.json", "r02_moment_traffic.json") if moment_form else ()) + ("r02_k3_traffic.json", "r01_j_k3_traffic.json"):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
             per_sample = tj.get("dram_bytes_per_sample_main_kernel",
@@ -612,7 +612,7 @@ def main():
                               "combinations of, as staircase GEMMs on DMMA -- %.0f executed multiply-adds per sample instead of "
                               "K(K+1)/2 + ... = %.0f; %d units of eight warp tasks; per 6 GB table chunk one launch per task "
                               "shape on forked streams, fed by pcq_mom_table_kernel; then fix-up and the K x K reconstruction; "
-                              "launch list profiles/r02_p_moment_launches.csv)"
+                              "launch list profiles/r02_q_moment_launches.csv)"
                               % (int(minfo[0]), minfo[2], flops / (2.0 * n), int(minfo[1])),
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
                     "achieved_note": "multiply-adds EXECUTED on the DMMA pipe (planner count, fragment padding included) x 2 / "
