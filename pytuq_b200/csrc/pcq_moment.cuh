@@ -111,19 +111,33 @@ MOM_HD double mom_pair(const MomGeom& g, const double* lin, const double* mom, d
         ++ne;
     }
     const int P1 = g.pt + 1, KS = g.B0 + 1;
+    // odometer over the k_e with a non-zero linearisation coefficient only (Hermite / Legendre products have every other
+    // coefficient zero by parity: 2^ne times fewer combinations than the full box)
+    const double* le[ME];
+    for (int e = 0; e < ne; ++e) {
+        le[e] = lin + (((size_t)dims[e] * P1 + av[e]) * P1 + bv[e]) * KS;
+        int k = 0;
+        while (k <= av[e] + bv[e] && le[e][k] == 0.0) ++k;
+        if (k > av[e] + bv[e]) return 0.0;              // cannot happen for a proper family: the top coefficient is not zero
+        kk[e] = k;
+    }
     double total = 0.0;
     for (;;) {
         double c = 1.0;
         int gd[ME], gk[ME], gn = 0;
         for (int e = 0; e < ne; ++e) {
-            c *= lin[(((size_t)dims[e] * P1 + av[e]) * P1 + bv[e]) * KS + kk[e]];
+            c *= le[e][kk[e]];
             if (kk[e] > 0) { gd[gn] = dims[e]; gk[gn] = kk[e]; ++gn; }
         }
-        if (c != 0.0) total += c * (gn == 0 ? nsamples : mom[mom_loc(g, gd, gk, gn, 0, 0)]);
+        total += c * (gn == 0 ? nsamples : mom[mom_loc(g, gd, gk, gn, 0, 0)]);
         int e = 0;
         while (e < ne) {
-            if (++kk[e] <= av[e] + bv[e]) break;
-            kk[e] = 0;
+            int k = kk[e] + 1;
+            while (k <= av[e] + bv[e] && le[e][k] == 0.0) ++k;
+            if (k <= av[e] + bv[e]) { kk[e] = k; break; }
+            k = 0;
+            while (le[e][k] == 0.0) ++k;
+            kk[e] = k;
             ++e;
         }
         if (e == ne) break;

@@ -54,6 +54,8 @@ def main():
     cases = small if args.cases == "small" else bench if args.cases == "bench" else small + bench
     if args.cases == "high":      # higher orders: the ratio of moments to Gram entries falls with p
         cases = [("HG", 20, 4, 200000, 1), ("HG", 10, 5, 1000000, 1), ("LU", 6, 8, 1000000, 1), ("nLU", 12, 4, 1000000, 2)]
+    if args.cases == "p4":
+        cases = [("HG", 20, 4, 200000, 1), ("HG", 20, 3, 1250000, 1)]
     if args.cases == "c2":
         cases = [("HG", 20, 3, 2500000, 1)]
     if args.cases == "prof":
