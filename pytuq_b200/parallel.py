@@ -79,6 +79,22 @@ _STAGE_BYTES = 64 << 20       # host chunk: large enough that the per-call cost 
 _pinned = {}
 
 
+def _stage_groups(n, rows, max_stages=None):
+    """Row ranges (r0, nr) of the host stages of n rows, `rows` per stage, gathered into groups of 1, 2, 4, .. max_stages
+    stages: one statistics call per group."""
+    max_stages = _GROUP_STAGES if max_stages is None else max_stages
+    stages, r0 = [], 0
+    while r0 < n:
+        stages.append((r0, min(rows, n - r0)))
+        r0 += stages[-1][1]
+    groups, i, size = [], 0, 1
+    while i < len(stages):
+        groups.append(stages[i:i + size])
+        i += size
+        size = min(2 * size, max_stages)
+    return groups
+
+
 def _pinned_pair(nbytes, dev):
     """Two reusable pinned staging buffers per device (double buffering of the H2D pipeline)."""
     import torch
@@ -195,15 +211,7 @@ def suffstats_pc(pcrv, x, y=None, jdim=0, distributed=None):
     # run once per group, not per stage: their per-call cost (launch tails of the task-shape kernels, the K x K
     # reconstruction of the moment form) is paid a handful of times per fit.  Groups ramp up (1, 2, 4, .. _GROUP_STAGES
     # stages) so that the first kernels start after one stage while the copies stay ahead of the kernels.
-    stages, r0 = [], 0
-    while r0 < N:
-        stages.append((r0, min(rows, N - r0)))
-        r0 += stages[-1][1]
-    groups, i, size = [], 0, 1
-    while i < len(stages):
-        groups.append(stages[i:i + size])
-        i += size
-        size = min(2 * size, _GROUP_STAGES)
+    groups = _stage_groups(N, rows)
     grows = max([sum(nr for _, nr in g) for g in groups], default=0)
     threaded_copy = os.environ.get("PCQ_PY_HOST_COPY", "threads") != "numpy"
     trace = {"wait_pinned": 0.0, "host_copy": 0.0, "enqueue_h2d": 0.0, "launch_call": 0.0} if os.environ.get("PCQ_PY_TRACE") else None

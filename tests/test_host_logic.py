@@ -272,3 +272,39 @@ def test_workflow_pieces_on_statistics():
         assert abs(sj.yvar(0) - np.std(Y[:, j]) ** 2) < 1e-13
         cf = rng.standard_normal(3); used = np.array([0, 2, 4])
         assert abs(sj.rss(cf, used) - np.sum((Y[:, j] - A[:, used] @ cf) ** 2)) < 1e-11
+
+
+def test_host_copy_rows_flat_and_strided():
+    """pcq_host_copy_rows (the pageable -> pinned copy of the staging pipelines): flat and strided blocks, below and above
+    the size where it goes multi-threaded, and its argument checks."""
+    from pytuq_b200 import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(0)
+    for rows, width, lds, ldd in [(0, 3, 3, 3), (7, 1, 1, 1), (1000, 21, 21, 21), (1000, 20, 23, 26), (60000, 21, 21, 21),
+                                  (60000, 20, 21, 27)]:
+        src = rng.standard_normal((max(rows, 1), lds))
+        dst = np.full((max(rows, 1), ldd), -7.0)
+        assert lib.pcq_host_copy_rows(dst.ctypes.data, ldd, src.ctypes.data, lds, width, rows) == 0
+        np.testing.assert_array_equal(dst[:rows, :width], src[:rows, :width])
+        assert (dst[:rows, width:] == -7.0).all() and (dst[rows:] == -7.0).all()
+    a = np.zeros((4, 4))
+    assert lib.pcq_host_copy_rows(a.ctypes.data, 3, a.ctypes.data, 4, 4, 4) != 0          # row stride below the width
+    assert lib.pcq_host_copy_rows(None, 4, a.ctypes.data, 4, 4, 4) != 0
+
+
+def test_stage_groups_cover_the_rows_once():
+    """Host rows of lreg.fit travel in stages gathered into groups of 1, 2, 4, .. stages (parallel._stage_groups): every row
+    once, in order, the first group one stage, no group above the cap."""
+    from pytuq_b200 import parallel
+    for n, rows, cap in [(0, 100, 8), (1, 100, 8), (100, 100, 8), (101, 100, 8), (12345, 100, 8), (12345, 100, 1), (999, 7, 4)]:
+        groups = parallel._stage_groups(n, rows, cap)
+        flat = [st for g in groups for st in g]
+        assert sum(nr for _, nr in flat) == n
+        pos = 0
+        for r0, nr in flat:
+            assert r0 == pos and 0 < nr <= rows
+            pos += nr
+        assert all(len(g) <= cap for g in groups)
+        if groups:
+            assert len(groups[0]) == 1
+            assert [len(g) for g in groups[:-1]] == [min(2 ** i, cap) for i in range(len(groups) - 1)]
