@@ -461,6 +461,7 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
                     if (nr <= 0 || nc <= 0) continue;
                     const int64_t base = H.base[(size_t)v * 2 + cls] + (cls ? (int64_t)w * H.wsize[v] : 0) +
                                          H.bandoff[((size_t)v * 2 + cls) * MOM_CSTR + a];
+                    if (getenv("PCQ_MOMENT_VERBOSE")) fprintf(stderr, "band node %d [%d,%d|%d) leaf %d cls %d a %d rows %lld cols %lld moments %lld\n", v, nd.lo, nd.mid, nd.hi, (int)leaf, cls, a, (long long)nr, (long long)nc, (long long)(nr * nc));
                     P.band(bundles, v, a, cls ? w : -1, nr, nc, base);
                     if (bundles.size() > 200000) { H.why = "too many tasks"; return; }
                 }
