@@ -118,6 +118,15 @@ def lib():
             raise PcqError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C pytuq_b200/csrc`. pytuq_b200 has no CPU fallback.")
+        # one process per GPU (torchrun): the ranks of a node share its host cores for the pageable <-> pinned staging
+        # copies; without a setting of the user's, each rank takes its share instead of the library's default of 16
+        if "PCQ_HOST_THREADS" not in os.environ:
+            try:
+                local = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+            except ValueError:
+                local = 1
+            if local > 1:
+                os.environ["PCQ_HOST_THREADS"] = str(max(2, (os.cpu_count() or 16) // local))
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)   # AttributeError if the symbol is not exported
