@@ -272,3 +272,24 @@ def test_more_outputs_than_the_moment_form_carries(fam, d, p, m, n, monkeypatch)
     assert _rel(_dev_stats(pc, mi, x, y, m, "1"), Sref) < 1e-12
     monkeypatch.delenv("PCQ_SYRK_TILE")
     assert _rel(_dev_stats(pc, mi, x, y, m, "0"), Sref) < 1e-12
+
+
+def test_planner_sweep_capacities_and_refusals():
+    """Total-order sets over germ dimensions 2..64 and orders 1..6: the planner serves exactly the shapes whose table of
+    1-D values fits (1 + 2 p d + m + 1 <= 256 slots), every unit within the kernel's capacities (<= 1280 functions,
+    <= 384 sub-functions), and executes fewer multiply-adds than the dense form wherever K is large."""
+    from math import comb
+    for d in (2, 5, 9, 16, 33, 50, 64):
+        for p in (1, 2, 3, 5, 6):
+            K = comb(d + p, p)
+            if K > 7000:
+                continue
+            mi = orc.get_mi(p, d)
+            for m in (0, 8):
+                rc, _, info = _host_stats_plan_only(mi, ["LU"] * d, m)
+                fits = 1 + 2 * p * d + m + 1 <= 256
+                assert (rc == 0) == fits, (d, p, m, rc)
+                if rc == 0:
+                    assert info[4] <= 1280 and info[5] <= 384 and info[1] >= 1
+                    if K >= 1000 and m == 0:
+                        assert info[3] < 0.7 * K * (K + 1) / 2, (d, p, info[3])
