@@ -67,7 +67,8 @@ def _rel(S, Sref):
 
 
 CASES = [("LU", 2, 2, 1), ("HG", 3, 2, 2), ("LU", 4, 3, 1), (["LU", "HG", "nLU", "nHG", "LU"], 5, 3, 2), ("HG", 7, 2, 0),
-         ("nLU", 6, 3, 1), ("nHG", 3, 4, 3), ("HG", 8, 3, 1), ("LU", 2, 7, 1), ("LU", 40, 2, 1), ("HG", 33, 1, 2)]
+         ("nLU", 6, 3, 1), ("nHG", 3, 4, 3), ("HG", 8, 3, 1), ("LU", 2, 7, 1), ("LU", 40, 2, 1), ("HG", 33, 1, 2),
+         ("HG", 20, 3, 1), ("LU", 50, 2, 2), ("HG", 10, 4, 1)]      # the last three: C2 (headline), C3 and a p = 4 shape
 
 
 @pytest.mark.parametrize("fam,d,p,m", CASES)
