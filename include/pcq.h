@@ -153,7 +153,8 @@ int pcq_eval_pc(pcq_plan* plan, const double* x_host, int64_t n, int64_t ldx,
  * in shared memory) and reconstructs S from them, whenever that is estimated faster than the pack + SYRK form and
  * n >= PCQ_MOMENT_MIN_N (32768).  Same S up to rounding (1e-15 relative to sqrt(S_ii S_jj)); it replaces the same
  * reference lines (lreg/anl.py:78,83, lreg/bcs.py:83-100, lreg/lreg.py:328-339).  PCQ_GRAM_MOMENT=0 disables it, =1
- * uses it for every n.
+ * uses it for every n.  The rule also keeps the dense form where the reconstruction would amplify rounding errors: Hermite
+ * sets of total order >= 7 (moments up to He_14 dwarf the entries they rebuild; PCQ_MOMENT_MAX_AMP, default 500).
  *   nord       >= 2 * max_k sum_i mi[k,i]
  *   rec_a_ext  (nord+1) x s, rec_a_ext[n*s+i] = PC1d_i.a(n);  rec_b_ext likewise   (rv/pcrv.py:755-777)
  */

@@ -54,6 +54,7 @@ struct MomHost {
     int nf_max = 0, nsub_max = 0;
     double clk_per_block = 0;         // estimated cycles of one 16-sample block summed over the units (one CTA)
     double mac_slots = 0;             // executed DMMA multiply-adds per sample
+    double amp = 0;                   // how much larger than a Gram entry the moments it is summed from can be (see mom_build)
     std::string why;                  // empty when the plan is usable
 
     MomGeom geom() const {
@@ -374,6 +375,25 @@ void mom_build(MomHost& H, int s, int nterms, const int32_t* mi, int nord, const
     }
     H.lin.assign((size_t)s * (pt + 1) * (pt + 1) * (H.B0 + 1), 0.0);
     for (int d = 0; d < s; ++d) linearise(ra, rb, p1[d], s, d, pt, H.B0, H.lin.data());
+    // Conditioning of the reconstruction: G_ii = sum_k c_aak m_k with m_0 = N h_0 the entry itself and the other m_k
+    // sampling noise of size ~ sqrt(N h_k) summed from terms of size ~ sqrt(h_k), h_k = ||psi_k||^2 (from the
+    // recurrence: h_n = -b_n h_{n-1} a_{n-1} / a_n).  amp = max_a sum_{k>=1} |c_aak| sqrt(h_k) / c_aa0 measures how far
+    // the rounding error of the moments is amplified relative to the entry: Legendre <= 2 a + 1, Hermite 16 / 47 / 134 /
+    // 386 at a = 3 .. 6 and super-exponential beyond.  The route rule keeps the dense form above PCQ_MOMENT_MAX_AMP (500).
+    for (int d = 0; d < s; ++d) {
+        std::vector<long double> h(H.B0 + 1, 1.0L);
+        for (int n = 1; n <= H.B0; ++n) {
+            const long double an = ra[(size_t)n * s + d], bn = rb[(size_t)n * s + d];
+            const long double am = n == 1 ? (long double)p1[d] : (long double)ra[(size_t)(n - 1) * s + d];
+            h[n] = fabsl(bn * h[n - 1] * am / an);
+        }
+        for (int a = 1; a <= pt; ++a) {
+            const double* c = H.lin.data() + (((size_t)d * (pt + 1) + a) * (pt + 1) + a) * (H.B0 + 1);
+            long double noise = 0.0L;
+            for (int k = 1; k <= 2 * a; ++k) noise += fabsl((long double)c[k]) * sqrtl(h[k]);
+            if (c[0] > 0.0) H.amp = std::max(H.amp, (double)(noise / (long double)c[0]));
+        }
+    }
 
     // sparse terms
     H.tdim.assign((size_t)nterms * width, -1);
@@ -729,7 +749,7 @@ extern "C" int pcq_debug_moments_host(int sdim, int nterms, const int32_t* mi, i
     mom_build(H, sdim, nterms, mi, nord, rec_a_ext, rec_b_ext, p1_scale, m);
     if (info) {
         info[0] = (double)H.nmom; info[1] = (double)H.units.size(); info[2] = H.clk_per_block; info[3] = H.mac_slots;
-        info[4] = H.nf_max; info[5] = H.nsub_max; info[6] = H.why.empty() ? 1.0 : 0.0; info[7] = (double)H.nodes.size();
+        info[4] = H.nf_max; info[5] = H.nsub_max; info[6] = H.why.empty() ? 1.0 : 0.0; info[7] = H.amp;
     }
     if (!H.why.empty()) { pcq_set_error("moment form not applicable: %s", H.why.c_str()); return PCQ_ERR_UNSUPPORTED; }
     if (s_out) {
@@ -1461,6 +1481,8 @@ bool mom_pays(const pcq_plan* p, const MomHost& H, int m, int64_t n) {
     const double syrk = (L * L / 2 * 1.04) / 64.0 / 0.89, mine = H.clk_per_block / MOM_BS;
     const double hz = 1.9e9 * p->num_sms;
     const double fixed = 0.31e-9 * (double)p->nterms * p->nterms + 1.5e-4;
+    const char* ae = getenv("PCQ_MOMENT_MAX_AMP");
+    if (H.amp > (ae ? atof(ae) : 500.0)) return false;          // high-order Hermite: the moments dwarf the entries they rebuild
     return mine * 1.1 <= syrk && (double)n * (syrk - mine) / hz >= 1.25 * fixed;
 }
 }  // namespace

@@ -294,3 +294,17 @@ def test_planner_sweep_capacities_and_refusals():
                     assert info[4] <= 1280 and info[5] <= 384 and info[1] >= 1
                     if K >= 1000 and m == 0:
                         assert info[3] < 0.7 * K * (K + 1) / 2, (d, p, info[3])
+
+
+def test_conditioning_estimate_of_the_reconstruction():
+    """info[7]: how much larger than a Gram entry the moments it is rebuilt from can be (max_a sum_k |c_aak| sqrt(h_k) / h_a).
+    He_3^2 = He_6 + 9 He_4 + 18 He_2 + 6 gives (sqrt(720) + 9 sqrt(24) + 18 sqrt(2)) / 6 = 16.06; Legendre stays below
+    2 a + 1; Hermite beyond order 6 exceeds the bound (500) above which the route rule keeps the dense form."""
+    amp = {}
+    for fam, d, p in [("HG", 20, 3), ("LU", 50, 2), ("LU", 6, 8), ("nLU", 6, 4), ("HG", 4, 6), ("HG", 3, 7), ("nHG", 3, 8)]:
+        rc, _, info = _host_stats_plan_only(orc.get_mi(p, d), [fam] * d, 1)
+        assert rc == 0
+        amp[(fam, p)] = info[7]
+    assert abs(amp[("HG", 3)] - (np.sqrt(720.0) + 9 * np.sqrt(24.0) + 18 * np.sqrt(2.0)) / 6.0) < 1e-9
+    assert amp[("LU", 2)] < 5 and amp[("LU", 8)] < 17 and amp[("nLU", 4)] < 9
+    assert amp[("HG", 6)] < 500 < amp[("HG", 7)] < amp[("nHG", 8)]
